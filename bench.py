@@ -1,0 +1,492 @@
+#!/usr/bin/env python
+"""bench.py -- VLQ hot path on B200: search QPS (+ encode Mvec/s) for BASELINE.json configs[1]
+(C=2^16 centroids, 32 neighbour lines, PQ m=16, synthetic SIFT-shaped 10M x 128 per GPU).
+
+  python bench.py [--gpus N] [--steps K] [--warmup W]            our arm (one process per GPU under torchrun for N>1)
+  python bench.py --impl reference [...]                          CPU arm: the reference's CPU code (IndexFlatL2 /
+                                                                  ProductQuantizer from oracle/_ref) for the stock
+                                                                  pieces + the oracle port for the VLQ-only search
+
+A "step" is one pass of the search hot path (coarse top-P -> line selection -> ADC scan + top-k [-> all-gather +
+merge for N>1]) over one batch of nq queries.  `value` is timed with the inputs resident in HBM; `e2e` goes through
+host (pinned) buffers with the H2D / D2H copies inside the timed region.  Prints ONE JSON line on rank 0.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--n", type=int, default=10_000_000, help="database vectors PER GPU")
+    ap.add_argument("--d", type=int, default=128)
+    ap.add_argument("--nlist", type=int, default=65536)
+    ap.add_argument("--nedge", type=int, default=32)
+    ap.add_argument("--m", type=int, default=16)
+    ap.add_argument("--nlambda", type=int, default=256)
+    ap.add_argument("--nq", type=int, default=10000)
+    ap.add_argument("--nprobe", type=int, default=64)
+    ap.add_argument("--w1", type=int, default=256)
+    ap.add_argument("--k", type=int, default=100)
+    ap.add_argument("--train-iters", type=int, default=4, help="coarse k-means iterations in the (untimed) setup")
+    ap.add_argument("--kc", type=int, default=1 << 18, help="mixture components of the synthetic generator")
+    ap.add_argument("--cpu-seconds", type=float, default=15.0, help="CPU-baseline budget in the default arm")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--quick", action="store_true", help="small sizes (for debugging the script itself)")
+    a = ap.parse_args()
+    if a.quick:
+        a.n, a.nlist, a.nq, a.kc = 400_000, 4096, 2000, 1 << 14
+    return a
+
+
+# ------------------------------------------------------------------------------------------------------- clocks
+class ClockSampler:
+    QUERY = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+             "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+             "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.gpu = gpu_index
+        self.proc = None
+        self.path = None
+
+    def start(self):
+        try:
+            fd, self.path = tempfile.mkstemp(suffix=".csv")
+            os.close(fd)
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", "-i", str(self.gpu), "--query-gpu=" + self.QUERY, "--format=csv,noheader,nounits",
+                 "-lms", "100"], stdout=open(self.path, "w"), stderr=subprocess.DEVNULL)
+        except Exception:
+            self.proc = None
+
+    def stop(self):
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        if self.proc is None:
+            return out
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        try:
+            for line in open(self.path):
+                f = [t.strip() for t in line.split(",")]
+                if len(f) < 9:
+                    continue
+                try:
+                    sm.append(float(f[1]))
+                    mx.append(float(f[2]))
+                except ValueError:
+                    continue
+                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
+                    if v.lower().startswith("active"):
+                        reasons.add(name)
+            os.unlink(self.path)
+        except Exception:
+            pass
+        if sm:
+            out.update(sm_mhz=float(np.median(sm)), sm_max_mhz=float(max(mx)), reasons=sorted(reasons), samples=len(sm))
+        return out
+
+
+# ------------------------------------------------------------------------------------------------------- CPU arm
+def cpu_search_baseline(po, model, lists_host, xq, P, W, k, budget_s, gpu_result=None):
+    """Times the oracle port of the VLQ search (the reference has no CPU VLQ) on a bounded sample of the queries,
+    against the SAME index.  Returns the cpu_baseline object (+ a parity summary against the GPU results)."""
+    T2 = po.term2(model["cent"], model["pq"])  # the reference precomputes this at train time (IVFPQ.cu:599-684)
+    off, codes, lamq, ids = lists_host
+    args = (model["cent"], model["edge"], model["edge_d2"], model["lambda_cb"], model["pq"], off, codes, lamq, ids)
+    ncores = po.num_threads()
+    probe = min(xq.shape[0], max(2 * ncores, 16))
+    t0 = time.time()
+    po.search(xq[:probe], *args, P=P, W=W, k=k, T2=T2)
+    per_q = (time.time() - t0) / probe
+    ns = int(min(xq.shape[0], max(probe, budget_s / max(per_q, 1e-9))))
+    t0 = time.time()
+    D, I = po.search(xq[:ns], *args, P=P, W=W, k=k, T2=T2)
+    dt = time.time() - t0
+    out = {"value": ns / dt, "unit": "queries/s", "cores": ncores, "kind": "port",
+           "sample": "%d of the %d queries against the same %d-vector index (oracle/vlq_oracle.c:vlqo_search, OpenMP "
+                     "over queries; the reference has no CPU implementation of VLQ search)" % (ns, xq.shape[0], len(ids))}
+    parity = None
+    if gpu_result is not None:
+        gD, gI = gpu_result
+        gD, gI = gD[:ns], gI[:ns]
+        qn = (xq[:ns].astype(np.float64) ** 2).sum(1, keepdims=True)
+        valid = I >= 0
+        rel = np.abs(gD - D)[valid] / (np.abs(D) + qn)[valid]
+        parity = {"queries": ns, "id_match": float((gI == I)[valid].mean()), "max_rel_dist_err": float(rel.max()),
+                  "set_overlap": float(np.mean([len(set(a) & set(b)) / max(1, len(set(b))) for a, b in zip(gI, I)]))}
+    return out, parity
+
+
+def run_reference(a):
+    """--impl reference: everything on the host cores; no CUDA library is loaded."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    from oracle import pyoracle as po
+    from vector_line_quantization_b200 import data
+
+    have_ref = po.ref_available()
+    ncores = po.num_threads()
+    C, E, M, d = a.nlist, a.nedge, a.m, a.d
+    t_setup = time.time()
+    nb = min(a.n, 100_000)  # bounded sample of the database (see `sample`)
+    xt = data.sift_like(max(C, 32768), d=d, kc=min(a.kc, 1 << 16), seed=1)
+    xb = data.sift_like(nb, d=d, kc=min(a.kc, 1 << 16), seed=2)
+    xq = data.sift_like(a.nq, d=d, kc=min(a.kc, 1 << 16), seed=3)
+    # codebooks: untimed setup.  CPU k-means at C=2^16 takes ~1 h on 8 cores, so centroids are a random sample of the
+    # training rows (search / encode cost does not depend on centroid quality); everything else follows the train path.
+    cent = xt[po.rand_perm(xt.shape[0], 1234)[:C]] + np.float32(0.25)
+    if have_ref:
+        Dg, Ig = po.ref_flat_search(cent, cent, E + 1)  # reference IndexFlatL2 (BLAS), GpuIndexFlat.cu:869-893
+        edge, ed2 = Ig[:, 1:].astype(np.int32).copy(), Dg[:, 1:].copy()
+        ed2 = np.maximum(ed2, 1e-3).astype(np.float32)
+    else:
+        edge, ed2 = po.knn_graph(cent, E)
+    x2 = xt[:32768]
+    A2 = (po.ref_flat_search(cent, x2, 1)[1][:, 0].astype(np.int32) if have_ref else po.l2_topk(x2, cent, 1)[1][:, 0].copy())
+    lst2, lam2 = po.line_stage(x2, A2, cent, edge, ed2)
+    lcb, _ = po.kmeans(lam2.reshape(-1, 1), a.nlambda, niter=10)
+    lcb = lcb.reshape(-1)
+    r2 = po.residual(x2, lst2, po.lambda_quantize(lam2, lcb), lcb, cent, edge)
+    pq = po.ref_pq_train(r2, M) if have_ref else np.stack(
+        [po.kmeans(r2[:, m * (d // M):(m + 1) * (d // M)], 256, niter=10)[0] for m in range(M)])
+    # encode the database sample (timed: the CPU encode rate)
+    t0 = time.time()
+    if have_ref:
+        A = po.ref_flat_search(cent, xb, 1)[1][:, 0].astype(np.int32)  # IndexFlatL2::search, the CPU twin of a2
+    else:
+        A = po.l2_topk(xb, cent, 1)[1][:, 0].copy()
+    lst, lam = po.line_stage(xb, A, cent, edge, ed2)
+    lamq = po.lambda_quantize(lam, lcb)
+    r = po.residual(xb, lst, lamq, lcb, cent, edge)
+    codes = po.ref_pq_compute_codes(r, pq) if have_ref else po.pq_encode(r, pq)
+    off, perm = po.build_lists(lst, C * E)
+    t_enc = time.time() - t0
+    T2 = po.term2(cent, pq)
+    args = (cent, edge, ed2, lcb, pq, off, codes[perm], lamq[perm], perm.astype(np.int64))
+    t_setup = time.time() - t_setup
+    # steps: each a bounded sample of the nq-query batch, sized for ~4 s
+    probe = min(a.nq, max(2 * ncores, 16))
+    t0 = time.time()
+    po.search(xq[:probe], *args, P=a.nprobe, W=a.w1, k=a.k, T2=T2)
+    per_q = (time.time() - t0) / probe
+    ns = int(min(a.nq, max(probe, 4.0 / max(per_q, 1e-9))))
+    for _ in range(a.warmup):
+        po.search(xq[:ns], *args, P=a.nprobe, W=a.w1, k=a.k, T2=T2)
+    times = []
+    for _ in range(a.steps):
+        t0 = time.time()
+        po.search(xq[:ns], *args, P=a.nprobe, W=a.w1, k=a.k, T2=T2)
+        times.append(time.time() - t0)
+    tot = sum(times)
+    qps = ns * a.steps / tot
+    sample = ("%d of %d queries per step against a %d-vector sample of the %d-vector database (same C/E/M geometry; "
+              "centroids = random training rows, no CPU k-means); stock pieces by the reference CPU library = %s"
+              % (ns, a.nq, nb, a.n, have_ref))
+    line = {
+        "impl": "reference", "metric": "vlq_search_qps", "value": qps, "unit": "queries/s", "n_gpus": a.gpus,
+        "steps": a.steps, "warmup": a.warmup, "ms_per_step": 1e3 * tot / a.steps, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": workload_config(a, a.gpus),
+        "cpu_baseline": {"value": qps, "unit": "queries/s", "cores": ncores, "kind": "port", "sample": sample},
+        "e2e": {"value": qps, "unit": "queries/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "encode": {"value": nb / t_enc / 1e6, "unit": "Mvec/s", "kind": "reference" if have_ref else "port",
+                   "sample": "%d vectors: IndexFlatL2 assign + oracle line stage + ProductQuantizer::compute_codes" % nb},
+        "setup_s": t_setup,
+    }
+    print(json.dumps(line))
+
+
+def workload_config(a, n_gpus):
+    return {
+        "workload": "BASELINE.json configs[1]: VLQ C=%d centroids x E=%d lines, PQ m=%d, nLambda=%d, d=%d, synthetic "
+                    "SIFT-shaped %d vectors per GPU; search nq=%d nprobe=%d w1=%d k=%d"
+                    % (a.nlist, a.nedge, a.m, a.nlambda, a.d, a.n, a.nq, a.nprobe, a.w1, a.k),
+        "db_vectors_per_gpu": a.n, "db_vectors_total": a.n * n_gpus, "nlist": a.nlist, "nedge": a.nedge, "m": a.m,
+        "nq": a.nq, "nprobe": a.nprobe, "w1": a.w1, "k": a.k,
+        "parallelism": "id-range database shards, queries replicated, NCCL all-gather of per-shard top-k + merge kernel"
+        if n_gpus > 1 else "single GPU",
+        "l2": "an L2-sized (256 MiB) buffer is overwritten between timed steps",
+    }
+
+
+# ------------------------------------------------------------------------------------------------------- our arm
+def run_b200(a):
+    import torch
+    import torch.distributed as dist
+
+    from vector_line_quantization_b200 import _abi, data, ops, train
+
+    _abi.lib()  # fail loudly without the CUDA extension
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    assert torch.cuda.is_available(), "bench.py (--impl b200) needs a GPU: there is no CPU fallback"
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    C, E, M, d, P, W, k, nq = a.nlist, a.nedge, a.m, a.d, a.nprobe, a.w1, a.k, a.nq
+
+    def log(*s):
+        if rank == 0:
+            print("[bench]", *s, file=sys.stderr, flush=True)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- setup (untimed): codebooks trained on the device; identical on all ranks (rank 0 broadcasts)
+    t0 = time.time()
+    nt = min(C * 64, 4 * a.n)
+    xt = data.sift_like_torch(nt, d=d, kc=a.kc, seed=1, device=dev)
+    model = train.train_vlq(xt, C, E, M, a.nlambda, niter=a.train_iters, pq_niter=10, exact_perm=False)
+    del xt
+    if world > 1:
+        for key in ("cent", "cnorm", "edge", "edge_d2", "lambda_cb", "pq"):
+            dist.broadcast(model[key], 0)
+    torch.cuda.synchronize()
+    log("trained codebooks in %.1f s" % (time.time() - t0))
+    cent, cn, edge, ed2, lcb, pq = (model[key] for key in ("cent", "cnorm", "edge", "edge_d2", "lambda_cb", "pq"))
+
+    # ---- encode this rank's shard (timed as its own stage: encode Mvec/s)
+    xb = data.sift_like_torch(a.n, d=d, kc=a.kc, seed=2 + rank, device=dev)
+    chunk = 1 << 20
+    id0 = rank * a.n
+    lists = None
+    barrier()
+    n_before = ops.launch_count()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev0.record()
+    parts = []
+    for s in range(0, a.n, chunk):
+        x = xb[s:s + chunk]
+        A, _ = ops.l2_assign(x, cent, cn, want_dist=False)
+        parts.append(ops.line_encode(x, A, cent, edge, ed2, lcb, pq))
+    new_list = torch.cat([p.list for p in parts])
+    ids = torch.arange(id0, id0 + a.n, dtype=torch.int64, device=dev)
+    lists = ops.build_lists(C * E, M, new_list, torch.cat([p.codes for p in parts]), torch.cat([p.lamq for p in parts]),
+                            torch.cat([p.kappa for p in parts]), ids)
+    ev1.record()
+    barrier()
+    enc_ms = torch.tensor([ev0.elapsed_time(ev1)], device=dev)
+    if world > 1:
+        dist.all_reduce(enc_ms, op=dist.ReduceOp.MAX)
+    enc_ms = float(enc_ms)
+    enc_launches = ops.launch_count() - n_before
+    del parts, new_list
+    log("encoded %d vectors/GPU in %.1f ms" % (a.n, enc_ms))
+
+    # ---- queries + exact ground truth (brute force over every shard, for recall)
+    xq = data.sift_like_torch(nq, d=d, kc=a.kc, seed=3, device=dev)
+    gt_d = torch.full((nq,), float("inf"), device=dev)
+    gt_i = torch.full((nq,), -1, dtype=torch.int64, device=dev)
+    qn = ops.row_norms(xq)
+    gchunk = 1 << 18
+    for s in range(0, a.n, gchunk):  # "centroids" = a database slice; argmin per query = exact 1-NN in the slice
+        sl = xb[s:s + gchunk]
+        i_, d_ = ops.l2_assign(xq, sl, add_xnorm=True)
+        better = d_ < gt_d
+        gt_d = torch.where(better, d_, gt_d)
+        gt_i = torch.where(better, i_.to(torch.int64) + (id0 + s), gt_i)
+    if world > 1:
+        all_d = [torch.empty_like(gt_d) for _ in range(world)]
+        all_i = [torch.empty_like(gt_i) for _ in range(world)]
+        dist.all_gather(all_d, gt_d)
+        dist.all_gather(all_i, gt_i)
+        sd, si = torch.stack(all_d), torch.stack(all_i)
+        best = sd.argmin(dim=0, keepdim=True)
+        gt_i = si.gather(0, best)[0]
+    del xb
+    torch.cuda.empty_cache()
+
+    # ---- the step
+    gD = torch.empty((world, nq, k), dtype=torch.float32, device=dev) if world > 1 else None
+    gI = torch.empty((world, nq, k), dtype=torch.int64, device=dev) if world > 1 else None
+
+    def step(q):
+        D, I = ops.search(q, cent, cn, edge, ed2, lcb, pq, lists, P, W, k)
+        if world > 1:
+            dist.all_gather_into_tensor(gD, D)
+            dist.all_gather_into_tensor(gI, I)
+            D, I = ops.merge_topk(gD, gI)
+        return D, I
+
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+
+    def timed(fn, steps, warmup):
+        for _ in range(warmup):
+            fn()
+        barrier()
+        evs = []
+        n0 = ops.launch_count()
+        for _ in range(steps):
+            flush.fill_(1)  # L2 flush, outside the timed events
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            fn()
+            e1.record()
+            evs.append((e0, e1))
+        barrier()
+        launches = ops.launch_count() - n0
+        ms = torch.tensor([sum(e0.elapsed_time(e1) for e0, e1 in evs)], device=dev)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return float(ms), launches
+
+    clocks = ClockSampler(local)
+    clocks.start()
+    result = {}
+
+    def dev_step():
+        result["DI"] = step(xq)
+
+    total_ms, launches = timed(dev_step, a.steps, a.warmup)
+    clk = clocks.stop()
+    D, I = result["DI"]
+
+    # ---- e2e: host (pinned) queries in, host results out, copies inside the timed region
+    hq = torch.empty((nq, d), dtype=torch.float32).pin_memory()
+    hq.copy_(xq.cpu())
+    hD = torch.empty((nq, k), dtype=torch.float32).pin_memory()
+    hI = torch.empty((nq, k), dtype=torch.int64).pin_memory()
+    dq = torch.empty_like(xq)
+
+    def e2e_step():
+        dq.copy_(hq, non_blocking=True)
+        D_, I_ = step(dq)
+        hD.copy_(D_, non_blocking=True)
+        hI.copy_(I_, non_blocking=True)
+
+    e2e_ms, _ = timed(e2e_step, a.steps, a.warmup)
+
+    # ---- per-stage device times of one step (CUDA events on the launching stream) -> roofline of the dominant kernel
+    def stage_times():
+        names = ["l2_distances", "select_rows", "select_lines", "scan_topk"]
+        acc = dict.fromkeys(names, 0.0)
+        cnt = dict.fromkeys(names, 0)
+        tile = 1024
+        Dbuf = torch.empty((tile, C), dtype=torch.float32, device=dev)
+        ed2f = ed2.reshape(-1)
+
+        def t(name, fn):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            r = fn()
+            e1.record()
+            pending.append((name, e0, e1))
+            return r
+
+        pending = []
+        for s in range(0, nq, tile):
+            qt = xq[s:s + tile]
+            Dm = t("l2_distances", lambda: ops.l2_distances(qt, cent, cn, out=Dbuf[: qt.shape[0]]))
+            _, cid = t("select_rows", lambda: ops.select_rows(Dm, P))
+            lst, t1, t6 = t("select_lines", lambda: ops.select_lines(Dm, cid, edge, ed2, W))
+            t("scan_topk", lambda: ops.scan_topk(qt, pq, lcb, lst, t1, t6, ed2f, lists, k))
+        torch.cuda.synchronize()
+        for name, e0, e1 in pending:
+            acc[name] += e0.elapsed_time(e1)
+            cnt[name] += 1
+        return acc, cnt
+
+    stage_times()
+    st_ms, st_cnt = stage_times()
+
+    # scanned entries per query (algorithmic bytes of the scan: SURVEY 8d)
+    lens = (lists.offsets[1:] - lists.offsets[:-1]).clamp_max(1024)
+    Dm = ops.l2_distances(xq[:1024].contiguous(), cent, cn)
+    _, cid = ops.select_rows(Dm, P)
+    lst, _, _ = ops.select_lines(Dm, cid, edge, ed2, W)
+    scanned_per_q = float(lens[lst.clamp_min(0).to(torch.int64)].mul(lst >= 0).sum(dim=1).float().mean())
+
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    hbm_peak = peaks.get("hbm_gbs", 6650.0)
+    tc_peak = peaks.get("bf16_tflops", 1590.0)
+    peak_src = "measured (MEASURED_PEAKS.json, burst: kernel timed alone)" if peaks else "fallback (B200_PROFILING.md)"
+    dominant = max(st_ms, key=st_ms.get)
+    per_launch_ms = st_ms[dominant] / max(1, st_cnt[dominant])
+    rows_per_launch = nq / max(1, st_cnt[dominant])
+    if dominant == "scan_topk":
+        alg = rows_per_launch * (scanned_per_q * (M + 1) + k * 8)
+        roof = {"bound": "hbm", "achieved": alg / (per_launch_ms * 1e-3) / 1e9, "peak": hbm_peak, "unit": "GB/s"}
+    elif dominant == "select_rows":
+        alg = rows_per_launch * C * 4.0
+        roof = {"bound": "hbm", "achieved": alg / (per_launch_ms * 1e-3) / 1e9, "peak": hbm_peak, "unit": "GB/s"}
+    else:
+        flops = rows_per_launch * 2.0 * C * d
+        roof = {"bound": "tensor", "achieved": flops / (per_launch_ms * 1e-3) / 1e12, "peak": tc_peak, "unit": "TFLOP/s"}
+    roof.update(frac=roof["achieved"] / roof["peak"], traffic=None, kernel=dominant, peak_source=peak_src,
+                ms_per_launch=per_launch_ms, stage_ms_per_step=st_ms)
+
+    # ---- recall (R@r of the true 1-NN, gpu/test/sift1b_query.cpp:334-347)
+    In = I.cpu().numpy()
+    gt = gt_i.cpu().numpy()
+    recall = {"R@1": data.recall_at(In, gt, 1), "R@10": data.recall_at(In, gt, 10), "R@100": data.recall_at(In, gt, min(100, k))}
+
+    # ---- CPU baseline on rank 0 (N=1 only): oracle port against the same index + parity on the sample
+    cpu_baseline, parity = None, None
+    if rank == 0 and world == 1 and not a.no_cpu_baseline:
+        from oracle import pyoracle as po  # checker / baseline only
+
+        mh = {key: model[key].cpu().numpy() for key in ("cent", "edge", "edge_d2", "lambda_cb", "pq")}
+        lh = (lists.offsets.cpu().numpy(), lists.codes.cpu().numpy(), lists.lamq.cpu().numpy(), lists.ids.cpu().numpy())
+        cpu_baseline, parity = cpu_search_baseline(po, mh, lh, xq.cpu().numpy(), P, W, k, a.cpu_seconds,
+                                                   (D.cpu().numpy(), In))
+
+    if rank == 0:
+        qps = nq * a.steps / (total_ms * 1e-3)
+        e2e_qps = nq * a.steps / (e2e_ms * 1e-3)
+        line = {
+            "metric": "vlq_search_qps", "value": qps * world, "unit": "queries/s" if world == 1 else "shard-queries/s",
+            "n_gpus": world, "steps": a.steps, "warmup": a.warmup, "ms_per_step": total_ms / a.steps,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": workload_config(a, world), "merged_qps": qps,
+            "e2e": {"value": e2e_qps * world, "unit": "queries/s" if world == 1 else "shard-queries/s",
+                    "h2d_bytes_per_step": nq * d * 4, "d2h_bytes_per_step": nq * k * 12, "merged_qps": e2e_qps},
+            "gpu_launches": launches, "roofline": roof, "cpu_baseline": cpu_baseline, "clocks": clk, "recall": recall,
+            "encode": {"value": a.n * world / (enc_ms * 1e-3) / 1e6, "unit": "Mvec/s", "ms": enc_ms,
+                       "gpu_launches": enc_launches,
+                       "tensor_frac": (a.n * 2.0 * C * d / (enc_ms * 1e-3) / 1e12) / peaks.get("bf16_tflops_sustained", 1400.0)},
+            "scanned_entries_per_query": scanned_per_q, "parity_vs_oracle": parity,
+        }
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    a = parse()
+    if a.impl == "reference":
+        run_reference(a)
+    else:
+        run_b200(a)
+
+
+if __name__ == "__main__":
+    main()

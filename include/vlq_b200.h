@@ -1,0 +1,181 @@
+/* vlq_b200.h -- C-ABI of the B200-native (sm_100a) VLQ hot path.
+ *
+ * This is the drop-in boundary: every entry point takes raw DEVICE pointers, explicit sizes, a
+ * caller-provided workspace where one is needed (paired with a *_workspace_bytes query) and a cudaStream_t passed as
+ * void*.  Functions return 0 on success, a negative VLQ_E* code for invalid arguments, or a positive cudaError_t.
+ * They never throw, never allocate device memory and never synchronise the stream (the only exceptions are the
+ * explicitly named memory / stream helpers at the bottom, which exist so that a host layer needs no CUDA headers).
+ *
+ * Each compute entry cites the reference interface it replaces (paths relative to the reference repository).
+ * There is no CPU fallback: if the CUDA library cannot be loaded the host layers fail loudly.
+ */
+#ifndef VLQ_B200_H
+#define VLQ_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define VLQ_OK 0
+#define VLQ_EINVAL (-1)    /* bad argument (null pointer, size out of range, unsupported d / M / k) */
+#define VLQ_EWORKSPACE (-2) /* workspace too small */
+#define VLQ_EUNSUPPORTED (-3)
+
+#define VLQ_MAX_K 1024      /* k, nprobe (P) and w1 (W) limits of the reference: gpu/GpuIndexFlat.cu:226-232,
+                               gpu/GpuIndexIVF.cu:201-207, gpu/impl/IVFPQ.cu:697-698 */
+#define VLQ_LIST_CAP 1024   /* lists are truncated to their first 1024 entries at scan time:
+                               gpu/impl/IVFUtils.cu:87, gpu/impl/PQScanMultiPassPrecomputed.cu:728 */
+
+typedef void* vlq_stream_t; /* cudaStream_t */
+
+const char* vlq_error_string(int code);
+const char* vlq_version(void);
+/* number of kernels this library has launched since load (bench.py's gpu_launches) */
+uint64_t vlq_launch_count(void);
+
+/* ------------------------------------------------------------------------------------------------------------------
+ * a1  row norms ||x_i||^2.                          replaces runL2Norm, gpu/impl/L2Norm.cu:34-173 (FlatIndex.cu:369-439)
+ * ---------------------------------------------------------------------------------------------------------------- */
+int vlq_row_norms(const float* x, int64_t n, int d, float* out, vlq_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------------------------
+ * a2  nearest centroid per vector (k = 1), exact fp32 CUDA-core path.
+ *     replaces runL2Distance(k=1) = runMatrixMult + l2SelectMin1 + sumAlongRows,
+ *     gpu/impl/Distance.cu:579-710, gpu/impl/L2Select.cu:25-121, gpu/impl/BroadcastSum.cu:677-698
+ *     (CPU twin knn_L2sqr, utils.cpp:833-901).
+ *     out_dist (nullable) = ||c||^2 - 2 x.c (+ ||x||^2 when add_xnorm).  Ties -> lowest centroid id.
+ * ---------------------------------------------------------------------------------------------------------------- */
+int vlq_l2_assign(const float* x, int64_t n, int d, const float* cent, const float* cnorm, int C, int add_xnorm,
+                  int* out_ids, float* out_dist, vlq_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------------------------
+ * a11 coarse distance matrix for a query tile, D[i][j] = ||c_j||^2 - 2 x_i.c_j  (NO ||x||^2, Distance.cu:287-290).
+ *     replaces runMatrixMult + the in-place "+||c||^2" of l2SelectMinK, gpu/impl/Distance.cu:352-373.
+ *     D is [n][ldD] with ldD >= C.
+ * ---------------------------------------------------------------------------------------------------------------- */
+int vlq_l2_distances(const float* x, int64_t n, int d, const float* cent, const float* cnorm, int C, float* D,
+                     int64_t ldD, vlq_stream_t stream);
+
+/* a11/a15 exact top-k per row, ascending, ties by lowest column; pads with (FLT_MAX, -1).  k <= VLQ_MAX_K.
+ *     replaces l2SelectMinK / BlockSelect, gpu/impl/L2Select.cu:124-165, gpu/utils/Select.cuh:77-277
+ *     (CPU twin Heap.h:89-323).  row_add (nullable) is added to the k winners of each row (sumAlongRows). */
+int vlq_select_rows(const float* D, int64_t n, int cols, int64_t ldD, int k, const float* row_add, float* out_val,
+                    int* out_idx, vlq_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------------------------
+ * a4  centroid kNN graph: E+1 nearest centroids by GEMM-form exact distance, rank 0 dropped.
+ *     replaces GpuIndexFlat::buildGraph / buildGraphNonPaged_, gpu/GpuIndexFlat.cu:375-429,869-893.
+ * ---------------------------------------------------------------------------------------------------------------- */
+size_t vlq_knn_graph_workspace_bytes(int C, int E);
+int vlq_knn_graph(const float* cent, const float* cnorm, int C, int d, int E, int* edge, float* edge_d2,
+                  void* workspace, size_t workspace_bytes, vlq_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------------------------
+ * a5-a8 fused line stage + lambda quantiser + residual + PQ encode.
+ *     replaces get1BinKernel_nms (gpu/GpuIndexFlat.cu:433-557, gpu/utils/triangle.cuh:54-87),
+ *     assignLambdaKernel (gpu/GpuIndexFlat.cu:559-602), calResidual (gpu/GpuIndexFlat.cu:1092-1129) and the PQ
+ *     encode of classifyAndAddVectors (gpu/GpuIndexIVFPQ.cu:646-706; CPU twin ProductQuantizer.cpp:311-336).
+ *     pq is (M, ksub=256, dsub) fp32.  Outputs (any may be NULL except out_list):
+ *       out_list[n]    = A*E + e            out_lambda[n] = float lambda (unquantised)
+ *       out_lamq[n]    = argmin_j (lambda - lambda_cb[j])^2
+ *       out_codes[n*M] = PQ codes of r = x - ((1-l)c_A + l c_s), l = lambda_cb[lamq]
+ *       out_kappa[n]   = ||p||^2 + 2 anchor.p   (query-independent part of the ADC distance)
+ *       out_residual[n*d]
+ *     If lambda_cb is NULL only out_list / out_lambda are produced (the training-time call assign1).
+ * ---------------------------------------------------------------------------------------------------------------- */
+int vlq_line_encode(const float* x, int64_t n, int d, const int* assign, const float* cent, const int* edge,
+                    const float* edge_d2, int E, const float* lambda_cb, int nL, const float* pq, int M,
+                    int* out_list, float* out_lambda, uint8_t* out_lamq, uint8_t* out_codes, float* out_kappa,
+                    float* out_residual, vlq_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------------------------
+ * a9  inverted-list construction: stable counting sort of n new entries (arrival order) behind n_old entries that
+ *     are already list-major.   replaces the host hash-map / per-byte copies / runUpdateListPointers /
+ *     runIVFPQInvertedListAppend of gpu/GpuIndexIVFPQ.cu:741-905, gpu/impl/InvertedListAppend.cu:20-120.
+ *     Layout (CSR): offsets[nlists+1] int64; codes[n][M], lamq[n], kappa[n], ids[n] in list-major order, insertion
+ *     order preserved inside a list (what the reference's per-list append produces).
+ * ---------------------------------------------------------------------------------------------------------------- */
+size_t vlq_build_lists_workspace_bytes(int64_t n_new, int64_t nlists);
+int vlq_build_lists(int64_t nlists, int M,
+                    /* existing lists (may be empty: n_old == 0, pointers NULL) */
+                    int64_t n_old, const int64_t* old_offsets, const uint8_t* old_codes, const uint8_t* old_lamq,
+                    const float* old_kappa, const int64_t* old_ids,
+                    /* new entries in arrival order */
+                    int64_t n_new, const int* new_list, const uint8_t* new_codes, const uint8_t* new_lamq,
+                    const float* new_kappa, const int64_t* new_ids,
+                    /* merged output, sized n_old + n_new */
+                    int64_t* out_offsets, uint8_t* out_codes, uint8_t* out_lamq, float* out_kappa, int64_t* out_ids,
+                    void* workspace, size_t workspace_bytes, vlq_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------------------------
+ * a12 query-time line selection: the W best of the P*E lines of the P probed centroids.
+ *     replaces sumAlongRowsWithOrder2 / runL2SelectMinGraph, gpu/impl/BroadcastSum.cu:477-560,819-860.
+ *     D is the coarse matrix of vlq_l2_distances; coarse_ids [nq][P].
+ *     Outputs [nq][W]: out_list = c*E+e (-1 padded), out_term1 = D[c], out_term6 = D[s]-D[c].
+ * ---------------------------------------------------------------------------------------------------------------- */
+int vlq_select_lines(const float* D, int64_t nq, int64_t ldD, const int* coarse_ids, int P, const int* edge,
+                     const float* edge_d2, int E, int W, int* out_list, float* out_term1, float* out_term6,
+                     vlq_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------------------------
+ * a13-a15 ADC scan of the selected lists fused with exact top-k.
+ *     replaces the term3 build (gpu/impl/IVFPQ.cu:1398-1432), pqScanPrecomputedMultiPassGraph
+ *     (gpu/impl/PQScanMultiPassPrecomputed.cu:675-881), runCalcListOffsetsGraph (gpu/impl/IVFUtils.cu:133-169),
+ *     pass1SelectLists / pass2SelectListsGraph (gpu/impl/IVFUtilsSelect1.cu:28-144, IVFUtilsSelect2.cu:398-569).
+ *     dist = term1 + l*term6 + (l*l-l)*term5 + kappa_i - 2 q.p(code_i),  l = lambda_cb[lamq_i]
+ *          = ||q - ((1-l)c + l s) - p(code_i)||^2 - ||q||^2              (same value as the reference's formula)
+ *     over the first min(len, cap) entries of each selected list; k smallest ascending, padded (FLT_MAX, -1).
+ *     edge_d2 is indexed by list id (term5).  k <= VLQ_MAX_K, W <= VLQ_MAX_K.
+ * ---------------------------------------------------------------------------------------------------------------- */
+int vlq_scan_topk(const float* q, int64_t nq, int d, const float* pq, int M, const float* lambda_cb, int nL,
+                  const int* line_list, const float* term1, const float* term6, const float* edge_d2, int W,
+                  const int64_t* offsets, const uint8_t* codes, const uint8_t* lamq, const float* kappa,
+                  const int64_t* ids, int k, int cap, float* outD, int64_t* outI, vlq_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------------------------
+ * a16 shard merge: k smallest of R*k candidates per query; D, I are [R][nq][k] (the all-gather layout).
+ *     replaces GpuIndexIVFPQ::merge / mergekernel, gpu/GpuIndexIVFPQ.cu:1467-1591 (CPU twin MetaIndexes.cpp:290-347).
+ * ---------------------------------------------------------------------------------------------------------------- */
+int vlq_merge_topk(const float* D, const int64_t* I, int R, int64_t nq, int k, float* outD, int64_t* outI,
+                   vlq_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------------------------
+ * f1 (next row) k-means centroid update on the device: deterministic per-centroid mean in row order + the
+ *     reference's empty-cluster split.    replaces km_update_centroids, utils.cpp:1369-1449.
+ * ---------------------------------------------------------------------------------------------------------------- */
+size_t vlq_km_update_workspace_bytes(int64_t n, int k);
+int vlq_km_update(const float* x, int64_t n, int d, const int* assign, int k, float* centroids, int* counts,
+                  void* workspace, size_t workspace_bytes, vlq_stream_t stream);
+
+/* small device utilities used by the host layer */
+int vlq_gather_rows(const float* src, int d, const int64_t* rows, int64_t n, float* dst, vlq_stream_t stream);
+int vlq_u8_to_f32(const uint8_t* src, int64_t count, float* dst, vlq_stream_t stream);
+int vlq_iota_i64(int64_t* dst, int64_t n, int64_t start, vlq_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------------------------
+ * Memory / stream helpers (these DO allocate / synchronise; they exist so host layers need no CUDA toolkit).
+ * ---------------------------------------------------------------------------------------------------------------- */
+int vlq_device_count(int* count);
+int vlq_set_device(int device);
+int vlq_get_device(int* device);
+int vlq_mem_info(size_t* free_bytes, size_t* total_bytes);
+int vlq_malloc(void** ptr, size_t bytes);
+int vlq_free(void* ptr);
+int vlq_malloc_host(void** ptr, size_t bytes); /* pinned */
+int vlq_free_host(void* ptr);
+int vlq_memcpy_h2d(void* dst, const void* src, size_t bytes, vlq_stream_t stream);
+int vlq_memcpy_d2h(void* dst, const void* src, size_t bytes, vlq_stream_t stream);
+int vlq_memcpy_d2d(void* dst, const void* src, size_t bytes, vlq_stream_t stream);
+int vlq_memset(void* dst, int value, size_t bytes, vlq_stream_t stream);
+int vlq_pointer_is_device(const void* ptr); /* 1 device, 0 host, <0 error */
+int vlq_stream_create(vlq_stream_t* stream);
+int vlq_stream_destroy(vlq_stream_t stream);
+int vlq_stream_synchronize(vlq_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* VLQ_B200_H */

@@ -1,0 +1,487 @@
+"""Parity of the CUDA path (through the C-ABI, lib/libvlq_b200.so) against the CPU oracle and the golden fixtures.
+
+Bars (north_star): list / lambda / PQ codes identical except documented near-ties (relative distance gap < 1e-5);
+top-k distances within 1e-4 relative; integer / index work (list build, merge, select indices) bit-exact.
+"""
+import os
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "vlq_small.npz")
+REL_TIE = 1e-5
+REL_DIST = 1e-4
+
+
+def T(a, dev, dtype=None):
+    import torch
+
+    t = torch.from_numpy(np.ascontiguousarray(a)).to(dev)
+    return t if dtype is None else t.to(dtype)
+
+
+def N(t):
+    return t.detach().cpu().numpy()
+
+
+def near_tie_rows(ids_a, ids_b, x, cent, rel=REL_TIE):
+    bad = np.nonzero(ids_a != ids_b)[0]
+    for i in bad:
+        da = np.sum((x[i].astype(np.float64) - cent[ids_a[i]]) ** 2)
+        db = np.sum((x[i].astype(np.float64) - cent[ids_b[i]]) ** 2)
+        assert abs(da - db) <= rel * max(da, db) + 1e-9, (int(i), da, db)
+    return len(bad)
+
+
+@pytest.fixture(scope="module")
+def ops(cuda):
+    from vector_line_quantization_b200 import ops as _ops
+
+    return _ops
+
+
+@pytest.fixture(scope="module")
+def g():
+    return dict(np.load(GOLD))
+
+
+# ------------------------------------------------------------------------------------------------ assignment (a1,a2)
+@pytest.mark.parametrize("n,d,C", [(1, 128, 7), (127, 128, 256), (1000, 96, 300), (4099, 128, 1024), (513, 20, 33),
+                                   (300, 1, 16)])
+def test_l2_assign_matches_oracle(ops, cuda, oracle, n, d, C):
+    rng = np.random.RandomState(n + d + C)
+    x = rng.normal(0, 30, (n, d)).astype(np.float32)
+    cent = rng.normal(0, 30, (C, d)).astype(np.float32)
+    ids, dist = ops.l2_assign(T(x, cuda), T(cent, cuda), add_xnorm=True)
+    Do, Io = oracle.l2_topk(x, cent, 1, add_xnorm=True)
+    ids, dist = N(ids), N(dist)
+    nbad = near_tie_rows(ids, Io[:, 0], x, cent)
+    assert nbad <= max(1, n // 1000)
+    ok = ids == Io[:, 0]
+    scale = np.sum(x.astype(np.float64) ** 2, axis=1)[ok] + 1.0
+    assert np.all(np.abs(dist[ok] - Do[ok, 0]) <= REL_DIST * scale)
+    cn = N(ops.row_norms(T(cent, cuda)))
+    np.testing.assert_allclose(cn, np.sum(cent.astype(np.float64) ** 2, axis=1), rtol=1e-5)
+
+
+def test_l2_assign_empty(ops, cuda):
+    import torch
+
+    x = torch.empty((0, 64), dtype=torch.float32, device=cuda)
+    cent = torch.randn((10, 64), device=cuda)
+    ids, dist = ops.l2_assign(x, cent)
+    assert ids.shape[0] == 0
+
+
+def test_l2_assign_golden(ops, cuda, g):
+    xb = g["xb"].astype(np.float32)
+    ids, dist = ops.l2_assign(T(xb, cuda), T(g["cent"], cuda))
+    assert near_tie_rows(N(ids), g["A"], xb, g["cent"]) <= 1
+    assert near_tie_rows(N(ids), g["ref_flat_assign_I"], xb, g["cent"]) <= 2  # vs the reference's IndexFlatL2
+
+
+# ------------------------------------------------------------------------------------------------ select (a11, a15)
+@pytest.mark.parametrize("n,cols,k", [(5, 10, 1), (37, 1000, 10), (16, 30000, 100), (9, 5000, 1024), (4, 50, 128),
+                                      (3, 1, 1)])
+def test_select_rows_exact(ops, cuda, n, cols, k):
+    """TestGpuSelect.cu:28-187 protocol: values equal the sorted prefix exactly; indices valid and distinct"""
+    rng = np.random.RandomState(cols + k)
+    D = np.round(rng.rand(n, cols), 3).astype(np.float32)  # 1000 distinct values: plenty of ties
+    val, idx = ops.select_rows(T(D, cuda), k)
+    val, idx = N(val), N(idx)
+    kk = min(k, cols)
+    want_order = np.lexsort((np.broadcast_to(np.arange(cols), D.shape), D), axis=1)[:, :kk]
+    want = np.take_along_axis(D, want_order, 1)
+    assert np.array_equal(val[:, :kk], want)
+    assert np.array_equal(idx[:, :kk], want_order)  # our select is deterministic: lowest index on ties
+    if k > cols:
+        assert np.all(idx[:, cols:] == -1) and np.all(val[:, cols:] == np.finfo(np.float32).max)
+
+
+def test_coarse_topP_matches_oracle(ops, cuda, oracle, small_model):
+    m = small_model
+    D = ops.l2_distances(T(m["xq"], cuda), T(m["cent"], cuda))
+    val, idx = ops.select_rows(D, 32)
+    Do, Io = oracle.l2_topk(m["xq"], m["cent"], 32, add_xnorm=False)
+    assert (N(idx) == Io).mean() > 0.995
+    scale = np.sum(m["xq"].astype(np.float64) ** 2, axis=1, keepdims=True)
+    assert np.all(np.abs(N(val) - Do) <= REL_DIST * scale)
+
+
+# ------------------------------------------------------------------------------------------------ graph (a4)
+def test_knn_graph_matches_oracle(ops, cuda, oracle, small_model, g):
+    for cent, E in [(small_model["cent"], 32), (g["cent"], int(g["E"]))]:
+        edge, ed2 = ops.knn_graph(T(cent, cuda), E)
+        eo, do = oracle.knn_graph(cent, E)
+        edge, ed2 = N(edge), N(ed2)
+        assert (edge == eo).mean() > 0.999
+        same = edge == eo
+        np.testing.assert_allclose(ed2[same], do[same], rtol=1e-4, atol=1e-2)
+        # mismatches must be distance ties
+        for c, e in np.argwhere(~same):
+            assert abs(ed2[c, e] - do[c, e]) <= 1e-5 * abs(do[c, e]) + 1e-3
+
+
+# ------------------------------------------------------------------------------------------------ encode (a5-a8)
+def _encode_both(ops, cuda, oracle, x, m, use_oracle_assign=True):
+    _, A = oracle.l2_topk(x, m["cent"], 1)
+    A = A[:, 0].copy()
+    enc = ops.line_encode(T(x, cuda), T(A, cuda), T(m["cent"], cuda), T(m["edge"], cuda), T(m["edge_d2"], cuda),
+                          T(m["lambda_cb"], cuda), T(m["pq"], cuda), want_residual=True)
+    lst, lam = oracle.line_stage(x, A, m["cent"], m["edge"], m["edge_d2"])
+    lamq = oracle.lambda_quantize(lam, m["lambda_cb"])
+    r = oracle.residual(x, lst, lamq, m["lambda_cb"], m["cent"], m["edge"])
+    codes = oracle.pq_encode(r, m["pq"])
+    return enc, dict(A=A, list=lst, lam=lam, lamq=lamq, residual=r, codes=codes)
+
+
+def _check_encode(enc, o, x, m):
+    lst, lam, lamq, codes = N(enc.list), N(enc.lam), N(enc.lamq), N(enc.codes)
+    n = x.shape[0]
+    same_line = lst == o["list"]
+    assert same_line.mean() > 0.999, same_line.mean()
+    # mismatching lines must be near-ties in point-to-line distance
+    x64, c64 = x.astype(np.float64), m["cent"].astype(np.float64)
+    E = m["edge"].shape[1]
+
+    def line_q2(i, l):
+        a = c64[l // E]
+        s = c64[m["edge"][l // E, l % E]]
+        t = np.dot(x64[i] - a, s - a) / np.dot(s - a, s - a)
+        return np.sum((x64[i] - (a + t * (s - a))) ** 2)
+
+    for i in np.nonzero(~same_line)[0]:
+        qa, qb = line_q2(i, lst[i]), line_q2(i, o["list"][i])
+        assert abs(qa - qb) <= 1e-4 * max(qa, qb) + 1e-6, (i, qa, qb)
+    ok = same_line
+    np.testing.assert_allclose(lam[ok], o["lam"][ok], rtol=1e-3, atol=1e-4)
+    same_lq = ok & (lamq == o["lamq"])
+    assert same_lq.sum() >= ok.sum() - max(2, n // 500)  # lambda exactly between two levels
+    # PQ codes identical wherever line and lambda level agree, except sub-space near-ties
+    cm = codes[same_lq] != o["codes"][same_lq]
+    assert cm.mean() < 2e-4, cm.mean()
+    M = codes.shape[1]
+    dsub = x.shape[1] // M
+    rows = np.nonzero(same_lq)[0]
+    for ri, mm in np.argwhere(cm):
+        i = rows[ri]
+        sub = o["residual"][i, mm * dsub:(mm + 1) * dsub].astype(np.float64)
+        da = np.sum((sub - m["pq"][mm, codes[i, mm]]) ** 2)
+        db = np.sum((sub - m["pq"][mm, o["codes"][i, mm]]) ** 2)
+        assert abs(da - db) <= REL_TIE * max(da, db) + 1e-9
+    res = N(enc.residual)
+    np.testing.assert_allclose(res[same_lq], o["residual"][same_lq], rtol=1e-5, atol=1e-3)
+    return same_lq
+
+
+def test_line_encode_matches_oracle(ops, cuda, oracle, small_model):
+    m = small_model
+    x = m["xb"][:7001]  # ragged: not a multiple of the CTA's 16 warps
+    enc, o = _encode_both(ops, cuda, oracle, x, m)
+    same = _check_encode(enc, o, x, m)
+    # kappa = ||p||^2 + 2 anchor.p  (DESIGN.md): check against float64
+    kap = N(enc.kappa)
+    E, M = m["E"], m["M"]
+    dsub = 128 // M
+    for i in np.nonzero(same)[0][::501]:
+        l = o["list"][i]
+        c, s = m["cent"][l // E].astype(np.float64), m["cent"][m["edge"][l // E, l % E]].astype(np.float64)
+        lh = float(m["lambda_cb"][o["lamq"][i]])
+        anchor = (1 - lh) * c + lh * s
+        p = np.concatenate([m["pq"][mm, o["codes"][i, mm]] for mm in range(M)]).astype(np.float64)
+        want = np.dot(p, p) + 2 * np.dot(anchor, p)
+        assert abs(kap[i] - want) <= 1e-5 * (abs(want) + np.linalg.norm(anchor) * np.linalg.norm(p))
+
+
+def test_line_encode_golden(ops, cuda, g):
+    xb = g["xb"].astype(np.float32)
+    enc = ops.line_encode(T(xb, cuda), T(g["A"], cuda), T(g["cent"], cuda), T(g["edge"], cuda), T(g["edge_d2"], cuda),
+                          T(g["lambda_cb"], cuda), T(g["pq"], cuda))
+    assert (N(enc.list) == g["list"]).mean() > 0.999
+    ok = N(enc.list) == g["list"]
+    assert (N(enc.lamq)[ok] == g["lamq"][ok]).mean() > 0.998
+    ok &= N(enc.lamq) == g["lamq"]
+    assert (N(enc.codes)[ok] == g["codes"][ok]).mean() > 0.9995
+
+
+def test_line_stage_only_mode(ops, cuda, oracle, small_model):
+    m = small_model
+    x = m["xt"][:2000]
+    _, A = oracle.l2_topk(x, m["cent"], 1)
+    A = A[:, 0].copy()
+    enc = ops.line_encode(T(x, cuda), T(A, cuda), T(m["cent"], cuda), T(m["edge"], cuda), T(m["edge_d2"], cuda))
+    lst, lam = oracle.line_stage(x, A, m["cent"], m["edge"], m["edge_d2"])
+    ok = N(enc.list) == lst
+    assert ok.mean() > 0.999
+    np.testing.assert_allclose(N(enc.lam)[ok], lam[ok], rtol=1e-3, atol=1e-4)
+
+
+def test_line_encode_d96_m8_e64(ops, cuda, oracle):
+    """DEEP-shaped geometry and the 64-edge graphs of the 1B drivers (the reference kernel is wrong there)"""
+    from vector_line_quantization_b200 import data
+
+    xt = data.deep_like(6000, kc=256, seed=5)
+    m = oracle.train_all(xt, nlist=128, E=64, M=8, nL=256, niter=5, pq_niter=5)
+    x = data.deep_like(3000, kc=256, seed=6)
+    enc, o = _encode_both(ops, cuda, oracle, x, m)
+    _check_encode(enc, o, x, m)
+
+
+# ------------------------------------------------------------------------------------------------ lists (a9)
+def test_build_lists_exact(ops, cuda, oracle):
+    import torch
+
+    rng = np.random.RandomState(4)
+    nlists, M, n1, n2 = 777, 16, 5000, 3001
+    lst = rng.randint(0, nlists, n1 + n2).astype(np.int32)
+    lst[rng.rand(n1 + n2) < 0.3] = 5  # one long list (> 2048 entries: global-memory sort path)
+    lst[::97] = -1  # invalid vectors are skipped (GpuIndexIVFPQ.cu:751-755)
+    codes = rng.randint(0, 256, (n1 + n2, M)).astype(np.uint8)
+    lamq = rng.randint(0, 256, n1 + n2).astype(np.uint8)
+    kappa = rng.rand(n1 + n2).astype(np.float32)
+    ids = (np.arange(n1 + n2) * 3 + 1).astype(np.int64)
+
+    def build(sl, old):
+        return ops.build_lists(nlists, M, T(lst[sl], cuda), T(codes[sl], cuda), T(lamq[sl], cuda), T(kappa[sl], cuda),
+                               T(ids[sl], cuda), old)
+
+    l1 = build(slice(0, n1), None)
+    l2 = build(slice(n1, n1 + n2), l1)
+    torch.cuda.synchronize()
+    valid = lst >= 0
+    offsets, perm = oracle.build_lists(lst[valid], nlists)
+    src = np.nonzero(valid)[0][perm]
+    nv = int(valid.sum())
+    assert np.array_equal(N(l2.offsets), offsets)
+    assert np.array_equal(N(l2.ids)[:nv], ids[src])
+    assert np.array_equal(N(l2.codes)[:nv], codes[src])
+    assert np.array_equal(N(l2.lamq)[:nv], lamq[src])
+    assert np.array_equal(N(l2.kappa)[:nv], kappa[src])
+
+
+def test_build_lists_empty_add(ops, cuda):
+    import torch
+
+    e = lambda dt, *s: torch.empty(s, dtype=dt, device=cuda)  # noqa: E731
+    l = ops.build_lists(10, 8, e(torch.int32, 0), e(torch.uint8, 0, 8), e(torch.uint8, 0), e(torch.float32, 0),
+                        e(torch.int64, 0))
+    assert N(l.offsets).tolist() == [0] * 11
+
+
+# ------------------------------------------------------------------------------------------------ search (a11-a15)
+def _gpu_index(ops, cuda, oracle, m, xb):
+    """encode + list build entirely on the device; returns resident tensors"""
+    import torch
+
+    cent = T(m["cent"], cuda)
+    cn = ops.row_norms(cent)
+    edge, ed2 = T(m["edge"], cuda), T(m["edge_d2"], cuda)
+    lcb, pq = T(m["lambda_cb"], cuda), T(m["pq"], cuda)
+    x = T(xb, cuda)
+    A, _ = ops.l2_assign(x, cent, cn)
+    enc = ops.line_encode(x, A, cent, edge, ed2, lcb, pq)
+    M = m["pq"].shape[0]
+    ids = torch.arange(xb.shape[0], dtype=torch.int64, device=cuda)
+    lists = ops.build_lists(m["cent"].shape[0] * m["edge"].shape[1], M, enc.list, enc.codes, enc.lamq, enc.kappa, ids)
+    return dict(cent=cent, cn=cn, edge=edge, ed2=ed2, lcb=lcb, pq=pq, lists=lists, enc=enc)
+
+
+def _oracle_index(oracle, m, lst, lamq, codes):
+    nl = m["cent"].shape[0] * m["edge"].shape[1]
+    offsets, perm = oracle.build_lists(lst, nl)
+    return offsets, codes[perm], lamq[perm], perm.astype(np.int64)
+
+
+@pytest.mark.parametrize("P,W,k,cap", [(16, 128, 10, 1024), (32, 256, 100, 1024), (8, 1024, 1024, 1024),
+                                       (16, 64, 50, 2), (1, 1, 1, 1024)])
+def test_search_matches_oracle(ops, cuda, oracle, small_model, P, W, k, cap):
+    """same index on both sides: the device-encoded lists are handed to the oracle, so only the query path differs"""
+    m = small_model
+    gi = _gpu_index(ops, cuda, oracle, m, m["xb"])
+    enc = gi["enc"]
+    off, codes_l, lamq_l, ids_l = _oracle_index(oracle, m, N(enc.list), N(enc.lamq), N(enc.codes))
+    assert np.array_equal(N(gi["lists"].offsets), off) and np.array_equal(N(gi["lists"].ids), ids_l)
+    D, I = ops.search(T(m["xq"], cuda), gi["cent"], gi["cn"], gi["edge"], gi["ed2"], gi["lcb"], gi["pq"], gi["lists"],
+                      P, W, k, cap)
+    Do, Io, _, lines, _ = oracle.search(m["xq"], m["cent"], m["edge"], m["edge_d2"], m["lambda_cb"], m["pq"], off,
+                                        codes_l, lamq_l, ids_l, P=P, W=W, k=k, cap=cap, want_debug=True)
+    D, I = N(D), N(I)
+    assert np.array_equal(I < 0, Io < 0)  # same padding
+    valid = Io >= 0
+    fmax = np.finfo(np.float32).max
+    assert np.all(D[~valid] == fmax) and np.all(Do[~valid] == fmax)
+    qn = np.sum(m["xq"].astype(np.float64) ** 2, axis=1, keepdims=True) * np.ones_like(D)
+    # distances are ||q-y||^2 - ||q||^2: tolerance relative to the magnitudes that were cancelled
+    assert np.all(np.abs(D[valid] - Do[valid]) <= REL_DIST * (np.abs(Do[valid]) + qn[valid]))
+    assert (I[valid] == Io[valid]).mean() > 0.99
+    assert np.all(np.diff(D, axis=1) >= 0)
+    # rank-insensitive: the returned id sets agree
+    agree = np.mean([len(set(I[i][valid[i]]) & set(Io[i][valid[i]])) / max(1, valid[i].sum()) for i in range(len(I))])
+    assert agree > 0.995
+
+
+def test_search_golden(ops, cuda, g):
+    import torch
+
+    perm = g["perm"]
+    C, E, M = int(g["C"]), int(g["E"]), int(g["M"])
+    cent = T(g["cent"], cuda)
+    cn = ops.row_norms(cent)
+    pqn = g["pq"]
+    # kappa for the golden (oracle-encoded) entries, computed here in float64 from the fixture itself
+    lst = g["list"][perm]
+    c = g["cent"][lst // E].astype(np.float64)
+    s = g["cent"][g["edge"][lst // E, lst % E]].astype(np.float64)
+    lh = g["lambda_cb"][g["lamq"][perm]].astype(np.float64)[:, None]
+    anchor = (1 - lh) * c + lh * s
+    p = np.concatenate([pqn[mm][g["codes"][perm][:, mm]] for mm in range(M)], axis=1).astype(np.float64)
+    kappa = (np.sum(p * p, axis=1) + 2 * np.sum(anchor * p, axis=1)).astype(np.float32)
+    from vector_line_quantization_b200.ops import Lists
+
+    lists = Lists(T(g["offsets"], cuda), T(g["codes"][perm], cuda), T(g["lamq"][perm], cuda), T(kappa, cuda),
+                  T(perm.astype(np.int64), cuda))
+    D, I = ops.search(T(g["xq"].astype(np.float32), cuda), cent, cn, T(g["edge"], cuda), T(g["edge_d2"], cuda),
+                      T(g["lambda_cb"], cuda), T(g["pq"], cuda), lists, int(g["P"]), int(g["W"]), int(g["k"]))
+    D, I = N(D), N(I)
+    assert (I == g["search_I"]).mean() > 0.98
+    qn = np.sum(g["xq"].astype(np.float64) ** 2, axis=1, keepdims=True)
+    assert np.all(np.abs(D - g["search_D"]) <= REL_DIST * (np.abs(g["search_D"]) + qn))
+    # lambda == 0 slice vs the reference's IndexIVFPQ is covered on the CPU side (test_oracle_vs_reference.py)
+    Dc, Ic = ops.search(T(g["xq"].astype(np.float32), cuda), cent, cn, T(g["edge"], cuda), T(g["edge_d2"], cuda),
+                        T(g["lambda_cb"], cuda), T(g["pq"], cuda), lists, int(g["P"]), int(g["W"]), int(g["k"]), cap=3)
+    assert (N(Ic) == g["search_cap3_I"]).mean() > 0.98
+    torch.cuda.synchronize()
+
+
+def test_select_lines_matches_oracle(ops, cuda, oracle, small_model):
+    m = small_model
+    P, W = 16, 128
+    D = ops.l2_distances(T(m["xq"], cuda), T(m["cent"], cuda))
+    _, cid = ops.select_rows(D, P)
+    lst, t1, t6 = ops.select_lines(D, cid, T(m["edge"], cuda), T(m["edge_d2"], cuda), W)
+    # an empty index is enough to get the oracle's line choice
+    nl = m["C"] * m["E"]
+    off = np.zeros(nl + 1, np.int64)
+    _, _, coarse, lines, _ = oracle.search(m["xq"], m["cent"], m["edge"], m["edge_d2"], m["lambda_cb"], m["pq"], off,
+                                           np.zeros((0, m["M"]), np.uint8), np.zeros(0, np.uint8),
+                                           np.zeros(0, np.int64), P=P, W=W, k=1, want_debug=True)
+    assert (N(cid) == coarse).mean() > 0.995
+    assert (N(lst) == lines).mean() > 0.98
+    agree = np.mean([len(set(a) & set(b)) / W for a, b in zip(N(lst), lines)])
+    assert agree > 0.99
+
+
+# ------------------------------------------------------------------------------------------------ merge (a16)
+@pytest.mark.parametrize("R,nq,k", [(2, 10, 1), (8, 33, 100), (4, 7, 1024), (1, 5, 16)])
+def test_merge_topk_exact(ops, cuda, oracle, R, nq, k):
+    rng = np.random.RandomState(R * 100 + k)
+    D = np.sort(rng.rand(R, nq, k).astype(np.float32), axis=2)
+    D[:, :, ::3] = np.round(D[:, :, ::3], 2)  # cross-shard ties
+    D = np.sort(D, axis=2)
+    I = rng.randint(0, 1 << 40, size=(R, nq, k)).astype(np.int64)
+    # shards with fewer than k results pad with (FLT_MAX, -1)
+    D[0, :, k // 2:] = np.finfo(np.float32).max
+    I[0, :, k // 2:] = -1
+    oD, oI = ops.merge_topk(T(D, cuda), T(I, cuda))
+    wD, wI = oracle.merge_topk(D, I)
+    assert np.array_equal(N(oD), wD)
+    assert np.array_equal(N(oI), wI)
+
+
+def test_sharded_search_equals_single(ops, cuda, oracle, small_model):
+    """id-range shards + merge == one index, exact up to ties"""
+    m = small_model
+    P, W, k = 16, 128, 20
+    xq = T(m["xq"], cuda)
+    whole = _gpu_index(ops, cuda, oracle, m, m["xb"])
+    D1, I1 = ops.search(xq, whole["cent"], whole["cn"], whole["edge"], whole["ed2"], whole["lcb"], whole["pq"],
+                        whole["lists"], P, W, k, cap=1 << 20)
+    import torch
+
+    Ds, Is = [], []
+    bounds = [0, 7000, 13000, 20000]
+    for a, b in zip(bounds[:-1], bounds[1:]):
+        sh = _gpu_index(ops, cuda, oracle, m, m["xb"][a:b])
+        d_, i_ = ops.search(xq, sh["cent"], sh["cn"], sh["edge"], sh["ed2"], sh["lcb"], sh["pq"], sh["lists"], P, W, k,
+                            cap=1 << 20)
+        Ds.append(d_)
+        Is.append(torch.where(i_ >= 0, i_ + a, i_))
+    Dm, Im = ops.merge_topk(torch.stack(Ds).contiguous(), torch.stack(Is).contiguous())
+    assert np.array_equal(N(Dm), N(D1))
+    assert (N(Im) == N(I1)).mean() > 0.999
+
+
+# ------------------------------------------------------------------------------------------------ k-means update (f1)
+def test_km_update_matches_reference_rule(ops, cuda, oracle):
+    rng = np.random.RandomState(8)
+    n, d, k = 5000, 24, 37
+    x = rng.normal(0, 5, (n, d)).astype(np.float32)
+    assign = rng.randint(0, k - 2, n).astype(np.int32)  # two empty clusters
+    cent, counts = ops.km_update(T(x, cuda), T(assign, cuda), k)
+    cent, counts = N(cent), N(counts)
+    assert np.array_equal(counts, np.bincount(assign, minlength=k))
+    for c in range(k):
+        rows = x[assign == c]
+        if len(rows) == 0:
+            assert np.all(cent[c] == 0)
+            continue
+        acc = np.zeros(d, np.float32)
+        for r in rows:  # row order, fp32 (utils.cpp:1385-1417)
+            acc += r
+        np.testing.assert_array_equal(cent[c], acc / np.float32(len(rows)))
+
+
+# ------------------------------------------------------------------------------------------------ size-independent properties
+def test_large_encode_roundtrip_properties(ops, cuda):
+    """at a size the oracle could not finish quickly: every returned distance equals the decode distance of the stored
+    code, results are sorted, and encode is deterministic (idempotent across runs)"""
+    import torch
+
+    from vector_line_quantization_b200 import data
+
+    torch.manual_seed(0)
+    n, d, C, E, M = 400_000, 128, 2048, 32, 16
+    x = data.sift_like_torch(n, d=d, kc=1 << 14, seed=2, device=cuda)
+    cent = x[torch.randperm(n, device=cuda)[:C]].contiguous() + 0.5
+    cn = ops.row_norms(cent)
+    edge, ed2 = ops.knn_graph(cent, E, cn)
+    lcb = torch.linspace(-0.2, 1.2, 256, device=cuda)
+    pq = (torch.randn((M, 256, d // M), device=cuda) * 12).contiguous()
+    A, _ = ops.l2_assign(x, cent, cn)
+    enc = ops.line_encode(x, A, cent, edge, ed2, lcb, pq)
+    enc2 = ops.line_encode(x, A, cent, edge, ed2, lcb, pq)
+    assert torch.equal(enc.codes, enc2.codes) and torch.equal(enc.list, enc2.list) and torch.equal(enc.lamq, enc2.lamq)
+    assert torch.equal(enc.list // E, A)
+    ids = torch.arange(n, dtype=torch.int64, device=cuda)
+    lists = ops.build_lists(C * E, M, enc.list, enc.codes, enc.lamq, enc.kappa, ids)
+    assert int(lists.offsets[-1]) == n
+    # checksum of checksums: the list-major arrays are a permutation of the arrival-order arrays
+    assert int(lists.ids.sum()) == n * (n - 1) // 2
+    assert int(lists.codes.to(torch.int64).sum()) == int(enc.codes.to(torch.int64).sum())
+    assert torch.equal(enc.lamq[lists.ids], lists.lamq) and torch.equal(enc.codes[lists.ids], lists.codes)
+    seg = torch.repeat_interleave(torch.arange(C * E, device=cuda), lists.offsets[1:] - lists.offsets[:-1])
+    assert torch.equal(enc.list[lists.ids].to(torch.int64), seg)
+    q = x[:256].contiguous()
+    k = 10
+    D, I = ops.search(q, cent, cn, edge, ed2, lcb, pq, lists, 32, 256, k)
+    assert bool((I[:, 0] >= 0).all())
+    assert bool((D[:, 1:] >= D[:, :-1]).all())
+    # decode identity in float64 on the device
+    I0 = I.clamp_min(0)
+    l = enc.list[I0].to(torch.int64)
+    c = cent[l // E].double()
+    s = cent[edge.reshape(-1)[l].to(torch.int64)].double()
+    lh = lcb[enc.lamq[I0].to(torch.int64)].double().unsqueeze(-1)
+    codes = enc.codes[I0].to(torch.int64)  # [nq][k][M]
+    p = torch.stack([pq[mm][codes[..., mm]] for mm in range(M)], dim=-2).reshape(q.shape[0], k, d).double()
+    y = (1 - lh) * c + lh * s + p
+    qd = q.double().unsqueeze(1)
+    want = ((qd - y) ** 2).sum(-1) - (qd ** 2).sum(-1)
+    err = (D.double() - want).abs()
+    tol = REL_DIST * (want.abs() + (qd ** 2).sum(-1))
+    assert bool((err[I >= 0] <= tol[I >= 0]).all())
+    # querying with database vectors: the vector itself must be among its own candidates almost always
+    hit = (I == torch.arange(256, device=cuda).unsqueeze(1)).any(dim=1).float().mean()
+    assert float(hit) > 0.5

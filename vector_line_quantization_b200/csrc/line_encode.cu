@@ -1,0 +1,283 @@
+// VLQ line stage + lambda quantiser + residual + PQ encode, fused.
+//
+// One warp per vector, persistent CTAs (grid = k x #SMs) with the PQ codebook staged once per CTA in shared memory in
+// a [m][t][code] layout (lane j reads word j: conflict free).  Per vector the warp
+//   1. keeps x in registers (lane j holds x[j + 32t]),
+//   2. gathers the E+1 centroid rows A, s_0..s_{E-1} through L2 (coalesced 128 B per lane-row),
+//   3. reduces the E+1 exact squared distances with shuffles, lane e then owns line e:
+//        lambda_e = -0.5 (a - b - c2)/c2,  q_e = b + lambda^2 c2 + lambda (a - b - c2)     (triangle.cuh:54-87)
+//   4. picks argmin q_e over 0 <= lambda_e <= 1, else the global argmin (ties -> lowest e)   (GpuIndexFlat.cu:517-550,
+//      intended semantics), quantises lambda against the 1-D codebook             (GpuIndexFlat.cu:579-596)
+//   5. forms r = x - ((1-l) c_A + l c_s) in registers                                        (GpuIndexFlat.cu:1111-1122)
+//   6. encodes r with the PQ: per sub-space arg-min over ksub codewords by direct differences, first minimum wins
+//      (ProductQuantizer.cpp:311-336), and emits kappa = ||p||^2 + 2 anchor.p for the scan.
+// Nothing but the final list id / lambda byte / M code bytes / kappa leaves the SM.
+#include "common.cuh"
+
+namespace vlq {
+
+constexpr int LE_WARPS = 16;
+constexpr int LE_THREADS = LE_WARPS * kWarp;
+constexpr int LE_MAX_E = 64;
+
+struct LineEncodeArgs {
+  const float* x;
+  int64_t n;
+  int d;
+  const int* assign;
+  const float* cent;
+  const int* edge;
+  const float* edge_d2;
+  int E;
+  const float* lambda_cb;
+  int nL;
+  const float* pq;  // (M, ksub, dsub)
+  int M, ksub, dsub;
+  int pq_in_smem;
+  int* out_list;
+  float* out_lambda;
+  uint8_t* out_lamq;
+  uint8_t* out_codes;
+  float* out_kappa;
+  float* out_residual;
+};
+
+template <int NPL>
+__global__ void __launch_bounds__(LE_THREADS, 1) line_encode_kernel(LineEncodeArgs a) {
+  extern __shared__ __align__(16) float smem[];
+  // layout: [pq transposed: M*dsub*ksub floats (optional)] [per-warp r: LE_WARPS*d] [per-warp codes: LE_WARPS*64 bytes]
+  const int d = a.d, E = a.E, M = a.M, ksub = a.ksub, dsub = a.dsub;
+  float* pqs = smem;
+  float* rbuf = smem + (a.pq_in_smem ? (size_t)M * dsub * ksub : 0);
+  uint8_t* cbuf = reinterpret_cast<uint8_t*>(rbuf + (size_t)LE_WARPS * d);
+  const int warp = threadIdx.x / kWarp, lane = threadIdx.x % kWarp;
+  const bool encode = a.lambda_cb != nullptr;
+
+  if (encode && a.pq_in_smem) {
+    // pq[(m*ksub + j)*dsub + t]  ->  pqs[(m*dsub + t)*ksub + j]
+    const int total = M * ksub * dsub;
+    for (int i = threadIdx.x; i < total; i += LE_THREADS) {
+      int t = i % dsub;
+      int j = (i / dsub) % ksub;
+      int m = i / (dsub * ksub);
+      pqs[(m * dsub + t) * ksub + j] = a.pq[i];
+    }
+  }
+  __syncthreads();
+
+  float* r_s = rbuf + (size_t)warp * d;
+  uint8_t* code_s = cbuf + warp * 64;
+
+  for (int64_t i = (int64_t)blockIdx.x * LE_WARPS + warp; i < a.n; i += (int64_t)gridDim.x * LE_WARPS) {
+    float xv[NPL];
+    const float* xr = a.x + i * d;
+#pragma unroll
+    for (int t = 0; t < NPL; t++) {
+      int j = lane + 32 * t;
+      xv[t] = j < d ? xr[j] : 0.f;
+    }
+    const int A = a.assign[i];
+    if (A < 0) {  // invalid vector (NaN input): the reference skips it (GpuIndexIVFPQ.cu:751-755)
+      if (lane == 0) {
+        a.out_list[i] = -1;
+        if (a.out_lambda) a.out_lambda[i] = 0.f;
+      }
+      continue;
+    }
+    const float* cA = a.cent + (int64_t)A * d;
+    float cAv[NPL];
+    float bp = 0.f;
+#pragma unroll
+    for (int t = 0; t < NPL; t++) {
+      int j = lane + 32 * t;
+      cAv[t] = j < d ? cA[j] : 0.f;
+      float df = xv[t] - cAv[t];
+      bp = fmaf(df, df, bp);
+    }
+    const float b = warp_sum(bp);
+
+    // lane e (+32) owns edge e
+    int my_s[2] = {0, 0};
+    float my_a[2] = {0.f, 0.f};
+    float my_c2[2] = {1.f, 1.f};
+#pragma unroll
+    for (int h = 0; h < 2; h++) {
+      int e = lane + 32 * h;
+      if (e < E) {
+        my_s[h] = a.edge[(int64_t)A * E + e];
+        my_c2[h] = a.edge_d2[(int64_t)A * E + e];
+      }
+    }
+    for (int e = 0; e < E; e++) {
+      const int s = __shfl_sync(kFull, my_s[e >> 5], e & 31);
+      const float* cs = a.cent + (int64_t)s * d;
+      float ap = 0.f;
+#pragma unroll
+      for (int t = 0; t < NPL; t++) {
+        int j = lane + 32 * t;
+        float cv = j < d ? cs[j] : 0.f;
+        float df = xv[t] - cv;
+        ap = fmaf(df, df, ap);
+      }
+      ap = warp_sum(ap);
+      if (lane == (e & 31)) my_a[e >> 5] = ap;
+    }
+    uint64_t kv = kKeyInf, ka = kKeyInf;
+    float my_lam[2];
+#pragma unroll
+    for (int h = 0; h < 2; h++) {
+      int e = lane + 32 * h;
+      float v = my_a[h] - b - my_c2[h];
+      float lam = -0.5f * v / my_c2[h];                                 // project()
+      float q2 = __fadd_rn(__fadd_rn(b, __fmul_rn(__fmul_rn(lam, lam), my_c2[h])), __fmul_rn(lam, v));  // dist2()
+      my_lam[h] = lam;
+      if (e < E) {
+        uint64_t key = make_key(q2, (uint32_t)e);
+        ka = key < ka ? key : ka;
+        if (lam >= 0.f && lam <= 1.f) kv = key < kv ? key : kv;
+      }
+    }
+    kv = warp_min_u64(kv);
+    ka = warp_min_u64(ka);
+    const uint64_t kbest = kv != kKeyInf ? kv : ka;
+    const int ebest = (int)key_payload(kbest);
+    const float lam = __shfl_sync(kFull, my_lam[ebest >> 5], ebest & 31);
+    const int sbest = __shfl_sync(kFull, my_s[ebest >> 5], ebest & 31);
+    if (lane == 0) {
+      a.out_list[i] = A * E + ebest;
+      if (a.out_lambda) a.out_lambda[i] = lam;
+    }
+    if (!encode) continue;
+
+    // ---- lambda quantiser: argmin_j (lam - cb[j])^2, lowest j on ties
+    uint64_t kl = kKeyInf;
+    for (int j = lane; j < a.nL; j += kWarp) {
+      float t = lam - a.lambda_cb[j];
+      uint64_t key = make_key(__fmul_rn(t, t), (uint32_t)j);
+      kl = key < kl ? key : kl;
+    }
+    kl = warp_min_u64(kl);
+    const int lq = (int)key_payload(kl);
+    const float lh = a.lambda_cb[lq];
+
+    // ---- residual (kept in registers + a per-warp smem copy for the sub-space walk)
+    const float* cs = a.cent + (int64_t)sbest * d;
+    float anc[NPL];
+    const float oml = 1.f - lh;
+    __syncwarp();
+#pragma unroll
+    for (int t = 0; t < NPL; t++) {
+      int j = lane + 32 * t;
+      float sv = j < d ? cs[j] : 0.f;
+      anc[t] = __fadd_rn(__fmul_rn(oml, cAv[t]), __fmul_rn(lh, sv));
+      float rv = __fsub_rn(xv[t], anc[t]);
+      if (j < d) {
+        r_s[j] = rv;
+        if (a.out_residual) a.out_residual[i * d + j] = rv;
+      }
+    }
+    __syncwarp();
+
+    // ---- PQ encode
+    for (int m = 0; m < M; m++) {
+      uint64_t kc = kKeyInf;
+      for (int j = lane; j < ksub; j += kWarp) {
+        float dis = 0.f;
+        if (a.pq_in_smem) {
+          const float* pp = pqs + (size_t)m * dsub * ksub + j;
+          for (int t = 0; t < dsub; t++) {
+            float df = r_s[m * dsub + t] - pp[t * ksub];
+            dis = __fadd_rn(dis, __fmul_rn(df, df));
+          }
+        } else {
+          const float* pp = a.pq + ((size_t)m * ksub + j) * dsub;
+          for (int t = 0; t < dsub; t++) {
+            float df = r_s[m * dsub + t] - pp[t];
+            dis = __fadd_rn(dis, __fmul_rn(df, df));
+          }
+        }
+        uint64_t key = make_key(dis, (uint32_t)j);
+        kc = key < kc ? key : kc;
+      }
+      kc = warp_min_u64(kc);
+      if (lane == 0) code_s[m] = (uint8_t)key_payload(kc);
+    }
+    __syncwarp();
+
+    // ---- kappa = ||p||^2 + 2 anchor.p
+    float kp = 0.f;
+#pragma unroll
+    for (int t = 0; t < NPL; t++) {
+      int j = lane + 32 * t;
+      if (j < d) {
+        int m = j / dsub, tt = j % dsub;
+        int code = code_s[m];
+        float pv = a.pq_in_smem ? pqs[(size_t)(m * dsub + tt) * ksub + code] : a.pq[((size_t)m * ksub + code) * dsub + tt];
+        kp = fmaf(pv, pv, kp);
+        kp = fmaf(2.f * anc[t], pv, kp);
+      }
+    }
+    kp = warp_sum(kp);
+    if (lane == 0) {
+      if (a.out_lamq) a.out_lamq[i] = (uint8_t)lq;
+      if (a.out_kappa) a.out_kappa[i] = kp;
+    }
+    if (a.out_codes)
+      for (int m = lane; m < M; m += kWarp) a.out_codes[i * M + m] = code_s[m];
+    __syncwarp();
+  }
+}
+
+}  // namespace vlq
+
+using namespace vlq;
+
+extern "C" int vlq_line_encode(const float* x, int64_t n, int d, const int* assign, const float* cent,
+                               const int* edge, const float* edge_d2, int E, const float* lambda_cb, int nL,
+                               const float* pq, int M, int* out_list, float* out_lambda, uint8_t* out_lamq,
+                               uint8_t* out_codes, float* out_kappa, float* out_residual, vlq_stream_t stream) {
+  if (!x || !assign || !cent || !edge || !edge_d2 || !out_list) return VLQ_EINVAL;
+  if (n < 0 || d <= 0 || d > 256 || E <= 0 || E > LE_MAX_E) return VLQ_EINVAL;
+  const int ksub = 256;
+  LineEncodeArgs a{};
+  a.x = x; a.n = n; a.d = d; a.assign = assign; a.cent = cent; a.edge = edge; a.edge_d2 = edge_d2; a.E = E;
+  a.lambda_cb = lambda_cb; a.nL = nL; a.pq = pq; a.M = M; a.ksub = ksub; a.dsub = M > 0 ? d / M : 0;
+  a.out_list = out_list; a.out_lambda = out_lambda; a.out_lamq = out_lamq; a.out_codes = out_codes;
+  a.out_kappa = out_kappa; a.out_residual = out_residual;
+  if (lambda_cb) {
+    if (!pq || M <= 0 || M > 64 || d % M != 0 || nL <= 0 || nL > 256) return VLQ_EINVAL;
+  }
+  if (n == 0) return VLQ_OK;
+  size_t pq_bytes = lambda_cb ? (size_t)M * a.dsub * ksub * sizeof(float) : 0;
+  size_t tail = (size_t)LE_WARPS * d * sizeof(float) + LE_WARPS * 64;
+  a.pq_in_smem = (lambda_cb && pq_bytes + tail <= 200 * 1024) ? 1 : 0;
+  size_t smem = (a.pq_in_smem ? pq_bytes : 0) + tail;
+  int dev = 0, sms = 148;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  int64_t need = div_up(n, LE_WARPS);
+  unsigned grid = (unsigned)(need < sms ? need : sms);
+  const int npl = (d + 31) / 32;
+  cudaStream_t st = as_stream(stream);
+#define VLQ_LE_CASE(N)                                                                                       \
+  case N: {                                                                                                  \
+    VLQ_CUDA_TRY(cudaFuncSetAttribute(line_encode_kernel<N>, cudaFuncAttributeMaxDynamicSharedMemorySize,    \
+                                      (int)smem));                                                           \
+    VLQ_LAUNCH(line_encode_kernel<N>, grid, LE_THREADS, smem, st, a);                                        \
+    break;                                                                                                   \
+  }
+  switch (npl) {
+    VLQ_LE_CASE(1)
+    VLQ_LE_CASE(2)
+    VLQ_LE_CASE(3)
+    VLQ_LE_CASE(4)
+    VLQ_LE_CASE(5)
+    VLQ_LE_CASE(6)
+    VLQ_LE_CASE(7)
+    VLQ_LE_CASE(8)
+    default:
+      return VLQ_EINVAL;
+  }
+#undef VLQ_LE_CASE
+  return last_error();
+}

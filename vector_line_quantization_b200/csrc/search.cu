@@ -1,0 +1,392 @@
+// Query-time kernels.
+//
+//  select_lines_kernel : one CTA per query; scores the P*E lines of the probed centroids from the coarse matrix D and
+//                        keeps the W best (exact block top-k).                      [BroadcastSum.cu:477-560]
+//  scan_topk_kernel    : one CTA per query; builds the per-query term3 table (-2 q_m.p_mj) in shared memory, walks
+//                        the selected lists as ONE flattened entry stream (so 5-entry lists and 1000-entry lists
+//                        use the lanes equally), 16-byte code loads, distance from the per-entry kappa and the
+//                        per-line scalars, fused exact top-k -- no intermediate distance array, no term2 tables.
+//                                                                                   [PQScanMultiPassPrecomputed.cu:675-881,
+//                                                                                    IVFUtils*.cu]
+//  merge_topk_kernel   : one CTA per query over the [R][nq][k] all-gather layout.     [GpuIndexIVFPQ.cu:1467-1518]
+//  knn_graph           : tiled C x C coarse matrix + top-(E+1) + drop rank 0.        [GpuIndexFlat.cu:869-893]
+#include <cfloat>
+
+#include "common.cuh"
+#include "topk.cuh"
+
+namespace vlq {
+
+constexpr int Q_THREADS = 256;
+
+// ------------------------------------------------------------------------------------------------ line selection
+__global__ void __launch_bounds__(Q_THREADS)
+select_lines_kernel(const float* __restrict__ D, int64_t ldD, const int* __restrict__ coarse_ids, int P,
+                    const int* __restrict__ edge, const float* __restrict__ edge_d2, int E, int W,
+                    int* __restrict__ out_list, float* __restrict__ out_term1, float* __restrict__ out_term6) {
+  extern __shared__ __align__(16) unsigned char smem[];
+  BlockTopK<Q_THREADS> sel;
+  sel.init(smem, W);
+  const int64_t q = blockIdx.x;
+  const float* Dq = D + q * ldD;
+  const int* cq = coarse_ids + q * P;
+  const int num = P * E;
+  const int rounds = (num + Q_THREADS - 1) / Q_THREADS;
+  for (int r = 0; r < rounds; r++) {
+    const int i = r * Q_THREADS + threadIdx.x;
+    bool valid = i < num;
+    float score = 0.f;
+    if (valid) {
+      const int c = cq[i / E];
+      valid = c >= 0;
+      if (valid) {
+        const int e = i % E;
+        const int s = edge[(int64_t)c * E + e];
+        const float a2 = Dq[s], b2 = Dq[c], c2 = edge_d2[(int64_t)c * E + e];
+        float v = __fsub_rn(a2, b2);
+        v = __fsub_rn(v, c2);
+        // BroadcastSum.cu:517: (v>0) ? b2 : b2 - 0.25 v^2 / c2
+        score = (v > 0.f) ? b2 : __fsub_rn(b2, __fdiv_rn(__fmul_rn(__fmul_rn(0.25f, v), v), c2));
+      }
+    }
+    sel.add(valid, make_key(score, (uint32_t)i));
+  }
+  sel.finish();
+  for (int w = threadIdx.x; w < W; w += Q_THREADS) {
+    const uint64_t key = sel.keys[w];
+    int list = -1;
+    float t1 = 0.f, t6 = 0.f;
+    if (key != kKeyInf) {
+      const int i = (int)key_payload(key);
+      const int c = cq[i / E], e = i % E;
+      const int s = edge[(int64_t)c * E + e];
+      list = c * E + e;
+      t1 = Dq[c];
+      t6 = __fsub_rn(Dq[s], Dq[c]);
+    }
+    out_list[q * W + w] = list;
+    out_term1[q * W + w] = t1;
+    out_term6[q * W + w] = t6;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ scan + top-k
+struct ScanArgs {
+  const float* q;
+  int d;
+  const float* pq;
+  int M, ksub, dsub;
+  const float* lambda_cb;
+  int nL;
+  const int* line_list;
+  const float* term1;
+  const float* term6;
+  const float* edge_d2;
+  int W;
+  const int64_t* offsets;
+  const uint8_t* codes;
+  const uint8_t* lamq;
+  const float* kappa;
+  const int64_t* ids;
+  int k, cap;
+  float* outD;
+  int64_t* outI;
+};
+
+template <int M_T>
+__device__ __forceinline__ float adc_sum(const uint8_t* __restrict__ code_ptr, const float* __restrict__ T3, int M,
+                                         int ksub) {
+  float acc = 0.f;
+  if (M_T == 16) {
+    const uint4 c = ld_nc_v4(code_ptr);
+    const uint32_t w[4] = {c.x, c.y, c.z, c.w};
+#pragma unroll
+    for (int t = 0; t < 4; t++)
+#pragma unroll
+      for (int b = 0; b < 4; b++) acc += T3[(t * 4 + b) * 256 + ((w[t] >> (8 * b)) & 0xff)];
+  } else if (M_T == 8) {
+    const uint2 c = ld_nc_v2(code_ptr);
+    const uint32_t w[2] = {c.x, c.y};
+#pragma unroll
+    for (int t = 0; t < 2; t++)
+#pragma unroll
+      for (int b = 0; b < 4; b++) acc += T3[(t * 4 + b) * 256 + ((w[t] >> (8 * b)) & 0xff)];
+  } else {
+    for (int m = 0; m < M; m++) acc += T3[m * ksub + code_ptr[m]];
+  }
+  return acc;
+}
+
+template <int M_T>
+__global__ void __launch_bounds__(Q_THREADS) scan_topk_kernel(ScanArgs a) {
+  extern __shared__ __align__(16) unsigned char smem[];
+  // smem: [topk keys S*8 + 16][T3 M*ksub f32][lambda nL f32][per line: start i64, prefix i32 (W+1), t1, t6, t5 f32]
+  const int M = a.M, ksub = a.ksub, dsub = a.dsub, W = a.W;
+  BlockTopK<Q_THREADS> sel;
+  size_t off = (topk_smem_bytes(a.k, Q_THREADS) + 15) & ~size_t(15);
+  float* T3 = reinterpret_cast<float*>(smem + off);
+  off += sizeof(float) * M * ksub;
+  float* lcb = reinterpret_cast<float*>(smem + off);
+  off += sizeof(float) * ((a.nL + 3) & ~3);
+  int64_t* lstart = reinterpret_cast<int64_t*>(smem + off);
+  off += sizeof(int64_t) * W;
+  int* prefix = reinterpret_cast<int*>(smem + off);
+  off += sizeof(int) * ((W + 1 + 3) & ~3);
+  float* lt1 = reinterpret_cast<float*>(smem + off);
+  off += sizeof(float) * W;
+  float* lt6 = reinterpret_cast<float*>(smem + off);
+  off += sizeof(float) * W;
+  float* lt5 = reinterpret_cast<float*>(smem + off);
+
+  sel.init(smem, a.k);
+  const int64_t qi = blockIdx.x;
+  const float* qv = a.q + qi * a.d;
+
+  // term3 table: T3[m][j] = -2 q_m . p_mj            (gpu/impl/IVFPQ.cu:1409-1432)
+  for (int i = threadIdx.x; i < M * ksub; i += Q_THREADS) {
+    const int m = i / ksub;
+    const float* p = a.pq + (size_t)i * dsub;
+    const float* qm = qv + m * dsub;
+    float ip = 0.f;
+    for (int t = 0; t < dsub; t++) ip = fmaf(qm[t], p[t], ip);
+    T3[i] = -2.f * ip;
+  }
+  for (int i = threadIdx.x; i < a.nL; i += Q_THREADS) lcb[i] = a.lambda_cb[i];
+  // line descriptors (lengths capped like gpu/impl/IVFUtils.cu:87)
+  for (int w = threadIdx.x; w < W; w += Q_THREADS) {
+    const int list = a.line_list[qi * W + w];
+    int len = 0;
+    int64_t st = 0;
+    float t5 = 0.f;
+    if (list >= 0) {
+      st = a.offsets[list];
+      int64_t l = a.offsets[list + 1] - st;
+      len = (int)(l < a.cap ? l : a.cap);
+      t5 = a.edge_d2[list];
+    }
+    lstart[w] = st;
+    prefix[w + 1] = len;  // turned into an inclusive scan below
+    lt1[w] = a.term1[qi * W + w];
+    lt6[w] = a.term6[qi * W + w];
+    lt5[w] = t5;
+  }
+  if (threadIdx.x == 0) prefix[0] = 0;
+  __syncthreads();
+  if (threadIdx.x < kWarp) {  // W <= 1024: one warp scans 32 chunks
+    const int lane = threadIdx.x;
+    const int chunk = (W + kWarp - 1) / kWarp;
+    const int b = lane * chunk, e = min(W, b + chunk);
+    int s = 0;
+    for (int w = b; w < e; w++) s += prefix[w + 1];
+    int inc = s;
+#pragma unroll
+    for (int o = 1; o < kWarp; o <<= 1) {
+      int t = __shfl_up_sync(kFull, inc, o);
+      if (lane >= o) inc += t;
+    }
+    int run = inc - s;
+    for (int w = b; w < e; w++) {
+      run += prefix[w + 1];
+      prefix[w + 1] = run;
+    }
+  }
+  __syncthreads();
+  const int total = prefix[W];
+
+  const int rounds = (total + Q_THREADS - 1) / Q_THREADS;
+  for (int r = 0; r < rounds; r++) {
+    const int pos = r * Q_THREADS + threadIdx.x;
+    const bool valid = pos < total;
+    float dist = 0.f;
+    if (valid) {
+      // list of this stream position: largest w with prefix[w] <= pos
+      int lo = 0, hi = W;
+      while (hi - lo > 1) {
+        int mid = (lo + hi) >> 1;
+        if (prefix[mid] <= pos) lo = mid; else hi = mid;
+      }
+      const int64_t ent = lstart[lo] + (pos - prefix[lo]);
+      const float la = lcb[a.lamq[ent]];
+      const float base = lt1[lo] + la * lt6[lo] + (la * la - la) * lt5[lo];
+      const float acc = adc_sum<M_T>(a.codes + ent * M, T3, M, ksub);
+      dist = (a.kappa[ent] + acc) + base;
+    }
+    sel.add(valid, make_key(dist, (uint32_t)pos));
+  }
+  sel.finish();
+  for (int i = threadIdx.x; i < a.k; i += Q_THREADS) {
+    const uint64_t key = sel.keys[i];
+    float dv = FLT_MAX;
+    int64_t id = -1;
+    if (key != kKeyInf) {
+      const int pos = (int)key_payload(key);
+      int lo = 0, hi = W;
+      while (hi - lo > 1) {
+        int mid = (lo + hi) >> 1;
+        if (prefix[mid] <= pos) lo = mid; else hi = mid;
+      }
+      dv = key_val(key);
+      id = a.ids[lstart[lo] + (pos - prefix[lo])];
+    }
+    a.outD[qi * a.k + i] = dv;
+    a.outI[qi * a.k + i] = id;
+  }
+}
+
+static size_t scan_smem_bytes(int k, int M, int ksub, int nL, int W) {
+  size_t off = (topk_smem_bytes(k, Q_THREADS) + 15) & ~size_t(15);
+  off += sizeof(float) * M * ksub;
+  off += sizeof(float) * ((nL + 3) & ~3);
+  off += sizeof(int64_t) * W;
+  off += sizeof(int) * ((W + 1 + 3) & ~3);
+  off += sizeof(float) * W * 3;
+  return off;
+}
+
+// ------------------------------------------------------------------------------------------------ shard merge
+__global__ void __launch_bounds__(Q_THREADS)
+merge_topk_kernel(const float* __restrict__ D, const int64_t* __restrict__ I, int R, int64_t nq, int k,
+                  float* __restrict__ outD, int64_t* __restrict__ outI) {
+  extern __shared__ __align__(16) unsigned char smem[];
+  BlockTopK<Q_THREADS> sel;
+  sel.init(smem, k);
+  const int64_t q = blockIdx.x;
+  const int num = R * k;
+  const int rounds = (num + Q_THREADS - 1) / Q_THREADS;
+  for (int r = 0; r < rounds; r++) {
+    const int i = r * Q_THREADS + threadIdx.x;
+    bool valid = i < num;
+    float v = 0.f;
+    if (valid) {
+      const int rank = i / k, pos = i % k;
+      v = D[((int64_t)rank * nq + q) * k + pos];
+      valid = I[((int64_t)rank * nq + q) * k + pos] >= 0;  // padding entries never win
+    }
+    sel.add(valid, make_key(v, (uint32_t)i));
+  }
+  sel.finish();
+  for (int i = threadIdx.x; i < k; i += Q_THREADS) {
+    const uint64_t key = sel.keys[i];
+    float dv = FLT_MAX;
+    int64_t id = -1;
+    if (key != kKeyInf) {
+      const int fi = (int)key_payload(key);
+      dv = key_val(key);
+      id = I[((int64_t)(fi / k) * nq + q) * k + (fi % k)];
+    }
+    outD[q * k + i] = dv;
+    outI[q * k + i] = id;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ graph helper
+__global__ void drop_rank0_kernel(const float* __restrict__ val, const int* __restrict__ idx, int64_t rows, int E,
+                                  int* __restrict__ edge, float* __restrict__ edge_d2) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= rows * E) return;
+  int64_t r = i / E;
+  int e = (int)(i % E);
+  edge[i] = idx[r * (E + 1) + 1 + e];
+  edge_d2[i] = val[r * (E + 1) + 1 + e];
+}
+
+static int graph_tile_rows(int C) {
+  int64_t tr = (int64_t)(16 << 20) / C;  // 64 MiB of fp32 per tile: stays in the 126 MB L2
+  if (tr < 128) tr = 128;
+  if (tr > C) tr = C;
+  return (int)tr;
+}
+
+}  // namespace vlq
+
+using namespace vlq;
+
+extern "C" {
+
+int vlq_select_lines(const float* D, int64_t nq, int64_t ldD, const int* coarse_ids, int P, const int* edge,
+                     const float* edge_d2, int E, int W, int* out_list, float* out_term1, float* out_term6,
+                     vlq_stream_t stream) {
+  if (!D || !coarse_ids || !edge || !edge_d2 || !out_list || !out_term1 || !out_term6) return VLQ_EINVAL;
+  if (nq < 0 || P <= 0 || P > VLQ_MAX_K || E <= 0 || W <= 0 || W > VLQ_MAX_K) return VLQ_EINVAL;
+  if (nq == 0) return VLQ_OK;
+  size_t smem = topk_smem_bytes(W, Q_THREADS);
+  VLQ_LAUNCH(select_lines_kernel, (unsigned)nq, Q_THREADS, smem, as_stream(stream), D, ldD, coarse_ids, P, edge,
+             edge_d2, E, W, out_list, out_term1, out_term6);
+  return last_error();
+}
+
+int vlq_scan_topk(const float* q, int64_t nq, int d, const float* pq, int M, const float* lambda_cb, int nL,
+                  const int* line_list, const float* term1, const float* term6, const float* edge_d2, int W,
+                  const int64_t* offsets, const uint8_t* codes, const uint8_t* lamq, const float* kappa,
+                  const int64_t* ids, int k, int cap, float* outD, int64_t* outI, vlq_stream_t stream) {
+  if (!q || !pq || !lambda_cb || !line_list || !term1 || !term6 || !edge_d2 || !offsets || !outD || !outI)
+    return VLQ_EINVAL;
+  if (nq < 0 || d <= 0 || M <= 0 || M > 64 || d % M != 0 || nL <= 0 || nL > 256 || W <= 0 || W > VLQ_MAX_K ||
+      k <= 0 || k > VLQ_MAX_K || cap <= 0 || cap > (1 << 20) / 1 || (int64_t)W * cap > (int64_t)0x7fffffff)
+    return VLQ_EINVAL;
+  if (nq == 0) return VLQ_OK;
+  ScanArgs a{};
+  a.q = q; a.d = d; a.pq = pq; a.M = M; a.ksub = 256; a.dsub = d / M; a.lambda_cb = lambda_cb; a.nL = nL;
+  a.line_list = line_list; a.term1 = term1; a.term6 = term6; a.edge_d2 = edge_d2; a.W = W; a.offsets = offsets;
+  a.codes = codes; a.lamq = lamq; a.kappa = kappa; a.ids = ids; a.k = k; a.cap = cap; a.outD = outD; a.outI = outI;
+  size_t smem = scan_smem_bytes(k, M, a.ksub, nL, W);
+  cudaStream_t st = as_stream(stream);
+  const bool al16 = (reinterpret_cast<uintptr_t>(codes) % 16) == 0;
+  if (M == 16 && al16) {
+    VLQ_CUDA_TRY(cudaFuncSetAttribute(scan_topk_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    VLQ_LAUNCH(scan_topk_kernel<16>, (unsigned)nq, Q_THREADS, smem, st, a);
+  } else if (M == 8 && al16) {
+    VLQ_CUDA_TRY(cudaFuncSetAttribute(scan_topk_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    VLQ_LAUNCH(scan_topk_kernel<8>, (unsigned)nq, Q_THREADS, smem, st, a);
+  } else {
+    VLQ_CUDA_TRY(cudaFuncSetAttribute(scan_topk_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    VLQ_LAUNCH(scan_topk_kernel<0>, (unsigned)nq, Q_THREADS, smem, st, a);
+  }
+  return last_error();
+}
+
+int vlq_merge_topk(const float* D, const int64_t* I, int R, int64_t nq, int k, float* outD, int64_t* outI,
+                   vlq_stream_t stream) {
+  if (!D || !I || !outD || !outI || R <= 0 || nq < 0 || k <= 0 || k > VLQ_MAX_K) return VLQ_EINVAL;
+  if (nq == 0) return VLQ_OK;
+  size_t smem = topk_smem_bytes(k, Q_THREADS);
+  VLQ_LAUNCH(merge_topk_kernel, (unsigned)nq, Q_THREADS, smem, as_stream(stream), D, I, R, nq, k, outD, outI);
+  return last_error();
+}
+
+size_t vlq_knn_graph_workspace_bytes(int C, int E) {
+  int tr = graph_tile_rows(C);
+  size_t b = (size_t)tr * C * sizeof(float);
+  b = (b + 255) & ~size_t(255);
+  b += ((size_t)tr * (E + 1) * sizeof(float) + 255) & ~size_t(255);
+  b += ((size_t)tr * (E + 1) * sizeof(int) + 255) & ~size_t(255);
+  return b;
+}
+
+int vlq_knn_graph(const float* cent, const float* cnorm, int C, int d, int E, int* edge, float* edge_d2,
+                  void* workspace, size_t workspace_bytes, vlq_stream_t stream) {
+  if (!cent || !cnorm || !edge || !edge_d2 || !workspace || C <= 1 || d <= 0 || E <= 0 || E + 1 > C ||
+      E + 1 > VLQ_MAX_K)
+    return VLQ_EINVAL;
+  if (workspace_bytes < vlq_knn_graph_workspace_bytes(C, E)) return VLQ_EWORKSPACE;
+  const int tr = graph_tile_rows(C);
+  unsigned char* p = static_cast<unsigned char*>(workspace);
+  float* Dt = reinterpret_cast<float*>(p);
+  size_t off = ((size_t)tr * C * sizeof(float) + 255) & ~size_t(255);
+  float* val = reinterpret_cast<float*>(p + off);
+  off += ((size_t)tr * (E + 1) * sizeof(float) + 255) & ~size_t(255);
+  int* idx = reinterpret_cast<int*>(p + off);
+  for (int r0 = 0; r0 < C; r0 += tr) {
+    const int rows = (C - r0) < tr ? (C - r0) : tr;
+    int rc = vlq_l2_distances(cent + (size_t)r0 * d, rows, d, cent, cnorm, C, Dt, C, stream);
+    if (rc) return rc;
+    // exact flag of the reference: + ||c_i||^2 on the winners (sumAlongRows)
+    rc = vlq_select_rows(Dt, rows, C, C, E + 1, cnorm + r0, val, idx, stream);
+    if (rc) return rc;
+    VLQ_LAUNCH(drop_rank0_kernel, (unsigned)div_up((int64_t)rows * E, 256), 256, 0, as_stream(stream), val, idx,
+               (int64_t)rows, E, edge + (size_t)r0 * E, edge_d2 + (size_t)r0 * E);
+  }
+  return last_error();
+}
+
+}  // extern "C"

@@ -1,0 +1,230 @@
+"""Device-resident operator layer: torch CUDA tensors in, torch CUDA tensors out, every op one C-ABI call.
+
+torch is plumbing here (device memory + the current stream); all arithmetic happens in lib/libvlq_b200.so.
+Each function names the C-ABI entry it calls; the reference interface that entry replaces is cited in
+include/vlq_b200.h.
+"""
+from collections import namedtuple
+
+import torch
+
+from . import _abi
+
+Lists = namedtuple("Lists", "offsets codes lamq kappa ids")  # CSR inverted lists (see csrc/lists.cu)
+
+
+def _stream():
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _ptr(t):
+    return 0 if t is None else t.data_ptr()
+
+
+def _chk(t, dtype, name):
+    if t is None:
+        return None
+    if not t.is_cuda:
+        raise ValueError("%s must be a CUDA tensor" % name)
+    if t.dtype != dtype:
+        raise ValueError("%s must be %s, got %s" % (name, dtype, t.dtype))
+    if not t.is_contiguous():
+        raise ValueError("%s must be contiguous" % name)
+    return t
+
+
+def launch_count():
+    return int(_abi.lib().vlq_launch_count())
+
+
+def row_norms(x):
+    x = _chk(x, torch.float32, "x")
+    n, d = x.shape
+    out = torch.empty(n, dtype=torch.float32, device=x.device)
+    _abi.call("vlq_row_norms", _ptr(x), n, d, _ptr(out), _stream())
+    return out
+
+
+def l2_assign(x, cent, cnorm=None, add_xnorm=True, want_dist=True):
+    """nearest centroid per row (a2): -> (ids int32 [n], dist f32 [n] or None)"""
+    x = _chk(x, torch.float32, "x")
+    cent = _chk(cent, torch.float32, "cent")
+    n, d = x.shape
+    if cnorm is None:
+        cnorm = row_norms(cent)
+    ids = torch.empty(n, dtype=torch.int32, device=x.device)
+    dist = torch.empty(n, dtype=torch.float32, device=x.device) if want_dist else None
+    _abi.call("vlq_l2_assign", _ptr(x), n, d, _ptr(cent), _ptr(cnorm), cent.shape[0], int(add_xnorm), _ptr(ids),
+              _ptr(dist), _stream())
+    return ids, dist
+
+
+def l2_distances(x, cent, cnorm=None, out=None):
+    """coarse matrix D = ||c||^2 - 2 x.c (a11)"""
+    x = _chk(x, torch.float32, "x")
+    cent = _chk(cent, torch.float32, "cent")
+    n, d = x.shape
+    C = cent.shape[0]
+    if cnorm is None:
+        cnorm = row_norms(cent)
+    D = out if out is not None else torch.empty((n, C), dtype=torch.float32, device=x.device)
+    _abi.call("vlq_l2_distances", _ptr(x), n, d, _ptr(cent), _ptr(cnorm), C, _ptr(D), D.stride(0), _stream())
+    return D
+
+
+def select_rows(D, k, row_add=None, cols=None):
+    """exact top-k per row ascending (a11/a15): -> (val f32 [n][k], idx int32 [n][k])"""
+    D = _chk(D, torch.float32, "D")
+    n = D.shape[0]
+    cols = D.shape[1] if cols is None else cols
+    val = torch.empty((n, k), dtype=torch.float32, device=D.device)
+    idx = torch.empty((n, k), dtype=torch.int32, device=D.device)
+    _abi.call("vlq_select_rows", _ptr(D), n, cols, D.stride(0), k, _ptr(row_add), _ptr(val), _ptr(idx), _stream())
+    return val, idx
+
+
+def knn_graph(cent, E, cnorm=None):
+    """centroid kNN graph (a4): -> (edge int32 [C][E], edge_d2 f32 [C][E])"""
+    cent = _chk(cent, torch.float32, "cent")
+    C, d = cent.shape
+    if cnorm is None:
+        cnorm = row_norms(cent)
+    edge = torch.empty((C, E), dtype=torch.int32, device=cent.device)
+    ed2 = torch.empty((C, E), dtype=torch.float32, device=cent.device)
+    wsb = _abi.lib().vlq_knn_graph_workspace_bytes(C, E)
+    ws = torch.empty(wsb, dtype=torch.uint8, device=cent.device)
+    _abi.call("vlq_knn_graph", _ptr(cent), _ptr(cnorm), C, d, E, _ptr(edge), _ptr(ed2), _ptr(ws), wsb, _stream())
+    return edge, ed2
+
+
+Encoded = namedtuple("Encoded", "list lam lamq codes kappa residual")
+
+
+def line_encode(x, assign, cent, edge, edge_d2, lambda_cb=None, pq=None, want_residual=False):
+    """fused line stage (+ lambda quantiser + residual + PQ encode when lambda_cb/pq are given) (a5-a8)"""
+    x = _chk(x, torch.float32, "x")
+    assign = _chk(assign, torch.int32, "assign")
+    cent = _chk(cent, torch.float32, "cent")
+    edge = _chk(edge, torch.int32, "edge")
+    edge_d2 = _chk(edge_d2, torch.float32, "edge_d2")
+    n, d = x.shape
+    E = edge.shape[1]
+    dev = x.device
+    out_list = torch.empty(n, dtype=torch.int32, device=dev)
+    out_lam = torch.empty(n, dtype=torch.float32, device=dev)
+    lamq = codes = kappa = resid = None
+    M = nL = 0
+    if lambda_cb is not None:
+        lambda_cb = _chk(lambda_cb, torch.float32, "lambda_cb")
+        pq = _chk(pq, torch.float32, "pq")
+        M, nL = pq.shape[0], lambda_cb.shape[0]
+        lamq = torch.empty(n, dtype=torch.uint8, device=dev)
+        codes = torch.empty((n, M), dtype=torch.uint8, device=dev)
+        kappa = torch.empty(n, dtype=torch.float32, device=dev)
+        if want_residual:
+            resid = torch.empty((n, d), dtype=torch.float32, device=dev)
+    _abi.call("vlq_line_encode", _ptr(x), n, d, _ptr(assign), _ptr(cent), _ptr(edge), _ptr(edge_d2), E,
+              _ptr(lambda_cb), nL, _ptr(pq), M, _ptr(out_list), _ptr(out_lam), _ptr(lamq), _ptr(codes), _ptr(kappa),
+              _ptr(resid), _stream())
+    return Encoded(out_list, out_lam, lamq, codes, kappa, resid)
+
+
+def build_lists(nlists, M, new_list, new_codes, new_lamq, new_kappa, new_ids, old=None):
+    """stable counting-sort append of new entries behind the existing CSR lists (a9) -> Lists"""
+    dev = new_list.device
+    n_new = new_list.shape[0]
+    n_old = 0 if old is None else old.ids.shape[0]
+    tot = n_old + n_new
+    out = Lists(
+        torch.empty(nlists + 1, dtype=torch.int64, device=dev),
+        torch.empty((tot, M), dtype=torch.uint8, device=dev),
+        torch.empty(tot, dtype=torch.uint8, device=dev),
+        torch.empty(tot, dtype=torch.float32, device=dev),
+        torch.empty(tot, dtype=torch.int64, device=dev),
+    )
+    wsb = _abi.lib().vlq_build_lists_workspace_bytes(n_new, nlists)
+    ws = torch.empty(wsb, dtype=torch.uint8, device=dev)
+    o = old if n_old > 0 else Lists(None, None, None, None, None)
+    _abi.call("vlq_build_lists", nlists, M, n_old, _ptr(o.offsets), _ptr(o.codes), _ptr(o.lamq), _ptr(o.kappa),
+              _ptr(o.ids), n_new, _ptr(_chk(new_list, torch.int32, "new_list")),
+              _ptr(_chk(new_codes, torch.uint8, "new_codes")), _ptr(_chk(new_lamq, torch.uint8, "new_lamq")),
+              _ptr(_chk(new_kappa, torch.float32, "new_kappa")), _ptr(_chk(new_ids, torch.int64, "new_ids")),
+              _ptr(out.offsets), _ptr(out.codes), _ptr(out.lamq), _ptr(out.kappa), _ptr(out.ids), _ptr(ws), wsb,
+              _stream())
+    return out
+
+
+def select_lines(D, coarse_ids, edge, edge_d2, W):
+    """query-time line selection (a12): -> (list int32 [nq][W], term1, term6 f32 [nq][W])"""
+    D = _chk(D, torch.float32, "D")
+    coarse_ids = _chk(coarse_ids, torch.int32, "coarse_ids")
+    nq, P = coarse_ids.shape
+    E = edge.shape[1]
+    dev = D.device
+    lst = torch.empty((nq, W), dtype=torch.int32, device=dev)
+    t1 = torch.empty((nq, W), dtype=torch.float32, device=dev)
+    t6 = torch.empty((nq, W), dtype=torch.float32, device=dev)
+    _abi.call("vlq_select_lines", _ptr(D), nq, D.stride(0), _ptr(coarse_ids), P, _ptr(edge), _ptr(edge_d2), E, W,
+              _ptr(lst), _ptr(t1), _ptr(t6), _stream())
+    return lst, t1, t6
+
+
+def scan_topk(q, pq, lambda_cb, line_list, term1, term6, edge_d2, lists, k, cap=1024):
+    """ADC scan of the selected lists fused with exact top-k (a13-a15): -> (D f32 [nq][k], I int64 [nq][k])"""
+    q = _chk(q, torch.float32, "q")
+    pq = _chk(pq, torch.float32, "pq")
+    nq, d = q.shape
+    M = pq.shape[0]
+    W = line_list.shape[1]
+    outD = torch.empty((nq, k), dtype=torch.float32, device=q.device)
+    outI = torch.empty((nq, k), dtype=torch.int64, device=q.device)
+    _abi.call("vlq_scan_topk", _ptr(q), nq, d, _ptr(pq), M, _ptr(lambda_cb), lambda_cb.shape[0],
+              _ptr(_chk(line_list, torch.int32, "line_list")), _ptr(term1), _ptr(term6), _ptr(edge_d2), W,
+              _ptr(lists.offsets), _ptr(lists.codes), _ptr(lists.lamq), _ptr(lists.kappa), _ptr(lists.ids), k, cap,
+              _ptr(outD), _ptr(outI), _stream())
+    return outD, outI
+
+
+def merge_topk(D, I):
+    """shard merge (a16): D, I are [R][nq][k] -> (nq,k)"""
+    D = _chk(D, torch.float32, "D")
+    I = _chk(I, torch.int64, "I")
+    R, nq, k = D.shape
+    outD = torch.empty((nq, k), dtype=torch.float32, device=D.device)
+    outI = torch.empty((nq, k), dtype=torch.int64, device=D.device)
+    _abi.call("vlq_merge_topk", _ptr(D), _ptr(I), R, nq, k, _ptr(outD), _ptr(outI), _stream())
+    return outD, outI
+
+
+def km_update(x, assign, k):
+    """k-means mean step, deterministic row order (f1): -> (centroids f32 [k][d], counts int32 [k])"""
+    x = _chk(x, torch.float32, "x")
+    assign = _chk(assign, torch.int32, "assign")
+    n, d = x.shape
+    cent = torch.empty((k, d), dtype=torch.float32, device=x.device)
+    counts = torch.empty(k, dtype=torch.int32, device=x.device)
+    wsb = _abi.lib().vlq_km_update_workspace_bytes(n, k)
+    ws = torch.empty(wsb, dtype=torch.uint8, device=x.device)
+    _abi.call("vlq_km_update", _ptr(x), n, d, _ptr(assign), k, _ptr(cent), _ptr(counts), _ptr(ws), wsb, _stream())
+    return cent, counts
+
+
+def search(q, cent, cnorm, edge, edge_d2, lambda_cb, pq, lists, P, W, k, cap=1024, tile=1024):
+    """Full query path on resident tensors (a11-a15), tiled over queries so the coarse matrix stays L2-sized."""
+    nq = q.shape[0]
+    C = cent.shape[0]
+    P = min(P, C)
+    outD = torch.empty((nq, k), dtype=torch.float32, device=q.device)
+    outI = torch.empty((nq, k), dtype=torch.int64, device=q.device)
+    Dbuf = torch.empty((min(tile, nq), C), dtype=torch.float32, device=q.device)
+    ed2_flat = edge_d2.reshape(-1)
+    for s in range(0, nq, tile):
+        e = min(nq, s + tile)
+        qt = q[s:e]
+        D = l2_distances(qt, cent, cnorm, out=Dbuf[: e - s])
+        _, cid = select_rows(D, P)
+        lst, t1, t6 = select_lines(D, cid, edge, edge_d2, W)
+        d_, i_ = scan_topk(qt, pq, lambda_cb, lst, t1, t6, ed2_flat, lists, k, cap)
+        outD[s:e] = d_
+        outI[s:e] = i_
+    return outD, outI
