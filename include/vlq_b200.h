@@ -52,6 +52,28 @@ int vlq_l2_assign(const float* x, int64_t n, int d, const float* cent, const flo
                   int* out_ids, float* out_dist, vlq_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------------------------------
+ * a2 / a11 on the tensor cores (tcgen05 + TMEM): same contracts as vlq_l2_assign / vlq_l2_distances.
+ *     replaces cublasSgemm via runMatrixMult (gpu/utils/MatrixMult.cu:90-147; call sites gpu/impl/Distance.cu:356-362,
+ *     679-685) + l2SelectMin1 (gpu/impl/L2Select.cu:25-121) -- the distance matrix is never materialised for k = 1.
+ *     Arithmetic: operands split into fp16 hi + lo after an exact power-of-two pre-scale, three tcgen05.mma passes
+ *     (hi.hi + hi.lo + lo.hi) accumulated in fp32 TMEM: fp32-GEMM-grade results ("precision").
+ *     Supported when vlq_tc_supported(d, C): d a multiple of 32, 32 <= d <= 128.  Other shapes use the exact fp32
+ *     CUDA-core entry points above (the host layer dispatches; both are CUDA, there is no CPU path).
+ *     cent_pack is produced once per codebook by vlq_tc_pack_centroids (packed fp16 tiles + padded ||c||^2);
+ *     `scale` must be the same power of two in the pack call and the query calls: choose it so that
+ *     max|c|*scale is about 2^9 (inputs up to 2^15/scale stay finite in fp16).
+ * ---------------------------------------------------------------------------------------------------------------- */
+int vlq_tc_supported(int d, int C);
+size_t vlq_tc_cent_pack_bytes(int C, int d);
+int vlq_tc_pack_centroids(const float* cent, const float* cnorm, int C, int d, float scale, void* cent_pack,
+                          vlq_stream_t stream);
+size_t vlq_l2_tc_workspace_bytes(int64_t n, int d, int C);
+int vlq_l2_assign_tc(const float* x, int64_t n, int d, const void* cent_pack, float scale, int C, int add_xnorm,
+                     int* out_ids, float* out_dist, void* workspace, size_t workspace_bytes, vlq_stream_t stream);
+int vlq_l2_distances_tc(const float* x, int64_t n, int d, const void* cent_pack, float scale, int C, float* D,
+                        int64_t ldD, void* workspace, size_t workspace_bytes, vlq_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------------------------
  * a11 coarse distance matrix for a query tile, D[i][j] = ||c_j||^2 - 2 x_i.c_j  (NO ||x||^2, Distance.cu:287-290).
  *     replaces runMatrixMult + the in-place "+||c||^2" of l2SelectMinK, gpu/impl/Distance.cu:352-373.
  *     D is [n][ldD] with ldD >= C.

@@ -1,0 +1,77 @@
+"""tcgen05 coarse-assignment kernels (csrc/assign_tc.cu) against the exact fp32 CUDA-core path and the CPU oracle."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def ops(cuda):
+    from vector_line_quantization_b200 import ops as _ops
+
+    return _ops
+
+
+def _data(n, C, d, seed, kind):
+    rng = np.random.RandomState(seed)
+    if kind == "sift":
+        x = np.clip(np.rint(rng.normal(60, 40, (n, d))), 0, 255).astype(np.float32)
+        c = (np.clip(rng.normal(60, 40, (C, d)), 0, 255) + rng.rand(C, d)).astype(np.float32)
+    else:  # deep-like: unit vectors
+        x = rng.normal(size=(n, d)).astype(np.float32)
+        x /= np.linalg.norm(x, axis=1, keepdims=True)
+        c = rng.normal(size=(C, d)).astype(np.float32)
+        c /= np.linalg.norm(c, axis=1, keepdims=True) * 1.1
+    return x, c
+
+
+@pytest.mark.parametrize("n,C,d,kind", [(256, 128, 128, "sift"), (1000, 1000, 128, "sift"), (5000, 4096, 96, "deep"),
+                                        (77, 333, 64, "deep"), (3000, 65536, 128, "sift"), (70000, 2048, 32, "sift")])
+def test_assign_tc_matches_exact(ops, cuda, oracle, n, C, d, kind):
+    import torch
+
+    x, c = _data(n, C, d, n + C, kind)
+    xt, ct = torch.from_numpy(x).to(cuda), torch.from_numpy(c).to(cuda)
+    pack = ops.CentPack(ct)
+    ids, dist = ops.l2_assign_tc(xt, pack, add_xnorm=True)
+    ids0, dist0 = ops.l2_assign(xt, ct, pack.cnorm, add_xnorm=True)
+    torch.cuda.synchronize()
+    ids, dist, ids0, dist0 = ids.cpu().numpy(), dist.cpu().numpy(), ids0.cpu().numpy(), dist0.cpu().numpy()
+    bad = np.nonzero(ids != ids0)[0]
+    x64, c64 = x.astype(np.float64), c.astype(np.float64)
+    for i in bad:  # only near-ties may differ (north_star: relative distance gap < 1e-5)
+        da, db = np.sum((x64[i] - c64[ids[i]]) ** 2), np.sum((x64[i] - c64[ids0[i]]) ** 2)
+        assert abs(da - db) <= 1e-5 * max(da, db) + 1e-12, (i, da, db)
+    assert len(bad) <= max(1, n // 2000)
+    ok = ids == ids0
+    scale = np.sum(x64 ** 2, axis=1)[ok] + np.sum(c64[ids0[ok]] ** 2, axis=1)
+    assert np.all(np.abs(dist[ok] - dist0[ok]) <= 2e-6 * scale + 1e-6)
+    if n * C <= 5_000_000:
+        _, Io = oracle.l2_topk(x, c, 1)
+        assert (ids == Io[:, 0]).mean() > 0.999
+
+
+@pytest.mark.parametrize("n,C,d", [(300, 1000, 128), (1024, 4096, 96), (50, 130, 64)])
+def test_distances_tc_matches_exact(ops, cuda, n, C, d):
+    import torch
+
+    x, c = _data(n, C, d, 7, "sift")
+    xt, ct = torch.from_numpy(x).to(cuda), torch.from_numpy(c).to(cuda)
+    pack = ops.CentPack(ct)
+    D = ops.l2_distances_tc(xt, pack)
+    D0 = ops.l2_distances(xt, ct, pack.cnorm)
+    ref = (c.astype(np.float64) ** 2).sum(1)[None, :] - 2 * x.astype(np.float64) @ c.astype(np.float64).T
+    mag = np.linalg.norm(x, axis=1)[:, None] * np.linalg.norm(c, axis=1)[None, :] + 1
+    err_tc = np.abs(D.cpu().numpy() - ref) / mag
+    err_simt = np.abs(D0.cpu().numpy() - ref) / mag
+    assert err_tc.max() < 3e-6, err_tc.max()       # fp32-GEMM grade
+    assert err_tc.max() < 8 * err_simt.max() + 1e-7
+
+
+def test_tc_rejects_unsupported_shapes(ops, cuda):
+    import torch
+
+    with pytest.raises(ValueError):
+        ops.CentPack(torch.randn(100, 20, device=cuda))
+    with pytest.raises(ValueError):
+        ops.CentPack(torch.randn(100, 256, device=cuda))

@@ -22,6 +22,12 @@ SIGNATURES = {
     "vlq_launch_count": (C.c_uint64, []),
     "vlq_row_norms": (_i, [_p, _l, _i, _p, _p]),
     "vlq_l2_assign": (_i, [_p, _l, _i, _p, _p, _i, _i, _p, _p, _p]),
+    "vlq_tc_supported": (_i, [_i, _i]),
+    "vlq_tc_cent_pack_bytes": (_z, [_i, _i]),
+    "vlq_tc_pack_centroids": (_i, [_p, _p, _i, _i, _f, _p, _p]),
+    "vlq_l2_tc_workspace_bytes": (_z, [_l, _i, _i]),
+    "vlq_l2_assign_tc": (_i, [_p, _l, _i, _p, _f, _i, _i, _p, _p, _p, _z, _p]),
+    "vlq_l2_distances_tc": (_i, [_p, _l, _i, _p, _f, _i, _p, _l, _p, _z, _p]),
     "vlq_l2_distances": (_i, [_p, _l, _i, _p, _p, _i, _p, _l, _p]),
     "vlq_select_rows": (_i, [_p, _l, _i, _l, _i, _p, _p, _p, _p]),
     "vlq_knn_graph_workspace_bytes": (_z, [_i, _i]),

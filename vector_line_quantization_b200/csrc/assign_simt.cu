@@ -279,8 +279,9 @@ extern "C" {
 uint64_t vlq_launch_count(void) { return g_launch_count.load(); }
 
 int vlq_row_norms(const float* x, int64_t n, int d, float* out, vlq_stream_t stream) {
-  if (!x || !out || n < 0 || d <= 0) return VLQ_EINVAL;
+  if (n < 0 || d <= 0) return VLQ_EINVAL;
   if (n == 0) return VLQ_OK;
+  if (!x || !out) return VLQ_EINVAL;
   const int warps = 8;
   VLQ_LAUNCH(row_norms_kernel, (unsigned)div_up(n, warps), warps * kWarp, 0, as_stream(stream), x, n, d, out);
   return last_error();
@@ -288,8 +289,9 @@ int vlq_row_norms(const float* x, int64_t n, int d, float* out, vlq_stream_t str
 
 int vlq_l2_assign(const float* x, int64_t n, int d, const float* cent, const float* cnorm, int C, int add_xnorm,
                   int* out_ids, float* out_dist, vlq_stream_t stream) {
-  if (!x || !cent || !cnorm || !out_ids || n < 0 || d <= 0 || C <= 0) return VLQ_EINVAL;
+  if (n < 0 || d <= 0 || C <= 0) return VLQ_EINVAL;
   if (n == 0) return VLQ_OK;
+  if (!x || !cent || !cnorm || !out_ids) return VLQ_EINVAL;
   VLQ_LAUNCH(l2_argmin_kernel, (unsigned)div_up(n, BM), GEMM_THREADS, 0, as_stream(stream), x, n, d, cent, cnorm, C,
              add_xnorm, out_ids, out_dist);
   return last_error();
@@ -297,8 +299,9 @@ int vlq_l2_assign(const float* x, int64_t n, int d, const float* cent, const flo
 
 int vlq_l2_distances(const float* x, int64_t n, int d, const float* cent, const float* cnorm, int C, float* D,
                      int64_t ldD, vlq_stream_t stream) {
-  if (!x || !cent || !cnorm || !D || n < 0 || d <= 0 || C <= 0 || ldD < C) return VLQ_EINVAL;
+  if (n < 0 || d <= 0 || C <= 0 || ldD < C) return VLQ_EINVAL;
   if (n == 0) return VLQ_OK;
+  if (!x || !cent || !cnorm || !D) return VLQ_EINVAL;
   if (div_up(n, BM) > 65535) return VLQ_EINVAL;  // callers tile queries (GpuIndex.cu:109-147 pages at 32Ki)
   dim3 grid((unsigned)div_up(C, BN), (unsigned)div_up(n, BM));
   VLQ_LAUNCH(l2_dist_store_kernel, grid, GEMM_THREADS, 0, as_stream(stream), x, n, d, cent, cnorm, C, D, ldD);
@@ -307,8 +310,9 @@ int vlq_l2_distances(const float* x, int64_t n, int d, const float* cent, const 
 
 int vlq_select_rows(const float* D, int64_t n, int cols, int64_t ldD, int k, const float* row_add, float* out_val,
                     int* out_idx, vlq_stream_t stream) {
-  if (!D || !out_val || !out_idx || n < 0 || cols <= 0 || k <= 0 || k > VLQ_MAX_K || ldD < cols) return VLQ_EINVAL;
+  if (n < 0 || cols <= 0 || k <= 0 || k > VLQ_MAX_K || ldD < cols) return VLQ_EINVAL;
   if (n == 0) return VLQ_OK;
+  if (!D || !out_val || !out_idx) return VLQ_EINVAL;
   size_t smem = topk_smem_bytes(k, SEL_THREADS);
   VLQ_LAUNCH(select_rows_kernel, (unsigned)n, SEL_THREADS, smem, as_stream(stream), D, cols, ldD, k, row_add,
              out_val, out_idx);
@@ -316,20 +320,23 @@ int vlq_select_rows(const float* D, int64_t n, int cols, int64_t ldD, int k, con
 }
 
 int vlq_gather_rows(const float* src, int d, const int64_t* rows, int64_t n, float* dst, vlq_stream_t stream) {
-  if (!src || !rows || !dst || d <= 0 || n < 0) return VLQ_EINVAL;
+  if (d <= 0 || n < 0) return VLQ_EINVAL;
   if (n == 0) return VLQ_OK;
+  if (!src || !rows || !dst) return VLQ_EINVAL;
   VLQ_LAUNCH(gather_rows_kernel, (unsigned)div_up(n, 8), 256, 0, as_stream(stream), src, d, rows, n, dst);
   return last_error();
 }
 int vlq_u8_to_f32(const uint8_t* src, int64_t count, float* dst, vlq_stream_t stream) {
-  if (!src || !dst || count < 0) return VLQ_EINVAL;
+  if (count < 0) return VLQ_EINVAL;
   if (count == 0) return VLQ_OK;
+  if (!src || !dst) return VLQ_EINVAL;
   VLQ_LAUNCH(u8_to_f32_kernel, 148 * 8, 256, 0, as_stream(stream), src, count, dst);
   return last_error();
 }
 int vlq_iota_i64(int64_t* dst, int64_t n, int64_t start, vlq_stream_t stream) {
-  if (!dst || n < 0) return VLQ_EINVAL;
+  if (n < 0) return VLQ_EINVAL;
   if (n == 0) return VLQ_OK;
+  if (!dst) return VLQ_EINVAL;
   VLQ_LAUNCH(iota_i64_kernel, 148 * 4, 256, 0, as_stream(stream), dst, n, start);
   return last_error();
 }

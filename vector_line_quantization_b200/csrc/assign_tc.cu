@@ -1,0 +1,598 @@
+// Coarse assignment on the 5th-generation tensor cores (north_star item 1).
+//
+//   D[i][j] = ||c_j||^2 - 2 x_i . c_j        i < n vectors,  j < C centroids,  K = d
+//
+// fp32-grade result from fp16 tensor-core passes: every operand is split x = x_hi + x_lo (two fp16 numbers, 22 bits of
+// mantissa together, after an exact power-of-two pre-scale that keeps both parts in fp16's normal range) and the
+// product is accumulated in fp32 TMEM as   x_hi.c_hi + x_hi.c_lo + x_lo.c_hi    (the dropped x_lo.c_lo term is
+// 2^-22 relative).  Three tcgen05.mma passes into the same accumulator; the error is at the level of an fp32 GEMM with
+// a different summation order, which is what north_star's "identical except near-ties < 1e-5" allows.
+//
+// Kernel (one CTA per SM, persistent over work items = 256-row block x centroid split):
+//   warp 0    producer : cp.async.bulk (TMA engine, SASS UBLKCP) of pre-packed operand tiles, mbarrier complete_tx
+//   warp 1    MMA issuer (one elected lane): tcgen05.mma.cta_group::1.kind::f16, M=128 x N=128 x K=16, SMEM descriptors
+//             on the no-swizzle K-major canonical layout the pack kernel writes; tcgen05.commit releases stages
+//   warps 2-5 epilogue : tcgen05.ld 32x32b.x32 (one accumulator row per thread) -> fused per-row arg-min
+//             (or D-tile store for the query path); TMEM accumulators are double buffered so the epilogue of
+//             centroid tile t overlaps the MMAs of tile t+1
+//   A (the 256 x d block of vectors, hi+lo) stays resident in SMEM for the whole centroid sweep; B (128 centroids x 32 K,
+//   hi+lo = 16 KiB) streams through a 4-stage ring.  256 rows per CTA halve the L2->SM operand traffic per vector
+//   compared with one 128-row tile (the sweep is otherwise L2-bandwidth bound at ~42 B/clk/SM).
+//
+// Packed operand layout (written by pack_rows_kernel; shared by A and B):
+//   [tile = row/128][part: hi,lo][kb = k/32][rg = (row%128)/8][kg = (k%32)/8][r8 = row%8][8 x fp16]
+//   i.e. 8x8 "core matrices" of 128 contiguous bytes; LBO (next core matrix along K) = 128 B, SBO (next 8 rows) = 512 B.
+#include <cuda_fp16.h>
+
+#include <cfloat>
+
+#include "common.cuh"
+
+namespace vlq {
+namespace tc {
+
+constexpr int TILE_ROWS = 128;               // UMMA M and N
+constexpr int KB = 32;                       // K elements per pipeline stage
+constexpr int TILE_KB_BYTES = TILE_ROWS * KB * 2;  // 8 KiB: one (tile, part, kb) block
+constexpr int STAGES = 4;
+constexpr int ROW_TILES = 2;                 // 256 rows per CTA
+constexpr int ACC_BUFS = 2;
+constexpr int TMEM_COLS = ROW_TILES * ACC_BUFS * TILE_ROWS;  // 512
+constexpr int THREADS = 192;
+constexpr int MAX_D = 128;
+
+__host__ __device__ inline int64_t packed_bytes(int64_t rows, int d) {
+  int64_t tiles = (rows + TILE_ROWS - 1) / TILE_ROWS;
+  return tiles * 2 * (d / KB) * TILE_KB_BYTES;
+}
+
+// ------------------------------------------------------------------------------------------------------ PTX helpers
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  uint32_t addr = smem_u32(bar);
+  asm volatile(
+      "{\n\t"
+      ".reg .pred P1;\n\t"
+      "WAIT_LOOP:\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n\t"
+      "@P1 bra DONE;\n\t"
+      "bra WAIT_LOOP;\n\t"
+      "DONE:\n\t"
+      "}" ::"r"(addr), "r"(parity)
+      : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void* smem_dst, const void* gmem_src, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                   smem_u32(smem_dst)),
+               "l"(gmem_src), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "elect.sync _|p, 0xffffffff;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t"
+      "}"
+      : "=r"(pred));
+  return pred != 0;
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+__device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc,
+                                         uint32_t accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t"
+      "}" ::"r"(tmem_d),
+      "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
+               : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+        "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+        "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// SMEM matrix descriptor, K-major, SWIZZLE_NONE (cute::UMMA::SmemDescriptor bit layout):
+//   [0,14) start address >> 4, [16,30) leading byte offset >> 4, [32,46) stride byte offset >> 4, [46,48) version = 1,
+//   [61,64) layout type = 0
+__device__ __forceinline__ uint64_t make_desc(uint32_t smem_addr) {
+  constexpr uint64_t LBO = 128 >> 4, SBO = 512 >> 4;
+  return (uint64_t)((smem_addr & 0x3FFFF) >> 4) | (LBO << 16) | (SBO << 32) | (1ull << 46);
+}
+// Instruction descriptor for kind::f16 (cute::UMMA::InstrDescriptor): c_format F32 = 1 @4, a/b format F16 = 0 @7/@10,
+// a/b major K = 0 @15/@16, N>>3 @17, M>>4 @24
+constexpr uint32_t kIdesc = (1u << 4) | ((uint32_t)(TILE_ROWS >> 3) << 17) | ((uint32_t)(TILE_ROWS >> 4) << 24);
+
+// ------------------------------------------------------------------------------------------------------ pack kernel
+// fp32 [rows][d] -> packed fp16 hi/lo tiles, values pre-multiplied by `scale` (a power of two: exact).
+// Rows in [rows, rows_padded) are written as zeros.
+__global__ void pack_rows_kernel(const float* __restrict__ x, int64_t rows, int64_t rows_padded, int d, float scale,
+                                 uint8_t* __restrict__ out) {
+  const int g8 = d / 8;  // 8-element groups per row
+  const int nkb = d / KB;
+  int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int64_t total = rows_padded * g8;
+  for (; idx < total; idx += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t row = idx / g8;
+    const int kg8 = (int)(idx % g8);
+    float v[8];
+    if (row < rows) {
+      const float4* p = reinterpret_cast<const float4*>(x + row * d + kg8 * 8);
+      float4 a = p[0], b = p[1];
+      v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+    } else {
+#pragma unroll
+      for (int t = 0; t < 8; t++) v[t] = 0.f;
+    }
+    __align__(16) __half hi[8];
+    __align__(16) __half lo[8];
+#pragma unroll
+    for (int t = 0; t < 8; t++) {
+      const float s = v[t] * scale;
+      const __half h = __float2half_rn(s);
+      hi[t] = h;
+      lo[t] = __float2half_rn(s - __half2float(h));
+    }
+    const int64_t tile = row / TILE_ROWS;
+    const int rr = (int)(row % TILE_ROWS);
+    const int kb = kg8 / (KB / 8), kg = kg8 % (KB / 8);
+    const int64_t base = (tile * 2) * (int64_t)nkb * TILE_KB_BYTES;
+    const int64_t inner = (int64_t)kb * TILE_KB_BYTES + (rr / 8) * 512 + kg * 128 + (rr % 8) * 16;
+    *reinterpret_cast<uint4*>(out + base + inner) = *reinterpret_cast<const uint4*>(hi);
+    *reinterpret_cast<uint4*>(out + base + (int64_t)nkb * TILE_KB_BYTES + inner) = *reinterpret_cast<const uint4*>(lo);
+  }
+}
+
+__global__ void pad_cnorm_kernel(const float* __restrict__ cnorm, int C, int Cpad, float* __restrict__ out) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < Cpad) out[i] = i < C ? cnorm[i] : __int_as_float(0x7f800000);
+}
+
+// ------------------------------------------------------------------------------------------------------ GEMM kernel
+struct Params {
+  const uint8_t* a_pack;   // packed vectors: row tiles of this launch
+  const uint8_t* b_pack;   // packed centroids
+  const float* cnorm_pad;  // [Cpad], +inf beyond C
+  int64_t n;               // valid rows
+  int C, d;
+  int n_row_blocks;        // ceil(n / 256)
+  int n_ctiles;            // Cpad / 128
+  int csplit;              // work item = (row block, centroid split)
+  int tiles_per_split;
+  float m2s;               // -2 / scale^2
+  unsigned long long* keys;  // mode 0: [n] packed (ordered distance << 32 | centroid)
+  float* D;                // mode 1: [n][ldD]
+  int64_t ldD;
+};
+
+template <int MODE>  // 0 = fused arg-min, 1 = store the distance tile
+__global__ void __launch_bounds__(THREADS, 1) l2_tc_kernel(const Params p) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  const int nkb = p.d / KB;
+  const int a_tile_bytes = 2 * nkb * TILE_KB_BYTES;  // one 128-row tile, hi+lo, all of K
+  uint8_t* a_s = smem;                                // [ROW_TILES][hi,lo][nkb][8 KiB]
+  uint8_t* b_s = a_s + ROW_TILES * a_tile_bytes;      // [STAGES][hi,lo][8 KiB]
+  float* cn_s = reinterpret_cast<float*>(b_s + STAGES * 2 * TILE_KB_BYTES);  // [ACC_BUFS][128]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(cn_s + ACC_BUFS * TILE_ROWS);
+  uint64_t* full = bars;                 // [STAGES]
+  uint64_t* empty = bars + STAGES;       // [STAGES]
+  uint64_t* a_full = bars + 2 * STAGES;  // [1]
+  uint64_t* a_empty = a_full + 1;        // [1]
+  uint64_t* t_full = a_empty + 1;        // [ACC_BUFS]
+  uint64_t* t_empty = t_full + ACC_BUFS; // [ACC_BUFS]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(t_empty + ACC_BUFS);
+
+  const int warp = threadIdx.x / 32;
+  const int lane = threadIdx.x % 32;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < STAGES; s++) {
+      mbar_init(&full[s], 1);
+      mbar_init(&empty[s], 1);
+    }
+    mbar_init(a_full, 1);
+    mbar_init(a_empty, 1);
+    for (int b = 0; b < ACC_BUFS; b++) {
+      mbar_init(&t_full[b], 1);
+      mbar_init(&t_empty[b], 128);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {  // TMEM allocation (whole warp), 512 columns
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
+                 "r"((uint32_t)TMEM_COLS)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  const int n_items = p.n_row_blocks * p.csplit;
+
+  if (warp == 0) {
+    // ===================================================================== producer
+    if (elect_one()) {
+      uint32_t stage = 0, phase = 0, item_phase = 0;
+      for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
+        const int rb = item / p.csplit, cs = item % p.csplit;
+        const int t0 = cs * p.tiles_per_split;
+        const int t1 = min(p.n_ctiles, t0 + p.tiles_per_split);
+        // A block (both row tiles are contiguous in the packed layout)
+        mbar_wait(a_empty, item_phase ^ 1);
+        mbar_arrive_expect_tx(a_full, ROW_TILES * a_tile_bytes);
+        const uint8_t* asrc = p.a_pack + (int64_t)rb * ROW_TILES * a_tile_bytes;
+        for (int c = 0; c < ROW_TILES * 2; c++)
+          bulk_g2s(a_s + c * (a_tile_bytes / 2), asrc + (int64_t)c * (a_tile_bytes / 2), a_tile_bytes / 2, a_full);
+        item_phase ^= 1;
+        for (int t = t0; t < t1; t++) {
+          const uint8_t* bsrc = p.b_pack + (int64_t)t * a_tile_bytes;
+          for (int kb = 0; kb < nkb; kb++) {
+            mbar_wait(&empty[stage], phase ^ 1);
+            mbar_arrive_expect_tx(&full[stage], 2 * TILE_KB_BYTES);
+            uint8_t* dst = b_s + stage * 2 * TILE_KB_BYTES;
+            bulk_g2s(dst, bsrc + (int64_t)kb * TILE_KB_BYTES, TILE_KB_BYTES, &full[stage]);                       // hi
+            bulk_g2s(dst + TILE_KB_BYTES, bsrc + (int64_t)(nkb + kb) * TILE_KB_BYTES, TILE_KB_BYTES, &full[stage]);  // lo
+            if (++stage == STAGES) {
+              stage = 0;
+              phase ^= 1;
+            }
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================================================================== MMA issuer
+    uint32_t stage = 0, phase = 0, item_phase = 0, acc_buf = 0, acc_phase = 0;
+    for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
+      const int cs = item % p.csplit;
+      const int t0 = cs * p.tiles_per_split;
+      const int t1 = min(p.n_ctiles, t0 + p.tiles_per_split);
+      mbar_wait(a_full, item_phase);
+      tc_fence_after();
+      for (int t = t0; t < t1; t++) {
+        mbar_wait(&t_empty[acc_buf], acc_phase ^ 1);
+        tc_fence_after();
+        for (int kb = 0; kb < nkb; kb++) {
+          mbar_wait(&full[stage], phase);
+          tc_fence_after();
+          if (elect_one()) {
+            const uint32_t b_hi = smem_u32(b_s + stage * 2 * TILE_KB_BYTES);
+            const uint32_t b_lo = b_hi + TILE_KB_BYTES;
+#pragma unroll
+            for (int r = 0; r < ROW_TILES; r++) {
+              const uint32_t a_hi = smem_u32(a_s + r * a_tile_bytes + kb * TILE_KB_BYTES);
+              const uint32_t a_lo = a_hi + nkb * TILE_KB_BYTES;
+              const uint32_t tacc = tmem_base + (acc_buf * ROW_TILES + r) * TILE_ROWS;
+#pragma unroll
+              for (int pass = 0; pass < 3; pass++) {
+                const uint32_t a0 = pass == 2 ? a_lo : a_hi;  // hi.hi, hi.lo, lo.hi
+                const uint32_t b0 = pass == 1 ? b_lo : b_hi;
+#pragma unroll
+                for (int k16 = 0; k16 < KB / 16; k16++) {
+                  umma_f16(tacc, make_desc(a0 + k16 * 256), make_desc(b0 + k16 * 256), kIdesc,
+                           (kb | pass | k16) != 0 ? 1u : 0u);
+                }
+              }
+            }
+          }
+          __syncwarp();
+          if (elect_one()) umma_commit(&empty[stage]);  // frees the B stage once these MMAs have read it
+          __syncwarp();
+          if (++stage == STAGES) {
+            stage = 0;
+            phase ^= 1;
+          }
+        }
+        if (elect_one()) umma_commit(&t_full[acc_buf]);  // accumulators of this centroid tile are complete
+        __syncwarp();
+        if (++acc_buf == ACC_BUFS) {
+          acc_buf = 0;
+          acc_phase ^= 1;
+        }
+      }
+      if (elect_one()) umma_commit(a_empty);  // all MMAs that read A have retired
+      __syncwarp();
+      item_phase ^= 1;
+    }
+  } else {
+    // ===================================================================== epilogue (warps 2..5, 128 threads)
+    const int et = threadIdx.x - 64;                  // 0..127
+    const int lane_grp = warp & 3;                    // TMEM lanes this warp may read: [32*lane_grp, +32)
+    const int row_in_tile = lane_grp * 32 + lane;
+    uint32_t acc_buf = 0, acc_phase = 0;
+    for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
+      const int rb = item / p.csplit, cs = item % p.csplit;
+      const int t0 = cs * p.tiles_per_split;
+      const int t1 = min(p.n_ctiles, t0 + p.tiles_per_split);
+      float best[ROW_TILES];
+      int bidx[ROW_TILES];
+#pragma unroll
+      for (int r = 0; r < ROW_TILES; r++) {
+        best[r] = __int_as_float(0x7f800000);
+        bidx[r] = 0x7fffffff;
+      }
+      for (int t = t0; t < t1; t++) {
+        // stage ||c||^2 of this centroid tile (safe: every epilogue thread passed the previous use of this slot
+        // before arriving on t_empty two tiles ago, and the named barrier below orders the writes before the reads)
+        cn_s[acc_buf * TILE_ROWS + et] = p.cnorm_pad[t * TILE_ROWS + et];
+        asm volatile("bar.sync 1, 128;" ::: "memory");
+        mbar_wait(&t_full[acc_buf], acc_phase);
+        tc_fence_after();
+        const float* cn = cn_s + acc_buf * TILE_ROWS;
+#pragma unroll
+        for (int r = 0; r < ROW_TILES; r++) {
+          const uint32_t taddr = tmem_base + ((uint32_t)(lane_grp * 32) << 16) + (acc_buf * ROW_TILES + r) * TILE_ROWS;
+          const int64_t row = ((int64_t)rb * ROW_TILES + r) * TILE_ROWS + row_in_tile;
+#pragma unroll 1
+          for (int c = 0; c < TILE_ROWS / 32; c++) {
+            uint32_t v[32];
+            tmem_ld32(taddr + c * 32, v);
+            tmem_ld_wait();
+            if (MODE == 0) {
+#pragma unroll
+              for (int i = 0; i < 32; i++) {
+                const float dv = fmaf(__uint_as_float(v[i]), p.m2s, cn[c * 32 + i]);
+                if (dv < best[r]) {
+                  best[r] = dv;
+                  bidx[r] = t * TILE_ROWS + c * 32 + i;
+                }
+              }
+            } else {
+              if (row < p.n) {
+                float* out = p.D + row * p.ldD + (int64_t)t * TILE_ROWS + c * 32;
+                const int col0 = t * TILE_ROWS + c * 32;
+#pragma unroll
+                for (int i = 0; i < 32; i += 4) {
+                  float4 o;
+                  o.x = fmaf(__uint_as_float(v[i + 0]), p.m2s, cn[c * 32 + i + 0]);
+                  o.y = fmaf(__uint_as_float(v[i + 1]), p.m2s, cn[c * 32 + i + 1]);
+                  o.z = fmaf(__uint_as_float(v[i + 2]), p.m2s, cn[c * 32 + i + 2]);
+                  o.w = fmaf(__uint_as_float(v[i + 3]), p.m2s, cn[c * 32 + i + 3]);
+                  if (col0 + i + 3 < p.C && (p.ldD & 3) == 0) {
+                    *reinterpret_cast<float4*>(out + i) = o;
+                  } else {
+                    if (col0 + i + 0 < p.C) out[i + 0] = o.x;
+                    if (col0 + i + 1 < p.C) out[i + 1] = o.y;
+                    if (col0 + i + 2 < p.C) out[i + 2] = o.z;
+                    if (col0 + i + 3 < p.C) out[i + 3] = o.w;
+                  }
+                }
+              }
+            }
+          }
+        }
+        tc_fence_before();
+        mbar_arrive(&t_empty[acc_buf]);
+        if (++acc_buf == ACC_BUFS) {
+          acc_buf = 0;
+          acc_phase ^= 1;
+        }
+      }
+      if (MODE == 0) {
+#pragma unroll
+        for (int r = 0; r < ROW_TILES; r++) {
+          const int64_t row = ((int64_t)rb * ROW_TILES + r) * TILE_ROWS + row_in_tile;
+          if (row < p.n && bidx[r] != 0x7fffffff) {
+            const unsigned long long key = make_key(best[r], (uint32_t)bidx[r]);
+            if (p.csplit == 1) p.keys[row] = key;
+            else atomicMin(&p.keys[row], key);
+          }
+        }
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)TMEM_COLS)
+                 : "memory");
+  }
+}
+
+// keys -> ids (+ distances, + ||x||^2)
+__global__ void finalize_keys_kernel(const unsigned long long* __restrict__ keys, int64_t n, const float* __restrict__ xnorm,
+                                     int* __restrict__ out_ids, float* __restrict__ out_dist) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const unsigned long long k = keys[i];
+  const bool ok = k != kKeyInf;
+  out_ids[i] = ok ? (int)key_payload(k) : -1;
+  if (out_dist) out_dist[i] = ok ? key_val(k) + (xnorm ? xnorm[i] : 0.f) : FLT_MAX;
+}
+
+__global__ void row_norms_f32_kernel(const float* __restrict__ x, int64_t n, int d, float* __restrict__ out) {
+  int64_t row = (int64_t)blockIdx.x * (blockDim.x / kWarp) + threadIdx.x / kWarp;
+  int lane = threadIdx.x % kWarp;
+  if (row >= n) return;
+  const float* xr = x + row * d;
+  float acc = 0.f;
+  for (int j = lane; j < d; j += kWarp) acc = fmaf(xr[j], xr[j], acc);
+  acc = warp_sum(acc);
+  if (lane == 0) out[row] = acc;
+}
+
+static size_t smem_bytes(int d) {
+  const int nkb = d / KB;
+  return (size_t)ROW_TILES * 2 * nkb * TILE_KB_BYTES + (size_t)STAGES * 2 * TILE_KB_BYTES +
+         ACC_BUFS * TILE_ROWS * sizeof(float) + 16 * sizeof(uint64_t) + 16;
+}
+
+static inline size_t align256(size_t v) { return (v + 255) & ~size_t(255); }
+
+constexpr int64_t CHUNK_ROWS = 1 << 18;  // rows packed + swept per launch (bounds the workspace)
+
+static bool supported(int d, int C) { return d >= KB && d <= MAX_D && d % KB == 0 && C >= 1; }
+
+static int num_sms() {
+  static int sms = 0;
+  if (!sms) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  }
+  return sms;
+}
+
+template <int MODE>
+static int launch(const Params& p, cudaStream_t st) {
+  const size_t smem = smem_bytes(p.d);
+  cudaError_t e = cudaFuncSetAttribute(l2_tc_kernel<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) return (int)e;
+  const int items = p.n_row_blocks * p.csplit;
+  const int grid = items < num_sms() ? items : num_sms();
+  VLQ_LAUNCH(l2_tc_kernel<MODE>, grid, THREADS, smem, st, p);
+  return last_error();
+}
+
+}  // namespace tc
+}  // namespace vlq
+
+using namespace vlq;
+
+extern "C" {
+
+int vlq_tc_supported(int d, int C) { return tc::supported(d, C) ? 1 : 0; }
+
+size_t vlq_tc_cent_pack_bytes(int C, int d) {
+  if (!tc::supported(d, C)) return 0;
+  const int64_t Cpad = div_up(C, tc::TILE_ROWS) * tc::TILE_ROWS;
+  return tc::align256((size_t)tc::packed_bytes(Cpad, d)) + tc::align256(sizeof(float) * Cpad);
+}
+
+int vlq_tc_pack_centroids(const float* cent, const float* cnorm, int C, int d, float scale, void* cent_pack,
+                          vlq_stream_t stream) {
+  if (!tc::supported(d, C) || !(scale > 0.f)) return VLQ_EUNSUPPORTED;
+  if (!cent || !cnorm || !cent_pack) return VLQ_EINVAL;
+  if ((reinterpret_cast<uintptr_t>(cent) & 15) || (reinterpret_cast<uintptr_t>(cent_pack) & 15)) return VLQ_EINVAL;
+  const int64_t Cpad = div_up(C, tc::TILE_ROWS) * tc::TILE_ROWS;
+  cudaStream_t st = as_stream(stream);
+  const int64_t total = Cpad * (d / 8);
+  VLQ_LAUNCH(tc::pack_rows_kernel, (unsigned)std::min<int64_t>(div_up(total, 256), 148 * 16), 256, 0, st, cent,
+             (int64_t)C, Cpad, d, scale, static_cast<uint8_t*>(cent_pack));
+  float* cn_pad = reinterpret_cast<float*>(static_cast<uint8_t*>(cent_pack) + tc::align256((size_t)tc::packed_bytes(Cpad, d)));
+  VLQ_LAUNCH(tc::pad_cnorm_kernel, (unsigned)div_up(Cpad, 256), 256, 0, st, cnorm, C, (int)Cpad, cn_pad);
+  return last_error();
+}
+
+size_t vlq_l2_tc_workspace_bytes(int64_t n, int d, int C) {
+  if (!tc::supported(d, C) || n < 0) return 0;
+  const int64_t rows = n < tc::CHUNK_ROWS ? n : tc::CHUNK_ROWS;
+  const int64_t rpad = div_up(rows, tc::TILE_ROWS * tc::ROW_TILES) * tc::TILE_ROWS * tc::ROW_TILES;
+  return tc::align256((size_t)tc::packed_bytes(rpad, d)) + tc::align256(sizeof(unsigned long long) * rows) +
+         tc::align256(sizeof(float) * rows) + 256;
+}
+
+static int tc_run(int mode, const float* x, int64_t n, int d, const void* cent_pack, float scale, int C, int add_xnorm,
+                  int* out_ids, float* out_dist, float* D, int64_t ldD, void* workspace, size_t workspace_bytes,
+                  vlq_stream_t stream) {
+  if (!tc::supported(d, C) || !(scale > 0.f)) return VLQ_EUNSUPPORTED;
+  if (n < 0) return VLQ_EINVAL;
+  if (n == 0) return VLQ_OK;
+  if (!x || !cent_pack || !workspace) return VLQ_EINVAL;
+  if (mode == 0 && !out_ids) return VLQ_EINVAL;
+  if (mode == 1 && (!D || ldD < C)) return VLQ_EINVAL;
+  if (reinterpret_cast<uintptr_t>(x) & 15) return VLQ_EINVAL;
+  if (workspace_bytes < vlq_l2_tc_workspace_bytes(n, d, C)) return VLQ_EWORKSPACE;
+  cudaStream_t st = as_stream(stream);
+  const int64_t Cpad = div_up(C, tc::TILE_ROWS) * tc::TILE_ROWS;
+  const uint8_t* b_pack = static_cast<const uint8_t*>(cent_pack);
+  const float* cn_pad = reinterpret_cast<const float*>(b_pack + tc::align256((size_t)tc::packed_bytes(Cpad, d)));
+  const int64_t chunk = n < tc::CHUNK_ROWS ? n : tc::CHUNK_ROWS;
+  const int64_t cpad_rows = div_up(chunk, tc::TILE_ROWS * tc::ROW_TILES) * tc::TILE_ROWS * tc::ROW_TILES;
+  uint8_t* ws = static_cast<uint8_t*>(workspace);
+  ws = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(ws) + 255) & ~uintptr_t(255));
+  uint8_t* a_pack = ws;
+  unsigned long long* keys = reinterpret_cast<unsigned long long*>(ws + tc::align256((size_t)tc::packed_bytes(cpad_rows, d)));
+  float* xnorm = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(keys) + tc::align256(sizeof(unsigned long long) * chunk));
+  const int sms = tc::num_sms();
+  for (int64_t r0 = 0; r0 < n; r0 += chunk) {
+    const int64_t rows = (n - r0) < chunk ? (n - r0) : chunk;
+    const int64_t rpad = div_up(rows, tc::TILE_ROWS * tc::ROW_TILES) * tc::TILE_ROWS * tc::ROW_TILES;
+    const int64_t total = rpad * (d / 8);
+    VLQ_LAUNCH(tc::pack_rows_kernel, (unsigned)std::min<int64_t>(div_up(total, 256), 148 * 16), 256, 0, st,
+               x + r0 * d, rows, rpad, d, scale, a_pack);
+    tc::Params p{};
+    p.a_pack = a_pack;
+    p.b_pack = b_pack;
+    p.cnorm_pad = cn_pad;
+    p.n = rows;
+    p.C = C;
+    p.d = d;
+    p.n_row_blocks = (int)(rpad / (tc::TILE_ROWS * tc::ROW_TILES));
+    p.n_ctiles = (int)(Cpad / tc::TILE_ROWS);
+    // few row blocks (query batches): split the centroid sweep so that every SM has work
+    int csplit = 1;
+    if (p.n_row_blocks < sms) {
+      csplit = sms / p.n_row_blocks;
+      if (csplit > p.n_ctiles) csplit = p.n_ctiles;
+      if (csplit < 1) csplit = 1;
+    }
+    p.tiles_per_split = (int)div_up(p.n_ctiles, csplit);
+    p.csplit = (int)div_up(p.n_ctiles, p.tiles_per_split);
+    p.m2s = -2.f / (scale * scale);
+    p.keys = keys;
+    p.D = mode == 1 ? D + r0 * ldD : nullptr;
+    p.ldD = ldD;
+    int rc;
+    if (mode == 0) {
+      VLQ_CUDA_TRY(cudaMemsetAsync(keys, 0xff, sizeof(unsigned long long) * rows, st));
+      rc = tc::launch<0>(p, st);
+      if (rc) return rc;
+      const float* xn = nullptr;
+      if (add_xnorm && out_dist) {
+        VLQ_LAUNCH(tc::row_norms_f32_kernel, (unsigned)div_up(rows, 8), 256, 0, st, x + r0 * d, rows, d, xnorm);
+        xn = xnorm;
+      }
+      VLQ_LAUNCH(tc::finalize_keys_kernel, (unsigned)div_up(rows, 256), 256, 0, st, keys, rows, xn, out_ids + r0,
+                 out_dist ? out_dist + r0 : nullptr);
+    } else {
+      rc = tc::launch<1>(p, st);
+      if (rc) return rc;
+    }
+  }
+  return last_error();
+}
+
+int vlq_l2_assign_tc(const float* x, int64_t n, int d, const void* cent_pack, float scale, int C, int add_xnorm,
+                     int* out_ids, float* out_dist, void* workspace, size_t workspace_bytes, vlq_stream_t stream) {
+  return tc_run(0, x, n, d, cent_pack, scale, C, add_xnorm, out_ids, out_dist, nullptr, 0, workspace, workspace_bytes,
+                stream);
+}
+
+int vlq_l2_distances_tc(const float* x, int64_t n, int d, const void* cent_pack, float scale, int C, float* D,
+                        int64_t ldD, void* workspace, size_t workspace_bytes, vlq_stream_t stream) {
+  return tc_run(1, x, n, d, cent_pack, scale, C, 0, nullptr, nullptr, D, ldD, workspace, workspace_bytes, stream);
+}
+
+}  // extern "C"

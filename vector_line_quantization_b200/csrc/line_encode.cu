@@ -236,8 +236,8 @@ extern "C" int vlq_line_encode(const float* x, int64_t n, int d, const int* assi
                                const int* edge, const float* edge_d2, int E, const float* lambda_cb, int nL,
                                const float* pq, int M, int* out_list, float* out_lambda, uint8_t* out_lamq,
                                uint8_t* out_codes, float* out_kappa, float* out_residual, vlq_stream_t stream) {
-  if (!x || !assign || !cent || !edge || !edge_d2 || !out_list) return VLQ_EINVAL;
   if (n < 0 || d <= 0 || d > 256 || E <= 0 || E > LE_MAX_E) return VLQ_EINVAL;
+  if (n > 0 && (!x || !assign || !cent || !edge || !edge_d2 || !out_list)) return VLQ_EINVAL;
   const int ksub = 256;
   LineEncodeArgs a{};
   a.x = x; a.n = n; a.d = d; a.assign = assign; a.cent = cent; a.edge = edge; a.edge_d2 = edge_d2; a.E = E;

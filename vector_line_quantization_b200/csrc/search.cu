@@ -306,9 +306,9 @@ extern "C" {
 int vlq_select_lines(const float* D, int64_t nq, int64_t ldD, const int* coarse_ids, int P, const int* edge,
                      const float* edge_d2, int E, int W, int* out_list, float* out_term1, float* out_term6,
                      vlq_stream_t stream) {
-  if (!D || !coarse_ids || !edge || !edge_d2 || !out_list || !out_term1 || !out_term6) return VLQ_EINVAL;
   if (nq < 0 || P <= 0 || P > VLQ_MAX_K || E <= 0 || W <= 0 || W > VLQ_MAX_K) return VLQ_EINVAL;
   if (nq == 0) return VLQ_OK;
+  if (!D || !coarse_ids || !edge || !edge_d2 || !out_list || !out_term1 || !out_term6) return VLQ_EINVAL;
   size_t smem = topk_smem_bytes(W, Q_THREADS);
   VLQ_LAUNCH(select_lines_kernel, (unsigned)nq, Q_THREADS, smem, as_stream(stream), D, ldD, coarse_ids, P, edge,
              edge_d2, E, W, out_list, out_term1, out_term6);
@@ -319,7 +319,7 @@ int vlq_scan_topk(const float* q, int64_t nq, int d, const float* pq, int M, con
                   const int* line_list, const float* term1, const float* term6, const float* edge_d2, int W,
                   const int64_t* offsets, const uint8_t* codes, const uint8_t* lamq, const float* kappa,
                   const int64_t* ids, int k, int cap, float* outD, int64_t* outI, vlq_stream_t stream) {
-  if (!q || !pq || !lambda_cb || !line_list || !term1 || !term6 || !edge_d2 || !offsets || !outD || !outI)
+  if (nq > 0 && (!q || !pq || !lambda_cb || !line_list || !term1 || !term6 || !edge_d2 || !offsets || !outD || !outI))
     return VLQ_EINVAL;
   if (nq < 0 || d <= 0 || M <= 0 || M > 64 || d % M != 0 || nL <= 0 || nL > 256 || W <= 0 || W > VLQ_MAX_K ||
       k <= 0 || k > VLQ_MAX_K || cap <= 0 || cap > (1 << 20) / 1 || (int64_t)W * cap > (int64_t)0x7fffffff)
@@ -347,8 +347,9 @@ int vlq_scan_topk(const float* q, int64_t nq, int d, const float* pq, int M, con
 
 int vlq_merge_topk(const float* D, const int64_t* I, int R, int64_t nq, int k, float* outD, int64_t* outI,
                    vlq_stream_t stream) {
-  if (!D || !I || !outD || !outI || R <= 0 || nq < 0 || k <= 0 || k > VLQ_MAX_K) return VLQ_EINVAL;
+  if (R <= 0 || nq < 0 || k <= 0 || k > VLQ_MAX_K) return VLQ_EINVAL;
   if (nq == 0) return VLQ_OK;
+  if (!D || !I || !outD || !outI) return VLQ_EINVAL;
   size_t smem = topk_smem_bytes(k, Q_THREADS);
   VLQ_LAUNCH(merge_topk_kernel, (unsigned)nq, Q_THREADS, smem, as_stream(stream), D, I, R, nq, k, outD, outI);
   return last_error();

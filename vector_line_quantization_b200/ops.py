@@ -209,8 +209,9 @@ def km_update(x, assign, k):
     return cent, counts
 
 
-def search(q, cent, cnorm, edge, edge_d2, lambda_cb, pq, lists, P, W, k, cap=1024, tile=1024):
-    """Full query path on resident tensors (a11-a15), tiled over queries so the coarse matrix stays L2-sized."""
+def search(q, cent, cnorm, edge, edge_d2, lambda_cb, pq, lists, P, W, k, cap=1024, tile=1024, pack=None):
+    """Full query path on resident tensors (a11-a15), tiled over queries so the coarse matrix stays L2-sized.
+    pack (a CentPack) routes the coarse distances through the tcgen05 kernel."""
     nq = q.shape[0]
     C = cent.shape[0]
     P = min(P, C)
@@ -221,10 +222,65 @@ def search(q, cent, cnorm, edge, edge_d2, lambda_cb, pq, lists, P, W, k, cap=102
     for s in range(0, nq, tile):
         e = min(nq, s + tile)
         qt = q[s:e]
-        D = l2_distances(qt, cent, cnorm, out=Dbuf[: e - s])
+        if pack is not None:
+            D = l2_distances_tc(qt, pack, out=Dbuf[: e - s])
+        else:
+            D = l2_distances(qt, cent, cnorm, out=Dbuf[: e - s])
         _, cid = select_rows(D, P)
         lst, t1, t6 = select_lines(D, cid, edge, edge_d2, W)
         d_, i_ = scan_topk(qt, pq, lambda_cb, lst, t1, t6, ed2_flat, lists, k, cap)
         outD[s:e] = d_
         outI[s:e] = i_
     return outD, outI
+
+
+# ------------------------------------------------------------------------------------------------ tensor-core coarse path
+class CentPack:
+    """Pre-packed centroids for the tcgen05 kernels (vlq_tc_pack_centroids): fp16 hi/lo tiles + padded ||c||^2."""
+
+    def __init__(self, cent, cnorm=None, scale=None):
+        cent = _chk(cent, torch.float32, "cent")
+        self.C, self.d = cent.shape
+        if not _abi.lib().vlq_tc_supported(self.d, self.C):
+            raise ValueError("tensor-core path needs d %% 32 == 0 and 32 <= d <= 128 (got d=%d)" % self.d)
+        self.cnorm = row_norms(cent) if cnorm is None else cnorm
+        if scale is None:
+            import math
+
+            mx = float(cent.abs().max())
+            scale = 2.0 ** (9 - math.ceil(math.log2(mx))) if mx > 0 else 1.0
+        self.scale = float(scale)
+        nbytes = _abi.lib().vlq_tc_cent_pack_bytes(self.C, self.d)
+        self.buf = torch.empty(nbytes, dtype=torch.uint8, device=cent.device)
+        _abi.call("vlq_tc_pack_centroids", _ptr(cent), _ptr(self.cnorm), self.C, self.d, self.scale, _ptr(self.buf),
+                  _stream())
+        self._ws = None
+
+    def workspace(self, n):
+        need = _abi.lib().vlq_l2_tc_workspace_bytes(n, self.d, self.C)
+        if self._ws is None or self._ws.numel() < need:
+            self._ws = torch.empty(need, dtype=torch.uint8, device=self.buf.device)
+        return self._ws
+
+
+def l2_assign_tc(x, pack, add_xnorm=True, want_dist=True):
+    """nearest centroid per row on the tensor cores (a2): -> (ids int32 [n], dist f32 [n] or None)"""
+    x = _chk(x, torch.float32, "x")
+    n, d = x.shape
+    ids = torch.empty(n, dtype=torch.int32, device=x.device)
+    dist = torch.empty(n, dtype=torch.float32, device=x.device) if want_dist else None
+    ws = pack.workspace(n)
+    _abi.call("vlq_l2_assign_tc", _ptr(x), n, d, _ptr(pack.buf), pack.scale, pack.C, int(add_xnorm), _ptr(ids),
+              _ptr(dist), _ptr(ws), ws.numel(), _stream())
+    return ids, dist
+
+
+def l2_distances_tc(x, pack, out=None):
+    """coarse matrix D = ||c||^2 - 2 x.c on the tensor cores (a11)"""
+    x = _chk(x, torch.float32, "x")
+    n, d = x.shape
+    D = out if out is not None else torch.empty((n, pack.C), dtype=torch.float32, device=x.device)
+    ws = pack.workspace(n)
+    _abi.call("vlq_l2_distances_tc", _ptr(x), n, d, _ptr(pack.buf), pack.scale, pack.C, _ptr(D), D.stride(0), _ptr(ws),
+              ws.numel(), _stream())
+    return D

@@ -95,8 +95,12 @@ def kmeans(x, k, niter=10, seed=1234, max_points_per_centroid=256, exact_perm=Tr
         perm = torch.randperm(n, generator=g, device=dev)[:k]
     cent = x[perm].contiguous()
     obj = []
+    use_tc = bool(ops._abi.lib().vlq_tc_supported(d, k))
     for it in range(niter):
-        ids, dist = ops.l2_assign(x, cent, add_xnorm=True)
+        if use_tc:  # tcgen05 assignment (fp32-grade split-fp16); other shapes (d=1 lambda, d=8 PQ) use the fp32 kernel
+            ids, dist = ops.l2_assign_tc(x, ops.CentPack(cent), add_xnorm=True, want_dist=verbose)
+        else:
+            ids, dist = ops.l2_assign(x, cent, add_xnorm=True)
         if verbose:
             obj.append(float(dist.sum()))
         cent, counts = ops.km_update(x, ids, k)
@@ -113,7 +117,8 @@ def train_vlq(xt, nlist, E, M, nL, nbits=8, niter=10, pq_niter=25, seed=1234, ex
     edge, ed2 = ops.knn_graph(cent, E, cnorm)
     n2 = min(xt.shape[0], (1 << nbits) * 128)
     x2 = xt[:n2].contiguous()
-    A, _ = ops.l2_assign(x2, cent, cnorm)
+    pack = ops.CentPack(cent, cnorm) if ops._abi.lib().vlq_tc_supported(d, nlist) else None
+    A, _ = ops.l2_assign_tc(x2, pack, want_dist=False) if pack is not None else ops.l2_assign(x2, cent, cnorm)
     st = ops.line_encode(x2, A, cent, edge, ed2)
     lcb, _ = kmeans(st.lam.reshape(-1, 1).contiguous(), nL, niter=niter, seed=seed, exact_perm=exact_perm)
     lcb = lcb.reshape(-1).contiguous()
@@ -126,4 +131,4 @@ def train_vlq(xt, nlist, E, M, nL, nbits=8, niter=10, pq_niter=25, seed=1234, ex
     for m in range(M):
         sub = r[:, m * dsub:(m + 1) * dsub].contiguous()
         pq[m], _ = kmeans(sub, 256, niter=pq_niter, seed=seed, exact_perm=exact_perm)
-    return dict(cent=cent, cnorm=cnorm, edge=edge, edge_d2=ed2, lambda_cb=lcb, pq=pq)
+    return dict(cent=cent, cnorm=cnorm, edge=edge, edge_d2=ed2, lambda_cb=lcb, pq=pq, pack=pack)
