@@ -113,6 +113,15 @@ int vlq_line_encode(const float* x, int64_t n, int d, const int* assign, const f
                     int* out_list, float* out_lambda, uint8_t* out_lamq, uint8_t* out_codes, float* out_kappa,
                     float* out_residual, vlq_stream_t stream);
 
+/* a6 stand-alone: lambda -> uint8 = argmin_j (lambda - lambda_cb[j])^2, lowest j on ties.
+ *     replaces assignLambdaKernel, gpu/GpuIndexFlat.cu:559-602 (host wrapper assignLambda :702-752). */
+int vlq_lambda_quantize(const float* lambda, int64_t n, const float* lambda_cb, int nL, uint8_t* out,
+                        vlq_stream_t stream);
+/* a7 stand-alone: r = x - ((1-l) c_A + l c_s), l = lambda_cb[lamq], list = A*E + e (rows with list < 0 give 0).
+ *     replaces calResidual, gpu/GpuIndexFlat.cu:1092-1129 (host wrapper compute_residual :1194-1258). */
+int vlq_line_residual(const float* x, int64_t n, int d, const int* list, const uint8_t* lamq, const float* lambda_cb,
+                      const float* cent, const int* edge, int E, float* residual, vlq_stream_t stream);
+
 /* ------------------------------------------------------------------------------------------------------------------
  * a9  inverted-list construction: stable counting sort of n new entries (arrival order) behind n_old entries that
  *     are already list-major.   replaces the host hash-map / per-byte copies / runUpdateListPointers /
@@ -131,6 +140,12 @@ int vlq_build_lists(int64_t nlists, int M,
                     /* merged output, sized n_old + n_new */
                     int64_t* out_offsets, uint8_t* out_codes, uint8_t* out_lamq, float* out_kappa, int64_t* out_ids,
                     void* workspace, size_t workspace_bytes, vlq_stream_t stream);
+
+/* a9 (loader): per-entry kappa = ||p||^2 + 2 anchor.p for list-major entries that arrive without it, i.e. lists read
+ *     from the reference's .dbIdx/.dbcodes/.dbcount/.dblas files (gpu/GpuIndexIVFPQ.cu:1813-2010). */
+int vlq_recompute_kappa(int64_t n, int64_t nlists, const int64_t* offsets, const uint8_t* codes, const uint8_t* lamq,
+                        const float* cent, int d, const int* edge, int E, const float* lambda_cb, const float* pq, int M,
+                        float* kappa, vlq_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------------------------------
  * a12 query-time line selection: the W best of the P*E lines of the P probed centroids.
@@ -176,6 +191,7 @@ int vlq_km_update(const float* x, int64_t n, int d, const int* assign, int k, fl
 int vlq_gather_rows(const float* src, int d, const int64_t* rows, int64_t n, float* dst, vlq_stream_t stream);
 int vlq_u8_to_f32(const uint8_t* src, int64_t count, float* dst, vlq_stream_t stream);
 int vlq_iota_i64(int64_t* dst, int64_t n, int64_t start, vlq_stream_t stream);
+int vlq_i32_to_i64(const int* src, int64_t n, int64_t* dst, vlq_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------------------------------
  * Memory / stream helpers (these DO allocate / synchronise; they exist so host layers need no CUDA toolkit).

@@ -1,0 +1,67 @@
+/* vlq_index_c.h -- C wrapper over the C++ host layer (vector_line_quantization_b200/host): the faiss::Index-shaped
+ * classes GpuIndexFlatL2 / GpuIndexIVFPQ(VLQ) / IndexProxy / IndexShards / Clustering, for ctypes / FFI callers.
+ * Every function returns 0 on success and -1 on failure (message: vlq_host_last_error(), thread-local).
+ * Data pointers (x, ids, D, I) may be host or device, like the reference's Index API (gpu/utils/CopyUtils.cuh:24-58).
+ * Mirrors: faiss::Index::{train,add,add_with_ids,search,reset} (Index.h:89-165), GpuIndexIVF::setNumProbes,
+ * GpuIndexIVFPQ::{w1_, merge, write/readCodebookToFile, write/readDbToFile, getList*} (gpu/GpuIndexIVFPQ.h:59-151). */
+#ifndef VLQ_INDEX_C_H
+#define VLQ_INDEX_C_H
+#include <stddef.h>
+#include <stdint.h>
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+const char* vlq_host_last_error(void);
+
+/* StandardGpuResources */
+int vlq_host_resources_new(int device, void** out);
+int vlq_host_resources_free(void* res);
+
+/* any index handle (flat, VLQ, proxy, shards): the faiss::Index virtual API */
+int vlq_host_index_free(void* index);
+int vlq_host_index_train(void* index, long n, const float* x);
+int vlq_host_index_add(void* index, long n, const float* x);
+int vlq_host_index_add_with_ids(void* index, long n, const float* x, const long* ids);
+int vlq_host_index_search(void* index, long n, const float* x, long k, float* distances, long* labels);
+int vlq_host_index_reset(void* index);
+long vlq_host_index_ntotal(void* index);
+int vlq_host_index_is_trained(void* index);
+
+/* GpuIndexFlatL2 + its VLQ helper surface */
+int vlq_host_flat_new(void* res, int d, int use_tensor_cores, void** out);
+int vlq_host_flat_assign(void* flat, long n, const float* x, int* labels);
+int vlq_host_flat_build_graph(void* flat, int nedge, float* distances, int* labels);
+
+/* Clustering::train over a GpuIndexFlatL2 assigner */
+int vlq_host_kmeans(void* res, int d, int k, long n, const float* x, int niter, int seed, float* centroids_out);
+
+/* GpuIndexIVFPQ with the VLQ constructor (res, d, nlist, M, bits, nedge, nLambda, METRIC_L2) */
+int vlq_host_vlq_new(void* res, int d, int nlist, int M, int bits, int nedge, int nlambda, int use_tensor_cores,
+                     void** out);
+int vlq_host_vlq_set_nprobe(void* index, int nprobe);
+int vlq_host_vlq_set_w1(void* index, int w1);
+int vlq_host_vlq_set_list_cap(void* index, int cap);
+int vlq_host_vlq_set_train_iters(void* index, int niter);
+/* sizes: coarse nlist*d, edge / edge_dist nlist*nedge, lambda_cb nlambda, pq 256*d */
+int vlq_host_vlq_get_codebooks(void* index, float* coarse, int* edge, float* edge_dist, float* lambda_cb, float* pq);
+int vlq_host_vlq_set_codebooks(void* index, const float* coarse, const int* edge, const float* edge_dist,
+                               const float* lambda_cb, const float* pq);
+int vlq_host_vlq_list_length(void* index, int list, int* out);
+int vlq_host_vlq_get_list(void* index, int list, unsigned char* codes, unsigned char* lambdas, long* ids);
+int vlq_host_vlq_merge(void* index, long* nns, float* dist, int k, int nq, int nprocess, float* distances, long* labels);
+int vlq_host_vlq_write_codebook(void* index, const char* name);
+int vlq_host_vlq_read_codebook(void* index, const char* name);
+int vlq_host_vlq_write_db(void* index, const char* name);
+int vlq_host_vlq_read_db(void* index, const char* name, int pronum, int rank);
+
+/* IndexProxy (replicas) / IndexShards (database shards); sub-indexes are borrowed */
+int vlq_host_proxy_new(void** out);
+int vlq_host_proxy_add_index(void* proxy, void* index);
+int vlq_host_shards_new(int d, int threaded, int successive_ids, void** out);
+int vlq_host_shards_add_shard(void* shards, void* index);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,225 @@
+"""The C++ host layer (faiss::Index-shaped classes, lib/libvlq_host.so) against the oracle: these read like the
+reference's own index tests (build an index through train/add/search, compare with a CPU twin)."""
+import os
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def vi(cuda):
+    from vector_line_quantization_b200 import index
+
+    index.host()
+    return index
+
+
+@pytest.fixture(scope="module")
+def res(vi):
+    return vi.StandardGpuResources(0)
+
+
+def test_flat_search_matches_oracle(vi, res, oracle):
+    from vector_line_quantization_b200 import data
+
+    xb = data.sift_like(5000, seed=1)
+    xq = data.sift_like(100, seed=2)
+    for use_tc in (True, False):
+        flat = vi.GpuIndexFlatL2(res, 128, use_tensor_cores=use_tc)
+        flat.add(xb[:3000])
+        flat.add(xb[3000:])
+        assert flat.ntotal == 5000
+        for k in (1, 10):
+            D, I = flat.search(xq, k)
+            Do, Io = oracle.l2_topk(xq, xb, k, add_xnorm=True)
+            assert (I == Io).mean() > 0.995
+            np.testing.assert_allclose(D, Do, rtol=2e-4, atol=1.0)
+        assert np.array_equal(flat.assign(xq), oracle.l2_topk(xq, xb, 1)[1][:, 0])
+    with pytest.raises(vi.FaissException):
+        flat.search(xq, 2000)  # k <= 1024
+    flat.reset()
+    assert flat.ntotal == 0
+
+
+def test_flat_accepts_device_pointers(vi, res, cuda):
+    import torch
+
+    from vector_line_quantization_b200 import data
+
+    xb = data.sift_like(2000, seed=3)
+    xq = data.sift_like(64, seed=4)
+    flat = vi.GpuIndexFlatL2(res, 128)
+    flat.add(torch.from_numpy(xb).to(cuda))
+    Dh, Ih = flat.search(xq, 5)
+    Dd, Id = flat.search(torch.from_numpy(xq).to(cuda), 5)
+    assert Dd.is_cuda and np.array_equal(Id.cpu().numpy(), Ih) and np.array_equal(Dd.cpu().numpy(), Dh)
+
+
+def test_kmeans_matches_oracle(vi, res, oracle):
+    from vector_line_quantization_b200 import data
+
+    x = data.sift_like(6000, kc=64, seed=31)
+    co, _ = oracle.kmeans(x, 40, niter=5, seed=1234)
+    cg = vi.kmeans(res, x, 40, niter=5, seed=1234)
+    np.testing.assert_allclose(cg, co, rtol=2e-3, atol=0.5)
+    assert np.mean(np.abs(cg - co) < 1e-2) > 0.95
+    # sub-sampling path (n > k * 256) and a non-tensor-core dimension
+    x2 = data.sift_like(3000, d=24, kc=16, seed=33)
+    co2, _ = oracle.kmeans(x2, 8, niter=4, seed=99)
+    cg2 = vi.kmeans(res, x2, 8, niter=4, seed=99)
+    np.testing.assert_allclose(cg2, co2, rtol=2e-3, atol=0.5)
+
+
+def _build(vi, res, m, xb, chunks=2):
+    idx = vi.GpuIndexIVFPQ(res, m["d"], m["C"], m["M"], 8, m["E"], 256)
+    idx.setCodebooks(m["cent"], m["edge"], m["edge_d2"], m["lambda_cb"], m["pq"])
+    step = (len(xb) + chunks - 1) // chunks
+    for s in range(0, len(xb), step):
+        idx.add(xb[s:s + step])
+    return idx
+
+
+def test_vlq_index_matches_oracle(vi, res, oracle, small_model):
+    m = small_model
+    idx = _build(vi, res, m, m["xb"], chunks=3)
+    assert idx.ntotal == len(m["xb"])
+    enc = oracle.encode_all(m["xb"], m["cent"], m["edge"], m["edge_d2"], m["lambda_cb"], m["pq"])
+    off, perm = oracle.build_lists(enc["list"], m["C"] * m["E"])
+    # stored lists == oracle encode, list by list (ids in insertion order; codes / lambda bytes identical up to near-ties)
+    mism = 0
+    for l in list(range(0, m["C"] * m["E"], 97)) + [int(np.argmax(np.diff(off)))]:
+        codes, las, ids = idx.getList(l)
+        want = perm[off[l]:off[l + 1]]
+        if not np.array_equal(ids, want):
+            mism += 1
+            continue
+        if len(want) == 0:
+            continue
+        assert (codes == enc["codes"][want]).mean() > 0.99 and (las == enc["lamq"][want]).mean() > 0.99
+    assert mism <= 2
+    idx.setNumProbes(16)
+    idx.w1_ = 128
+    D, I = idx.search(m["xq"], 20)
+    Do, Io = oracle.search(m["xq"], m["cent"], m["edge"], m["edge_d2"], m["lambda_cb"], m["pq"], off,
+                           enc["codes"][perm], enc["lamq"][perm], perm.astype(np.int64), P=16, W=128, k=20)
+    assert (I == Io).mean() > 0.98
+    qn = (m["xq"].astype(np.float64) ** 2).sum(1, keepdims=True)
+    same = I == Io
+    assert np.all(np.abs(D - Do)[same] <= 1e-4 * (np.abs(Do) + qn)[same])
+
+
+def test_vlq_train_on_device(vi, res, oracle, small_model):
+    """train() end to end on the device; quality must match the oracle-trained model (same algorithm, same seeds)"""
+    from vector_line_quantization_b200 import data
+
+    m = small_model
+    idx = vi.GpuIndexIVFPQ(res, 128, m["C"], m["M"], 8, m["E"], 256)
+    assert not idx.is_trained
+    with pytest.raises(vi.FaissException):
+        idx.add(m["xb"][:10])  # "Index not trained"
+    idx.setTrainIters(6)
+    idx.train(m["xt"])
+    assert idx.is_trained
+    cb = idx.codebooks()
+    # same k-means as the oracle (identical RNG + update rule): centroids agree up to assignment near-ties
+    assert np.mean(np.abs(cb["cent"] - m["cent"]) < 0.05) > 0.9
+    eo, _ = oracle.knn_graph(cb["cent"], m["E"])
+    assert (cb["edge"] == eo).mean() > 0.999
+    idx.add(m["xb"])
+    idx.setNumProbes(32)
+    idx.w1_ = 256
+    _, I = idx.search(m["xq"], 100)
+    _, gt = oracle.l2_topk(m["xq"], m["xb"], 1)
+    r_gpu = data.recall_at(I, gt[:, 0], 100)
+    enc = oracle.encode_all(m["xb"], m["cent"], m["edge"], m["edge_d2"], m["lambda_cb"], m["pq"])
+    off, perm = oracle.build_lists(enc["list"], m["C"] * m["E"])
+    _, Io = oracle.search(m["xq"], m["cent"], m["edge"], m["edge_d2"], m["lambda_cb"], m["pq"], off, enc["codes"][perm],
+                          enc["lamq"][perm], perm.astype(np.int64), P=32, W=256, k=100)
+    r_cpu = data.recall_at(Io, gt[:, 0], 100)
+    assert r_gpu > 0.8 and abs(r_gpu - r_cpu) < 0.08, (r_gpu, r_cpu)
+
+
+def test_file_formats_roundtrip_and_rank_slices(vi, res, small_model, tmp_path):
+    m = small_model
+    idx = _build(vi, res, m, m["xb"])
+    idx.setNumProbes(16)
+    idx.w1_ = 128
+    D0, I0 = idx.search(m["xq"], 10)
+    name = str(tmp_path / "vlqdb")
+    idx.writeCodebookToFile(name)
+    idx.writeDbToFile(name)
+    L = m["C"] * m["E"]
+    n = len(m["xb"])
+    assert os.path.getsize(name + ".dbcount") == 4 * L and os.path.getsize(name + ".dbIdx") == 8 * n
+    assert os.path.getsize(name + ".dbcodes") == m["M"] * n and os.path.getsize(name + ".dblas") == n
+    assert os.path.getsize(name + ".ppqt") == 4 * (m["C"] * 128 + 256 * 128 + 2 * L + 2 * 256)
+    idx2 = vi.GpuIndexIVFPQ(res, 128, m["C"], m["M"], 8, m["E"], 256)
+    idx2.readCodebookFromFile(name)
+    idx2.readDbFromFile(name)
+    idx2.setNumProbes(16)
+    idx2.w1_ = 128
+    D1, I1 = idx2.search(m["xq"], 10)
+    assert np.array_equal(I1, I0) and np.array_equal(D1, D0)
+    # list-range slices over 3 "ranks" + merge == the whole index (gpu/test/sift1b16_query.cpp:323,405-430)
+    Ds, Is = [], []
+    for r in range(3):
+        part = vi.GpuIndexIVFPQ(res, 128, m["C"], m["M"], 8, m["E"], 256)
+        part.readCodebookFromFile(name)
+        part.readDbFromFile(name, 3, r)
+        part.setNumProbes(16)
+        part.w1_ = 128
+        d_, i_ = part.search(m["xq"], 10)
+        Ds.append(d_)
+        Is.append(i_)
+    assert sum(1 for _ in Is) == 3
+    Dm, Im = idx.merge(np.stack(Is), np.stack(Ds))
+    assert np.array_equal(Dm, D0) and (Im == I0).mean() > 0.999
+
+
+def test_shards_and_proxy(vi, res, small_model):
+    m = small_model
+    whole = _build(vi, res, m, m["xb"])
+    whole.setNumProbes(16)
+    whole.w1_ = 128
+    whole.setListCap(1 << 20)
+    D0, I0 = whole.search(m["xq"], 10)
+    shards = vi.IndexShards(128, threaded=True, successive_ids=True)
+    subs = []
+    for a, b in [(0, 9000), (9000, 20000)]:
+        s = _build(vi, res, m, m["xb"][a:b])
+        s.setNumProbes(16)
+        s.w1_ = 128
+        s.setListCap(1 << 20)
+        subs.append(s)
+        shards.add_shard(s)
+    assert shards.ntotal == 20000
+    D1, I1 = shards.search(m["xq"], 10)
+    assert np.array_equal(D1, D0) and (I1 == I0).mean() > 0.999
+    proxy = vi.IndexProxy()
+    rep = _build(vi, res, m, m["xb"])
+    rep.setNumProbes(16)
+    rep.w1_ = 128
+    rep.setListCap(1 << 20)
+    proxy.addIndex(whole)
+    proxy.addIndex(rep)
+    D2, I2 = proxy.search(m["xq"], 10)
+    assert np.array_equal(D2, D0) and np.array_equal(I2, I0)
+
+
+def test_add_with_ids_and_reset(vi, res, small_model):
+    m = small_model
+    idx = vi.GpuIndexIVFPQ(res, 128, m["C"], m["M"], 8, m["E"], 256)
+    idx.setCodebooks(m["cent"], m["edge"], m["edge_d2"], m["lambda_cb"], m["pq"])
+    ids = np.arange(5000, dtype=np.int64) * 7 + 3
+    idx.add_with_ids(m["xb"][:5000], ids)
+    idx.setNumProbes(8)
+    idx.w1_ = 64
+    _, I = idx.search(m["xb"][:50], 5)  # database vectors as queries
+    assert np.all((I[I >= 0] - 3) % 7 == 0)
+    assert np.mean(I[:, 0] == ids[:50]) > 0.5
+    idx.reset()
+    assert idx.ntotal == 0
+    D, I = idx.search(m["xq"], 3)
+    assert np.all(I == -1) and np.all(D == np.finfo(np.float32).max)

@@ -33,8 +33,11 @@ SIGNATURES = {
     "vlq_knn_graph_workspace_bytes": (_z, [_i, _i]),
     "vlq_knn_graph": (_i, [_p, _p, _i, _i, _i, _p, _p, _p, _z, _p]),
     "vlq_line_encode": (_i, [_p, _l, _i, _p, _p, _p, _p, _i, _p, _i, _p, _i, _p, _p, _p, _p, _p, _p, _p]),
+    "vlq_lambda_quantize": (_i, [_p, _l, _p, _i, _p, _p]),
+    "vlq_line_residual": (_i, [_p, _l, _i, _p, _p, _p, _p, _p, _i, _p, _p]),
     "vlq_build_lists_workspace_bytes": (_z, [_l, _l]),
     "vlq_build_lists": (_i, [_l, _i, _l, _p, _p, _p, _p, _p, _l, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _z, _p]),
+    "vlq_recompute_kappa": (_i, [_l, _l, _p, _p, _p, _p, _i, _p, _i, _p, _p, _i, _p, _p]),
     "vlq_select_lines": (_i, [_p, _l, _l, _p, _i, _p, _p, _i, _i, _p, _p, _p, _p]),
     "vlq_scan_topk": (_i, [_p, _l, _i, _p, _i, _p, _i, _p, _p, _p, _p, _i, _p, _p, _p, _p, _p, _i, _i, _p, _p, _p]),
     "vlq_merge_topk": (_i, [_p, _p, _i, _l, _i, _p, _p, _p]),
@@ -43,6 +46,7 @@ SIGNATURES = {
     "vlq_gather_rows": (_i, [_p, _i, _p, _l, _p, _p]),
     "vlq_u8_to_f32": (_i, [_p, _l, _p, _p]),
     "vlq_iota_i64": (_i, [_p, _l, _l, _p]),
+    "vlq_i32_to_i64": (_i, [_p, _l, _p, _p]),
     "vlq_device_count": (_i, [C.POINTER(_i)]),
     "vlq_set_device": (_i, [_i]),
     "vlq_get_device": (_i, [C.POINTER(_i)]),

@@ -228,9 +228,87 @@ __global__ void __launch_bounds__(LE_THREADS, 1) line_encode_kernel(LineEncodeAr
   }
 }
 
+// ---- stand-alone a6 / a7 (the reference exposes them as separate GpuIndexFlat methods; the add path uses the fused kernel)
+__global__ void lambda_quantize_kernel(const float* __restrict__ lam, int64_t n, const float* __restrict__ cb, int nL,
+                                       uint8_t* __restrict__ out) {
+  __shared__ float cbs[256];
+  for (int j = threadIdx.x; j < nL; j += blockDim.x) cbs[j] = cb[j];
+  __syncthreads();
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const float l = lam[i];
+  float best = 0.f;
+  int bj = 0;
+  for (int j = 0; j < nL; j++) {  // argmin_j (l - cb[j])^2, lowest j on ties (GpuIndexFlat.cu:579-596)
+    const float t = l - cbs[j];
+    const float dd = __fmul_rn(t, t);
+    if (j == 0 || dd < best) {
+      best = dd;
+      bj = j;
+    }
+  }
+  out[i] = (uint8_t)bj;
+}
+
+__global__ void line_residual_kernel(const float* __restrict__ x, int64_t n, int d, const int* __restrict__ list,
+                                     const uint8_t* __restrict__ lamq, const float* __restrict__ cb,
+                                     const float* __restrict__ cent, const int* __restrict__ edge, int E,
+                                     float* __restrict__ r) {
+  int64_t i = (int64_t)blockIdx.x * (blockDim.x / kWarp) + threadIdx.x / kWarp;
+  if (i >= n) return;
+  const int lane = threadIdx.x % kWarp;
+  const int l = list[i];
+  if (l < 0) {
+    for (int j = lane; j < d; j += kWarp) r[i * d + j] = 0.f;
+    return;
+  }
+  const int A = l / E;
+  const int s = edge[l];
+  const float lh = cb[lamq[i]];
+  const float oml = 1.f - lh;
+  for (int j = lane; j < d; j += kWarp) {  // GpuIndexFlat.cu:1111-1122
+    const float anchor = __fadd_rn(__fmul_rn(oml, cent[(int64_t)A * d + j]), __fmul_rn(lh, cent[(int64_t)s * d + j]));
+    r[i * d + j] = __fsub_rn(x[i * d + j], anchor);
+  }
+}
+
+__global__ void i32_to_i64_kernel(const int* __restrict__ src, int64_t n, int64_t* __restrict__ dst) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (; i < n; i += stride) dst[i] = src[i];
+}
+
 }  // namespace vlq
 
 using namespace vlq;
+
+extern "C" int vlq_lambda_quantize(const float* lambda, int64_t n, const float* lambda_cb, int nL, uint8_t* out,
+                                   vlq_stream_t stream) {
+  if (n < 0 || nL <= 0 || nL > 256) return VLQ_EINVAL;
+  if (n == 0) return VLQ_OK;
+  if (!lambda || !lambda_cb || !out) return VLQ_EINVAL;
+  VLQ_LAUNCH(lambda_quantize_kernel, (unsigned)div_up(n, 256), 256, 0, as_stream(stream), lambda, n, lambda_cb, nL, out);
+  return last_error();
+}
+
+extern "C" int vlq_line_residual(const float* x, int64_t n, int d, const int* list, const uint8_t* lamq,
+                                 const float* lambda_cb, const float* cent, const int* edge, int E, float* residual,
+                                 vlq_stream_t stream) {
+  if (n < 0 || d <= 0 || E <= 0) return VLQ_EINVAL;
+  if (n == 0) return VLQ_OK;
+  if (!x || !list || !lamq || !lambda_cb || !cent || !edge || !residual) return VLQ_EINVAL;
+  VLQ_LAUNCH(line_residual_kernel, (unsigned)div_up(n, 8), 256, 0, as_stream(stream), x, n, d, list, lamq, lambda_cb,
+             cent, edge, E, residual);
+  return last_error();
+}
+
+extern "C" int vlq_i32_to_i64(const int* src, int64_t n, int64_t* dst, vlq_stream_t stream) {
+  if (n < 0) return VLQ_EINVAL;
+  if (n == 0) return VLQ_OK;
+  if (!src || !dst) return VLQ_EINVAL;
+  VLQ_LAUNCH(i32_to_i64_kernel, 148 * 4, 256, 0, as_stream(stream), src, n, dst);
+  return last_error();
+}
 
 extern "C" int vlq_line_encode(const float* x, int64_t n, int d, const int* assign, const float* cent,
                                const int* edge, const float* edge_d2, int E, const float* lambda_cb, int nL,

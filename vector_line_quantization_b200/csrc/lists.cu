@@ -265,6 +265,40 @@ static ListWs carve(void* ws, int64_t n_new, int64_t nlists) {
   return w;
 }
 
+// ---------------------------------------------------------------------------------------------- kappa for loaded lists
+// kappa = ||p||^2 + 2 anchor.p for entries that arrive without it (lists read from the reference's .db* files).
+// Same per-lane order of operations as line_encode_kernel, so a reloaded index scans bit-identically.
+__global__ void recompute_kappa_kernel(int64_t n, int64_t nlists, const int64_t* __restrict__ offsets,
+                                       const uint8_t* __restrict__ codes, const uint8_t* __restrict__ lamq,
+                                       const float* __restrict__ cent, int d, const int* __restrict__ edge, int E,
+                                       const float* __restrict__ lambda_cb, const float* __restrict__ pq, int M,
+                                       float* __restrict__ kappa) {
+  const int lane = threadIdx.x % kWarp;
+  const int dsub = d / M;
+  for (int64_t i = (int64_t)blockIdx.x * (blockDim.x / kWarp) + threadIdx.x / kWarp; i < n;
+       i += (int64_t)gridDim.x * (blockDim.x / kWarp)) {
+    int64_t lo = 0, hi = nlists;  // list of entry i: largest l with offsets[l] <= i
+    while (hi - lo > 1) {
+      int64_t mid = (lo + hi) >> 1;
+      if (offsets[mid] <= i) lo = mid; else hi = mid;
+    }
+    const int A = (int)(lo / E);
+    const int s = edge[lo];
+    const float lh = lambda_cb[lamq[i]];
+    const float oml = 1.f - lh;
+    float kp = 0.f;
+    for (int j = lane; j < d; j += kWarp) {
+      const float anc = __fadd_rn(__fmul_rn(oml, cent[(int64_t)A * d + j]), __fmul_rn(lh, cent[(int64_t)s * d + j]));
+      const int m = j / dsub, tt = j % dsub;
+      const float pv = pq[((size_t)m * 256 + codes[i * M + m]) * dsub + tt];
+      kp = fmaf(pv, pv, kp);
+      kp = fmaf(2.f * anc, pv, kp);
+    }
+    kp = warp_sum(kp);
+    if (lane == 0) kappa[i] = kp;
+  }
+}
+
 // ---------------------------------------------------------------------------------------------- k-means update (f1)
 // Deterministic restatement of km_update_centroids' accumulation (utils.cpp:1385-1417): rows are grouped by centroid
 // with the same stable counting sort as the list build, then one warp per centroid adds its rows IN ROW ORDER
@@ -300,6 +334,17 @@ __global__ void km_mean_kernel(const float* __restrict__ x, int d, const uint32_
 }  // namespace vlq
 
 using namespace vlq;
+
+extern "C" int vlq_recompute_kappa(int64_t n, int64_t nlists, const int64_t* offsets, const uint8_t* codes,
+                                   const uint8_t* lamq, const float* cent, int d, const int* edge, int E,
+                                   const float* lambda_cb, const float* pq, int M, float* kappa, vlq_stream_t stream) {
+  if (n < 0 || nlists <= 0 || d <= 0 || E <= 0 || M <= 0 || d % M != 0) return VLQ_EINVAL;
+  if (n == 0) return VLQ_OK;
+  if (!offsets || !codes || !lamq || !cent || !edge || !lambda_cb || !pq || !kappa) return VLQ_EINVAL;
+  VLQ_LAUNCH(recompute_kappa_kernel, 148 * 8, 256, 0, as_stream(stream), n, nlists, offsets, codes, lamq, cent, d, edge,
+             E, lambda_cb, pq, M, kappa);
+  return last_error();
+}
 
 extern "C" size_t vlq_km_update_workspace_bytes(int64_t n, int k) { return carve(nullptr, n, k).bytes; }
 

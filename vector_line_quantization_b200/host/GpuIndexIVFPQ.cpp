@@ -1,0 +1,490 @@
+#include "GpuIndexIVFPQ.h"
+
+#include <algorithm>
+#include <cfloat>
+#include <cmath>
+#include <cstring>
+#include <fstream>
+
+namespace faiss {
+namespace gpu {
+
+// ================================================================================================ GpuIndexIVF
+GpuIndexIVF::GpuIndexIVF(GpuResources* resources, int dims, faiss::MetricType metric, int nlist, GpuIndexIVFConfig config)
+    : Index(dims, metric), resources_(resources), ivfConfig_(config), nlist_(nlist), nprobe_(1), quantizer_(nullptr) {
+  VLQ_THROW_IF_NOT_MSG(resources != nullptr, "GpuResources must not be null");
+  VLQ_THROW_IF_NOT_MSG(nlist > 0, "nlist must be > 0");
+  VLQ_THROW_IF_NOT_MSG(metric == faiss::METRIC_L2, "only METRIC_L2 is on the VLQ hot path");
+  is_trained = false;
+  cp_.niter = 10;  // gpu/GpuIndexIVF.cu:50
+  GpuIndexFlatConfig fc = config.flatConfig;
+  fc.device = config.device;
+  quantizer_ = new GpuIndexFlatL2(resources, dims, fc);
+}
+GpuIndexIVF::~GpuIndexIVF() { delete quantizer_; }
+
+void GpuIndexIVF::setNumProbes(int nprobe) {
+  VLQ_THROW_IF_NOT_MSG(nprobe > 0 && nprobe <= 1024, "nprobe must be from 1 to 1024");
+  nprobe_ = nprobe;
+}
+
+void GpuIndexIVF::add(Index::idx_t n, const float* x) { add_with_ids(n, x, nullptr); }
+
+void GpuIndexIVF::trainQuantizer_(Index::idx_t n, const float* x) {
+  if (n == 0) return;
+  if (quantizer_->is_trained && quantizer_->ntotal == nlist_) {
+    if (verbose) printf("IVF quantizer does not need training.\n");
+    return;
+  }
+  if (verbose) printf("Training IVF quantizer on %ld vectors in %dD\n", n, d);
+  quantizer_->reset();
+  Clustering clus(d, nlist_, cp_);
+  clus.verbose = verbose;
+  clus.train(n, x, *quantizer_);  // leaves the final centroids in the quantizer (Clustering.cpp:187-192)
+  quantizer_->is_trained = true;
+  VLQ_THROW_IF_NOT(quantizer_->ntotal == nlist_);
+}
+
+// ================================================================================================ GpuIndexIVFPQ (VLQ)
+GpuIndexIVFPQ::GpuIndexIVFPQ(GpuResources* resources, int dims, int nlist, int subQuantizers, int bitsPerCode,
+                             int nedge, int nLambda, faiss::MetricType metric, GpuIndexIVFPQConfig config)
+    : GpuIndexIVF(resources, dims, metric, nlist, config), nLambda_(nLambda), numedge_(nedge), begin_(0), end_(0),
+      w1_(256), edgeInfo_(nullptr), edgeDistInfo_(nullptr), lambdaInfo_(nullptr), constInfo_(nullptr), listCap_(VLQ_LIST_CAP),
+      ivfpqConfig_(config), subQuantizers_(subQuantizers), bitsPerCode_(bitsPerCode), reserveVecs_(0), nListed_(0),
+      nPending_(0), capPending_(0) {
+  VLQ_THROW_IF_NOT_MSG(bitsPerCode == 8, "the scan kernels are written for 8-bit PQ codes");
+  VLQ_THROW_IF_NOT_MSG(subQuantizers > 0 && subQuantizers <= 64 && dims % subQuantizers == 0,
+                       "number of sub-quantizers must divide the dimension (and be <= 64)");
+  VLQ_THROW_IF_NOT_MSG(nedge >= 1 && nedge <= 64 && nedge < nlist, "nedge must be in [1, 64] and < nlist");
+  VLQ_THROW_IF_NOT_MSG(nLambda >= 1 && nLambda <= 256, "nLambda must be in [1, 256]");
+  VLQ_THROW_IF_NOT_MSG(dims <= 256, "dims must be <= 256");
+  VLQ_THROW_IF_NOT_MSG((int64_t)nlist * nedge <= (int64_t)0x7fffffff, "nlist * nedge must fit in 31 bits");
+  edgeInfo_ = new int[(size_t)nlist * nedge]();
+  edgeDistInfo_ = new float[(size_t)nlist * nedge]();
+  lambdaInfo_ = new float[256]();
+  constInfo_ = new float[256]();
+  pqHost_.resize((size_t)256 * dims);
+}
+
+GpuIndexIVFPQ::~GpuIndexIVFPQ() {
+  delete[] edgeInfo_;
+  delete[] edgeDistInfo_;
+  delete[] lambdaInfo_;
+  delete[] constInfo_;
+}
+
+void GpuIndexIVFPQ::reserveMemory(size_t numVecs) { reserveVecs_ = numVecs; }
+
+void GpuIndexIVFPQ::reset() {
+  DeviceScope scope(ivfConfig_.device);
+  resources_->syncDefaultStream();
+  lOffsets_.release();
+  lCodes_.release();
+  lLamq_.release();
+  lKappa_.release();
+  lIds_.release();
+  nListed_ = 0;
+  nPending_ = 0;
+  ntotal = 0;
+}
+
+void GpuIndexIVFPQ::uploadTables_() {
+  vlq_stream_t st = resources_->getDefaultStream();
+  const size_t L = (size_t)nlist_ * numedge_;
+  dEdge_.resize(L * sizeof(int));
+  dEdgeDist_.resize(L * sizeof(float));
+  dLambda_.resize((size_t)nLambda_ * sizeof(float));
+  dPq_.resize(pqHost_.size() * sizeof(float));
+  VLQ_CALL(vlq_memcpy_h2d(dEdge_.get(), edgeInfo_, dEdge_.bytes(), st));
+  VLQ_CALL(vlq_memcpy_h2d(dEdgeDist_.get(), edgeDistInfo_, dEdgeDist_.bytes(), st));
+  VLQ_CALL(vlq_memcpy_h2d(dLambda_.get(), lambdaInfo_, dLambda_.bytes(), st));
+  VLQ_CALL(vlq_memcpy_h2d(dPq_.get(), pqHost_.data(), dPq_.bytes(), st));
+  for (int j = 0; j < nLambda_; j++) constInfo_[j] = lambdaInfo_[j] * lambdaInfo_[j] - lambdaInfo_[j];
+  resources_->syncDefaultStream();
+}
+
+void GpuIndexIVFPQ::buildGraph_() {  // gpu/GpuIndexIVFPQ.cu:937-953
+  quantizer_->buildGraph(nlist_, numedge_, edgeDistInfo_, edgeInfo_);
+}
+
+void GpuIndexIVFPQ::setCodebooks(const float* coarse, const int* edge, const float* edgeDist, const float* lambdaCb,
+                                 const float* pq) {
+  DeviceScope scope(ivfConfig_.device);
+  quantizer_->reset();
+  quantizer_->add(nlist_, coarse);
+  quantizer_->is_trained = true;
+  const size_t L = (size_t)nlist_ * numedge_;
+  std::memcpy(edgeInfo_, edge, L * sizeof(int));
+  std::memcpy(edgeDistInfo_, edgeDist, L * sizeof(float));
+  std::memcpy(lambdaInfo_, lambdaCb, (size_t)nLambda_ * sizeof(float));
+  std::memcpy(pqHost_.data(), pq, pqHost_.size() * sizeof(float));
+  uploadTables_();
+  is_trained = true;
+}
+
+// GpuIndexIVFPQ::train (gpu/GpuIndexIVFPQ.cu:1160-1178) + trainResidualQuantizer_ (:345-403)
+void GpuIndexIVFPQ::train(Index::idx_t n, const float* x) {
+  DeviceScope scope(ivfConfig_.device);
+  if (is_trained) {
+    VLQ_THROW_IF_NOT(quantizer_->is_trained && quantizer_->ntotal == nlist_);
+    return;
+  }
+  VLQ_THROW_IF_NOT_MSG(n >= nlist_, "need at least nlist training vectors");
+  vlq_stream_t st = resources_->getDefaultStream();
+  DeviceBuffer xin;
+  const float* dxAll = static_cast<const float*>(toDevice(x, (size_t)n * d * sizeof(float), xin, st));
+  resources_->syncDefaultStream();
+  trainQuantizer_(n, dxAll);
+  buildGraph_();
+
+  // residual quantizer on the first min(n, 2^bits * 128) rows (gpu/GpuIndexIVFPQ.cu:345-352)
+  const Index::idx_t n2 = std::min<Index::idx_t>(n, ((Index::idx_t)1 << bitsPerCode_) * 128);
+  const size_t L = (size_t)nlist_ * numedge_;
+  DeviceBuffer de(L * sizeof(int)), ded(L * sizeof(float));
+  VLQ_CALL(vlq_memcpy_h2d(de.get(), edgeInfo_, de.bytes(), st));
+  VLQ_CALL(vlq_memcpy_h2d(ded.get(), edgeDistInfo_, ded.bytes(), st));
+  DeviceBuffer dA((size_t)n2 * sizeof(int)), dList((size_t)n2 * sizeof(int)), dLam((size_t)n2 * sizeof(float));
+  quantizer_->assignDevice(dxAll, n2, dA.as<int>(), nullptr, false);
+  VLQ_CALL(vlq_line_encode(dxAll, n2, d, dA.as<int>(), quantizer_->deviceVectors(), de.as<int>(), ded.as<float>(),
+                           numedge_, nullptr, 0, nullptr, 0, dList.as<int>(), dLam.as<float>(), nullptr, nullptr,
+                           nullptr, nullptr, st));
+  {  // 1-D lambda codebook: Clustering(1, nLambda, cp_) over a d = 1 flat index (:365-372)
+    GpuIndexFlatConfig fc;
+    fc.device = ivfConfig_.device;
+    GpuIndexFlatL2 lq(resources_, 1, fc);
+    Clustering clus(1, nLambda_, cp_);
+    clus.train(n2, dLam.as<float>(), lq);
+    std::memcpy(lambdaInfo_, clus.centroids.data(), (size_t)nLambda_ * sizeof(float));
+  }
+  DeviceBuffer dcb((size_t)nLambda_ * sizeof(float)), dLq((size_t)n2), dRes((size_t)n2 * d * sizeof(float));
+  VLQ_CALL(vlq_memcpy_h2d(dcb.get(), lambdaInfo_, dcb.bytes(), st));
+  VLQ_CALL(vlq_lambda_quantize(dLam.as<float>(), n2, dcb.as<float>(), nLambda_, dLq.as<uint8_t>(), st));
+  VLQ_CALL(vlq_line_residual(dxAll, n2, d, dList.as<int>(), dLq.as<uint8_t>(), dcb.as<float>(),
+                             quantizer_->deviceVectors(), de.as<int>(), numedge_, dRes.as<float>(), st));
+  resources_->syncDefaultStream();
+  faiss::ProductQuantizer pq(d, subQuantizers_, bitsPerCode_);  // CPU class in the reference (:383-385); device k-means here
+  pq.verbose = verbose;
+  pq.train((int)n2, dRes.as<float>(), resources_);
+  pqHost_ = pq.centroids;
+  uploadTables_();
+  is_trained = true;
+}
+
+void GpuIndexIVFPQ::ensurePending_(size_t extra) {
+  const size_t need = nPending_ + extra;
+  if (need <= capPending_) return;
+  vlq_stream_t st = resources_->getDefaultStream();
+  size_t cap = std::max(std::max(need, capPending_ * 2), std::max<size_t>(reserveVecs_, 1 << 16));
+  const int M = subQuantizers_;
+  DeviceBuffer nl(cap * sizeof(int)), nc(cap * M), nq(cap), nk(cap * sizeof(float)), ni(cap * sizeof(int64_t));
+  if (nPending_) {
+    VLQ_CALL(vlq_memcpy_d2d(nl.get(), pList_.get(), nPending_ * sizeof(int), st));
+    VLQ_CALL(vlq_memcpy_d2d(nc.get(), pCodes_.get(), nPending_ * M, st));
+    VLQ_CALL(vlq_memcpy_d2d(nq.get(), pLamq_.get(), nPending_, st));
+    VLQ_CALL(vlq_memcpy_d2d(nk.get(), pKappa_.get(), nPending_ * sizeof(float), st));
+    VLQ_CALL(vlq_memcpy_d2d(ni.get(), pIds_.get(), nPending_ * sizeof(int64_t), st));
+    resources_->syncDefaultStream();
+  }
+  pList_.swap(nl);
+  pCodes_.swap(nc);
+  pLamq_.swap(nq);
+  pKappa_.swap(nk);
+  pIds_.swap(ni);
+  capPending_ = cap;
+}
+
+// classifyAndAddVectors (gpu/GpuIndexIVFPQ.cu:577-908), entirely on the device: coarse NN -> fused line stage / lambda
+// quantiser / residual / PQ encode -> append to the pending arena.  Tiles of <= 512 Ki vectors like gpu/GpuIndex.cu:75-106.
+void GpuIndexIVFPQ::add_with_ids(Index::idx_t n, const float* x, const long* xids) {
+  VLQ_THROW_IF_NOT_MSG(is_trained, "Index not trained");
+  if (n == 0) return;
+  VLQ_THROW_IF_NOT(n > 0 && x);
+  DeviceScope scope(ivfConfig_.device);
+  vlq_stream_t st = resources_->getDefaultStream();
+  ensurePending_((size_t)n);
+  const Index::idx_t tile = (Index::idx_t)1 << 19;
+  const int M = subQuantizers_;
+  DeviceBuffer xin, dA;
+  for (Index::idx_t s = 0; s < n; s += tile) {
+    const Index::idx_t m = std::min(tile, n - s);
+    const float* dx = static_cast<const float*>(toDevice(x + (size_t)s * d, (size_t)m * d * sizeof(float), xin, st));
+    dA.reserve((size_t)m * sizeof(int));
+    quantizer_->assignDevice(dx, m, dA.as<int>(), nullptr, false);
+    const size_t o = nPending_;
+    VLQ_CALL(vlq_line_encode(dx, m, d, dA.as<int>(), quantizer_->deviceVectors(), dEdge_.as<int>(),
+                             dEdgeDist_.as<float>(), numedge_, dLambda_.as<float>(), nLambda_, dPq_.as<float>(), M,
+                             pList_.as<int>() + o, nullptr, pLamq_.as<uint8_t>() + o, pCodes_.as<uint8_t>() + o * M,
+                             pKappa_.as<float>() + o, nullptr, st));
+    if (xids) {
+      if (vlq_pointer_is_device(xids) == 1)
+        VLQ_CALL(vlq_memcpy_d2d(pIds_.as<int64_t>() + o, xids + s, (size_t)m * sizeof(int64_t), st));
+      else
+        VLQ_CALL(vlq_memcpy_h2d(pIds_.as<int64_t>() + o, xids + s, (size_t)m * sizeof(int64_t), st));
+    } else {
+      VLQ_CALL(vlq_iota_i64(pIds_.as<int64_t>() + o, m, (int64_t)(ntotal + s), st));
+    }
+    nPending_ += (size_t)m;
+    resources_->syncDefaultStream();  // the staging buffer is reused by the next tile
+  }
+  ntotal += n;
+}
+
+void GpuIndexIVFPQ::commit_() const {
+  const int64_t L = (int64_t)nlist_ * numedge_;
+  if (nPending_ == 0 && lOffsets_.get()) return;
+  vlq_stream_t st = resources_->getDefaultStream();
+  const int M = subQuantizers_;
+  const size_t tot = nListed_ + nPending_;
+  DeviceBuffer no((size_t)(L + 1) * sizeof(int64_t)), nc(tot * M), nq(tot), nk(tot * sizeof(float)), ni(tot * sizeof(int64_t));
+  const size_t wsb = vlq_build_lists_workspace_bytes((int64_t)nPending_, L);
+  scratch_.reserve(wsb);
+  VLQ_CALL(vlq_build_lists(L, M, (int64_t)nListed_, lOffsets_.as<int64_t>(), lCodes_.as<uint8_t>(), lLamq_.as<uint8_t>(),
+                           lKappa_.as<float>(), lIds_.as<int64_t>(), (int64_t)nPending_, pList_.as<int>(),
+                           pCodes_.as<uint8_t>(), pLamq_.as<uint8_t>(), pKappa_.as<float>(), pIds_.as<int64_t>(),
+                           no.as<int64_t>(), nc.as<uint8_t>(), nq.as<uint8_t>(), nk.as<float>(), ni.as<int64_t>(),
+                           scratch_.get(), scratch_.bytes(), st));
+  // vectors the encoder skipped (list id < 0) are not stored: the live count is offsets[L]
+  int64_t live = 0;
+  VLQ_CALL(vlq_memcpy_d2h(&live, no.as<int64_t>() + L, sizeof(int64_t), st));
+  resources_->syncDefaultStream();
+  lOffsets_.swap(no);
+  lCodes_.swap(nc);
+  lLamq_.swap(nq);
+  lKappa_.swap(nk);
+  lIds_.swap(ni);
+  nListed_ = (size_t)live;
+  nPending_ = 0;
+}
+
+// searchImpl_ -> IVFPQ::queryGraph (gpu/GpuIndexIVFPQ.cu:1400-1464, gpu/impl/IVFPQ.cu:685-775)
+void GpuIndexIVFPQ::search(Index::idx_t n, const float* x, Index::idx_t k, float* distances, Index::idx_t* labels) const {
+  VLQ_THROW_IF_NOT_MSG(is_trained, "Index not trained");
+  VLQ_THROW_IF_NOT_MSG(k >= 1 && k <= VLQ_MAX_K, "k must be in [1, 1024]");
+  VLQ_THROW_IF_NOT_MSG(w1_ >= 1 && w1_ <= VLQ_MAX_K, "w1_ must be in [1, 1024]");
+  if (n == 0) return;
+  DeviceScope scope(ivfConfig_.device);
+  commit_();
+  vlq_stream_t st = resources_->getDefaultStream();
+  const int P = std::min(nprobe_, nlist_);
+  const int W = w1_;
+  const int M = subQuantizers_;
+  const Index::idx_t page = 32768;  // gpu/GpuIndex.cu:109-147
+  const Index::idx_t tile = std::max<Index::idx_t>(64, std::min<Index::idx_t>(1024, ((Index::idx_t)1 << 26) / nlist_));
+  DeviceBuffer xin, outD, outI;
+  DeviceBuffer& dmat = scratch_;
+  dmat.reserve((size_t)tile * nlist_ * sizeof(float));
+  scratchB_.reserve((size_t)tile * (P * (sizeof(float) + sizeof(int)) + W * (sizeof(int) + 2 * sizeof(float))));
+  float* cval = scratchB_.as<float>();
+  int* cidx = reinterpret_cast<int*>(cval + (size_t)tile * P);
+  int* lline = cidx + (size_t)tile * P;
+  float* t1 = reinterpret_cast<float*>(lline + (size_t)tile * W);
+  float* t6 = t1 + (size_t)tile * W;
+  for (Index::idx_t p0 = 0; p0 < n; p0 += page) {
+    const Index::idx_t pn = std::min(page, n - p0);
+    const float* dx = static_cast<const float*>(toDevice(x + (size_t)p0 * d, (size_t)pn * d * sizeof(float), xin, st));
+    outD.reserve((size_t)pn * k * sizeof(float));
+    outI.reserve((size_t)pn * k * sizeof(int64_t));
+    for (Index::idx_t s = 0; s < pn; s += tile) {
+      const Index::idx_t m = std::min(tile, pn - s);
+      const float* q = dx + (size_t)s * d;
+      quantizer_->distancesDevice(q, m, dmat.as<float>(), nlist_);
+      VLQ_CALL(vlq_select_rows(dmat.as<float>(), m, nlist_, nlist_, P, nullptr, cval, cidx, st));
+      VLQ_CALL(vlq_select_lines(dmat.as<float>(), m, nlist_, cidx, P, dEdge_.as<int>(), dEdgeDist_.as<float>(),
+                                numedge_, W, lline, t1, t6, st));
+      VLQ_CALL(vlq_scan_topk(q, m, d, dPq_.as<float>(), M, dLambda_.as<float>(), nLambda_, lline, t1, t6,
+                             dEdgeDist_.as<float>(), W, lOffsets_.as<int64_t>(), lCodes_.as<uint8_t>(),
+                             lLamq_.as<uint8_t>(), lKappa_.as<float>(), lIds_.as<int64_t>(), (int)k, listCap_,
+                             outD.as<float>() + (size_t)s * k, outI.as<int64_t>() + (size_t)s * k, st));
+    }
+    fromDevice(distances + (size_t)p0 * k, outD.get(), (size_t)pn * k * sizeof(float), st);
+    fromDevice(labels + (size_t)p0 * k, outI.get(), (size_t)pn * k * sizeof(int64_t), st);
+    resources_->syncDefaultStream();
+  }
+}
+
+// ---------------------------------------------------------------------------------------------- list accessors
+int GpuIndexIVFPQ::getListLength(int listId) const {
+  VLQ_THROW_IF_NOT(listId >= 0 && listId < nlist_ * numedge_);
+  DeviceScope scope(ivfConfig_.device);
+  commit_();
+  int64_t o[2];
+  VLQ_CALL(vlq_memcpy_d2h(o, lOffsets_.as<int64_t>() + listId, sizeof(o), resources_->getDefaultStream()));
+  resources_->syncDefaultStream();
+  return (int)(o[1] - o[0]);
+}
+
+template <typename T>
+static std::vector<T> fetchList(const DeviceBuffer& offsets, const DeviceBuffer& data, int listId, size_t per,
+                                GpuResources* res) {
+  int64_t o[2];
+  VLQ_CALL(vlq_memcpy_d2h(o, offsets.as<int64_t>() + listId, sizeof(o), res->getDefaultStream()));
+  res->syncDefaultStream();
+  std::vector<T> out((size_t)(o[1] - o[0]) * per);
+  if (!out.empty()) {
+    VLQ_CALL(vlq_memcpy_d2h(out.data(), data.as<T>() + (size_t)o[0] * per, out.size() * sizeof(T), res->getDefaultStream()));
+    res->syncDefaultStream();
+  }
+  return out;
+}
+
+std::vector<unsigned char> GpuIndexIVFPQ::getListCodes(int listId) const {
+  VLQ_THROW_IF_NOT(listId >= 0 && listId < nlist_ * numedge_);
+  DeviceScope scope(ivfConfig_.device);
+  commit_();
+  return fetchList<unsigned char>(lOffsets_, lCodes_, listId, subQuantizers_, resources_);
+}
+std::vector<unsigned char> GpuIndexIVFPQ::getListLambdas(int listId) const {
+  VLQ_THROW_IF_NOT(listId >= 0 && listId < nlist_ * numedge_);
+  DeviceScope scope(ivfConfig_.device);
+  commit_();
+  return fetchList<unsigned char>(lOffsets_, lLamq_, listId, 1, resources_);
+}
+std::vector<long> GpuIndexIVFPQ::getListIndices(int listId) const {
+  VLQ_THROW_IF_NOT(listId >= 0 && listId < nlist_ * numedge_);
+  DeviceScope scope(ivfConfig_.device);
+  commit_();
+  return fetchList<long>(lOffsets_, lIds_, listId, 1, resources_);
+}
+
+void GpuIndexIVFPQ::merge(faiss::Index::idx_t* nns, float* dist, int k, int nq, int nprocess, float* distances,
+                          faiss::Index::idx_t* labels) const {
+  VLQ_THROW_IF_NOT(k >= 1 && k <= VLQ_MAX_K && nq >= 0 && nprocess >= 1);
+  if (nq == 0) return;
+  DeviceScope scope(ivfConfig_.device);
+  vlq_stream_t st = resources_->getDefaultStream();
+  const size_t cnt = (size_t)nprocess * nq * k;
+  DeviceBuffer din, iin, od((size_t)nq * k * sizeof(float)), oi((size_t)nq * k * sizeof(int64_t));
+  const float* dD = static_cast<const float*>(toDevice(dist, cnt * sizeof(float), din, st));
+  const int64_t* dI = static_cast<const int64_t*>(toDevice(nns, cnt * sizeof(int64_t), iin, st));
+  VLQ_CALL(vlq_merge_topk(dD, dI, nprocess, nq, k, od.as<float>(), oi.as<int64_t>(), st));
+  fromDevice(distances, od.get(), od.bytes(), st);
+  fromDevice(labels, oi.get(), oi.bytes(), st);
+  resources_->syncDefaultStream();
+}
+
+// ---------------------------------------------------------------------------------------------- reference file formats
+void GpuIndexIVFPQ::writeCodebookToFile(const std::string& name) {  // <name>.ppqt, gpu/GpuIndexIVFPQ.cu:1731-1758
+  VLQ_THROW_IF_NOT_MSG(is_trained, "Index not trained");
+  DeviceScope scope(ivfConfig_.device);
+  std::vector<float> cent((size_t)nlist_ * d);
+  VLQ_CALL(vlq_memcpy_d2h(cent.data(), quantizer_->deviceVectors(), cent.size() * sizeof(float), resources_->getDefaultStream()));
+  resources_->syncDefaultStream();
+  std::ofstream f((name + ".ppqt").c_str(), std::ofstream::out | std::ofstream::binary);
+  VLQ_THROW_IF_NOT_MSG(f.good(), "cannot open codebook file for writing");
+  const size_t L = (size_t)nlist_ * numedge_;
+  f.write((const char*)cent.data(), cent.size() * sizeof(float));
+  f.write((const char*)pqHost_.data(), pqHost_.size() * sizeof(float));
+  f.write((const char*)edgeInfo_, L * sizeof(int));
+  f.write((const char*)edgeDistInfo_, L * sizeof(float));
+  f.write((const char*)lambdaInfo_, (size_t)nLambda_ * sizeof(float));
+  f.write((const char*)constInfo_, (size_t)nLambda_ * sizeof(float));
+}
+
+void GpuIndexIVFPQ::readCodebookFromFile(const std::string& name) {  // gpu/GpuIndexIVFPQ.cu:1774-1810
+  std::ifstream f((name + ".ppqt").c_str(), std::ifstream::in | std::ifstream::binary);
+  VLQ_THROW_IF_NOT_MSG(f.good(), "cannot open codebook file");
+  const size_t L = (size_t)nlist_ * numedge_;
+  std::vector<float> cent((size_t)nlist_ * d), pq(pqHost_.size()), ed(L), lam(nLambda_), cst(nLambda_);
+  std::vector<int> e(L);
+  f.read((char*)cent.data(), cent.size() * sizeof(float));
+  f.read((char*)pq.data(), pq.size() * sizeof(float));
+  f.read((char*)e.data(), L * sizeof(int));
+  f.read((char*)ed.data(), L * sizeof(float));
+  f.read((char*)lam.data(), lam.size() * sizeof(float));
+  f.read((char*)cst.data(), cst.size() * sizeof(float));
+  VLQ_THROW_IF_NOT_MSG(f.good(), "codebook file is truncated");
+  setCodebooks(cent.data(), e.data(), ed.data(), lam.data(), pq.data());
+}
+
+void GpuIndexIVFPQ::writeDbToFile(const std::string& name) {  // .dbIdx .dbcodes .dbcount .dblas, :1813-1844
+  DeviceScope scope(ivfConfig_.device);
+  commit_();
+  vlq_stream_t st = resources_->getDefaultStream();
+  const size_t L = (size_t)nlist_ * numedge_;
+  std::vector<int64_t> off(L + 1);
+  std::vector<long> ids(nListed_);
+  std::vector<uint8_t> codes(nListed_ * subQuantizers_), las(nListed_);
+  VLQ_CALL(vlq_memcpy_d2h(off.data(), lOffsets_.get(), off.size() * sizeof(int64_t), st));
+  if (nListed_) {
+    VLQ_CALL(vlq_memcpy_d2h(ids.data(), lIds_.get(), ids.size() * sizeof(long), st));
+    VLQ_CALL(vlq_memcpy_d2h(codes.data(), lCodes_.get(), codes.size(), st));
+    VLQ_CALL(vlq_memcpy_d2h(las.data(), lLamq_.get(), las.size(), st));
+  }
+  resources_->syncDefaultStream();
+  std::vector<int> counts(L);
+  for (size_t l = 0; l < L; l++) counts[l] = (int)(off[l + 1] - off[l]);
+  std::ofstream fi((name + ".dbIdx").c_str(), std::ofstream::binary), fc((name + ".dbcodes").c_str(), std::ofstream::binary),
+      fn((name + ".dbcount").c_str(), std::ofstream::binary), fl((name + ".dblas").c_str(), std::ofstream::binary);
+  VLQ_THROW_IF_NOT_MSG(fi.good() && fc.good() && fn.good() && fl.good(), "cannot open database files for writing");
+  fi.write((const char*)ids.data(), ids.size() * sizeof(long));  // list-major, insertion order inside a list
+  fc.write((const char*)codes.data(), codes.size());
+  fl.write((const char*)las.data(), las.size());
+  fn.write((const char*)counts.data(), counts.size() * sizeof(int));
+}
+
+void GpuIndexIVFPQ::installLists_(const std::vector<int>& counts, const std::vector<uint8_t>& codes,
+                                  const std::vector<uint8_t>& las, const std::vector<long>& ids) {
+  vlq_stream_t st = resources_->getDefaultStream();
+  const size_t L = (size_t)nlist_ * numedge_;
+  std::vector<int64_t> off(L + 1, 0);
+  for (size_t l = 0; l < L; l++) off[l + 1] = off[l] + counts[l];
+  const size_t tot = (size_t)off[L];
+  VLQ_THROW_IF_NOT(ids.size() == tot && las.size() == tot && codes.size() == tot * subQuantizers_);
+  reset();
+  lOffsets_.resize((L + 1) * sizeof(int64_t));
+  lCodes_.resize(std::max<size_t>(1, codes.size()));
+  lLamq_.resize(std::max<size_t>(1, tot));
+  lKappa_.resize(std::max<size_t>(1, tot) * sizeof(float));
+  lIds_.resize(std::max<size_t>(1, tot) * sizeof(int64_t));
+  VLQ_CALL(vlq_memcpy_h2d(lOffsets_.get(), off.data(), off.size() * sizeof(int64_t), st));
+  if (tot) {
+    VLQ_CALL(vlq_memcpy_h2d(lCodes_.get(), codes.data(), codes.size(), st));
+    VLQ_CALL(vlq_memcpy_h2d(lLamq_.get(), las.data(), tot, st));
+    VLQ_CALL(vlq_memcpy_h2d(lIds_.get(), ids.data(), tot * sizeof(int64_t), st));
+    VLQ_CALL(vlq_recompute_kappa((int64_t)tot, (int64_t)L, lOffsets_.as<int64_t>(), lCodes_.as<uint8_t>(),
+                                 lLamq_.as<uint8_t>(), quantizer_->deviceVectors(), d, dEdge_.as<int>(), numedge_,
+                                 dLambda_.as<float>(), dPq_.as<float>(), subQuantizers_, lKappa_.as<float>(), st));
+  }
+  resources_->syncDefaultStream();
+  nListed_ = tot;
+  ntotal = (Index::idx_t)tot;
+}
+
+void GpuIndexIVFPQ::readDbFromFile(const std::string& name) { readDbFromFile(name, 1, 0); }
+
+// rank keeps the lists [L/P*rank, L/P*(rank+1)) and zeroes the other counts (gpu/GpuIndexIVFPQ.cu:2106-2163)
+void GpuIndexIVFPQ::readDbFromFile(const std::string& name, int pronum, int rank) {
+  VLQ_THROW_IF_NOT_MSG(is_trained, "read the codebook first");
+  VLQ_THROW_IF_NOT(pronum >= 1 && rank >= 0 && rank < pronum);
+  DeviceScope scope(ivfConfig_.device);
+  const size_t L = (size_t)nlist_ * numedge_;
+  std::vector<int> counts(L);
+  std::ifstream fn((name + ".dbcount").c_str(), std::ifstream::binary);
+  VLQ_THROW_IF_NOT_MSG(fn.good(), "cannot open .dbcount");
+  fn.read((char*)counts.data(), L * sizeof(int));
+  VLQ_THROW_IF_NOT_MSG(fn.good(), ".dbcount is truncated");
+  const size_t per = L / pronum;
+  const size_t l0 = per * rank, l1 = (rank == pronum - 1) ? L : per * (rank + 1);
+  size_t skip = 0, keep = 0;
+  for (size_t l = 0; l < L; l++) {
+    if (l < l0) skip += counts[l];
+    else if (l < l1) keep += counts[l];
+    if (l < l0 || l >= l1) counts[l] = 0;
+  }
+  std::vector<long> ids(keep);
+  std::vector<uint8_t> codes(keep * subQuantizers_), las(keep);
+  std::ifstream fi((name + ".dbIdx").c_str(), std::ifstream::binary), fc((name + ".dbcodes").c_str(), std::ifstream::binary),
+      fl((name + ".dblas").c_str(), std::ifstream::binary);
+  VLQ_THROW_IF_NOT_MSG(fi.good() && fc.good() && fl.good(), "cannot open database files");
+  fi.seekg((std::streamoff)(skip * sizeof(long)));
+  fc.seekg((std::streamoff)(skip * subQuantizers_));
+  fl.seekg((std::streamoff)skip);
+  fi.read((char*)ids.data(), keep * sizeof(long));
+  fc.read((char*)codes.data(), codes.size());
+  fl.read((char*)las.data(), keep);
+  VLQ_THROW_IF_NOT_MSG((keep == 0) || (fi.good() && fc.good() && fl.good()), "database files are truncated");
+  installLists_(counts, codes, las, ids);
+}
+
+}  // namespace gpu
+}  // namespace faiss

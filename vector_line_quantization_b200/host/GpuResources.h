@@ -1,0 +1,46 @@
+// Per-device resources (replaces gpu/GpuResources.h + gpu/StandardGpuResources.cpp:18-172): one stream, a grow-only
+// device scratch arena and a pinned staging buffer.  The reference's cuBLAS handle / temp-memory stack are not needed:
+// the GEMMs are our own tcgen05 kernels and every C-ABI call receives an explicit workspace.
+#pragma once
+#include "DeviceBuffer.h"
+
+namespace faiss {
+namespace gpu {
+
+class GpuResources {
+ public:
+  virtual ~GpuResources() {}
+  virtual int getDevice() const = 0;
+  virtual vlq_stream_t getDefaultStream() = 0;
+  virtual void syncDefaultStream() = 0;
+};
+
+class StandardGpuResources : public GpuResources {
+ public:
+  explicit StandardGpuResources(int device = 0);
+  ~StandardGpuResources() override;
+  int getDevice() const override { return device_; }
+  vlq_stream_t getDefaultStream() override { return stream_; }
+  void syncDefaultStream() override;
+  /// kept for source compatibility with the reference (gpu/StandardGpuResources.h): sizes are managed on demand
+  void noTempMemory() {}
+  void setTempMemory(size_t) {}
+  void setPinnedMemory(size_t) {}
+
+ private:
+  int device_;
+  vlq_stream_t stream_;
+};
+
+/// binds the calling thread to the resource's device for the lifetime of the scope (reference DeviceScope)
+class DeviceScope {
+ public:
+  explicit DeviceScope(int device);
+  ~DeviceScope();
+
+ private:
+  int prev_;
+};
+
+}  // namespace gpu
+}  // namespace faiss

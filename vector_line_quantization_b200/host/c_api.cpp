@@ -1,0 +1,169 @@
+#include "vlq_index_c.h"
+
+#include <cstring>
+#include <string>
+
+#include "GpuIndexIVFPQ.h"
+#include "IndexProxy.h"
+
+using namespace faiss;
+using namespace faiss::gpu;
+
+static thread_local std::string g_err;
+
+#define GUARD(body)                    \
+  try {                                \
+    body;                              \
+    return 0;                          \
+  } catch (const std::exception& e) {  \
+    g_err = e.what();                  \
+    return -1;                         \
+  } catch (...) {                      \
+    g_err = "unknown C++ exception";   \
+    return -1;                         \
+  }
+
+static Index* I(void* h) { return static_cast<Index*>(h); }
+static GpuIndexIVFPQ* V(void* h) {
+  GpuIndexIVFPQ* p = dynamic_cast<GpuIndexIVFPQ*>(static_cast<Index*>(h));
+  if (!p) throw FaissException("handle is not a VLQ index");
+  return p;
+}
+static GpuIndexFlat* F(void* h) {
+  GpuIndexFlat* p = dynamic_cast<GpuIndexFlat*>(static_cast<Index*>(h));
+  if (!p) throw FaissException("handle is not a flat index");
+  return p;
+}
+
+extern "C" {
+
+const char* vlq_host_last_error(void) { return g_err.c_str(); }
+
+int vlq_host_resources_new(int device, void** out) { GUARD(*out = new StandardGpuResources(device)) }
+int vlq_host_resources_free(void* res) { GUARD(delete static_cast<StandardGpuResources*>(res)) }
+
+int vlq_host_index_free(void* index) { GUARD(delete I(index)) }
+int vlq_host_index_train(void* index, long n, const float* x) { GUARD(I(index)->train(n, x)) }
+int vlq_host_index_add(void* index, long n, const float* x) { GUARD(I(index)->add(n, x)) }
+int vlq_host_index_add_with_ids(void* index, long n, const float* x, const long* ids) {
+  GUARD(I(index)->add_with_ids(n, x, ids))
+}
+int vlq_host_index_search(void* index, long n, const float* x, long k, float* distances, long* labels) {
+  GUARD(I(index)->search(n, x, k, distances, labels))
+}
+int vlq_host_index_reset(void* index) { GUARD(I(index)->reset()) }
+long vlq_host_index_ntotal(void* index) { return I(index)->ntotal; }
+int vlq_host_index_is_trained(void* index) { return I(index)->is_trained ? 1 : 0; }
+
+int vlq_host_flat_new(void* res, int d, int use_tensor_cores, void** out) {
+  GUARD({
+    GpuIndexFlatConfig cfg;
+    cfg.device = static_cast<GpuResources*>(res)->getDevice();
+    cfg.useTensorCores = use_tensor_cores != 0;
+    *out = static_cast<Index*>(new GpuIndexFlatL2(static_cast<GpuResources*>(res), d, cfg));
+  })
+}
+int vlq_host_flat_assign(void* flat, long n, const float* x, int* labels) { GUARD(F(flat)->assignFlat(n, x, labels, 1)) }
+int vlq_host_flat_build_graph(void* flat, int nedge, float* distances, int* labels) {
+  GUARD(F(flat)->buildGraph(F(flat)->ntotal, nedge, distances, labels))
+}
+
+int vlq_host_kmeans(void* res, int d, int k, long n, const float* x, int niter, int seed, float* centroids_out) {
+  GUARD({
+    GpuResources* r = static_cast<GpuResources*>(res);
+    ClusteringParameters cp;
+    cp.niter = niter;
+    cp.seed = seed;
+    Clustering clus(d, k, cp);
+    GpuIndexFlatConfig cfg;
+    cfg.device = r->getDevice();
+    GpuIndexFlatL2 assigner(r, d, cfg);
+    clus.train(n, x, assigner);
+    std::memcpy(centroids_out, clus.centroids.data(), sizeof(float) * (size_t)d * k);
+  })
+}
+
+int vlq_host_vlq_new(void* res, int d, int nlist, int M, int bits, int nedge, int nlambda, int use_tensor_cores,
+                     void** out) {
+  GUARD({
+    GpuResources* r = static_cast<GpuResources*>(res);
+    GpuIndexIVFPQConfig cfg;
+    cfg.device = r->getDevice();
+    cfg.flatConfig.useTensorCores = use_tensor_cores != 0;
+    *out = static_cast<Index*>(new GpuIndexIVFPQ(r, d, nlist, M, bits, nedge, nlambda, METRIC_L2, cfg));
+  })
+}
+int vlq_host_vlq_set_nprobe(void* index, int nprobe) { GUARD(V(index)->setNumProbes(nprobe)) }
+int vlq_host_vlq_set_w1(void* index, int w1) {
+  GUARD({
+    VLQ_THROW_IF_NOT_MSG(w1 >= 1 && w1 <= VLQ_MAX_K, "w1 must be in [1, 1024]");
+    V(index)->w1_ = w1;
+  })
+}
+int vlq_host_vlq_set_list_cap(void* index, int cap) {
+  GUARD({
+    VLQ_THROW_IF_NOT_MSG(cap >= 1, "cap must be >= 1");
+    V(index)->listCap_ = cap;
+  })
+}
+int vlq_host_vlq_set_train_iters(void* index, int niter) { GUARD(V(index)->cp_.niter = niter) }
+int vlq_host_vlq_get_codebooks(void* index, float* coarse, int* edge, float* edge_dist, float* lambda_cb, float* pq) {
+  GUARD({
+    GpuIndexIVFPQ* v = V(index);
+    VLQ_THROW_IF_NOT_MSG(v->is_trained, "Index not trained");
+    const size_t L = (size_t)v->getNumLists() * v->numedge_;
+    GpuIndexFlat* q = v->getQuantizer();
+    VLQ_CALL(vlq_memcpy_d2h(coarse, q->deviceVectors(), (size_t)v->getNumLists() * v->d * sizeof(float),
+                            q->resources()->getDefaultStream()));
+    q->resources()->syncDefaultStream();
+    std::memcpy(edge, v->edgeInfo_, L * sizeof(int));
+    std::memcpy(edge_dist, v->edgeDistInfo_, L * sizeof(float));
+    std::memcpy(lambda_cb, v->lambdaInfo_, (size_t)v->nLambda_ * sizeof(float));
+    std::memcpy(pq, v->pqCentroids().data(), v->pqCentroids().size() * sizeof(float));
+  })
+}
+int vlq_host_vlq_set_codebooks(void* index, const float* coarse, const int* edge, const float* edge_dist,
+                               const float* lambda_cb, const float* pq) {
+  GUARD(V(index)->setCodebooks(coarse, edge, edge_dist, lambda_cb, pq))
+}
+int vlq_host_vlq_list_length(void* index, int list, int* out) { GUARD(*out = V(index)->getListLength(list)) }
+int vlq_host_vlq_get_list(void* index, int list, unsigned char* codes, unsigned char* lambdas, long* ids) {
+  GUARD({
+    auto c = V(index)->getListCodes(list);
+    auto l = V(index)->getListLambdas(list);
+    auto i = V(index)->getListIndices(list);
+    if (codes && !c.empty()) std::memcpy(codes, c.data(), c.size());
+    if (lambdas && !l.empty()) std::memcpy(lambdas, l.data(), l.size());
+    if (ids && !i.empty()) std::memcpy(ids, i.data(), i.size() * sizeof(long));
+  })
+}
+int vlq_host_vlq_merge(void* index, long* nns, float* dist, int k, int nq, int nprocess, float* distances, long* labels) {
+  GUARD(V(index)->merge(nns, dist, k, nq, nprocess, distances, labels))
+}
+int vlq_host_vlq_write_codebook(void* index, const char* name) { GUARD(V(index)->writeCodebookToFile(name)) }
+int vlq_host_vlq_read_codebook(void* index, const char* name) { GUARD(V(index)->readCodebookFromFile(name)) }
+int vlq_host_vlq_write_db(void* index, const char* name) { GUARD(V(index)->writeDbToFile(name)) }
+int vlq_host_vlq_read_db(void* index, const char* name, int pronum, int rank) {
+  GUARD(V(index)->readDbFromFile(name, pronum, rank))
+}
+
+int vlq_host_proxy_new(void** out) { GUARD(*out = static_cast<Index*>(new IndexProxy())) }
+int vlq_host_proxy_add_index(void* proxy, void* index) {
+  GUARD({
+    IndexProxy* p = dynamic_cast<IndexProxy*>(I(proxy));
+    VLQ_THROW_IF_NOT_MSG(p, "handle is not an IndexProxy");
+    p->addIndex(I(index));
+  })
+}
+int vlq_host_shards_new(int d, int threaded, int successive_ids, void** out) {
+  GUARD(*out = static_cast<Index*>(new IndexShards(d, threaded != 0, successive_ids != 0)))
+}
+int vlq_host_shards_add_shard(void* shards, void* index) {
+  GUARD({
+    IndexShards* s = dynamic_cast<IndexShards*>(I(shards));
+    VLQ_THROW_IF_NOT_MSG(s, "handle is not an IndexShards");
+    s->add_shard(I(index));
+  })
+}
+
+}  // extern "C"
