@@ -204,7 +204,8 @@ void GpuIndexIVFPQ::add_with_ids(Index::idx_t n, const float* x, const long* xid
   ensurePending_((size_t)n);
   const Index::idx_t tile = (Index::idx_t)1 << 19;
   const int M = subQuantizers_;
-  DeviceBuffer xin, dA;
+  DeviceBuffer& xin = addIn_;
+  DeviceBuffer& dA = addA_;
   for (Index::idx_t s = 0; s < n; s += tile) {
     const Index::idx_t m = std::min(tile, n - s);
     const float* dx = static_cast<const float*>(toDevice(x + (size_t)s * d, (size_t)m * d * sizeof(float), xin, st));
@@ -270,7 +271,9 @@ void GpuIndexIVFPQ::search(Index::idx_t n, const float* x, Index::idx_t k, float
   const int M = subQuantizers_;
   const Index::idx_t page = 32768;  // gpu/GpuIndex.cu:109-147
   const Index::idx_t tile = std::max<Index::idx_t>(64, std::min<Index::idx_t>(1024, ((Index::idx_t)1 << 26) / nlist_));
-  DeviceBuffer xin, outD, outI;
+  DeviceBuffer& xin = qIn_;
+  DeviceBuffer& outD = outD_;
+  DeviceBuffer& outI = outI_;
   DeviceBuffer& dmat = scratch_;
   dmat.reserve((size_t)tile * nlist_ * sizeof(float));
   scratchB_.reserve((size_t)tile * (P * (sizeof(float) + sizeof(int)) + W * (sizeof(int) + 2 * sizeof(float))));
