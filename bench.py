@@ -138,11 +138,31 @@ def cpu_search_baseline(po, model, lists_host, xq, P, W, k, budget_s, gpu_result
     return out, parity
 
 
+class _StdoutToStderr:
+    """the reference library printf()s progress lines; keep fd 1 clean for the ONE JSON line"""
+
+    def __enter__(self):
+        sys.stdout.flush()
+        self.saved = os.dup(1)
+        os.dup2(2, 1)
+
+    def __exit__(self, *exc):
+        sys.stdout.flush()
+        os.dup2(self.saved, 1)
+        os.close(self.saved)
+
+
 def run_reference(a):
     """--impl reference: everything on the host cores; no CUDA library is loaded."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
+    with _StdoutToStderr():
+        line = _run_reference(a)
+    print(json.dumps(line))
+
+
+def _run_reference(a):
     from oracle import pyoracle as po
     from vector_line_quantization_b200 import data
 
@@ -215,7 +235,7 @@ def run_reference(a):
                    "sample": "%d vectors: IndexFlatL2 assign + oracle line stage + ProductQuantizer::compute_codes" % nb},
         "setup_s": t_setup,
     }
-    print(json.dumps(line))
+    return line
 
 
 def workload_config(a, n_gpus):
@@ -279,7 +299,7 @@ def run_b200(a):
         return ops.l2_assign(x_, cent, cn, want_dist=False)[0]
 
     # ---- encode this rank's shard (timed as its own stage: encode Mvec/s)
-    xb = data.sift_like_torch(a.n, d=d, kc=a.kc, seed=2 + rank, device=dev)
+    xb = data.sift_like_torch(a.n, d=d, kc=a.kc, seed=1000 + rank, device=dev)  # queries use seed 3
     chunk = 1 << 20
     id0 = rank * a.n
     lists = None
@@ -369,6 +389,7 @@ def run_b200(a):
 
     clocks = ClockSampler(local)
     clocks.start()
+    time.sleep(0.5)  # let nvidia-smi come up: the timed region is only tens of milliseconds long
     result = {}
 
     def dev_step():
@@ -379,7 +400,6 @@ def run_b200(a):
     total_ms, launches = timed(dev_step, a.steps, a.warmup)
     if prof == "search":
         torch.cuda.profiler.stop()
-    clk = clocks.stop()
     D, I = result["DI"]
 
     # ---- e2e: the reference-facing API (C++ host layer: GpuIndexIVFPQ::add_with_ids / ::search) with HOST buffers;
@@ -447,6 +467,7 @@ def run_b200(a):
         dist.all_reduce(e2e_t, op=dist.ReduceOp.MAX)
     e2e_ms = float(e2e_t) * 1e3
     host_matches_ops = bool((hI.to(dev) == I).all()) and bool((hD.to(dev) == D).all())
+    clk = clocks.stop()  # sampled across the device-timed steps and the e2e steps
 
     # ---- per-stage device times of one step (CUDA events on the launching stream) -> roofline of the dominant kernel
     def stage_times():

@@ -225,20 +225,29 @@ l2_argmin_kernel(const float* __restrict__ x, int64_t n, int d, const float* __r
 
 // ------------------------------------------------------------------------------------------------- row select (a15)
 constexpr int SEL_THREADS = 256;
+constexpr int SEL_BATCH = 4;
 __global__ void __launch_bounds__(SEL_THREADS)
-select_rows_kernel(const float* __restrict__ D, int cols, int64_t ldD, int k, const float* __restrict__ row_add,
+select_rows_kernel(const float* __restrict__ D, int cols, int64_t ldD, int k, int cap, const float* __restrict__ row_add,
                    float* __restrict__ out_val, int* __restrict__ out_idx) {
   extern __shared__ __align__(16) unsigned char smem[];
-  BlockTopK<SEL_THREADS> sel;
-  sel.init(smem, k);
+  BlockSelect<SEL_THREADS> sel;
+  sel.init(smem, k, cap, SEL_BATCH);
   const int64_t row = blockIdx.x;
   const float* dr = D + row * ldD;
-  const int rounds = (cols + SEL_THREADS - 1) / SEL_THREADS;
-  for (int r = 0; r < rounds; r++) {
-    int j = r * SEL_THREADS + threadIdx.x;
-    bool valid = j < cols;
-    float v = valid ? dr[j] : 0.f;
-    sel.add(valid, make_key(v, (uint32_t)j));
+  for (int base = 0; base < cols; base += SEL_BATCH * SEL_THREADS) {
+    float v[SEL_BATCH];
+#pragma unroll
+    for (int b = 0; b < SEL_BATCH; b++) {  // all loads of the batch in flight before the first compare
+      const int j = base + b * SEL_THREADS + threadIdx.x;
+      v[b] = j < cols ? dr[j] : 0.f;
+    }
+    bool any = false;
+#pragma unroll
+    for (int b = 0; b < SEL_BATCH; b++) {
+      const int j = base + b * SEL_THREADS + threadIdx.x;
+      any |= sel.offer(j < cols, make_key(v[b], (uint32_t)j));
+    }
+    sel.end_batch(any);
   }
   sel.finish();
   const float add = row_add ? row_add[row] : 0.f;
@@ -313,8 +322,9 @@ int vlq_select_rows(const float* D, int64_t n, int cols, int64_t ldD, int k, con
   if (n < 0 || cols <= 0 || k <= 0 || k > VLQ_MAX_K || ldD < cols) return VLQ_EINVAL;
   if (n == 0) return VLQ_OK;
   if (!D || !out_val || !out_idx) return VLQ_EINVAL;
-  size_t smem = topk_smem_bytes(k, SEL_THREADS);
-  VLQ_LAUNCH(select_rows_kernel, (unsigned)n, SEL_THREADS, smem, as_stream(stream), D, cols, ldD, k, row_add,
+  const int cap = select_capacity(k, SEL_THREADS, SEL_BATCH, cols);
+  const size_t smem = select_smem_bytes(cap);
+  VLQ_LAUNCH(select_rows_kernel, (unsigned)n, SEL_THREADS, smem, as_stream(stream), D, cols, ldD, k, cap, row_add,
              out_val, out_idx);
   return last_error();
 }

@@ -20,36 +20,42 @@ namespace vlq {
 constexpr int Q_THREADS = 256;
 
 // ------------------------------------------------------------------------------------------------ line selection
+constexpr int Q_BATCH = 4;
+
 __global__ void __launch_bounds__(Q_THREADS)
 select_lines_kernel(const float* __restrict__ D, int64_t ldD, const int* __restrict__ coarse_ids, int P,
-                    const int* __restrict__ edge, const float* __restrict__ edge_d2, int E, int W,
+                    const int* __restrict__ edge, const float* __restrict__ edge_d2, int E, int W, int cap,
                     int* __restrict__ out_list, float* __restrict__ out_term1, float* __restrict__ out_term6) {
   extern __shared__ __align__(16) unsigned char smem[];
-  BlockTopK<Q_THREADS> sel;
-  sel.init(smem, W);
+  BlockSelect<Q_THREADS> sel;
+  sel.init(smem, W, cap, Q_BATCH);
   const int64_t q = blockIdx.x;
   const float* Dq = D + q * ldD;
   const int* cq = coarse_ids + q * P;
   const int num = P * E;
-  const int rounds = (num + Q_THREADS - 1) / Q_THREADS;
-  for (int r = 0; r < rounds; r++) {
-    const int i = r * Q_THREADS + threadIdx.x;
-    bool valid = i < num;
-    float score = 0.f;
-    if (valid) {
-      const int c = cq[i / E];
-      valid = c >= 0;
+  for (int base = 0; base < num; base += Q_BATCH * Q_THREADS) {
+    bool any = false;
+#pragma unroll
+    for (int b = 0; b < Q_BATCH; b++) {
+      const int i = base + b * Q_THREADS + threadIdx.x;
+      bool valid = i < num;
+      float score = 0.f;
       if (valid) {
-        const int e = i % E;
-        const int s = edge[(int64_t)c * E + e];
-        const float a2 = Dq[s], b2 = Dq[c], c2 = edge_d2[(int64_t)c * E + e];
-        float v = __fsub_rn(a2, b2);
-        v = __fsub_rn(v, c2);
-        // BroadcastSum.cu:517: (v>0) ? b2 : b2 - 0.25 v^2 / c2
-        score = (v > 0.f) ? b2 : __fsub_rn(b2, __fdiv_rn(__fmul_rn(__fmul_rn(0.25f, v), v), c2));
+        const int c = cq[i / E];
+        valid = c >= 0;
+        if (valid) {
+          const int e = i % E;
+          const int s = edge[(int64_t)c * E + e];
+          const float a2 = Dq[s], b2 = Dq[c], c2 = edge_d2[(int64_t)c * E + e];
+          float v = __fsub_rn(a2, b2);
+          v = __fsub_rn(v, c2);
+          // BroadcastSum.cu:517: (v>0) ? b2 : b2 - 0.25 v^2 / c2
+          score = (v > 0.f) ? b2 : __fsub_rn(b2, __fdiv_rn(__fmul_rn(__fmul_rn(0.25f, v), v), c2));
+        }
       }
+      any |= sel.offer(valid, make_key(score, (uint32_t)i));
     }
-    sel.add(valid, make_key(score, (uint32_t)i));
+    sel.end_batch(any);
   }
   sel.finish();
   for (int w = threadIdx.x; w < W; w += Q_THREADS) {
@@ -89,6 +95,7 @@ struct ScanArgs {
   const float* kappa;
   const int64_t* ids;
   int k, cap;
+  int sel_cap;
   float* outD;
   int64_t* outI;
 };
@@ -122,8 +129,8 @@ __global__ void __launch_bounds__(Q_THREADS) scan_topk_kernel(ScanArgs a) {
   extern __shared__ __align__(16) unsigned char smem[];
   // smem: [topk keys S*8 + 16][T3 M*ksub f32][lambda nL f32][per line: start i64, prefix i32 (W+1), t1, t6, t5 f32]
   const int M = a.M, ksub = a.ksub, dsub = a.dsub, W = a.W;
-  BlockTopK<Q_THREADS> sel;
-  size_t off = (topk_smem_bytes(a.k, Q_THREADS) + 15) & ~size_t(15);
+  BlockSelect<Q_THREADS> sel;
+  size_t off = (select_smem_bytes(a.sel_cap) + 15) & ~size_t(15);
   float* T3 = reinterpret_cast<float*>(smem + off);
   off += sizeof(float) * M * ksub;
   float* lcb = reinterpret_cast<float*>(smem + off);
@@ -138,7 +145,7 @@ __global__ void __launch_bounds__(Q_THREADS) scan_topk_kernel(ScanArgs a) {
   off += sizeof(float) * W;
   float* lt5 = reinterpret_cast<float*>(smem + off);
 
-  sel.init(smem, a.k);
+  sel.init(smem, a.k, a.sel_cap, Q_BATCH);
   const int64_t qi = blockIdx.x;
   const float* qv = a.q + qi * a.d;
 
@@ -193,25 +200,29 @@ __global__ void __launch_bounds__(Q_THREADS) scan_topk_kernel(ScanArgs a) {
   __syncthreads();
   const int total = prefix[W];
 
-  const int rounds = (total + Q_THREADS - 1) / Q_THREADS;
-  for (int r = 0; r < rounds; r++) {
-    const int pos = r * Q_THREADS + threadIdx.x;
-    const bool valid = pos < total;
-    float dist = 0.f;
-    if (valid) {
-      // list of this stream position: largest w with prefix[w] <= pos
-      int lo = 0, hi = W;
-      while (hi - lo > 1) {
-        int mid = (lo + hi) >> 1;
-        if (prefix[mid] <= pos) lo = mid; else hi = mid;
+  for (int base = 0; base < total; base += Q_BATCH * Q_THREADS) {
+    bool any = false;
+#pragma unroll
+    for (int b = 0; b < Q_BATCH; b++) {
+      const int pos = base + b * Q_THREADS + threadIdx.x;
+      const bool valid = pos < total;
+      float dist = 0.f;
+      if (valid) {
+        // list of this stream position: largest w with prefix[w] <= pos
+        int lo = 0, hi = W;
+        while (hi - lo > 1) {
+          int mid = (lo + hi) >> 1;
+          if (prefix[mid] <= pos) lo = mid; else hi = mid;
+        }
+        const int64_t ent = lstart[lo] + (pos - prefix[lo]);
+        const float la = lcb[a.lamq[ent]];
+        const float base_d = lt1[lo] + la * lt6[lo] + (la * la - la) * lt5[lo];
+        const float acc = adc_sum<M_T>(a.codes + ent * M, T3, M, ksub);
+        dist = (a.kappa[ent] + acc) + base_d;
       }
-      const int64_t ent = lstart[lo] + (pos - prefix[lo]);
-      const float la = lcb[a.lamq[ent]];
-      const float base = lt1[lo] + la * lt6[lo] + (la * la - la) * lt5[lo];
-      const float acc = adc_sum<M_T>(a.codes + ent * M, T3, M, ksub);
-      dist = (a.kappa[ent] + acc) + base;
+      any |= sel.offer(valid, make_key(dist, (uint32_t)pos));
     }
-    sel.add(valid, make_key(dist, (uint32_t)pos));
+    sel.end_batch(any);
   }
   sel.finish();
   for (int i = threadIdx.x; i < a.k; i += Q_THREADS) {
@@ -233,8 +244,8 @@ __global__ void __launch_bounds__(Q_THREADS) scan_topk_kernel(ScanArgs a) {
   }
 }
 
-static size_t scan_smem_bytes(int k, int M, int ksub, int nL, int W) {
-  size_t off = (topk_smem_bytes(k, Q_THREADS) + 15) & ~size_t(15);
+static size_t scan_smem_bytes(int sel_cap, int M, int ksub, int nL, int W) {
+  size_t off = (select_smem_bytes(sel_cap) + 15) & ~size_t(15);
   off += sizeof(float) * M * ksub;
   off += sizeof(float) * ((nL + 3) & ~3);
   off += sizeof(int64_t) * W;
@@ -245,24 +256,28 @@ static size_t scan_smem_bytes(int k, int M, int ksub, int nL, int W) {
 
 // ------------------------------------------------------------------------------------------------ shard merge
 __global__ void __launch_bounds__(Q_THREADS)
-merge_topk_kernel(const float* __restrict__ D, const int64_t* __restrict__ I, int R, int64_t nq, int k,
+merge_topk_kernel(const float* __restrict__ D, const int64_t* __restrict__ I, int R, int64_t nq, int k, int cap,
                   float* __restrict__ outD, int64_t* __restrict__ outI) {
   extern __shared__ __align__(16) unsigned char smem[];
-  BlockTopK<Q_THREADS> sel;
-  sel.init(smem, k);
+  BlockSelect<Q_THREADS> sel;
+  sel.init(smem, k, cap, Q_BATCH);
   const int64_t q = blockIdx.x;
   const int num = R * k;
-  const int rounds = (num + Q_THREADS - 1) / Q_THREADS;
-  for (int r = 0; r < rounds; r++) {
-    const int i = r * Q_THREADS + threadIdx.x;
-    bool valid = i < num;
-    float v = 0.f;
-    if (valid) {
-      const int rank = i / k, pos = i % k;
-      v = D[((int64_t)rank * nq + q) * k + pos];
-      valid = I[((int64_t)rank * nq + q) * k + pos] >= 0;  // padding entries never win
+  for (int base = 0; base < num; base += Q_BATCH * Q_THREADS) {
+    bool any = false;
+#pragma unroll
+    for (int b = 0; b < Q_BATCH; b++) {
+      const int i = base + b * Q_THREADS + threadIdx.x;
+      bool valid = i < num;
+      float v = 0.f;
+      if (valid) {
+        const int rank = i / k, pos = i % k;
+        v = D[((int64_t)rank * nq + q) * k + pos];
+        valid = I[((int64_t)rank * nq + q) * k + pos] >= 0;  // padding entries never win
+      }
+      any |= sel.offer(valid, make_key(v, (uint32_t)i));
     }
-    sel.add(valid, make_key(v, (uint32_t)i));
+    sel.end_batch(any);
   }
   sel.finish();
   for (int i = threadIdx.x; i < k; i += Q_THREADS) {
@@ -309,9 +324,10 @@ int vlq_select_lines(const float* D, int64_t nq, int64_t ldD, const int* coarse_
   if (nq < 0 || P <= 0 || P > VLQ_MAX_K || E <= 0 || W <= 0 || W > VLQ_MAX_K) return VLQ_EINVAL;
   if (nq == 0) return VLQ_OK;
   if (!D || !coarse_ids || !edge || !edge_d2 || !out_list || !out_term1 || !out_term6) return VLQ_EINVAL;
-  size_t smem = topk_smem_bytes(W, Q_THREADS);
+  const int cap = select_capacity(W, Q_THREADS, Q_BATCH, (long long)P * E);
+  const size_t smem = select_smem_bytes(cap);
   VLQ_LAUNCH(select_lines_kernel, (unsigned)nq, Q_THREADS, smem, as_stream(stream), D, ldD, coarse_ids, P, edge,
-             edge_d2, E, W, out_list, out_term1, out_term6);
+             edge_d2, E, W, cap, out_list, out_term1, out_term6);
   return last_error();
 }
 
@@ -329,7 +345,8 @@ int vlq_scan_topk(const float* q, int64_t nq, int d, const float* pq, int M, con
   a.q = q; a.d = d; a.pq = pq; a.M = M; a.ksub = 256; a.dsub = d / M; a.lambda_cb = lambda_cb; a.nL = nL;
   a.line_list = line_list; a.term1 = term1; a.term6 = term6; a.edge_d2 = edge_d2; a.W = W; a.offsets = offsets;
   a.codes = codes; a.lamq = lamq; a.kappa = kappa; a.ids = ids; a.k = k; a.cap = cap; a.outD = outD; a.outI = outI;
-  size_t smem = scan_smem_bytes(k, M, a.ksub, nL, W);
+  a.sel_cap = select_capacity(k, Q_THREADS, Q_BATCH, (long long)W * cap);
+  size_t smem = scan_smem_bytes(a.sel_cap, M, a.ksub, nL, W);
   cudaStream_t st = as_stream(stream);
   const bool al16 = (reinterpret_cast<uintptr_t>(codes) % 16) == 0;
   if (M == 16 && al16) {
@@ -350,8 +367,9 @@ int vlq_merge_topk(const float* D, const int64_t* I, int R, int64_t nq, int k, f
   if (R <= 0 || nq < 0 || k <= 0 || k > VLQ_MAX_K) return VLQ_EINVAL;
   if (nq == 0) return VLQ_OK;
   if (!D || !I || !outD || !outI) return VLQ_EINVAL;
-  size_t smem = topk_smem_bytes(k, Q_THREADS);
-  VLQ_LAUNCH(merge_topk_kernel, (unsigned)nq, Q_THREADS, smem, as_stream(stream), D, I, R, nq, k, outD, outI);
+  const int cap = select_capacity(k, Q_THREADS, Q_BATCH, (long long)R * k);
+  const size_t smem = select_smem_bytes(cap);
+  VLQ_LAUNCH(merge_topk_kernel, (unsigned)nq, Q_THREADS, smem, as_stream(stream), D, I, R, nq, k, cap, outD, outI);
   return last_error();
 }
 

@@ -1,9 +1,15 @@
-// Exact block-wide top-k (k <= 1024) on 64-bit keys = (order-preserving float bits << 32) | payload.
+// Exact block-wide k-selection (k <= 1024) on 64-bit keys = (order-preserving float bits << 32) | payload.
 //
-// Replaces the reference's BlockSelect/WarpSelect (gpu/utils/Select.cuh:77-277, MergeNetwork*.cuh) and the CPU heaps
-// (Heap.h:89-323).  Design: threshold filter + shared-memory pending buffer + block bitonic sort on overflow.
-// Because the key embeds the payload (column / stream position), ties resolve deterministically to the lowest
-// payload, independent of thread scheduling -- the reference leaves tie order unspecified (TestGpuSelect.cu:84-112).
+// Replaces the reference's BlockSelect / WarpSelect thread-queue + bitonic merge networks (gpu/utils/Select.cuh:77-277,
+// MergeNetwork*.cuh) and the CPU heaps (Heap.h:89-323).  Design:
+//   * candidates that beat the current threshold are appended to a shared-memory buffer (one atomicAdd each);
+//     __syncthreads_count gives every thread the same conservative fill level with ONE barrier per batch;
+//   * when the buffer could overflow it is compacted to the k smallest keys by an 8-pass byte-wise RADIX SELECT
+//     (256-bin shared histogram per pass, warp-shuffle prefix scan to find the digit of the k-th key) -- O(n) work
+//     instead of the O(n log^2 n) sorting network a flush used to cost; the k-th key becomes the new threshold;
+//   * finish(): one last radix select, then a bitonic sort of just the k survivors.
+// Keys are unique (the payload is the column / stream position), so ties resolve deterministically to the lowest
+// payload, independent of thread scheduling; the reference leaves tie order unspecified (TestGpuSelect.cu:84-112).
 #pragma once
 #include "common.cuh"
 
@@ -15,42 +21,150 @@ __host__ __device__ inline int next_pow2(int v) {
   return p;
 }
 
-// shared-memory footprint (bytes) of a BlockTopK for a given k and thread count
-__host__ __device__ inline int topk_sort_size(int k, int threads) {
-  return next_pow2(k + (2 * threads > k ? 2 * threads : k));
+constexpr int kSelMaxItems = 16;  // buffer capacity <= 16 * THREADS
+
+// buffer capacity for a selection of k out of (at most) `total` candidates, appended in batches of `batch` per thread
+__host__ __device__ inline int select_capacity(int k, int threads, int batch, long long total) {
+  long long want = total < 4096 ? total : 4096;
+  int lo = k + batch * threads;  // one full batch must always fit behind k survivors
+  if (want < lo) want = lo;
+  int cap = next_pow2((int)want);
+  if (cap > kSelMaxItems * threads) cap = kSelMaxItems * threads;
+  return cap;
 }
-__host__ __device__ inline size_t topk_smem_bytes(int k, int threads) {
-  return sizeof(uint64_t) * topk_sort_size(k, threads) + 16;
-}
+__host__ __device__ inline size_t select_smem_bytes(int cap) { return sizeof(uint64_t) * cap + sizeof(int) * (256 + 8); }
 
 template <int THREADS>
-struct BlockTopK {
-  uint64_t* keys;  // [S]; [0,k) current best ascending, [k,S) pending
-  int* cnt;        // pending count
-  int S, k, PB;
+struct BlockSelect {
+  uint64_t* keys;  // [cap]
+  int* hist;       // [256]
+  int* meta;       // [0] append cursor, [1] chosen digit, [2] remaining rank
+  int cap, k, batch;
+  int fill;        // conservative fill level, identical in every thread
+  uint64_t thr;    // only keys < thr can still enter the result
 
-  // smem must hold topk_smem_bytes(k, THREADS) bytes, 8-byte aligned
-  __device__ void init(void* smem, int k_) {
+  // smem: select_smem_bytes(cap) bytes, 8-byte aligned.  cap >= k + batch*THREADS (see select_capacity).
+  __device__ void init(void* smem, int k_, int cap_, int batch_) {
     k = k_;
-    S = topk_sort_size(k_, THREADS);
-    PB = S - k;
+    cap = cap_;
+    batch = batch_;
     keys = reinterpret_cast<uint64_t*>(smem);
-    cnt = reinterpret_cast<int*>(keys + S);
-    for (int i = threadIdx.x; i < S; i += THREADS) keys[i] = kKeyInf;
-    if (threadIdx.x == 0) *cnt = 0;
+    hist = reinterpret_cast<int*>(keys + cap);
+    meta = hist + 256;
+    fill = 0;
+    thr = kKeyInf;
+    if (threadIdx.x == 0) meta[0] = 0;
     __syncthreads();
   }
 
-  __device__ __forceinline__ uint64_t threshold() const { return keys[k - 1]; }
+  // non-collective part of a batch: call up to `batch` times per thread, then end_batch() once (collective)
+  __device__ __forceinline__ bool offer(bool valid, uint64_t key) {
+    if (valid && key < thr) {
+      const int slot = atomicAdd(&meta[0], 1);
+      keys[slot] = key;
+      return true;
+    }
+    return false;
+  }
+  // collective; `any` = this thread appended at least one key in the batch
+  __device__ __forceinline__ void end_batch(bool any) {
+    fill += batch * __syncthreads_count(any);  // barrier + identical conservative count in every thread
+    if (fill > cap - batch * THREADS) compact();
+  }
 
-  __device__ void sort_all() {
+  // collective: keep the k smallest keys of keys[0..n) (unsorted) in keys[0..k), thr = k-th smallest
+  __device__ void compact() {
+    __syncthreads();
+    const int n = meta[0];
+    if (n <= k) {  // nothing to drop; the conservative counter was too pessimistic
+      fill = n;
+      __syncthreads();
+      return;
+    }
+    // ---- radix select of the k-th smallest key, most significant byte first
+    uint64_t prefix = 0;
+    int need = k;  // rank (1-based) of the wanted key among the keys matching `prefix`
+#pragma unroll 1
+    for (int pass = 7; pass >= 0; pass--) {
+      hist[threadIdx.x & 255] = 0;
+      if (THREADS < 256)
+        for (int j = threadIdx.x; j < 256; j += THREADS) hist[j] = 0;
+      __syncthreads();
+      const int shift = pass * 8;
+      for (int i = threadIdx.x; i < n; i += THREADS) {
+        const uint64_t key = keys[i];
+        const bool match = pass == 7 ? true : ((key >> (shift + 8)) == prefix);
+        if (match) atomicAdd(&hist[(int)((key >> shift) & 255)], 1);
+      }
+      __syncthreads();
+      if (threadIdx.x < kWarp) {  // lane l owns bins [8l, 8l+8)
+        const int lane = threadIdx.x;
+        int c[8], s = 0;
+#pragma unroll
+        for (int j = 0; j < 8; j++) {
+          c[j] = hist[lane * 8 + j];
+          s += c[j];
+        }
+        int inc = s;
+#pragma unroll
+        for (int o = 1; o < kWarp; o <<= 1) {
+          int t = __shfl_up_sync(kFull, inc, o);
+          if (lane >= o) inc += t;
+        }
+        int before = inc - s;  // keys in bins below this lane's range
+        if (before < need && need <= inc) {  // the wanted key lies in this lane's bins
+#pragma unroll
+          for (int j = 0; j < 8; j++) {
+            if (need <= before + c[j]) {
+              meta[1] = lane * 8 + j;
+              meta[2] = need - before;
+              break;
+            }
+            before += c[j];
+          }
+        }
+      }
+      __syncthreads();
+      prefix = (prefix << 8) | (uint64_t)meta[1];
+      need = meta[2];
+    }
+    const uint64_t kth = prefix;  // exactly k keys are <= kth (keys are unique)
+    // ---- compaction through registers (in-place writes would race with other threads' reads)
+    uint64_t mine[kSelMaxItems];
+#pragma unroll
+    for (int t = 0; t < kSelMaxItems; t++) {
+      const int i = threadIdx.x + t * THREADS;
+      mine[t] = i < n ? keys[i] : kKeyInf;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) meta[0] = 0;
+    __syncthreads();
+#pragma unroll
+    for (int t = 0; t < kSelMaxItems; t++) {
+      if (mine[t] <= kth) {
+        const int slot = atomicAdd(&meta[0], 1);
+        keys[slot] = mine[t];
+      }
+    }
+    thr = kth;
+    fill = k;
+    __syncthreads();
+  }
+
+  // collective: afterwards keys[0..k) hold the k smallest keys ascending, padded with kKeyInf
+  __device__ void finish() {
+    compact();
+    const int n = meta[0] < k ? meta[0] : k;
+    const int S = next_pow2(k);  // S <= cap because cap >= k + batch*THREADS and cap is a power of two
+    for (int i = n + threadIdx.x; i < S; i += THREADS) keys[i] = kKeyInf;
+    __syncthreads();
     for (int k2 = 2; k2 <= S; k2 <<= 1) {
       for (int j = k2 >> 1; j > 0; j >>= 1) {
         for (int t = threadIdx.x; t < (S >> 1); t += THREADS) {
-          int i = 2 * t - (t & (j - 1));  // index with bit j cleared
-          int l = i | j;
-          bool up = (i & k2) == 0;
-          uint64_t a = keys[i], b = keys[l];
+          const int i = 2 * t - (t & (j - 1));
+          const int l = i | j;
+          const bool up = (i & k2) == 0;
+          const uint64_t a = keys[i], b = keys[l];
           if ((a > b) == up) {
             keys[i] = b;
             keys[l] = a;
@@ -58,36 +172,6 @@ struct BlockTopK {
         }
         __syncthreads();
       }
-    }
-  }
-
-  __device__ void flush() {
-    sort_all();
-    for (int i = k + threadIdx.x; i < S; i += THREADS) keys[i] = kKeyInf;
-    if (threadIdx.x == 0) *cnt = 0;
-    __syncthreads();
-  }
-
-  // Collective: every thread of the block calls this the same number of times; at most one candidate per call.
-  __device__ __forceinline__ void add(bool valid, uint64_t key) {
-    if (valid && key < keys[k - 1]) {
-      int slot = atomicAdd(cnt, 1);
-      keys[k + slot] = key;  // slot < PB is guaranteed by the flush rule below
-    }
-    __syncthreads();
-    int c = *cnt;
-    __syncthreads();
-    if (c > PB - THREADS) flush();
-  }
-
-  // Collective: after this, keys[0..k) hold the k smallest keys ascending (kKeyInf padded).
-  __device__ void finish() {
-    __syncthreads();
-    if (*cnt > 0) {
-      __syncthreads();
-      flush();
-    } else {
-      __syncthreads();
     }
   }
 };
