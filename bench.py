@@ -474,7 +474,7 @@ def run_b200(a):
         names = ["l2_distances", "select_rows", "select_lines", "scan_topk"]
         acc = dict.fromkeys(names, 0.0)
         cnt = dict.fromkeys(names, 0)
-        tile = 1024
+        tile = 4096
         Dbuf = torch.empty((tile, C), dtype=torch.float32, device=dev)
         ed2f = ed2.reshape(-1)
 

@@ -225,7 +225,7 @@ l2_argmin_kernel(const float* __restrict__ x, int64_t n, int d, const float* __r
 
 // ------------------------------------------------------------------------------------------------- row select (a15)
 constexpr int SEL_THREADS = 256;
-constexpr int SEL_BATCH = 4;
+constexpr int SEL_BATCH = 8;
 __global__ void __launch_bounds__(SEL_THREADS)
 select_rows_kernel(const float* __restrict__ D, int cols, int64_t ldD, int k, int cap, const float* __restrict__ row_add,
                    float* __restrict__ out_val, int* __restrict__ out_idx) {
@@ -245,7 +245,7 @@ select_rows_kernel(const float* __restrict__ D, int cols, int64_t ldD, int k, in
 #pragma unroll
     for (int b = 0; b < SEL_BATCH; b++) {
       const int j = base + b * SEL_THREADS + threadIdx.x;
-      any |= sel.offer(j < cols, make_key(v[b], (uint32_t)j));
+      any |= sel.offer_f(j < cols, v[b], (uint32_t)j);
     }
     sel.end_batch(any);
   }

@@ -134,8 +134,10 @@ constexpr uint32_t kIdesc = (1u << 4) | ((uint32_t)(TILE_ROWS >> 3) << 17) | ((u
 // ------------------------------------------------------------------------------------------------------ pack kernel
 // fp32 [rows][d] -> packed fp16 hi/lo tiles, values pre-multiplied by `scale` (a power of two: exact).
 // Rows in [rows, rows_padded) are written as zeros.
+// lo_flags (nullable): lo_flags[row / 256] is set when any lo part of that 256-row block is non-zero; blocks whose rows
+// are exactly representable in fp16 (e.g. uint8-valued SIFT data) let the MMA issuer skip the x_lo.c_hi pass.
 __global__ void pack_rows_kernel(const float* __restrict__ x, int64_t rows, int64_t rows_padded, int d, float scale,
-                                 uint8_t* __restrict__ out) {
+                                 uint8_t* __restrict__ out, int* __restrict__ lo_flags) {
   const int g8 = d / 8;  // 8-element groups per row
   const int nkb = d / KB;
   int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -154,12 +156,19 @@ __global__ void pack_rows_kernel(const float* __restrict__ x, int64_t rows, int6
     }
     __align__(16) __half hi[8];
     __align__(16) __half lo[8];
+    bool lo_nz = false;
 #pragma unroll
     for (int t = 0; t < 8; t++) {
       const float s = v[t] * scale;
       const __half h = __float2half_rn(s);
       hi[t] = h;
-      lo[t] = __float2half_rn(s - __half2float(h));
+      const float rem = s - __half2float(h);
+      lo[t] = __float2half_rn(rem);
+      lo_nz |= rem != 0.f;
+    }
+    if (lo_flags && lo_nz) {
+      int* f = lo_flags + row / (TILE_ROWS * ROW_TILES);
+      if (*reinterpret_cast<volatile int*>(f) == 0) atomicOr(f, 1);
     }
     const int64_t tile = row / TILE_ROWS;
     const int rr = (int)(row % TILE_ROWS);
@@ -181,6 +190,7 @@ struct Params {
   const uint8_t* a_pack;   // packed vectors: row tiles of this launch
   const uint8_t* b_pack;   // packed centroids
   const float* cnorm_pad;  // [Cpad], +inf beyond C
+  const int* a_lo_flags;   // [n_row_blocks]: 0 = the lo part of this vector block is identically zero
   int64_t n;               // valid rows
   int C, d;
   int n_row_blocks;        // ceil(n / 256)
@@ -279,6 +289,7 @@ __global__ void __launch_bounds__(THREADS, 1) l2_tc_kernel(const Params p) {
       const int t1 = min(p.n_ctiles, t0 + p.tiles_per_split);
       mbar_wait(a_full, item_phase);
       tc_fence_after();
+      const int npass = (p.a_lo_flags[item / p.csplit] != 0) ? 3 : 2;  // warp-uniform
       for (int t = t0; t < t1; t++) {
         mbar_wait(&t_empty[acc_buf], acc_phase ^ 1);
         tc_fence_after();
@@ -295,6 +306,7 @@ __global__ void __launch_bounds__(THREADS, 1) l2_tc_kernel(const Params p) {
               const uint32_t tacc = tmem_base + (acc_buf * ROW_TILES + r) * TILE_ROWS;
 #pragma unroll
               for (int pass = 0; pass < 3; pass++) {
+                if (pass >= npass) break;
                 const uint32_t a0 = pass == 2 ? a_lo : a_hi;  // hi.hi, hi.lo, lo.hi
                 const uint32_t b0 = pass == 1 ? b_lo : b_hi;
 #pragma unroll
@@ -499,7 +511,7 @@ int vlq_tc_pack_centroids(const float* cent, const float* cnorm, int C, int d, f
   cudaStream_t st = as_stream(stream);
   const int64_t total = Cpad * (d / 8);
   VLQ_LAUNCH(tc::pack_rows_kernel, (unsigned)std::min<int64_t>(div_up(total, 256), 148 * 16), 256, 0, st, cent,
-             (int64_t)C, Cpad, d, scale, static_cast<uint8_t*>(cent_pack));
+             (int64_t)C, Cpad, d, scale, static_cast<uint8_t*>(cent_pack), (int*)nullptr);
   float* cn_pad = reinterpret_cast<float*>(static_cast<uint8_t*>(cent_pack) + tc::align256((size_t)tc::packed_bytes(Cpad, d)));
   VLQ_LAUNCH(tc::pad_cnorm_kernel, (unsigned)div_up(Cpad, 256), 256, 0, st, cnorm, C, (int)Cpad, cn_pad);
   return last_error();
@@ -510,7 +522,7 @@ size_t vlq_l2_tc_workspace_bytes(int64_t n, int d, int C) {
   const int64_t rows = n < tc::CHUNK_ROWS ? n : tc::CHUNK_ROWS;
   const int64_t rpad = div_up(rows, tc::TILE_ROWS * tc::ROW_TILES) * tc::TILE_ROWS * tc::ROW_TILES;
   return tc::align256((size_t)tc::packed_bytes(rpad, d)) + tc::align256(sizeof(unsigned long long) * rows) +
-         tc::align256(sizeof(float) * rows) + 256;
+         tc::align256(sizeof(float) * rows) + tc::align256(sizeof(int) * (rpad / (tc::TILE_ROWS * tc::ROW_TILES))) + 256;
 }
 
 static int tc_run(int mode, const float* x, int64_t n, int d, const void* cent_pack, float scale, int C, int add_xnorm,
@@ -535,17 +547,21 @@ static int tc_run(int mode, const float* x, int64_t n, int d, const void* cent_p
   uint8_t* a_pack = ws;
   unsigned long long* keys = reinterpret_cast<unsigned long long*>(ws + tc::align256((size_t)tc::packed_bytes(cpad_rows, d)));
   float* xnorm = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(keys) + tc::align256(sizeof(unsigned long long) * chunk));
+  int* lo_flags = reinterpret_cast<int*>(reinterpret_cast<uint8_t*>(xnorm) + tc::align256(sizeof(float) * chunk));
   const int sms = tc::num_sms();
   for (int64_t r0 = 0; r0 < n; r0 += chunk) {
     const int64_t rows = (n - r0) < chunk ? (n - r0) : chunk;
     const int64_t rpad = div_up(rows, tc::TILE_ROWS * tc::ROW_TILES) * tc::TILE_ROWS * tc::ROW_TILES;
     const int64_t total = rpad * (d / 8);
+    const int nblocks = (int)(rpad / (tc::TILE_ROWS * tc::ROW_TILES));
+    VLQ_CUDA_TRY(cudaMemsetAsync(lo_flags, 0, sizeof(int) * nblocks, st));
     VLQ_LAUNCH(tc::pack_rows_kernel, (unsigned)std::min<int64_t>(div_up(total, 256), 148 * 16), 256, 0, st,
-               x + r0 * d, rows, rpad, d, scale, a_pack);
+               x + r0 * d, rows, rpad, d, scale, a_pack, lo_flags);
     tc::Params p{};
     p.a_pack = a_pack;
     p.b_pack = b_pack;
     p.cnorm_pad = cn_pad;
+    p.a_lo_flags = lo_flags;
     p.n = rows;
     p.C = C;
     p.d = d;

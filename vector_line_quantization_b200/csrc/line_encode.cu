@@ -16,7 +16,7 @@
 
 namespace vlq {
 
-constexpr int LE_WARPS = 16;
+constexpr int LE_WARPS = 24;
 constexpr int LE_THREADS = LE_WARPS * kWarp;
 constexpr int LE_MAX_E = 64;
 
@@ -41,6 +41,21 @@ struct LineEncodeArgs {
   float* out_kappa;
   float* out_residual;
 };
+
+// Reduce 32 per-lane partial sums v[0..32) across the warp so that lane l ends with the total of v[l] (in v[0]):
+// 31 shuffles instead of 32 x 5, and the additions pair up exactly like the xor-butterfly of warp_sum (same bits).
+__device__ __forceinline__ void warp_transpose_reduce32(float (&v)[32], int lane) {
+#pragma unroll
+  for (int o = 16; o >= 1; o >>= 1) {
+    const bool up = (lane & o) != 0;
+#pragma unroll
+    for (int j = 0; j < o; j++) {
+      const float send = up ? v[j] : v[j + o];
+      const float keep = up ? v[j + o] : v[j];
+      v[j] = keep + __shfl_xor_sync(kFull, send, o);
+    }
+  }
+}
 
 template <int NPL>
 __global__ void __launch_bounds__(LE_THREADS, 1) line_encode_kernel(LineEncodeArgs a) {
@@ -108,19 +123,25 @@ __global__ void __launch_bounds__(LE_THREADS, 1) line_encode_kernel(LineEncodeAr
         my_c2[h] = a.edge_d2[(int64_t)A * E + e];
       }
     }
-    for (int e = 0; e < E; e++) {
-      const int s = __shfl_sync(kFull, my_s[e >> 5], e & 31);
-      const float* cs = a.cent + (int64_t)s * d;
-      float ap = 0.f;
+    for (int g = 0; g * 32 < E; g++) {  // 32 edges at a time: lane-private partial sums, one transposed reduction
+      float part[32];
 #pragma unroll
-      for (int t = 0; t < NPL; t++) {
-        int j = lane + 32 * t;
-        float cv = j < d ? cs[j] : 0.f;
-        float df = xv[t] - cv;
-        ap = fmaf(df, df, ap);
+      for (int ee = 0; ee < 32; ee++) {
+        const int e = g * 32 + ee;
+        const int s = __shfl_sync(kFull, my_s[g], ee);  // edges beyond E read centroid 0 (result unused)
+        const float* cs = a.cent + (int64_t)(e < E ? s : 0) * d;
+        float ap = 0.f;
+#pragma unroll
+        for (int t = 0; t < NPL; t++) {
+          int j = lane + 32 * t;
+          float cv = j < d ? cs[j] : 0.f;
+          float df = xv[t] - cv;
+          ap = fmaf(df, df, ap);
+        }
+        part[ee] = ap;
       }
-      ap = warp_sum(ap);
-      if (lane == (e & 31)) my_a[e >> 5] = ap;
+      warp_transpose_reduce32(part, lane);
+      my_a[g] = part[0];
     }
     uint64_t kv = kKeyInf, ka = kKeyInf;
     float my_lam[2];
@@ -178,26 +199,38 @@ __global__ void __launch_bounds__(LE_THREADS, 1) line_encode_kernel(LineEncodeAr
     }
     __syncwarp();
 
-    // ---- PQ encode
+    // ---- PQ encode: lane owns codewords lane + 32c; distances accumulate over t in order (ProductQuantizer.cpp:311-336)
     for (int m = 0; m < M; m++) {
       uint64_t kc = kKeyInf;
-      for (int j = lane; j < ksub; j += kWarp) {
-        float dis = 0.f;
-        if (a.pq_in_smem) {
-          const float* pp = pqs + (size_t)m * dsub * ksub + j;
-          for (int t = 0; t < dsub; t++) {
-            float df = r_s[m * dsub + t] - pp[t * ksub];
-            dis = __fadd_rn(dis, __fmul_rn(df, df));
-          }
-        } else {
-          const float* pp = a.pq + ((size_t)m * ksub + j) * dsub;
-          for (int t = 0; t < dsub; t++) {
-            float df = r_s[m * dsub + t] - pp[t];
-            dis = __fadd_rn(dis, __fmul_rn(df, df));
+      if (a.pq_in_smem && ksub == 256) {
+        float dis[8];
+#pragma unroll
+        for (int c = 0; c < 8; c++) dis[c] = 0.f;
+        const float* pp = pqs + (size_t)m * dsub * ksub + lane;
+        for (int t = 0; t < dsub; t++) {
+          const float rt = r_s[m * dsub + t];
+#pragma unroll
+          for (int c = 0; c < 8; c++) {
+            const float df = rt - pp[t * ksub + 32 * c];
+            dis[c] = fmaf(df, df, dis[c]);
           }
         }
-        uint64_t key = make_key(dis, (uint32_t)j);
-        kc = key < kc ? key : kc;
+#pragma unroll
+        for (int c = 0; c < 8; c++) {
+          const uint64_t key = make_key(dis[c], (uint32_t)(lane + 32 * c));
+          kc = key < kc ? key : kc;
+        }
+      } else {
+        for (int j = lane; j < ksub; j += kWarp) {
+          const float* pp = a.pq + ((size_t)m * ksub + j) * dsub;
+          float dis = 0.f;
+          for (int t = 0; t < dsub; t++) {
+            const float df = r_s[m * dsub + t] - pp[t];
+            dis = fmaf(df, df, dis);
+          }
+          const uint64_t key = make_key(dis, (uint32_t)j);
+          kc = key < kc ? key : kc;
+        }
       }
       kc = warp_min_u64(kc);
       if (lane == 0) code_s[m] = (uint8_t)key_payload(kc);

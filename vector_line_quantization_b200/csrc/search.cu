@@ -53,7 +53,7 @@ select_lines_kernel(const float* __restrict__ D, int64_t ldD, const int* __restr
           score = (v > 0.f) ? b2 : __fsub_rn(b2, __fdiv_rn(__fmul_rn(__fmul_rn(0.25f, v), v), c2));
         }
       }
-      any |= sel.offer(valid, make_key(score, (uint32_t)i));
+      any |= sel.offer_f(valid, score, (uint32_t)i);
     }
     sel.end_batch(any);
   }
@@ -220,7 +220,7 @@ __global__ void __launch_bounds__(Q_THREADS) scan_topk_kernel(ScanArgs a) {
         const float acc = adc_sum<M_T>(a.codes + ent * M, T3, M, ksub);
         dist = (a.kappa[ent] + acc) + base_d;
       }
-      any |= sel.offer(valid, make_key(dist, (uint32_t)pos));
+      any |= sel.offer_f(valid, dist, (uint32_t)pos);
     }
     sel.end_batch(any);
   }
@@ -275,7 +275,7 @@ merge_topk_kernel(const float* __restrict__ D, const int64_t* __restrict__ I, in
         v = D[((int64_t)rank * nq + q) * k + pos];
         valid = I[((int64_t)rank * nq + q) * k + pos] >= 0;  // padding entries never win
       }
-      any |= sel.offer(valid, make_key(v, (uint32_t)i));
+      any |= sel.offer_f(valid, v, (uint32_t)i);
     }
     sel.end_batch(any);
   }

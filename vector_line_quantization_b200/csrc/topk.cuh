@@ -42,6 +42,7 @@ struct BlockSelect {
   int cap, k, batch;
   int fill;        // conservative fill level, identical in every thread
   uint64_t thr;    // only keys < thr can still enter the result
+  float thr_f;     // float view of thr: one FSETP rejects almost every candidate before a key is even built
 
   // smem: select_smem_bytes(cap) bytes, 8-byte aligned.  cap >= k + batch*THREADS (see select_capacity).
   __device__ void init(void* smem, int k_, int cap_, int batch_) {
@@ -53,6 +54,7 @@ struct BlockSelect {
     meta = hist + 256;
     fill = 0;
     thr = kKeyInf;
+    thr_f = __int_as_float(0x7f800000);
     if (threadIdx.x == 0) meta[0] = 0;
     __syncthreads();
   }
@@ -63,6 +65,18 @@ struct BlockSelect {
       const int slot = atomicAdd(&meta[0], 1);
       keys[slot] = key;
       return true;
+    }
+    return false;
+  }
+  // same, from the raw value: the cheap float compare comes first (NaN values never enter)
+  __device__ __forceinline__ bool offer_f(bool valid, float v, uint32_t payload) {
+    if (valid && v <= thr_f) {
+      const uint64_t key = make_key(v, payload);
+      if (key < thr) {
+        const int slot = atomicAdd(&meta[0], 1);
+        keys[slot] = key;
+        return true;
+      }
     }
     return false;
   }
@@ -147,6 +161,7 @@ struct BlockSelect {
       }
     }
     thr = kth;
+    thr_f = key_val(kth);
     fill = k;
     __syncthreads();
   }

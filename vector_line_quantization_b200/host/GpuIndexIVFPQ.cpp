@@ -270,7 +270,7 @@ void GpuIndexIVFPQ::search(Index::idx_t n, const float* x, Index::idx_t k, float
   const int W = w1_;
   const int M = subQuantizers_;
   const Index::idx_t page = 32768;  // gpu/GpuIndex.cu:109-147
-  const Index::idx_t tile = std::max<Index::idx_t>(64, std::min<Index::idx_t>(1024, ((Index::idx_t)1 << 26) / nlist_));
+  const Index::idx_t tile = std::max<Index::idx_t>(64, std::min<Index::idx_t>(4096, ((Index::idx_t)1 << 28) / nlist_));
   DeviceBuffer& xin = qIn_;
   DeviceBuffer& outD = outD_;
   DeviceBuffer& outI = outI_;

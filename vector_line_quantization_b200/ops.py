@@ -209,7 +209,7 @@ def km_update(x, assign, k):
     return cent, counts
 
 
-def search(q, cent, cnorm, edge, edge_d2, lambda_cb, pq, lists, P, W, k, cap=1024, tile=1024, pack=None):
+def search(q, cent, cnorm, edge, edge_d2, lambda_cb, pq, lists, P, W, k, cap=1024, tile=4096, pack=None):
     """Full query path on resident tensors (a11-a15), tiled over queries so the coarse matrix stays L2-sized.
     pack (a CentPack) routes the coarse distances through the tcgen05 kernel."""
     nq = q.shape[0]
