@@ -471,11 +471,12 @@ def run_b200(a):
 
     # ---- per-stage device times of one step (CUDA events on the launching stream) -> roofline of the dominant kernel
     def stage_times():
-        names = ["l2_distances", "select_rows", "select_lines", "scan_topk"]
+        names = ["l2_distances", "select_rows", "select_lines", "coarse_select_lines", "scan_topk"]
         acc = dict.fromkeys(names, 0.0)
         cnt = dict.fromkeys(names, 0)
         tile = 4096
         Dbuf = torch.empty((tile, C), dtype=torch.float32, device=dev)
+        bbuf = torch.empty((tile, ops.num_buckets(C)), dtype=torch.float32, device=dev)
         ed2f = ed2.reshape(-1)
 
         def t(name, fn):
@@ -490,11 +491,13 @@ def run_b200(a):
         for s in range(0, nq, tile):
             qt = xq[s:s + tile]
             if use_tc:
-                Dm = t("l2_distances", lambda: ops.l2_distances_tc(qt, pack, out=Dbuf[: qt.shape[0]]))
+                bm = bbuf[: qt.shape[0]]
+                Dm = t("l2_distances", lambda: ops.l2_distances_tc(qt, pack, out=Dbuf[: qt.shape[0]], bucket_min=bm))
+                lst, t1, t6 = t("coarse_select_lines", lambda: ops.coarse_select_lines(Dm, bm, C, P, edge, ed2, W))
             else:
                 Dm = t("l2_distances", lambda: ops.l2_distances(qt, cent, cn, out=Dbuf[: qt.shape[0]]))
-            _, cid = t("select_rows", lambda: ops.select_rows(Dm, P))
-            lst, t1, t6 = t("select_lines", lambda: ops.select_lines(Dm, cid, edge, ed2, W))
+                _, cid = t("select_rows", lambda: ops.select_rows(Dm, P))
+                lst, t1, t6 = t("select_lines", lambda: ops.select_lines(Dm, cid, edge, ed2, W))
             t("scan_topk", lambda: ops.scan_topk(qt, pq, lcb, lst, t1, t6, ed2f, lists, k))
         torch.cuda.synchronize()
         for name, e0, e1 in pending:
@@ -526,7 +529,7 @@ def run_b200(a):
     if dominant == "scan_topk":
         alg = rows_per_launch * (scanned_per_q * (M + 1) + k * 8)
         roof = {"bound": "hbm", "achieved": alg / (per_launch_ms * 1e-3) / 1e9, "peak": hbm_peak, "unit": "GB/s"}
-    elif dominant == "select_rows":
+    elif dominant in ("select_rows", "select_lines", "coarse_select_lines"):
         alg = rows_per_launch * C * 4.0
         roof = {"bound": "hbm", "achieved": alg / (per_launch_ms * 1e-3) / 1e9, "peak": hbm_peak, "unit": "GB/s"}
     else:

@@ -70,8 +70,11 @@ int vlq_tc_pack_centroids(const float* cent, const float* cnorm, int C, int d, f
 size_t vlq_l2_tc_workspace_bytes(int64_t n, int d, int C);
 int vlq_l2_assign_tc(const float* x, int64_t n, int d, const void* cent_pack, float scale, int C, int add_xnorm,
                      int* out_ids, float* out_dist, void* workspace, size_t workspace_bytes, vlq_stream_t stream);
+/* bucket_min (nullable): [n][vlq_tc_num_buckets(C)], the minimum of every 32-column bucket of D, produced by the GEMM
+ * epilogue for free; vlq_coarse_select_lines uses it to find the top-P centroids from 2*P*32 bytes instead of 4*C. */
+int vlq_tc_num_buckets(int C);
 int vlq_l2_distances_tc(const float* x, int64_t n, int d, const void* cent_pack, float scale, int C, float* D,
-                        int64_t ldD, void* workspace, size_t workspace_bytes, vlq_stream_t stream);
+                        int64_t ldD, float* bucket_min, void* workspace, size_t workspace_bytes, vlq_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------------------------------
  * a11 coarse distance matrix for a query tile, D[i][j] = ||c_j||^2 - 2 x_i.c_j  (NO ||x||^2, Distance.cu:287-290).
@@ -156,6 +159,14 @@ int vlq_recompute_kappa(int64_t n, int64_t nlists, const int64_t* offsets, const
 int vlq_select_lines(const float* D, int64_t nq, int64_t ldD, const int* coarse_ids, int P, const int* edge,
                      const float* edge_d2, int E, int W, int* out_list, float* out_term1, float* out_term6,
                      vlq_stream_t stream);
+
+/* a11 + a12 fused (tensor-core query path): top-P centroids found through the bucket minima of
+ *     vlq_l2_distances_tc, then the line selection of vlq_select_lines, in one kernel.  Same outputs as
+ *     vlq_select_rows(k=P) + vlq_select_lines; out_coarse (nullable) [nq][P] receives the top-P centroid ids.
+ *     replaces l2SelectMinK + sumAlongRowsWithOrder2, gpu/impl/L2Select.cu:124-165, gpu/impl/BroadcastSum.cu:477-560. */
+int vlq_coarse_select_lines(const float* D, int64_t nq, int64_t ldD, const float* bucket_min, int nb, int C, int P,
+                            const int* edge, const float* edge_d2, int E, int W, int* out_coarse, int* out_list,
+                            float* out_term1, float* out_term6, vlq_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------------------------------
  * a13-a15 ADC scan of the selected lists fused with exact top-k.

@@ -75,3 +75,32 @@ def test_tc_rejects_unsupported_shapes(ops, cuda):
         ops.CentPack(torch.randn(100, 20, device=cuda))
     with pytest.raises(ValueError):
         ops.CentPack(torch.randn(100, 256, device=cuda))
+
+
+@pytest.mark.parametrize("nq,C,d,P,W,E", [(100, 4096, 128, 64, 256, 32), (33, 1000, 96, 16, 100, 8), (10, 130, 64, 200, 1024, 16),
+                                          (7, 65536, 128, 64, 1024, 32)])
+def test_fused_coarse_select_equals_two_step(ops, cuda, nq, C, d, P, W, E):
+    """bucket-minimum route == select_rows(k=P) + select_lines on the same distance matrix, bit for bit"""
+    import torch
+
+    x, c = _data(nq, C, d, 11, "sift")
+    xt, ct = torch.from_numpy(x).to(cuda), torch.from_numpy(c).to(cuda)
+    pack = ops.CentPack(ct)
+    bm = torch.empty((nq, ops.num_buckets(C)), dtype=torch.float32, device=cuda)
+    D = ops.l2_distances_tc(xt, pack, bucket_min=bm)
+    # bucket minima really are the minima of the 32-column buckets
+    Dp = torch.full((nq, ops.num_buckets(C) * 32), float("inf"), device=cuda)
+    Dp[:, :C] = D
+    assert torch.equal(bm, Dp.view(nq, -1, 32).min(dim=2).values)
+    g = torch.Generator(device="cpu").manual_seed(5)
+    edge = torch.stack([torch.randperm(C, generator=g)[:E] for _ in range(C)]).to(torch.int32).to(cuda) if C <= 4096 else \
+        torch.randint(0, C, (C, E), generator=g, dtype=torch.int32).to(cuda)
+    ed2 = (torch.rand((C, E), generator=g) * 1000 + 1).to(cuda)
+    Pk = min(P, C)
+    _, cid = ops.select_rows(D, Pk)
+    if Pk < P:
+        cid = torch.cat([cid, torch.full((nq, P - Pk), -1, dtype=torch.int32, device=cuda)], dim=1).contiguous()
+    l0, a0, b0 = ops.select_lines(D, cid, edge, ed2, W)
+    l1, a1, b1, cid1 = ops.coarse_select_lines(D, bm, C, P, edge, ed2, W, want_coarse=True)
+    assert torch.equal(cid1, cid)
+    assert torch.equal(l1, l0) and torch.equal(a1, a0) and torch.equal(b1, b0)

@@ -27,7 +27,8 @@ SIGNATURES = {
     "vlq_tc_pack_centroids": (_i, [_p, _p, _i, _i, _f, _p, _p]),
     "vlq_l2_tc_workspace_bytes": (_z, [_l, _i, _i]),
     "vlq_l2_assign_tc": (_i, [_p, _l, _i, _p, _f, _i, _i, _p, _p, _p, _z, _p]),
-    "vlq_l2_distances_tc": (_i, [_p, _l, _i, _p, _f, _i, _p, _l, _p, _z, _p]),
+    "vlq_tc_num_buckets": (_i, [_i]),
+    "vlq_l2_distances_tc": (_i, [_p, _l, _i, _p, _f, _i, _p, _l, _p, _p, _z, _p]),
     "vlq_l2_distances": (_i, [_p, _l, _i, _p, _p, _i, _p, _l, _p]),
     "vlq_select_rows": (_i, [_p, _l, _i, _l, _i, _p, _p, _p, _p]),
     "vlq_knn_graph_workspace_bytes": (_z, [_i, _i]),
@@ -39,6 +40,7 @@ SIGNATURES = {
     "vlq_build_lists": (_i, [_l, _i, _l, _p, _p, _p, _p, _p, _l, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _z, _p]),
     "vlq_recompute_kappa": (_i, [_l, _l, _p, _p, _p, _p, _i, _p, _i, _p, _p, _i, _p, _p]),
     "vlq_select_lines": (_i, [_p, _l, _l, _p, _i, _p, _p, _i, _i, _p, _p, _p, _p]),
+    "vlq_coarse_select_lines": (_i, [_p, _l, _l, _p, _i, _i, _i, _p, _p, _i, _i, _p, _p, _p, _p, _p]),
     "vlq_scan_topk": (_i, [_p, _l, _i, _p, _i, _p, _i, _p, _p, _p, _p, _i, _p, _p, _p, _p, _p, _i, _i, _p, _p, _p]),
     "vlq_merge_topk": (_i, [_p, _p, _i, _l, _i, _p, _p, _p]),
     "vlq_km_update_workspace_bytes": (_z, [_l, _i]),

@@ -34,11 +34,14 @@ namespace tc {
 constexpr int TILE_ROWS = 128;               // UMMA M and N
 constexpr int KB = 32;                       // K elements per pipeline stage
 constexpr int TILE_KB_BYTES = TILE_ROWS * KB * 2;  // 8 KiB: one (tile, part, kb) block
-constexpr int STAGES = 4;
+constexpr int STAGES = 3;
+constexpr int STG_ROW_BYTES = 144;            // 32 floats + 16 B pad: conflict-free 128-bit row writes and reads
+constexpr int STG_WARP_BYTES = 32 * STG_ROW_BYTES;  // per-epilogue-warp transpose buffer (MODE 1)
 constexpr int ROW_TILES = 2;                 // 256 rows per CTA
 constexpr int ACC_BUFS = 2;
 constexpr int TMEM_COLS = ROW_TILES * ACC_BUFS * TILE_ROWS;  // 512
-constexpr int THREADS = 192;
+constexpr int EPI_WARPS = 8;                 // 2 warps per TMEM lane group: each takes one half of the 128 columns
+constexpr int THREADS = 64 + EPI_WARPS * 32; // producer warp + MMA warp + epilogue warps
 constexpr int MAX_D = 128;
 
 __host__ __device__ inline int64_t packed_bytes(int64_t rows, int d) {
@@ -201,6 +204,7 @@ struct Params {
   unsigned long long* keys;  // mode 0: [n] packed (ordered distance << 32 | centroid)
   float* D;                // mode 1: [n][ldD]
   int64_t ldD;
+  float* bmin;             // mode 1 (nullable): [n][n_ctiles*4] minimum of every 32-column bucket of D
 };
 
 template <int MODE>  // 0 = fused arg-min, 1 = store the distance tile
@@ -211,7 +215,8 @@ __global__ void __launch_bounds__(THREADS, 1) l2_tc_kernel(const Params p) {
   uint8_t* a_s = smem;                                // [ROW_TILES][hi,lo][nkb][8 KiB]
   uint8_t* b_s = a_s + ROW_TILES * a_tile_bytes;      // [STAGES][hi,lo][8 KiB]
   float* cn_s = reinterpret_cast<float*>(b_s + STAGES * 2 * TILE_KB_BYTES);  // [ACC_BUFS][128]
-  uint64_t* bars = reinterpret_cast<uint64_t*>(cn_s + ACC_BUFS * TILE_ROWS);
+  uint8_t* stg_s = reinterpret_cast<uint8_t*>(cn_s + ACC_BUFS * TILE_ROWS);  // [EPI_WARPS][32 rows][144 B] (MODE 1)
+  uint64_t* bars = reinterpret_cast<uint64_t*>(stg_s + (MODE == 1 ? EPI_WARPS * STG_WARP_BYTES : 0));
   uint64_t* full = bars;                 // [STAGES]
   uint64_t* empty = bars + STAGES;       // [STAGES]
   uint64_t* a_full = bars + 2 * STAGES;  // [1]
@@ -232,7 +237,7 @@ __global__ void __launch_bounds__(THREADS, 1) l2_tc_kernel(const Params p) {
     mbar_init(a_empty, 1);
     for (int b = 0; b < ACC_BUFS; b++) {
       mbar_init(&t_full[b], 1);
-      mbar_init(&t_empty[b], 128);
+      mbar_init(&t_empty[b], EPI_WARPS * 32);
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -337,10 +342,12 @@ __global__ void __launch_bounds__(THREADS, 1) l2_tc_kernel(const Params p) {
       item_phase ^= 1;
     }
   } else {
-    // ===================================================================== epilogue (warps 2..5, 128 threads)
-    const int et = threadIdx.x - 64;                  // 0..127
+    // ===================================================================== epilogue (warps 2..9, 256 threads)
+    const int et = threadIdx.x - 64;                  // 0..255
     const int lane_grp = warp & 3;                    // TMEM lanes this warp may read: [32*lane_grp, +32)
+    const int col_half = (warp - 2) >> 2;             // which 64 of the tile's 128 columns this warp handles
     const int row_in_tile = lane_grp * 32 + lane;
+    const int nb = p.n_ctiles * 4;
     uint32_t acc_buf = 0, acc_phase = 0;
     for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
       const int rb = item / p.csplit, cs = item % p.csplit;
@@ -353,53 +360,81 @@ __global__ void __launch_bounds__(THREADS, 1) l2_tc_kernel(const Params p) {
         best[r] = __int_as_float(0x7f800000);
         bidx[r] = 0x7fffffff;
       }
+      float cn_next = (et < TILE_ROWS && t0 < t1) ? p.cnorm_pad[t0 * TILE_ROWS + et] : 0.f;
       for (int t = t0; t < t1; t++) {
         // stage ||c||^2 of this centroid tile (safe: every epilogue thread passed the previous use of this slot
-        // before arriving on t_empty two tiles ago, and the named barrier below orders the writes before the reads)
-        cn_s[acc_buf * TILE_ROWS + et] = p.cnorm_pad[t * TILE_ROWS + et];
-        asm volatile("bar.sync 1, 128;" ::: "memory");
+        // before arriving on t_empty two tiles ago, and the named barrier below orders the writes before the reads).
+        // The value was fetched one tile ahead so that its L2 latency is off the per-tile critical path.
+        if (et < TILE_ROWS) {
+          cn_s[acc_buf * TILE_ROWS + et] = cn_next;
+          if (t + 1 < t1) cn_next = p.cnorm_pad[(t + 1) * TILE_ROWS + et];
+        }
+        asm volatile("bar.sync 1, 256;" ::: "memory");
         mbar_wait(&t_full[acc_buf], acc_phase);
         tc_fence_after();
-        const float* cn = cn_s + acc_buf * TILE_ROWS;
+        const float* cn = cn_s + acc_buf * TILE_ROWS + col_half * 64;
 #pragma unroll
         for (int r = 0; r < ROW_TILES; r++) {
-          const uint32_t taddr = tmem_base + ((uint32_t)(lane_grp * 32) << 16) + (acc_buf * ROW_TILES + r) * TILE_ROWS;
+          const uint32_t taddr = tmem_base + ((uint32_t)(lane_grp * 32) << 16) +
+                                 (acc_buf * ROW_TILES + r) * TILE_ROWS + col_half * 64;
           const int64_t row = ((int64_t)rb * ROW_TILES + r) * TILE_ROWS + row_in_tile;
-#pragma unroll 1
-          for (int c = 0; c < TILE_ROWS / 32; c++) {
-            uint32_t v[32];
-            tmem_ld32(taddr + c * 32, v);
-            tmem_ld_wait();
+          uint32_t v[2][32];
+          tmem_ld32(taddr, v[0]);  // both 32-column chunks in flight before the first use
+          tmem_ld32(taddr + 32, v[1]);
+          tmem_ld_wait();
+#pragma unroll
+          for (int c = 0; c < 2; c++) {
+            const int col0 = t * TILE_ROWS + col_half * 64 + c * 32;
             if (MODE == 0) {
 #pragma unroll
               for (int i = 0; i < 32; i++) {
-                const float dv = fmaf(__uint_as_float(v[i]), p.m2s, cn[c * 32 + i]);
+                const float dv = fmaf(__uint_as_float(v[c][i]), p.m2s, cn[c * 32 + i]);
                 if (dv < best[r]) {
                   best[r] = dv;
-                  bidx[r] = t * TILE_ROWS + c * 32 + i;
+                  bidx[r] = col0 + i;
                 }
               }
             } else {
-              if (row < p.n) {
-                float* out = p.D + row * p.ldD + (int64_t)t * TILE_ROWS + c * 32;
-                const int col0 = t * TILE_ROWS + c * 32;
+              // D tile: registers -> per-warp shared-memory transpose -> coalesced 128-byte row segments
+              // (a thread owns one ROW of the accumulator; storing straight from registers would make every warp
+              //  store instruction touch 32 different lines with 16 bytes each: measured 1.9 TB/s instead of ~6)
+              float mn = __int_as_float(0x7f800000);
+              uint8_t* stg = stg_s + (warp - 2) * STG_WARP_BYTES;
+              float4* srow = reinterpret_cast<float4*>(stg + lane * STG_ROW_BYTES);
 #pragma unroll
-                for (int i = 0; i < 32; i += 4) {
-                  float4 o;
-                  o.x = fmaf(__uint_as_float(v[i + 0]), p.m2s, cn[c * 32 + i + 0]);
-                  o.y = fmaf(__uint_as_float(v[i + 1]), p.m2s, cn[c * 32 + i + 1]);
-                  o.z = fmaf(__uint_as_float(v[i + 2]), p.m2s, cn[c * 32 + i + 2]);
-                  o.w = fmaf(__uint_as_float(v[i + 3]), p.m2s, cn[c * 32 + i + 3]);
-                  if (col0 + i + 3 < p.C && (p.ldD & 3) == 0) {
-                    *reinterpret_cast<float4*>(out + i) = o;
+              for (int i = 0; i < 32; i += 4) {
+                float4 o;
+                o.x = fmaf(__uint_as_float(v[c][i + 0]), p.m2s, cn[c * 32 + i + 0]);
+                o.y = fmaf(__uint_as_float(v[c][i + 1]), p.m2s, cn[c * 32 + i + 1]);
+                o.z = fmaf(__uint_as_float(v[c][i + 2]), p.m2s, cn[c * 32 + i + 2]);
+                o.w = fmaf(__uint_as_float(v[c][i + 3]), p.m2s, cn[c * 32 + i + 3]);
+                mn = fminf(fminf(mn, fminf(o.x, o.y)), fminf(o.z, o.w));
+                srow[i >> 2] = o;
+              }
+              if (row < p.n && p.bmin) p.bmin[row * nb + (col0 >> 5)] = mn;
+              __syncwarp();
+              const int cg = lane & 7;  // 8 lanes cover the 32 columns of one row, 4 rows per instruction
+              const int64_t row_base = ((int64_t)rb * ROW_TILES + r) * TILE_ROWS + lane_grp * 32;
+              const bool vec_ok = (p.ldD & 3) == 0 && col0 + cg * 4 + 3 < p.C;
+#pragma unroll
+              for (int it = 0; it < 8; it++) {
+                const int rr = it * 4 + (lane >> 3);
+                const float4 o = *reinterpret_cast<const float4*>(stg + rr * STG_ROW_BYTES + cg * 16);
+                const int64_t grow = row_base + rr;
+                if (grow < p.n) {
+                  float* out = p.D + grow * p.ldD + col0 + cg * 4;
+                  if (vec_ok) {
+                    *reinterpret_cast<float4*>(out) = o;
                   } else {
-                    if (col0 + i + 0 < p.C) out[i + 0] = o.x;
-                    if (col0 + i + 1 < p.C) out[i + 1] = o.y;
-                    if (col0 + i + 2 < p.C) out[i + 2] = o.z;
-                    if (col0 + i + 3 < p.C) out[i + 3] = o.w;
+                    const int cc = col0 + cg * 4;
+                    if (cc + 0 < p.C) out[0] = o.x;
+                    if (cc + 1 < p.C) out[1] = o.y;
+                    if (cc + 2 < p.C) out[2] = o.z;
+                    if (cc + 3 < p.C) out[3] = o.w;
                   }
                 }
               }
+              __syncwarp();
             }
           }
         }
@@ -414,11 +449,8 @@ __global__ void __launch_bounds__(THREADS, 1) l2_tc_kernel(const Params p) {
 #pragma unroll
         for (int r = 0; r < ROW_TILES; r++) {
           const int64_t row = ((int64_t)rb * ROW_TILES + r) * TILE_ROWS + row_in_tile;
-          if (row < p.n && bidx[r] != 0x7fffffff) {
-            const unsigned long long key = make_key(best[r], (uint32_t)bidx[r]);
-            if (p.csplit == 1) p.keys[row] = key;
-            else atomicMin(&p.keys[row], key);
-          }
+          if (row < p.n && bidx[r] != 0x7fffffff)  // two column halves (and csplit sweeps) combine through the key
+            atomicMin(&p.keys[row], make_key(best[r], (uint32_t)bidx[r]));
         }
       }
     }
@@ -457,7 +489,7 @@ __global__ void row_norms_f32_kernel(const float* __restrict__ x, int64_t n, int
 static size_t smem_bytes(int d) {
   const int nkb = d / KB;
   return (size_t)ROW_TILES * 2 * nkb * TILE_KB_BYTES + (size_t)STAGES * 2 * TILE_KB_BYTES +
-         ACC_BUFS * TILE_ROWS * sizeof(float) + 16 * sizeof(uint64_t) + 16;
+         ACC_BUFS * TILE_ROWS * sizeof(float) + (size_t)EPI_WARPS * STG_WARP_BYTES + 16 * sizeof(uint64_t) + 16;
 }
 
 static inline size_t align256(size_t v) { return (v + 255) & ~size_t(255); }
@@ -526,8 +558,8 @@ size_t vlq_l2_tc_workspace_bytes(int64_t n, int d, int C) {
 }
 
 static int tc_run(int mode, const float* x, int64_t n, int d, const void* cent_pack, float scale, int C, int add_xnorm,
-                  int* out_ids, float* out_dist, float* D, int64_t ldD, void* workspace, size_t workspace_bytes,
-                  vlq_stream_t stream) {
+                  int* out_ids, float* out_dist, float* D, int64_t ldD, float* bmin, void* workspace,
+                  size_t workspace_bytes, vlq_stream_t stream) {
   if (!tc::supported(d, C) || !(scale > 0.f)) return VLQ_EUNSUPPORTED;
   if (n < 0) return VLQ_EINVAL;
   if (n == 0) return VLQ_OK;
@@ -580,6 +612,7 @@ static int tc_run(int mode, const float* x, int64_t n, int d, const void* cent_p
     p.keys = keys;
     p.D = mode == 1 ? D + r0 * ldD : nullptr;
     p.ldD = ldD;
+    p.bmin = (mode == 1 && bmin) ? bmin + r0 * (int64_t)(Cpad / 32) : nullptr;
     int rc;
     if (mode == 0) {
       VLQ_CUDA_TRY(cudaMemsetAsync(keys, 0xff, sizeof(unsigned long long) * rows, st));
@@ -602,13 +635,16 @@ static int tc_run(int mode, const float* x, int64_t n, int d, const void* cent_p
 
 int vlq_l2_assign_tc(const float* x, int64_t n, int d, const void* cent_pack, float scale, int C, int add_xnorm,
                      int* out_ids, float* out_dist, void* workspace, size_t workspace_bytes, vlq_stream_t stream) {
-  return tc_run(0, x, n, d, cent_pack, scale, C, add_xnorm, out_ids, out_dist, nullptr, 0, workspace, workspace_bytes,
-                stream);
+  return tc_run(0, x, n, d, cent_pack, scale, C, add_xnorm, out_ids, out_dist, nullptr, 0, nullptr, workspace,
+                workspace_bytes, stream);
 }
 
 int vlq_l2_distances_tc(const float* x, int64_t n, int d, const void* cent_pack, float scale, int C, float* D,
-                        int64_t ldD, void* workspace, size_t workspace_bytes, vlq_stream_t stream) {
-  return tc_run(1, x, n, d, cent_pack, scale, C, 0, nullptr, nullptr, D, ldD, workspace, workspace_bytes, stream);
+                        int64_t ldD, float* bucket_min, void* workspace, size_t workspace_bytes, vlq_stream_t stream) {
+  return tc_run(1, x, n, d, cent_pack, scale, C, 0, nullptr, nullptr, D, ldD, bucket_min, workspace, workspace_bytes,
+                stream);
 }
+
+int vlq_tc_num_buckets(int C) { return (int)(div_up(C, tc::TILE_ROWS) * tc::TILE_ROWS / 32); }
 
 }  // extern "C"

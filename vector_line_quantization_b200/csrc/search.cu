@@ -76,6 +76,126 @@ select_lines_kernel(const float* __restrict__ D, int64_t ldD, const int* __restr
   }
 }
 
+// ------------------------------------------------------------------------------------------------ fused top-P + lines
+// a11 + a12 in one CTA per query, driven by the bucket minima the GEMM epilogue emits (vlq_l2_distances_tc):
+//   1. the P buckets (32 consecutive centroids each) with the smallest minima contain every top-P centroid,
+//   2. exact top-P among those P*32 entries of D (one 128-byte line per bucket instead of the whole 4*C-byte row),
+//   3. line scoring of the P*E lines and top-W, as select_lines_kernel.
+__global__ void __launch_bounds__(Q_THREADS)
+coarse_select_lines_kernel(const float* __restrict__ D, int64_t ldD, const float* __restrict__ bmin, int nb, int C,
+                           int P, const int* __restrict__ edge, const float* __restrict__ edge_d2, int E, int W, int cap,
+                           int* __restrict__ out_coarse, int* __restrict__ out_list, float* __restrict__ out_term1,
+                           float* __restrict__ out_term6) {
+  extern __shared__ __align__(16) unsigned char smem[];
+  int* bk_s = reinterpret_cast<int*>(smem + ((select_smem_bytes(cap) + 15) & ~size_t(15)));  // [1024] bucket ids
+  int* cq_s = bk_s + VLQ_MAX_K;                                                              // [1024] top-P centroids
+  BlockSelect<Q_THREADS> sel;
+  const int64_t q = blockIdx.x;
+  const float* Dq = D + q * ldD;
+  const float* bq = bmin + q * nb;
+  // ---- 1: P smallest bucket minima
+  const int Pb = P < nb ? P : nb;
+  sel.init(smem, Pb, cap, Q_BATCH);
+  for (int base = 0; base < nb; base += Q_BATCH * Q_THREADS) {
+    float v[Q_BATCH];
+#pragma unroll
+    for (int b = 0; b < Q_BATCH; b++) {
+      const int j = base + b * Q_THREADS + threadIdx.x;
+      v[b] = j < nb ? bq[j] : 0.f;
+    }
+    bool any = false;
+#pragma unroll
+    for (int b = 0; b < Q_BATCH; b++) {
+      const int j = base + b * Q_THREADS + threadIdx.x;
+      any |= sel.offer_f(j < nb, v[b], (uint32_t)j);
+    }
+    sel.end_batch(any);
+  }
+  sel.finish();
+  for (int i = threadIdx.x; i < Pb; i += Q_THREADS) {
+    const uint64_t key = sel.keys[i];
+    bk_s[i] = key != kKeyInf ? (int)key_payload(key) : -1;
+  }
+  __syncthreads();
+  // ---- 2: exact top-P among the candidate buckets
+  const int Pk = P < C ? P : C;
+  sel.init(smem, Pk, cap, Q_BATCH);
+  const int ncand = Pb * 32;
+  for (int base = 0; base < ncand; base += Q_BATCH * Q_THREADS) {
+    float v[Q_BATCH];
+    int col[Q_BATCH];
+#pragma unroll
+    for (int b = 0; b < Q_BATCH; b++) {
+      const int i = base + b * Q_THREADS + threadIdx.x;
+      col[b] = -1;
+      v[b] = 0.f;
+      if (i < ncand) {
+        const int bk = bk_s[i >> 5];
+        const int c = bk * 32 + (i & 31);
+        if (bk >= 0 && c < C) {
+          col[b] = c;
+          v[b] = Dq[c];
+        }
+      }
+    }
+    bool any = false;
+#pragma unroll
+    for (int b = 0; b < Q_BATCH; b++) any |= sel.offer_f(col[b] >= 0, v[b], (uint32_t)col[b]);
+    sel.end_batch(any);
+  }
+  sel.finish();
+  for (int i = threadIdx.x; i < P; i += Q_THREADS) {
+    const uint64_t key = i < Pk ? sel.keys[i] : kKeyInf;
+    const int c = key != kKeyInf ? (int)key_payload(key) : -1;
+    cq_s[i] = c;
+    if (out_coarse) out_coarse[q * P + i] = c;
+  }
+  __syncthreads();
+  // ---- 3: the W best of the P*E lines (BroadcastSum.cu:505-552)
+  sel.init(smem, W, cap, Q_BATCH);
+  const int num = P * E;
+  for (int base = 0; base < num; base += Q_BATCH * Q_THREADS) {
+    bool any = false;
+#pragma unroll
+    for (int b = 0; b < Q_BATCH; b++) {
+      const int i = base + b * Q_THREADS + threadIdx.x;
+      bool valid = i < num;
+      float score = 0.f;
+      if (valid) {
+        const int c = cq_s[i / E];
+        valid = c >= 0;
+        if (valid) {
+          const int e = i % E;
+          const int s = edge[(int64_t)c * E + e];
+          const float a2 = Dq[s], b2 = Dq[c], c2 = edge_d2[(int64_t)c * E + e];
+          float v = __fsub_rn(a2, b2);
+          v = __fsub_rn(v, c2);
+          score = (v > 0.f) ? b2 : __fsub_rn(b2, __fdiv_rn(__fmul_rn(__fmul_rn(0.25f, v), v), c2));
+        }
+      }
+      any |= sel.offer_f(valid, score, (uint32_t)i);
+    }
+    sel.end_batch(any);
+  }
+  sel.finish();
+  for (int w = threadIdx.x; w < W; w += Q_THREADS) {
+    const uint64_t key = sel.keys[w];
+    int list = -1;
+    float t1 = 0.f, t6 = 0.f;
+    if (key != kKeyInf) {
+      const int i = (int)key_payload(key);
+      const int c = cq_s[i / E], e = i % E;
+      const int s = edge[(int64_t)c * E + e];
+      list = c * E + e;
+      t1 = Dq[c];
+      t6 = __fsub_rn(Dq[s], Dq[c]);
+    }
+    out_list[q * W + w] = list;
+    out_term1[q * W + w] = t1;
+    out_term6[q * W + w] = t6;
+  }
+}
+
 // ------------------------------------------------------------------------------------------------ scan + top-k
 struct ScanArgs {
   const float* q;
@@ -328,6 +448,26 @@ int vlq_select_lines(const float* D, int64_t nq, int64_t ldD, const int* coarse_
   const size_t smem = select_smem_bytes(cap);
   VLQ_LAUNCH(select_lines_kernel, (unsigned)nq, Q_THREADS, smem, as_stream(stream), D, ldD, coarse_ids, P, edge,
              edge_d2, E, W, cap, out_list, out_term1, out_term6);
+  return last_error();
+}
+
+int vlq_coarse_select_lines(const float* D, int64_t nq, int64_t ldD, const float* bucket_min, int nb, int C, int P,
+                            const int* edge, const float* edge_d2, int E, int W, int* out_coarse, int* out_list,
+                            float* out_term1, float* out_term6, vlq_stream_t stream) {
+  if (nq < 0 || P <= 0 || P > VLQ_MAX_K || E <= 0 || W <= 0 || W > VLQ_MAX_K || C <= 0 || nb <= 0 || ldD < C ||
+      (int64_t)nb * 32 < C)
+    return VLQ_EINVAL;
+  if (nq == 0) return VLQ_OK;
+  if (!D || !bucket_min || !edge || !edge_d2 || !out_list || !out_term1 || !out_term6) return VLQ_EINVAL;
+  const int kmax = P > W ? P : W;
+  long long total = (long long)P * E;
+  if (total < (long long)P * 32) total = (long long)P * 32;
+  if (total < nb) total = nb;
+  const int cap = select_capacity(kmax, Q_THREADS, Q_BATCH, total);
+  const size_t smem = ((select_smem_bytes(cap) + 15) & ~size_t(15)) + 2 * VLQ_MAX_K * sizeof(int);
+  VLQ_CUDA_TRY(cudaFuncSetAttribute(coarse_select_lines_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  VLQ_LAUNCH(coarse_select_lines_kernel, (unsigned)nq, Q_THREADS, smem, as_stream(stream), D, ldD, bucket_min, nb, C, P,
+             edge, edge_d2, E, W, cap, out_coarse, out_list, out_term1, out_term6);
   return last_error();
 }
 

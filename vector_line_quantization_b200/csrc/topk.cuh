@@ -32,7 +32,7 @@ __host__ __device__ inline int select_capacity(int k, int threads, int batch, lo
   if (cap > kSelMaxItems * threads) cap = kSelMaxItems * threads;
   return cap;
 }
-__host__ __device__ inline size_t select_smem_bytes(int cap) { return sizeof(uint64_t) * cap + sizeof(int) * (256 + 8); }
+__host__ __device__ inline size_t select_smem_bytes(int cap) { return sizeof(uint64_t) * cap + sizeof(int) * (256 + 8); }  // keys | hist[256] (8-byte aligned) | meta[8]
 
 template <int THREADS>
 struct BlockSelect {
@@ -95,11 +95,37 @@ struct BlockSelect {
       __syncthreads();
       return;
     }
-    // ---- radix select of the k-th smallest key, most significant byte first
-    uint64_t prefix = 0;
+    // ---- radix select of the k-th smallest key, most significant byte first.
+    // (a) the bytes above the first one in which min and max differ are skipped (clustered keys would serialise on one
+    // shared-memory counter there); (b) as soon as the wanted key is alone in its bin it is looked up directly (the
+    // payload bytes rarely need their own passes).  (__match_any_sync aggregation was measured: slower.)
+    uint64_t kmin = kKeyInf, kmax = 0;
+    for (int i = threadIdx.x; i < n; i += THREADS) {
+      const uint64_t key = keys[i];
+      kmin = key < kmin ? key : kmin;
+      kmax = key > kmax ? key : kmax;
+    }
+    kmin = warp_min_u64(kmin);
+    kmax = ~warp_min_u64(~kmax);
+    uint64_t* red = reinterpret_cast<uint64_t*>(hist);  // 256 ints = 128 u64: [0..31] minima, [32..63] maxima
+    if ((threadIdx.x & 31) == 0) {
+      red[threadIdx.x >> 5] = kmin;
+      red[32 + (threadIdx.x >> 5)] = kmax;
+    }
+    __syncthreads();
+    for (int w = 0; w < THREADS / 32; w++) {
+      kmin = red[w] < kmin ? red[w] : kmin;
+      kmax = red[32 + w] > kmax ? red[32 + w] : kmax;
+    }
+    __syncthreads();
+    const uint64_t diff = kmin ^ kmax;
+    const int top = diff ? (63 - __clzll((long long)diff)) >> 3 : 0;  // most significant byte that varies
+    uint64_t prefix = top == 7 ? 0 : (kmin >> ((top + 1) * 8));
     int need = k;  // rank (1-based) of the wanted key among the keys matching `prefix`
+    uint64_t kth = 0;
+    bool found = false;
 #pragma unroll 1
-    for (int pass = 7; pass >= 0; pass--) {
+    for (int pass = top; pass >= 0; pass--) {
       hist[threadIdx.x & 255] = 0;
       if (THREADS < 256)
         for (int j = threadIdx.x; j < 256; j += THREADS) hist[j] = 0;
@@ -132,6 +158,7 @@ struct BlockSelect {
             if (need <= before + c[j]) {
               meta[1] = lane * 8 + j;
               meta[2] = need - before;
+              meta[3] = c[j];
               break;
             }
             before += c[j];
@@ -141,8 +168,21 @@ struct BlockSelect {
       __syncthreads();
       prefix = (prefix << 8) | (uint64_t)meta[1];
       need = meta[2];
+      const int in_bin = meta[3];
+      if (in_bin == 1 && pass > 0) {  // block-uniform: the wanted key is the only one with this prefix
+        for (int i = threadIdx.x; i < n; i += THREADS) {
+          const uint64_t key = keys[i];
+          if ((key >> shift) == prefix) *reinterpret_cast<uint64_t*>(hist) = key;
+        }
+        __syncthreads();
+        kth = *reinterpret_cast<uint64_t*>(hist);
+        found = true;
+        __syncthreads();
+        break;
+      }
     }
-    const uint64_t kth = prefix;  // exactly k keys are <= kth (keys are unique)
+    if (!found) kth = prefix;
+    // exactly k keys are <= kth (keys are unique)
     // ---- compaction through registers (in-place writes would race with other threads' reads)
     uint64_t mine[kSelMaxItems];
 #pragma unroll

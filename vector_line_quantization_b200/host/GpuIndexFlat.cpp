@@ -125,14 +125,15 @@ void GpuIndexFlat::assignDevice(const float* dx, Index::idx_t n, int* dLabels, f
   }
 }
 
-void GpuIndexFlat::distancesDevice(const float* dx, Index::idx_t n, float* dD, Index::idx_t ldD) const {
+void GpuIndexFlat::distancesDevice(const float* dx, Index::idx_t n, float* dD, Index::idx_t ldD, float* bucketMin) const {
   vlq_stream_t st = resources_->getDefaultStream();
   if (pack_.get()) {
     const size_t ws = vlq_l2_tc_workspace_bytes(n, d, (int)ntotal);
     scratch_.reserve(ws);
-    VLQ_CALL(vlq_l2_distances_tc(dx, n, d, pack_.get(), packScale_, (int)ntotal, dD, ldD, scratch_.get(),
+    VLQ_CALL(vlq_l2_distances_tc(dx, n, d, pack_.get(), packScale_, (int)ntotal, dD, ldD, bucketMin, scratch_.get(),
                                  scratch_.bytes(), st));
   } else {
+    VLQ_THROW_IF_NOT_MSG(bucketMin == nullptr, "bucket minima are produced by the tensor-core path only");
     VLQ_CALL(vlq_l2_distances(dx, n, d, vecs_.as<float>(), norms_.as<float>(), (int)ntotal, dD, ldD, st));
   }
 }

@@ -276,12 +276,16 @@ void GpuIndexIVFPQ::search(Index::idx_t n, const float* x, Index::idx_t k, float
   DeviceBuffer& outI = outI_;
   DeviceBuffer& dmat = scratch_;
   dmat.reserve((size_t)tile * nlist_ * sizeof(float));
-  scratchB_.reserve((size_t)tile * (P * (sizeof(float) + sizeof(int)) + W * (sizeof(int) + 2 * sizeof(float))));
+  const bool tc = quantizer_->devicePack() != nullptr;
+  const int nb = vlq_tc_num_buckets(nlist_);
+  scratchB_.reserve((size_t)tile * (P * (sizeof(float) + sizeof(int)) + W * (sizeof(int) + 2 * sizeof(float)) +
+                                    (tc ? nb * sizeof(float) : 0)));
   float* cval = scratchB_.as<float>();
   int* cidx = reinterpret_cast<int*>(cval + (size_t)tile * P);
   int* lline = cidx + (size_t)tile * P;
   float* t1 = reinterpret_cast<float*>(lline + (size_t)tile * W);
   float* t6 = t1 + (size_t)tile * W;
+  float* bmin = t6 + (size_t)tile * W;
   for (Index::idx_t p0 = 0; p0 < n; p0 += page) {
     const Index::idx_t pn = std::min(page, n - p0);
     const float* dx = static_cast<const float*>(toDevice(x + (size_t)p0 * d, (size_t)pn * d * sizeof(float), xin, st));
@@ -290,10 +294,16 @@ void GpuIndexIVFPQ::search(Index::idx_t n, const float* x, Index::idx_t k, float
     for (Index::idx_t s = 0; s < pn; s += tile) {
       const Index::idx_t m = std::min(tile, pn - s);
       const float* q = dx + (size_t)s * d;
-      quantizer_->distancesDevice(q, m, dmat.as<float>(), nlist_);
-      VLQ_CALL(vlq_select_rows(dmat.as<float>(), m, nlist_, nlist_, P, nullptr, cval, cidx, st));
-      VLQ_CALL(vlq_select_lines(dmat.as<float>(), m, nlist_, cidx, P, dEdge_.as<int>(), dEdgeDist_.as<float>(),
-                                numedge_, W, lline, t1, t6, st));
+      if (tc) {  // tensor-core GEMM emits bucket minima; top-P and the line selection are one fused kernel
+        quantizer_->distancesDevice(q, m, dmat.as<float>(), nlist_, bmin);
+        VLQ_CALL(vlq_coarse_select_lines(dmat.as<float>(), m, nlist_, bmin, nb, nlist_, P, dEdge_.as<int>(),
+                                         dEdgeDist_.as<float>(), numedge_, W, nullptr, lline, t1, t6, st));
+      } else {
+        quantizer_->distancesDevice(q, m, dmat.as<float>(), nlist_);
+        VLQ_CALL(vlq_select_rows(dmat.as<float>(), m, nlist_, nlist_, P, nullptr, cval, cidx, st));
+        VLQ_CALL(vlq_select_lines(dmat.as<float>(), m, nlist_, cidx, P, dEdge_.as<int>(), dEdgeDist_.as<float>(),
+                                  numedge_, W, lline, t1, t6, st));
+      }
       VLQ_CALL(vlq_scan_topk(q, m, d, dPq_.as<float>(), M, dLambda_.as<float>(), nLambda_, lline, t1, t6,
                              dEdgeDist_.as<float>(), W, lOffsets_.as<int64_t>(), lCodes_.as<uint8_t>(),
                              lLamq_.as<uint8_t>(), lKappa_.as<float>(), lIds_.as<int64_t>(), (int)k, listCap_,

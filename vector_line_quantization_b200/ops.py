@@ -218,16 +218,18 @@ def search(q, cent, cnorm, edge, edge_d2, lambda_cb, pq, lists, P, W, k, cap=102
     outD = torch.empty((nq, k), dtype=torch.float32, device=q.device)
     outI = torch.empty((nq, k), dtype=torch.int64, device=q.device)
     Dbuf = torch.empty((min(tile, nq), C), dtype=torch.float32, device=q.device)
+    bbuf = torch.empty((min(tile, nq), num_buckets(C)), dtype=torch.float32, device=q.device) if pack is not None else None
     ed2_flat = edge_d2.reshape(-1)
     for s in range(0, nq, tile):
         e = min(nq, s + tile)
         qt = q[s:e]
-        if pack is not None:
-            D = l2_distances_tc(qt, pack, out=Dbuf[: e - s])
+        if pack is not None:  # tensor-core GEMM (+ bucket minima) -> fused top-P / line selection
+            D = l2_distances_tc(qt, pack, out=Dbuf[: e - s], bucket_min=bbuf[: e - s])
+            lst, t1, t6 = coarse_select_lines(D, bbuf[: e - s], C, P, edge, edge_d2, W)
         else:
             D = l2_distances(qt, cent, cnorm, out=Dbuf[: e - s])
-        _, cid = select_rows(D, P)
-        lst, t1, t6 = select_lines(D, cid, edge, edge_d2, W)
+            _, cid = select_rows(D, P)
+            lst, t1, t6 = select_lines(D, cid, edge, edge_d2, W)
         d_, i_ = scan_topk(qt, pq, lambda_cb, lst, t1, t6, ed2_flat, lists, k, cap)
         outD[s:e] = d_
         outI[s:e] = i_
@@ -275,12 +277,31 @@ def l2_assign_tc(x, pack, add_xnorm=True, want_dist=True):
     return ids, dist
 
 
-def l2_distances_tc(x, pack, out=None):
-    """coarse matrix D = ||c||^2 - 2 x.c on the tensor cores (a11)"""
+def l2_distances_tc(x, pack, out=None, bucket_min=None):
+    """coarse matrix D = ||c||^2 - 2 x.c on the tensor cores (a11); bucket_min ([n][num_buckets] f32) optionally
+    receives the minimum of every 32-column bucket (input of coarse_select_lines)"""
     x = _chk(x, torch.float32, "x")
     n, d = x.shape
     D = out if out is not None else torch.empty((n, pack.C), dtype=torch.float32, device=x.device)
     ws = pack.workspace(n)
-    _abi.call("vlq_l2_distances_tc", _ptr(x), n, d, _ptr(pack.buf), pack.scale, pack.C, _ptr(D), D.stride(0), _ptr(ws),
-              ws.numel(), _stream())
+    _abi.call("vlq_l2_distances_tc", _ptr(x), n, d, _ptr(pack.buf), pack.scale, pack.C, _ptr(D), D.stride(0),
+              _ptr(bucket_min), _ptr(ws), ws.numel(), _stream())
     return D
+
+
+def num_buckets(C):
+    return int(_abi.lib().vlq_tc_num_buckets(C))
+
+
+def coarse_select_lines(D, bucket_min, C, P, edge, edge_d2, W, want_coarse=False):
+    """fused top-P (through the bucket minima) + line selection (a11 + a12)"""
+    nq = D.shape[0]
+    E = edge.shape[1]
+    dev = D.device
+    lst = torch.empty((nq, W), dtype=torch.int32, device=dev)
+    t1 = torch.empty((nq, W), dtype=torch.float32, device=dev)
+    t6 = torch.empty((nq, W), dtype=torch.float32, device=dev)
+    cid = torch.empty((nq, P), dtype=torch.int32, device=dev) if want_coarse else None
+    _abi.call("vlq_coarse_select_lines", _ptr(D), nq, D.stride(0), _ptr(bucket_min), bucket_min.shape[1], C, P,
+              _ptr(edge), _ptr(edge_d2), E, W, _ptr(cid), _ptr(lst), _ptr(t1), _ptr(t6), _stream())
+    return (lst, t1, t6, cid) if want_coarse else (lst, t1, t6)
