@@ -411,6 +411,7 @@ def run_b200(a):
     hidx.setCodebooks(*(model[key].cpu().numpy() for key in ("cent", "edge", "edge_d2", "lambda_cb", "pq")))
     hidx.setNumProbes(P)
     hidx.w1_ = W
+    hidx.reserveMemory(a.n)  # GpuIndexIVFPQ::reserveMemory, as the reference drivers do before a bulk load
     add_chunk = 2_000_000  # the reference drivers ingest 2 M vectors per add (gpu/test/sift1b_createdb.cpp:276-289)
     hx = torch.empty((min(add_chunk, a.n), d), dtype=torch.float32).pin_memory()
     hids = torch.empty(min(add_chunk, a.n), dtype=torch.int64).pin_memory()

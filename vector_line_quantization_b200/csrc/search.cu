@@ -81,6 +81,19 @@ select_lines_kernel(const float* __restrict__ D, int64_t ldD, const int* __restr
 //   1. the P buckets (32 consecutive centroids each) with the smallest minima contain every top-P centroid,
 //   2. exact top-P among those P*32 entries of D (one 128-byte line per bucket instead of the whole 4*C-byte row),
 //   3. line scoring of the P*E lines and top-W, as select_lines_kernel.
+// i / E and i % E for the (line = centroid slot * E + edge) enumeration; E is a power of two in every driver config
+struct EdgeDiv {
+  int E, shift;
+  __device__ __forceinline__ explicit EdgeDiv(int E_) : E(E_), shift(-1) {
+    if ((E_ & (E_ - 1)) == 0) {
+      shift = 0;
+      while ((1 << shift) < E_) shift++;
+    }
+  }
+  __device__ __forceinline__ int div(int i) const { return shift >= 0 ? (i >> shift) : (i / E); }
+  __device__ __forceinline__ int mod(int i) const { return shift >= 0 ? (i & (E - 1)) : (i % E); }
+};
+
 __global__ void __launch_bounds__(Q_THREADS)
 coarse_select_lines_kernel(const float* __restrict__ D, int64_t ldD, const float* __restrict__ bmin, int nb, int C,
                            int P, const int* __restrict__ edge, const float* __restrict__ edge_d2, int E, int W, int cap,
@@ -90,6 +103,7 @@ coarse_select_lines_kernel(const float* __restrict__ D, int64_t ldD, const float
   int* bk_s = reinterpret_cast<int*>(smem + ((select_smem_bytes(cap) + 15) & ~size_t(15)));  // [1024] bucket ids
   int* cq_s = bk_s + VLQ_MAX_K;                                                              // [1024] top-P centroids
   BlockSelect<Q_THREADS> sel;
+  const EdgeDiv ed(E);
   const int64_t q = blockIdx.x;
   const float* Dq = D + q * ldD;
   const float* bq = bmin + q * nb;
@@ -162,10 +176,10 @@ coarse_select_lines_kernel(const float* __restrict__ D, int64_t ldD, const float
       bool valid = i < num;
       float score = 0.f;
       if (valid) {
-        const int c = cq_s[i / E];
+        const int c = cq_s[ed.div(i)];
         valid = c >= 0;
         if (valid) {
-          const int e = i % E;
+          const int e = ed.mod(i);
           const int s = edge[(int64_t)c * E + e];
           const float a2 = Dq[s], b2 = Dq[c], c2 = edge_d2[(int64_t)c * E + e];
           float v = __fsub_rn(a2, b2);
@@ -184,7 +198,7 @@ coarse_select_lines_kernel(const float* __restrict__ D, int64_t ldD, const float
     float t1 = 0.f, t6 = 0.f;
     if (key != kKeyInf) {
       const int i = (int)key_payload(key);
-      const int c = cq_s[i / E], e = i % E;
+      const int c = cq_s[ed.div(i)], e = ed.mod(i);
       const int s = edge[(int64_t)c * E + e];
       list = c * E + e;
       t1 = Dq[c];

@@ -34,6 +34,46 @@ __host__ __device__ inline int select_capacity(int k, int threads, int batch, lo
 }
 __host__ __device__ inline size_t select_smem_bytes(int cap) { return sizeof(uint64_t) * cap + sizeof(int) * (256 + 8); }  // keys | hist[256] (8-byte aligned) | meta[8]
 
+// Bitonic sort of 32*R keys by ONE warp: lane l holds keys l, l+32, ... in registers; partners at distance < 32 are
+// exchanged with shuffles, larger distances are register-to-register.  No block barriers.
+template <int R>
+__device__ __forceinline__ void warp_bitonic_sort(uint64_t* keys) {
+  const int lane = threadIdx.x & 31;
+  uint64_t v[R];
+#pragma unroll
+  for (int r = 0; r < R; r++) v[r] = keys[lane + 32 * r];
+#pragma unroll
+  for (int k2 = 2; k2 <= 32 * R; k2 <<= 1) {
+#pragma unroll
+    for (int j = k2 >> 1; j > 0; j >>= 1) {
+      if (j >= 32) {
+#pragma unroll
+        for (int r = 0; r < R; r++) {
+          if ((r & (j >> 5)) == 0) {
+            const bool up = ((lane + 32 * r) & k2) == 0;
+            const uint64_t a = v[r], b = v[r | (j >> 5)];
+            if ((a > b) == up) {
+              v[r] = b;
+              v[r | (j >> 5)] = a;
+            }
+          }
+        }
+      } else {
+        const bool lower = (lane & j) == 0;
+#pragma unroll
+        for (int r = 0; r < R; r++) {
+          const uint64_t pth = __shfl_xor_sync(kFull, v[r], j);
+          const bool up = ((lane + 32 * r) & k2) == 0;
+          const bool take_min = lower == up;
+          v[r] = take_min ? (pth < v[r] ? pth : v[r]) : (pth > v[r] ? pth : v[r]);
+        }
+      }
+    }
+  }
+#pragma unroll
+  for (int r = 0; r < R; r++) keys[lane + 32 * r] = v[r];
+}
+
 template <int THREADS>
 struct BlockSelect {
   uint64_t* keys;  // [cap]
@@ -99,28 +139,26 @@ struct BlockSelect {
     // (a) the bytes above the first one in which min and max differ are skipped (clustered keys would serialise on one
     // shared-memory counter there); (b) as soon as the wanted key is alone in its bin it is looked up directly (the
     // payload bytes rarely need their own passes).  (__match_any_sync aggregation was measured: slower.)
-    uint64_t kmin = kKeyInf, kmax = 0;
+    const uint64_t key0 = keys[0];
+    unsigned dhi = 0, dlo = 0;  // OR of (key ^ key0): the highest set bit marks the most significant varying byte
     for (int i = threadIdx.x; i < n; i += THREADS) {
-      const uint64_t key = keys[i];
-      kmin = key < kmin ? key : kmin;
-      kmax = key > kmax ? key : kmax;
+      const uint64_t x = keys[i] ^ key0;
+      dhi |= (unsigned)(x >> 32);
+      dlo |= (unsigned)x;
     }
-    kmin = warp_min_u64(kmin);
-    kmax = ~warp_min_u64(~kmax);
-    uint64_t* red = reinterpret_cast<uint64_t*>(hist);  // 256 ints = 128 u64: [0..31] minima, [32..63] maxima
+    dhi = __reduce_or_sync(kFull, dhi);
+    dlo = __reduce_or_sync(kFull, dlo);
+    if (threadIdx.x < 2) hist[threadIdx.x] = 0;
+    __syncthreads();
     if ((threadIdx.x & 31) == 0) {
-      red[threadIdx.x >> 5] = kmin;
-      red[32 + (threadIdx.x >> 5)] = kmax;
+      if (dhi) atomicOr(reinterpret_cast<unsigned*>(&hist[0]), dhi);
+      if (dlo) atomicOr(reinterpret_cast<unsigned*>(&hist[1]), dlo);
     }
     __syncthreads();
-    for (int w = 0; w < THREADS / 32; w++) {
-      kmin = red[w] < kmin ? red[w] : kmin;
-      kmax = red[32 + w] > kmax ? red[32 + w] : kmax;
-    }
+    const uint64_t diff = ((uint64_t)(unsigned)hist[0] << 32) | (unsigned)hist[1];
     __syncthreads();
-    const uint64_t diff = kmin ^ kmax;
     const int top = diff ? (63 - __clzll((long long)diff)) >> 3 : 0;  // most significant byte that varies
-    uint64_t prefix = top == 7 ? 0 : (kmin >> ((top + 1) * 8));
+    uint64_t prefix = top == 7 ? 0 : (key0 >> ((top + 1) * 8));
     int need = k;  // rank (1-based) of the wanted key among the keys matching `prefix`
     uint64_t kth = 0;
     bool found = false;
@@ -187,6 +225,7 @@ struct BlockSelect {
     uint64_t mine[kSelMaxItems];
 #pragma unroll
     for (int t = 0; t < kSelMaxItems; t++) {
+      if (t * THREADS >= n) break;  // block-uniform
       const int i = threadIdx.x + t * THREADS;
       mine[t] = i < n ? keys[i] : kKeyInf;
     }
@@ -195,6 +234,7 @@ struct BlockSelect {
     __syncthreads();
 #pragma unroll
     for (int t = 0; t < kSelMaxItems; t++) {
+      if (t * THREADS >= n) break;
       if (mine[t] <= kth) {
         const int slot = atomicAdd(&meta[0], 1);
         keys[slot] = mine[t];
@@ -210,9 +250,18 @@ struct BlockSelect {
   __device__ void finish() {
     compact();
     const int n = meta[0] < k ? meta[0] : k;
-    const int S = next_pow2(k);  // S <= cap because cap >= k + batch*THREADS and cap is a power of two
+    int S = next_pow2(k);  // S <= cap because cap >= k + batch*THREADS and cap is a power of two
+    if (S < 32) S = 32;
     for (int i = n + threadIdx.x; i < S; i += THREADS) keys[i] = kKeyInf;
     __syncthreads();
+    if (S <= 64) {  // one warp sorts in registers (no barriers per step); measured slower than the block network for S >= 128
+      if (threadIdx.x < kWarp) {
+        if (S == 32) warp_bitonic_sort<1>(keys);
+        else warp_bitonic_sort<2>(keys);
+      }
+      __syncthreads();
+      return;
+    }
     for (int k2 = 2; k2 <= S; k2 <<= 1) {
       for (int j = k2 >> 1; j > 0; j >>= 1) {
         for (int t = threadIdx.x; t < (S >> 1); t += THREADS) {

@@ -15,14 +15,19 @@ void Index::assign(idx_t n, const float* x, idx_t* labels, idx_t k) {
 namespace gpu {
 
 // ------------------------------------------------------------------------------------------------ resources
-StandardGpuResources::StandardGpuResources(int device) : device_(device), stream_(nullptr) {
+StandardGpuResources::StandardGpuResources(int device) : device_(device), stream_(nullptr), copyStream_(nullptr) {
   DeviceScope scope(device_);
   VLQ_CALL(vlq_stream_create(&stream_));
+  VLQ_CALL(vlq_stream_create(&copyStream_));
 }
 StandardGpuResources::~StandardGpuResources() {
   if (stream_) {
     vlq_stream_synchronize(stream_);
     vlq_stream_destroy(stream_);
+  }
+  if (copyStream_) {
+    vlq_stream_synchronize(copyStream_);
+    vlq_stream_destroy(copyStream_);
   }
 }
 void StandardGpuResources::syncDefaultStream() { VLQ_CALL(vlq_stream_synchronize(stream_)); }

@@ -204,11 +204,23 @@ void GpuIndexIVFPQ::add_with_ids(Index::idx_t n, const float* x, const long* xid
   ensurePending_((size_t)n);
   const Index::idx_t tile = (Index::idx_t)1 << 19;
   const int M = subQuantizers_;
-  DeviceBuffer& xin = addIn_;
+  const bool onDevice = vlq_pointer_is_device(x) == 1;
+  vlq_stream_t cs = resources_->getAsyncCopyStream();
   DeviceBuffer& dA = addA_;
+  // host input: tile i+1 is staged on the copy stream while tile i is encoded on the compute stream
+  auto stage = [&](Index::idx_t s, int slot) -> const float* {
+    const Index::idx_t m = std::min(tile, n - s);
+    if (onDevice) return x + (size_t)s * d;
+    addIn_[slot].reserve((size_t)tile * d * sizeof(float));
+    VLQ_CALL(vlq_memcpy_h2d(addIn_[slot].get(), x + (size_t)s * d, (size_t)m * d * sizeof(float), cs));
+    return addIn_[slot].as<float>();
+  };
+  const float* cur = stage(0, 0);
+  if (!onDevice) VLQ_CALL(vlq_stream_synchronize(cs));
+  int slot = 0;
   for (Index::idx_t s = 0; s < n; s += tile) {
     const Index::idx_t m = std::min(tile, n - s);
-    const float* dx = static_cast<const float*>(toDevice(x + (size_t)s * d, (size_t)m * d * sizeof(float), xin, st));
+    const float* dx = cur;
     dA.reserve((size_t)m * sizeof(int));
     quantizer_->assignDevice(dx, m, dA.as<int>(), nullptr, false);
     const size_t o = nPending_;
@@ -225,7 +237,10 @@ void GpuIndexIVFPQ::add_with_ids(Index::idx_t n, const float* x, const long* xid
       VLQ_CALL(vlq_iota_i64(pIds_.as<int64_t>() + o, m, (int64_t)(ntotal + s), st));
     }
     nPending_ += (size_t)m;
-    resources_->syncDefaultStream();  // the staging buffer is reused by the next tile
+    if (s + tile < n) cur = stage(s + tile, slot ^ 1);  // overlaps the kernels just launched
+    if (!onDevice) VLQ_CALL(vlq_stream_synchronize(cs));
+    resources_->syncDefaultStream();  // the staging buffer of this tile is reused two tiles later
+    slot ^= 1;
   }
   ntotal += n;
 }

@@ -13,6 +13,8 @@ class GpuResources {
   virtual int getDevice() const = 0;
   virtual vlq_stream_t getDefaultStream() = 0;
   virtual void syncDefaultStream() = 0;
+  /// second stream for host->device staging that overlaps compute (reference: getAsyncCopyStream)
+  virtual vlq_stream_t getAsyncCopyStream() = 0;
 };
 
 class StandardGpuResources : public GpuResources {
@@ -22,6 +24,7 @@ class StandardGpuResources : public GpuResources {
   int getDevice() const override { return device_; }
   vlq_stream_t getDefaultStream() override { return stream_; }
   void syncDefaultStream() override;
+  vlq_stream_t getAsyncCopyStream() override { return copyStream_; }
   /// kept for source compatibility with the reference (gpu/StandardGpuResources.h): sizes are managed on demand
   void noTempMemory() {}
   void setTempMemory(size_t) {}
@@ -30,6 +33,7 @@ class StandardGpuResources : public GpuResources {
  private:
   int device_;
   vlq_stream_t stream_;
+  vlq_stream_t copyStream_;
 };
 
 /// binds the calling thread to the resource's device for the lifetime of the scope (reference DeviceScope)

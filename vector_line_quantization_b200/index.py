@@ -186,6 +186,9 @@ class GpuIndexIVFPQ(Index):
     def setListCap(self, cap):
         _call("vlq_host_vlq_set_list_cap", self.h, int(cap))
 
+    def reserveMemory(self, num_vecs):
+        _call("vlq_host_vlq_reserve_memory", self.h, C.c_long(int(num_vecs)))
+
     def setTrainIters(self, niter):
         _call("vlq_host_vlq_set_train_iters", self.h, int(niter))
 
