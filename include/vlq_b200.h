@@ -177,11 +177,15 @@ int vlq_coarse_select_lines(const float* D, int64_t nq, int64_t ldD, const float
  *          = ||q - ((1-l)c + l s) - p(code_i)||^2 - ||q||^2              (same value as the reference's formula)
  *     over the first min(len, cap) entries of each selected list; k smallest ascending, padded (FLT_MAX, -1).
  *     edge_d2 is indexed by list id (term5).  k <= VLQ_MAX_K, W <= VLQ_MAX_K.
+ *     workspace (optional, vlq_scan_topk_workspace_bytes): holds the term-3 tables of the batch, built by one
+ *     persistent kernel with the PQ codebook in shared memory; with workspace == NULL every query CTA builds its own.
  * ---------------------------------------------------------------------------------------------------------------- */
+size_t vlq_scan_topk_workspace_bytes(int64_t nq, int M);
 int vlq_scan_topk(const float* q, int64_t nq, int d, const float* pq, int M, const float* lambda_cb, int nL,
                   const int* line_list, const float* term1, const float* term6, const float* edge_d2, int W,
                   const int64_t* offsets, const uint8_t* codes, const uint8_t* lamq, const float* kappa,
-                  const int64_t* ids, int k, int cap, float* outD, int64_t* outI, vlq_stream_t stream);
+                  const int64_t* ids, int k, int cap, float* outD, int64_t* outI, void* workspace,
+                  size_t workspace_bytes, vlq_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------------------------------
  * a16 shard merge: k smallest of R*k candidates per query; D, I are [R][nq][k] (the all-gather layout).

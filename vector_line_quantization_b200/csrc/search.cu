@@ -230,33 +230,40 @@ struct ScanArgs {
   const int64_t* ids;
   int k, cap;
   int sel_cap;
+  const float* t3;  // optional precomputed term-3 tables [nq][M*ksub] (term3_kernel); nullptr = build in the kernel
   float* outD;
   int64_t* outI;
 };
 
+// PQ codes of one entry held in registers (16-byte / 8-byte vector loads for M = 16 / 8; byte loads otherwise)
 template <int M_T>
-__device__ __forceinline__ float adc_sum(const uint8_t* __restrict__ code_ptr, const float* __restrict__ T3, int M,
-                                         int ksub) {
-  float acc = 0.f;
-  if (M_T == 16) {
-    const uint4 c = ld_nc_v4(code_ptr);
-    const uint32_t w[4] = {c.x, c.y, c.z, c.w};
-#pragma unroll
-    for (int t = 0; t < 4; t++)
-#pragma unroll
-      for (int b = 0; b < 4; b++) acc += T3[(t * 4 + b) * 256 + ((w[t] >> (8 * b)) & 0xff)];
-  } else if (M_T == 8) {
-    const uint2 c = ld_nc_v2(code_ptr);
-    const uint32_t w[2] = {c.x, c.y};
-#pragma unroll
-    for (int t = 0; t < 2; t++)
-#pragma unroll
-      for (int b = 0; b < 4; b++) acc += T3[(t * 4 + b) * 256 + ((w[t] >> (8 * b)) & 0xff)];
-  } else {
-    for (int m = 0; m < M; m++) acc += T3[m * ksub + code_ptr[m]];
+struct CodeRegs {
+  uint32_t w[M_T == 16 ? 4 : (M_T == 8 ? 2 : 1)];
+  const uint8_t* ptr;
+  __device__ __forceinline__ void load(const uint8_t* __restrict__ code_ptr) {
+    if (M_T == 16) {
+      const uint4 c = ld_nc_v4(code_ptr);
+      w[0] = c.x; w[1] = c.y; w[2] = c.z; w[3] = c.w;
+    } else if (M_T == 8) {
+      const uint2 c = ld_nc_v2(code_ptr);
+      w[0] = c.x; w[1] = c.y;
+    } else {
+      ptr = code_ptr;
+    }
   }
-  return acc;
-}
+  __device__ __forceinline__ float adc(const float* __restrict__ T3, int M, int ksub) const {
+    float acc = 0.f;
+    if (M_T == 16 || M_T == 8) {
+#pragma unroll
+      for (int t = 0; t < M_T / 4; t++)
+#pragma unroll
+        for (int b = 0; b < 4; b++) acc += T3[(t * 4 + b) * 256 + ((w[t] >> (8 * b)) & 0xff)];
+    } else {
+      for (int m = 0; m < M; m++) acc += T3[m * ksub + ptr[m]];
+    }
+    return acc;
+  }
+};
 
 template <int M_T>
 __global__ void __launch_bounds__(Q_THREADS) scan_topk_kernel(ScanArgs a) {
@@ -284,6 +291,11 @@ __global__ void __launch_bounds__(Q_THREADS) scan_topk_kernel(ScanArgs a) {
   const float* qv = a.q + qi * a.d;
 
   // term3 table: T3[m][j] = -2 q_m . p_mj            (gpu/impl/IVFPQ.cu:1409-1432)
+  if (a.t3) {  // precomputed by term3_kernel (PQ codebook read once per CTA there instead of once per query here)
+    const float4* src = reinterpret_cast<const float4*>(a.t3 + (size_t)qi * M * ksub);
+    float4* dst = reinterpret_cast<float4*>(T3);
+    for (int i = threadIdx.x; i < (M * ksub) / 4; i += Q_THREADS) dst[i] = src[i];
+  } else
   for (int i = threadIdx.x; i < M * ksub; i += Q_THREADS) {
     const int m = i / ksub;
     const float* p = a.pq + (size_t)i * dsub;
@@ -335,24 +347,48 @@ __global__ void __launch_bounds__(Q_THREADS) scan_topk_kernel(ScanArgs a) {
   const int total = prefix[W];
 
   for (int base = 0; base < total; base += Q_BATCH * Q_THREADS) {
+    // phase A: which list / entry each stream position is; phase B: all global loads of the batch in flight;
+    // phase C: arithmetic.  (Interleaving them serialises ~3 DRAM latencies per entry.)
+    int lo_[Q_BATCH];
+    int64_t ent_[Q_BATCH];
+#pragma unroll
+    for (int b = 0; b < Q_BATCH; b++) {
+      const int pos = base + b * Q_THREADS + threadIdx.x;
+      int lo = 0, hi = W;
+      if (pos < total) {
+        while (hi - lo > 1) {  // list of this stream position: largest w with prefix[w] <= pos
+          int mid = (lo + hi) >> 1;
+          if (prefix[mid] <= pos) lo = mid; else hi = mid;
+        }
+      }
+      lo_[b] = lo;
+      ent_[b] = pos < total ? lstart[lo] + (pos - prefix[lo]) : -1;
+    }
+    CodeRegs<M_T> cr[Q_BATCH];
+    uint8_t lq[Q_BATCH];
+    float kp[Q_BATCH];
+#pragma unroll
+    for (int b = 0; b < Q_BATCH; b++) {
+      lq[b] = 0;
+      kp[b] = 0.f;
+      if (ent_[b] >= 0) {
+        cr[b].load(a.codes + ent_[b] * M);
+        lq[b] = a.lamq[ent_[b]];
+        kp[b] = a.kappa[ent_[b]];
+      }
+    }
     bool any = false;
 #pragma unroll
     for (int b = 0; b < Q_BATCH; b++) {
       const int pos = base + b * Q_THREADS + threadIdx.x;
-      const bool valid = pos < total;
+      const bool valid = ent_[b] >= 0;
       float dist = 0.f;
       if (valid) {
-        // list of this stream position: largest w with prefix[w] <= pos
-        int lo = 0, hi = W;
-        while (hi - lo > 1) {
-          int mid = (lo + hi) >> 1;
-          if (prefix[mid] <= pos) lo = mid; else hi = mid;
-        }
-        const int64_t ent = lstart[lo] + (pos - prefix[lo]);
-        const float la = lcb[a.lamq[ent]];
+        const int lo = lo_[b];
+        const float la = lcb[lq[b]];
         const float base_d = lt1[lo] + la * lt6[lo] + (la * la - la) * lt5[lo];
-        const float acc = adc_sum<M_T>(a.codes + ent * M, T3, M, ksub);
-        dist = (a.kappa[ent] + acc) + base_d;
+        const float acc = cr[b].adc(T3, M, ksub);
+        dist = (kp[b] + acc) + base_d;
       }
       any |= sel.offer_f(valid, dist, (uint32_t)pos);
     }
@@ -375,6 +411,34 @@ __global__ void __launch_bounds__(Q_THREADS) scan_topk_kernel(ScanArgs a) {
     }
     a.outD[qi * a.k + i] = dv;
     a.outI[qi * a.k + i] = id;
+  }
+}
+
+// term-3 tables for a batch of queries: T3[q][m][j] = -2 q_m . p_mj (gpu/impl/IVFPQ.cu:1409-1432).  Persistent CTAs
+// stage the PQ codebook once in shared memory (natural (m, j, t) layout, plain coalesced copy) and walk the queries;
+// thread j owns codeword j of every sub-quantizer, so the table rows are written coalesced.  Same fmaf chain (t
+// ascending) as the in-kernel build, hence bit-identical tables.
+__global__ void __launch_bounds__(Q_THREADS)
+term3_kernel(const float* __restrict__ q, int64_t nq, int d, const float* __restrict__ pq, int M, int dsub,
+             float* __restrict__ t3) {
+  extern __shared__ __align__(16) float t3s[];
+  float* pqs = t3s;                          // [M][256][dsub]
+  float* qs = t3s + (size_t)M * 256 * dsub;  // [d]
+  const int total4 = (M * 256 * dsub) / 4;   // d % 4 == 0 is checked by the launcher
+  for (int i = threadIdx.x; i < total4; i += Q_THREADS)
+    reinterpret_cast<float4*>(pqs)[i] = reinterpret_cast<const float4*>(pq)[i];
+  for (int64_t qi = blockIdx.x; qi < nq; qi += gridDim.x) {
+    __syncthreads();
+    for (int j = threadIdx.x; j < d; j += Q_THREADS) qs[j] = q[qi * d + j];
+    __syncthreads();
+    float* out = t3 + (size_t)qi * M * 256;
+    for (int m = 0; m < M; m++) {
+      const float* pp = pqs + ((size_t)m * 256 + threadIdx.x) * dsub;
+      const float* qm = qs + m * dsub;
+      float ip = 0.f;
+      for (int t = 0; t < dsub; t++) ip = fmaf(qm[t], pp[t], ip);
+      out[m * 256 + threadIdx.x] = -2.f * ip;
+    }
   }
 }
 
@@ -485,10 +549,13 @@ int vlq_coarse_select_lines(const float* D, int64_t nq, int64_t ldD, const float
   return last_error();
 }
 
+size_t vlq_scan_topk_workspace_bytes(int64_t nq, int M) { return (size_t)(nq > 0 ? nq : 0) * M * 256 * sizeof(float); }
+
 int vlq_scan_topk(const float* q, int64_t nq, int d, const float* pq, int M, const float* lambda_cb, int nL,
                   const int* line_list, const float* term1, const float* term6, const float* edge_d2, int W,
                   const int64_t* offsets, const uint8_t* codes, const uint8_t* lamq, const float* kappa,
-                  const int64_t* ids, int k, int cap, float* outD, int64_t* outI, vlq_stream_t stream) {
+                  const int64_t* ids, int k, int cap, float* outD, int64_t* outI, void* workspace,
+                  size_t workspace_bytes, vlq_stream_t stream) {
   if (nq > 0 && (!q || !pq || !lambda_cb || !line_list || !term1 || !term6 || !edge_d2 || !offsets || !outD || !outI))
     return VLQ_EINVAL;
   if (nq < 0 || d <= 0 || M <= 0 || M > 64 || d % M != 0 || nL <= 0 || nL > 256 || W <= 0 || W > VLQ_MAX_K ||
@@ -500,6 +567,17 @@ int vlq_scan_topk(const float* q, int64_t nq, int d, const float* pq, int M, con
   a.line_list = line_list; a.term1 = term1; a.term6 = term6; a.edge_d2 = edge_d2; a.W = W; a.offsets = offsets;
   a.codes = codes; a.lamq = lamq; a.kappa = kappa; a.ids = ids; a.k = k; a.cap = cap; a.outD = outD; a.outI = outI;
   a.sel_cap = select_capacity(k, Q_THREADS, Q_BATCH, (long long)W * cap);
+  a.t3 = nullptr;
+  const size_t t3_bytes = (size_t)nq * M * 256 * sizeof(float);
+  const size_t pq_smem = ((size_t)M * 256 * a.dsub + d) * sizeof(float);
+  if (workspace && workspace_bytes >= t3_bytes && pq_smem <= 200 * 1024 && d % 4 == 0 &&
+      ((reinterpret_cast<uintptr_t>(workspace) | reinterpret_cast<uintptr_t>(pq)) & 15) == 0) {
+    float* t3 = static_cast<float*>(workspace);
+    VLQ_CUDA_TRY(cudaFuncSetAttribute(term3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pq_smem));
+    const unsigned grid = (unsigned)(nq < 148 ? nq : 148);
+    VLQ_LAUNCH(term3_kernel, grid, Q_THREADS, pq_smem, as_stream(stream), q, nq, d, pq, M, a.dsub, t3);
+    a.t3 = t3;
+  }
   size_t smem = scan_smem_bytes(a.sel_cap, M, a.ksub, nL, W);
   cudaStream_t st = as_stream(stream);
   const bool al16 = (reinterpret_cast<uintptr_t>(codes) % 16) == 0;

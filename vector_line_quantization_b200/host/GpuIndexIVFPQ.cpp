@@ -301,6 +301,7 @@ void GpuIndexIVFPQ::search(Index::idx_t n, const float* x, Index::idx_t k, float
   float* t1 = reinterpret_cast<float*>(lline + (size_t)tile * W);
   float* t6 = t1 + (size_t)tile * W;
   float* bmin = t6 + (size_t)tile * W;
+  t3ws_.reserve(vlq_scan_topk_workspace_bytes(tile, M));
   for (Index::idx_t p0 = 0; p0 < n; p0 += page) {
     const Index::idx_t pn = std::min(page, n - p0);
     const float* dx = static_cast<const float*>(toDevice(x + (size_t)p0 * d, (size_t)pn * d * sizeof(float), xin, st));
@@ -322,7 +323,8 @@ void GpuIndexIVFPQ::search(Index::idx_t n, const float* x, Index::idx_t k, float
       VLQ_CALL(vlq_scan_topk(q, m, d, dPq_.as<float>(), M, dLambda_.as<float>(), nLambda_, lline, t1, t6,
                              dEdgeDist_.as<float>(), W, lOffsets_.as<int64_t>(), lCodes_.as<uint8_t>(),
                              lLamq_.as<uint8_t>(), lKappa_.as<float>(), lIds_.as<int64_t>(), (int)k, listCap_,
-                             outD.as<float>() + (size_t)s * k, outI.as<int64_t>() + (size_t)s * k, st));
+                             outD.as<float>() + (size_t)s * k, outI.as<int64_t>() + (size_t)s * k, t3ws_.get(),
+                             t3ws_.bytes(), st));
     }
     fromDevice(distances + (size_t)p0 * k, outD.get(), (size_t)pn * k * sizeof(float), st);
     fromDevice(labels + (size_t)p0 * k, outI.get(), (size_t)pn * k * sizeof(int64_t), st);

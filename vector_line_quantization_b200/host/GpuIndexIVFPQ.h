@@ -127,7 +127,7 @@ class GpuIndexIVFPQ : public GpuIndexIVF {
   // pending (encoded, arrival order)
   mutable DeviceBuffer pList_, pCodes_, pLamq_, pKappa_, pIds_;
   mutable size_t nPending_, capPending_;
-  mutable DeviceBuffer scratch_, scratchB_, qIn_, outD_, outI_, addIn_[2], addA_;  // grow-only staging / workspace
+  mutable DeviceBuffer scratch_, scratchB_, qIn_, outD_, outI_, addIn_[2], addA_, t3ws_;  // grow-only staging / workspace
 };
 
 }  // namespace gpu
