@@ -225,7 +225,7 @@ l2_argmin_kernel(const float* __restrict__ x, int64_t n, int d, const float* __r
 
 // ------------------------------------------------------------------------------------------------- row select (a15)
 constexpr int SEL_THREADS = 256;
-constexpr int SEL_BATCH = 8;
+constexpr int SEL_BATCH = 4;
 __global__ void __launch_bounds__(SEL_THREADS)
 select_rows_kernel(const float* __restrict__ D, int cols, int64_t ldD, int k, int cap, const float* __restrict__ row_add,
                    float* __restrict__ out_val, int* __restrict__ out_idx) {

@@ -230,6 +230,7 @@ struct ScanArgs {
   const int64_t* ids;
   int k, cap;
   int sel_cap;
+  int owner_cap;    // stream positions covered by the shared-memory owner table (0 = always binary search)
   const float* t3;  // optional precomputed term-3 tables [nq][M*ksub] (term3_kernel); nullptr = build in the kernel
   float* outD;
   int64_t* outI;
@@ -285,6 +286,8 @@ __global__ void __launch_bounds__(Q_THREADS) scan_topk_kernel(ScanArgs a) {
   float* lt6 = reinterpret_cast<float*>(smem + off);
   off += sizeof(float) * W;
   float* lt5 = reinterpret_cast<float*>(smem + off);
+  off += sizeof(float) * W;
+  uint16_t* owner = reinterpret_cast<uint16_t*>(smem + off);  // [owner_cap] line slot of every stream position
 
   sel.init(smem, a.k, a.sel_cap, Q_BATCH);
   const int64_t qi = blockIdx.x;
@@ -345,6 +348,12 @@ __global__ void __launch_bounds__(Q_THREADS) scan_topk_kernel(ScanArgs a) {
   }
   __syncthreads();
   const int total = prefix[W];
+  const bool use_owner = total <= a.owner_cap;  // block-uniform
+  if (use_owner) {  // each line writes its slot over its own range of stream positions (lists are short here)
+    for (int w = threadIdx.x; w < W; w += Q_THREADS)
+      for (int p = prefix[w]; p < prefix[w + 1]; p++) owner[p] = (uint16_t)w;
+    __syncthreads();
+  }
 
   for (int base = 0; base < total; base += Q_BATCH * Q_THREADS) {
     // phase A: which list / entry each stream position is; phase B: all global loads of the batch in flight;
@@ -356,9 +365,13 @@ __global__ void __launch_bounds__(Q_THREADS) scan_topk_kernel(ScanArgs a) {
       const int pos = base + b * Q_THREADS + threadIdx.x;
       int lo = 0, hi = W;
       if (pos < total) {
-        while (hi - lo > 1) {  // list of this stream position: largest w with prefix[w] <= pos
-          int mid = (lo + hi) >> 1;
-          if (prefix[mid] <= pos) lo = mid; else hi = mid;
+        if (use_owner) {
+          lo = owner[pos];
+        } else {
+          while (hi - lo > 1) {  // list of this stream position: largest w with prefix[w] <= pos
+            int mid = (lo + hi) >> 1;
+            if (prefix[mid] <= pos) lo = mid; else hi = mid;
+          }
         }
       }
       lo_[b] = lo;
@@ -432,7 +445,18 @@ term3_kernel(const float* __restrict__ q, int64_t nq, int d, const float* __rest
     for (int j = threadIdx.x; j < d; j += Q_THREADS) qs[j] = q[qi * d + j];
     __syncthreads();
     float* out = t3 + (size_t)qi * M * 256;
-    for (int m = 0; m < M; m++) {
+    int m = 0;
+    for (; m + 4 <= M; m += 4) {  // four independent fmaf chains in flight (one chain per sub-quantizer)
+      float ip[4] = {0.f, 0.f, 0.f, 0.f};
+      for (int t = 0; t < dsub; t++) {
+#pragma unroll
+        for (int u = 0; u < 4; u++)
+          ip[u] = fmaf(qs[(m + u) * dsub + t], pqs[((size_t)(m + u) * 256 + threadIdx.x) * dsub + t], ip[u]);
+      }
+#pragma unroll
+      for (int u = 0; u < 4; u++) out[(m + u) * 256 + threadIdx.x] = -2.f * ip[u];
+    }
+    for (; m < M; m++) {
       const float* pp = pqs + ((size_t)m * 256 + threadIdx.x) * dsub;
       const float* qm = qs + m * dsub;
       float ip = 0.f;
@@ -442,13 +466,14 @@ term3_kernel(const float* __restrict__ q, int64_t nq, int d, const float* __rest
   }
 }
 
-static size_t scan_smem_bytes(int sel_cap, int M, int ksub, int nL, int W) {
+static size_t scan_smem_bytes(int sel_cap, int M, int ksub, int nL, int W, int owner_cap) {
   size_t off = (select_smem_bytes(sel_cap) + 15) & ~size_t(15);
   off += sizeof(float) * M * ksub;
   off += sizeof(float) * ((nL + 3) & ~3);
   off += sizeof(int64_t) * W;
   off += sizeof(int) * ((W + 1 + 3) & ~3);
   off += sizeof(float) * W * 3;
+  off += sizeof(uint16_t) * owner_cap;
   return off;
 }
 
@@ -578,7 +603,8 @@ int vlq_scan_topk(const float* q, int64_t nq, int d, const float* pq, int M, con
     VLQ_LAUNCH(term3_kernel, grid, Q_THREADS, pq_smem, as_stream(stream), q, nq, d, pq, M, a.dsub, t3);
     a.t3 = t3;
   }
-  size_t smem = scan_smem_bytes(a.sel_cap, M, a.ksub, nL, W);
+  a.owner_cap = (int)((long long)W * cap < 4096 ? (long long)W * cap : 4096);
+  size_t smem = scan_smem_bytes(a.sel_cap, M, a.ksub, nL, W, a.owner_cap);
   cudaStream_t st = as_stream(stream);
   const bool al16 = (reinterpret_cast<uintptr_t>(codes) % 16) == 0;
   if (M == 16 && al16) {

@@ -25,7 +25,8 @@ constexpr int kSelMaxItems = 16;  // buffer capacity <= 16 * THREADS
 
 // buffer capacity for a selection of k out of (at most) `total` candidates, appended in batches of `batch` per thread
 __host__ __device__ inline int select_capacity(int k, int threads, int batch, long long total) {
-  long long want = total < 4096 ? total : 4096;
+  long long want = total < 2048 ? total : 2048;  // small buffer: more CTAs per SM, and the first compaction sets a
+                                                 // threshold early so that most later candidates are never stored
   int lo = k + batch * threads;  // one full batch must always fit behind k survivors
   if (want < lo) want = lo;
   int cap = next_pow2((int)want);
