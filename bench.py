@@ -47,6 +47,8 @@ def parse():
     ap.add_argument("--cpu-seconds", type=float, default=15.0, help="CPU-baseline budget in the default arm")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-tc", action="store_true", help="use the exact fp32 CUDA-core kernels for the coarse stage")
+    ap.add_argument("--shape", default="sift", choices=["sift", "deep"], help="sift: d=128 uint8-valued; deep: d=96 unit-norm (use --d 96 --m 8)")
+    ap.add_argument("--u8", action="store_true", help="e2e encode ingests uint8 host vectors (add_with_ids_u8), sift shape only")
     ap.add_argument("--quick", action="store_true", help="small sizes (for debugging the script itself)")
     a = ap.parse_args()
     if a.quick:
@@ -241,8 +243,8 @@ def _run_reference(a):
 def workload_config(a, n_gpus):
     return {
         "workload": "BASELINE.json configs[1]: VLQ C=%d centroids x E=%d lines, PQ m=%d, nLambda=%d, d=%d, synthetic "
-                    "SIFT-shaped %d vectors per GPU; search nq=%d nprobe=%d w1=%d k=%d"
-                    % (a.nlist, a.nedge, a.m, a.nlambda, a.d, a.n, a.nq, a.nprobe, a.w1, a.k),
+                    "%s-shaped %d vectors per GPU; search nq=%d nprobe=%d w1=%d k=%d"
+                    % (a.nlist, a.nedge, a.m, a.nlambda, a.d, a.shape.upper(), a.n, a.nq, a.nprobe, a.w1, a.k),
         "db_vectors_per_gpu": a.n, "db_vectors_total": a.n * n_gpus, "nlist": a.nlist, "nedge": a.nedge, "m": a.m,
         "nq": a.nq, "nprobe": a.nprobe, "w1": a.w1, "k": a.k,
         "parallelism": "id-range database shards, queries replicated, NCCL all-gather of per-shard top-k + merge kernel"
@@ -281,7 +283,8 @@ def run_b200(a):
     # ---- setup (untimed): codebooks trained on the device; identical on all ranks (rank 0 broadcasts)
     t0 = time.time()
     nt = min(C * 64, 4 * a.n)
-    xt = data.sift_like_torch(nt, d=d, kc=a.kc, seed=1, device=dev)
+    gen = data.SyntheticGen(a.shape, d=d, kc=a.kc, device=dev)
+    xt = torch.cat([gen.chunk(7000 + i, min(1 << 20, nt - i * (1 << 20))) for i in range((nt + (1 << 20) - 1) >> 20)])
     model = train.train_vlq(xt, C, E, M, a.nlambda, niter=a.train_iters, pq_niter=10, exact_perm=False)
     del xt
     if world > 1:
@@ -298,9 +301,14 @@ def run_b200(a):
             return ops.l2_assign_tc(x_, pack, want_dist=False)[0]
         return ops.l2_assign(x_, cent, cn, want_dist=False)[0]
 
-    # ---- encode this rank's shard (timed as its own stage: encode Mvec/s)
-    xb = data.sift_like_torch(a.n, d=d, kc=a.kc, seed=1000 + rank, device=dev)  # queries use seed 3
+    # ---- encode this rank's shard (timed as its own stage: encode Mvec/s).  The database is streamed in 1 Mi-vector
+    #      chunks from a deterministic generator (a 1B-scale shard does not fit in one fp32 tensor); generation is
+    #      outside the timed events.
     chunk = 1 << 20
+
+    def db_chunk(s):  # rows [s, s + chunk) of this rank's shard
+        return gen.chunk((1000 + rank) * 1000003 + s // chunk, min(chunk, a.n - s))
+
     id0 = rank * a.n
     lists = None
     barrier()
@@ -308,41 +316,55 @@ def run_b200(a):
     if prof == "encode":
         torch.cuda.profiler.start()
     n_before = ops.launch_count()
-    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    ev0.record()
+    evs = []
     parts = []
     for s in range(0, a.n, chunk):
-        x = xb[s:s + chunk]
+        x = db_chunk(s)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
         A = assign(x)
         parts.append(ops.line_encode(x, A, cent, edge, ed2, lcb, pq))
+        e1.record()
+        evs.append((e0, e1))
+        parts[-1] = ops.Encoded(parts[-1].list, None, parts[-1].lamq, parts[-1].codes, parts[-1].kappa, None)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
     new_list = torch.cat([p.list for p in parts])
     ids = torch.arange(id0, id0 + a.n, dtype=torch.int64, device=dev)
     lists = ops.build_lists(C * E, M, new_list, torch.cat([p.codes for p in parts]), torch.cat([p.lamq for p in parts]),
                             torch.cat([p.kappa for p in parts]), ids)
-    ev1.record()
+    e1.record()
+    evs.append((e0, e1))
     barrier()
     if prof == "encode":
         torch.cuda.profiler.stop()
-    enc_ms = torch.tensor([ev0.elapsed_time(ev1)], device=dev)
+    enc_ms = torch.tensor([sum(x0.elapsed_time(x1) for x0, x1 in evs)], device=dev)
     if world > 1:
         dist.all_reduce(enc_ms, op=dist.ReduceOp.MAX)
     enc_ms = float(enc_ms)
     enc_launches = ops.launch_count() - n_before
-    del parts, new_list
+    del parts, new_list, ids
+    torch.cuda.empty_cache()
     log("encoded %d vectors/GPU in %.1f ms" % (a.n, enc_ms))
 
     # ---- queries + exact ground truth (brute force over every shard, for recall)
-    xq = data.sift_like_torch(nq, d=d, kc=a.kc, seed=3, device=dev)
+    xq = gen.chunk(3, nq)
     gt_d = torch.full((nq,), float("inf"), device=dev)
     gt_i = torch.full((nq,), -1, dtype=torch.int64, device=dev)
-    qn = ops.row_norms(xq)
     gchunk = 1 << 18
-    for s in range(0, a.n, gchunk):  # "centroids" = a database slice; argmin per query = exact 1-NN in the slice
-        sl = xb[s:s + gchunk]
-        i_, d_ = ops.l2_assign(xq, sl, add_xnorm=True)
-        better = d_ < gt_d
-        gt_d = torch.where(better, d_, gt_d)
-        gt_i = torch.where(better, i_.to(torch.int64) + (id0 + s), gt_i)
+    exact_gt = a.n <= 20_000_000  # beyond that the brute force runs on the tensor-core kernel (fp32-grade)
+    for s0 in range(0, a.n, chunk):
+        xc = db_chunk(s0)
+        for s in range(0, xc.shape[0], gchunk):  # "centroids" = a database slice; argmin per query = exact 1-NN in the slice
+            sl = xc[s:s + gchunk]
+            if exact_gt or not use_tc:
+                i_, d_ = ops.l2_assign(xq, sl, add_xnorm=True)
+            else:
+                i_, d_ = ops.l2_assign_tc(xq, ops.CentPack(sl), add_xnorm=True)
+            better = d_ < gt_d
+            gt_d = torch.where(better, d_, gt_d)
+            gt_i = torch.where(better, i_.to(torch.int64) + (id0 + s0 + s), gt_i)
+        del xc
     if world > 1:
         all_d = [torch.empty_like(gt_d) for _ in range(world)]
         all_i = [torch.empty_like(gt_i) for _ in range(world)]
@@ -351,8 +373,6 @@ def run_b200(a):
         sd, si = torch.stack(all_d), torch.stack(all_i)
         best = sd.argmin(dim=0, keepdim=True)
         gt_i = si.gather(0, best)[0]
-    xb_keep = xb
-    del xb
 
     # ---- the step
     gD = torch.empty((world, nq, k), dtype=torch.float32, device=dev) if world > 1 else None
@@ -412,17 +432,23 @@ def run_b200(a):
     hidx.setNumProbes(P)
     hidx.w1_ = W
     hidx.reserveMemory(a.n)  # GpuIndexIVFPQ::reserveMemory, as the reference drivers do before a bulk load
-    add_chunk = 2_000_000  # the reference drivers ingest 2 M vectors per add (gpu/test/sift1b_createdb.cpp:276-289)
-    hx = torch.empty((min(add_chunk, a.n), d), dtype=torch.float32).pin_memory()
+    add_chunk = 2 * chunk  # the reference drivers ingest 2 M vectors per add (gpu/test/sift1b_createdb.cpp:276-289)
+    use_u8 = a.u8 and a.shape == "sift"
+    hx = torch.empty((min(add_chunk, a.n), d), dtype=torch.uint8 if use_u8 else torch.float32).pin_memory()
     hids = torch.empty(min(add_chunk, a.n), dtype=torch.int64).pin_memory()
     enc_e2e_s = 0.0
     for s in range(0, a.n, add_chunk):
         m_ = min(add_chunk, a.n - s)
-        hx[:m_].copy_(xb_keep[s:s + m_])  # staging the synthetic rows on the host is not part of the timed region
+        for s2 in range(s, s + m_, chunk):  # staging the synthetic rows on the host is not part of the timed region
+            xc = db_chunk(s2)
+            hx[s2 - s:s2 - s + xc.shape[0]].copy_(xc.to(torch.uint8) if use_u8 else xc)
         hids[:m_].copy_(torch.arange(id0 + s, id0 + s + m_, dtype=torch.int64))
         torch.cuda.synchronize()
         t0 = time.perf_counter()
-        hidx.add_with_ids(hx[:m_], hids[:m_])
+        if use_u8:
+            hidx.add_with_ids_u8(hx[:m_], hids[:m_])
+        else:
+            hidx.add_with_ids(hx[:m_], hids[:m_])
         enc_e2e_s += time.perf_counter() - t0
     t0 = time.perf_counter()
     hidx.search(xq[:8].cpu().numpy(), k)  # first search commits the pending entries into the CSR lists
@@ -432,7 +458,7 @@ def run_b200(a):
     if world > 1:
         dist.all_reduce(enc_e2e, op=dist.ReduceOp.MAX)
     enc_e2e_s = float(enc_e2e)
-    del xb_keep, hx
+    del hx
     torch.cuda.empty_cache()
 
     hq = torch.empty((nq, d), dtype=torch.float32).pin_memory()
@@ -567,8 +593,9 @@ def run_b200(a):
             "gpu_launches": launches, "roofline": roof, "cpu_baseline": cpu_baseline, "clocks": clk, "recall": recall,
             "encode": {"value": a.n * world / (enc_ms * 1e-3) / 1e6, "unit": "Mvec/s", "ms": enc_ms,
                        "e2e": {"value": a.n * world / enc_e2e_s / 1e6, "unit": "Mvec/s",
-                               "h2d_bytes_per_vector": d * 4 + 8, "note": "GpuIndexIVFPQ::add_with_ids from pinned host "
-                               "memory in 2 M-vector chunks + list commit"},
+                               "h2d_bytes_per_vector": (d if use_u8 else d * 4) + 8,
+                               "note": "GpuIndexIVFPQ::add_with_ids%s from pinned host memory in 2 Mi-vector chunks + "
+                                       "list commit" % ("_u8" if use_u8 else "")},
                        "gpu_launches": enc_launches,
                        "tensor_frac": (a.n * 2.0 * C * d / (enc_ms * 1e-3) / 1e12) / peaks.get("bf16_tflops_sustained", 1400.0)},
             "scanned_entries_per_query": scanned_per_q, "parity_vs_oracle": parity,

@@ -43,6 +43,8 @@ int vlq_host_vlq_set_nprobe(void* index, int nprobe);
 int vlq_host_vlq_set_w1(void* index, int w1);
 int vlq_host_vlq_set_list_cap(void* index, int cap);
 int vlq_host_vlq_set_train_iters(void* index, int niter);
+/* uint8-valued vectors: bytes over PCIe, widened on the device (ids may be NULL: sequential) */
+int vlq_host_vlq_add_with_ids_u8(void* index, long n, const unsigned char* x, const long* ids);
 int vlq_host_vlq_reserve_memory(void* index, long num_vecs); /* GpuIndexIVFPQ::reserveMemory */
 /* sizes: coarse nlist*d, edge / edge_dist nlist*nedge, lambda_cb nlambda, pq 256*d */
 int vlq_host_vlq_get_codebooks(void* index, float* coarse, int* edge, float* edge_dist, float* lambda_cb, float* pq);

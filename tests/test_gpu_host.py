@@ -223,3 +223,20 @@ def test_add_with_ids_and_reset(vi, res, small_model):
     assert idx.ntotal == 0
     D, I = idx.search(m["xq"], 3)
     assert np.all(I == -1) and np.all(D == np.finfo(np.float32).max)
+
+
+def test_add_u8_equals_add_f32(vi, res, small_model):
+    """uint8 ingestion (bytes over PCIe, widened on the device) stores exactly what the fp32 path stores"""
+    m = small_model
+    xb = m["xb"][:6000]
+    assert np.array_equal(xb, xb.astype(np.uint8).astype(np.float32))  # SIFT-shaped data is uint8-valued
+    a = _build(vi, res, m, xb, chunks=1)
+    b = vi.GpuIndexIVFPQ(res, m["d"], m["C"], m["M"], 8, m["E"], 256)
+    b.setCodebooks(m["cent"], m["edge"], m["edge_d2"], m["lambda_cb"], m["pq"])
+    b.add_with_ids_u8(xb.astype(np.uint8), np.arange(6000, dtype=np.int64))
+    for idx in (a, b):
+        idx.setNumProbes(16)
+        idx.w1_ = 128
+    Da, Ia = a.search(m["xq"], 10)
+    Db, Ib = b.search(m["xq"], 10)
+    assert np.array_equal(Ia, Ib) and np.array_equal(Da, Db)

@@ -47,6 +47,37 @@ def sift_like_torch(n, d=128, kc=1 << 18, sigma=24.0, seed=1, centre_seed=1234, 
     return out
 
 
+class SyntheticGen:
+    """Chunk-wise deterministic generator on the GPU (bench.py streams databases that do not fit in one tensor).
+    shape "sift": uint8-valued, d=128-like mixture; shape "deep": unit-norm float vectors."""
+
+    def __init__(self, shape="sift", d=128, kc=1 << 18, sigma=None, centre_seed=1234, device="cuda"):
+        import torch
+
+        self.shape, self.d, self.kc, self.device = shape, d, kc, device
+        g = torch.Generator(device=device)
+        g.manual_seed(centre_seed)
+        if shape == "sift":
+            self.sigma = 24.0 if sigma is None else sigma
+            self.centres = torch.randint(0, 128, (kc, d), generator=g, device=device, dtype=torch.int32).to(torch.float32)
+        else:
+            self.sigma = 0.08 if sigma is None else sigma
+            c = torch.randn((kc, d), generator=g, device=device)
+            self.centres = c / c.norm(dim=1, keepdim=True)
+
+    def chunk(self, seed, n, dtype=None):
+        import torch
+
+        g = torch.Generator(device=self.device)
+        g.manual_seed(int(seed))
+        j = torch.randint(0, self.kc, (n,), generator=g, device=self.device)
+        x = self.centres[j] + self.sigma * torch.randn((n, self.d), generator=g, device=self.device)
+        if self.shape == "sift":
+            x = x.round_().clamp_(0, 255)
+            return x.to(dtype) if dtype is not None else x
+        return x / x.norm(dim=1, keepdim=True)
+
+
 def recall_at(I, gt, r):
     """fraction of queries whose true 1-NN (gt[i]) is among the first r returned labels
     (gpu/test/sift1b_query.cpp:334-347, tests/demo_sift1M.cpp:233-246)"""

@@ -195,32 +195,46 @@ void GpuIndexIVFPQ::ensurePending_(size_t extra) {
 
 // classifyAndAddVectors (gpu/GpuIndexIVFPQ.cu:577-908), entirely on the device: coarse NN -> fused line stage / lambda
 // quantiser / residual / PQ encode -> append to the pending arena.  Tiles of <= 512 Ki vectors like gpu/GpuIndex.cu:75-106.
-void GpuIndexIVFPQ::add_with_ids(Index::idx_t n, const float* x, const long* xids) {
+void GpuIndexIVFPQ::add_with_ids(Index::idx_t n, const float* x, const long* xids) { addTiles_(n, x, false, xids); }
+
+// uint8 input (SIFT1B .bvecs payload): 4x fewer bytes over PCIe, widened to fp32 on the device (exact)
+void GpuIndexIVFPQ::add_with_ids_u8(Index::idx_t n, const uint8_t* x, const long* xids) { addTiles_(n, x, true, xids); }
+
+void GpuIndexIVFPQ::addTiles_(Index::idx_t n, const void* xv, bool isU8, const long* xids) {
   VLQ_THROW_IF_NOT_MSG(is_trained, "Index not trained");
   if (n == 0) return;
-  VLQ_THROW_IF_NOT(n > 0 && x);
+  VLQ_THROW_IF_NOT(n > 0 && xv);
   DeviceScope scope(ivfConfig_.device);
   vlq_stream_t st = resources_->getDefaultStream();
   ensurePending_((size_t)n);
   const Index::idx_t tile = (Index::idx_t)1 << 19;
   const int M = subQuantizers_;
-  const bool onDevice = vlq_pointer_is_device(x) == 1;
+  const size_t esz = isU8 ? 1 : sizeof(float);
+  const uint8_t* xb = static_cast<const uint8_t*>(xv);
+  const bool onDevice = vlq_pointer_is_device(xv) == 1;
   vlq_stream_t cs = resources_->getAsyncCopyStream();
   DeviceBuffer& dA = addA_;
   // host input: tile i+1 is staged on the copy stream while tile i is encoded on the compute stream
-  auto stage = [&](Index::idx_t s, int slot) -> const float* {
+  auto stage = [&](Index::idx_t s, int slot) -> const void* {
     const Index::idx_t m = std::min(tile, n - s);
-    if (onDevice) return x + (size_t)s * d;
-    addIn_[slot].reserve((size_t)tile * d * sizeof(float));
-    VLQ_CALL(vlq_memcpy_h2d(addIn_[slot].get(), x + (size_t)s * d, (size_t)m * d * sizeof(float), cs));
-    return addIn_[slot].as<float>();
+    if (onDevice) return xb + (size_t)s * d * esz;
+    addIn_[slot].reserve((size_t)tile * d * esz);
+    VLQ_CALL(vlq_memcpy_h2d(addIn_[slot].get(), xb + (size_t)s * d * esz, (size_t)m * d * esz, cs));
+    return addIn_[slot].get();
   };
-  const float* cur = stage(0, 0);
+  const void* cur = stage(0, 0);
   if (!onDevice) VLQ_CALL(vlq_stream_synchronize(cs));
   int slot = 0;
   for (Index::idx_t s = 0; s < n; s += tile) {
     const Index::idx_t m = std::min(tile, n - s);
-    const float* dx = cur;
+    const float* dx;
+    if (isU8) {
+      addF32_.reserve((size_t)tile * d * sizeof(float));
+      VLQ_CALL(vlq_u8_to_f32(static_cast<const uint8_t*>(cur), (int64_t)m * d, addF32_.as<float>(), st));
+      dx = addF32_.as<float>();
+    } else {
+      dx = static_cast<const float*>(cur);
+    }
     dA.reserve((size_t)m * sizeof(int));
     quantizer_->assignDevice(dx, m, dA.as<int>(), nullptr, false);
     const size_t o = nPending_;

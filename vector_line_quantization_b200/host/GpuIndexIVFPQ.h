@@ -72,6 +72,9 @@ class GpuIndexIVFPQ : public GpuIndexIVF {
 
   void train(Index::idx_t n, const float* x) override;
   void add_with_ids(Index::idx_t n, const float* x, const long* xids) override;
+  /// uint8-valued vectors (the SIFT1B .bvecs payload the reference drivers widen on the host,
+  /// gpu/test/sift1b_createdb.cpp:276-289): copied as bytes, widened to fp32 on the device
+  void add_with_ids_u8(Index::idx_t n, const uint8_t* x, const long* xids);
   void search(Index::idx_t n, const float* x, Index::idx_t k, float* distances, Index::idx_t* labels) const override;
   void reset() override;
 
@@ -110,6 +113,7 @@ class GpuIndexIVFPQ : public GpuIndexIVF {
   void uploadTables_();
   void commit_() const;  ///< merge pending entries into the CSR lists (lazy: first search / list access after adds)
   void ensurePending_(size_t extra);
+  void addTiles_(Index::idx_t n, const void* x, bool isU8, const long* xids);
   void installLists_(const std::vector<int>& counts, const std::vector<uint8_t>& codes, const std::vector<uint8_t>& las,
                      const std::vector<long>& ids);
 
@@ -127,7 +131,7 @@ class GpuIndexIVFPQ : public GpuIndexIVF {
   // pending (encoded, arrival order)
   mutable DeviceBuffer pList_, pCodes_, pLamq_, pKappa_, pIds_;
   mutable size_t nPending_, capPending_;
-  mutable DeviceBuffer scratch_, scratchB_, qIn_, outD_, outI_, addIn_[2], addA_, t3ws_;  // grow-only staging / workspace
+  mutable DeviceBuffer scratch_, scratchB_, qIn_, outD_, outI_, addIn_[2], addA_, addF32_, t3ws_;  // grow-only staging / workspace
 };
 
 }  // namespace gpu

@@ -106,6 +106,9 @@ int vlq_host_vlq_set_list_cap(void* index, int cap) {
     V(index)->listCap_ = cap;
   })
 }
+int vlq_host_vlq_add_with_ids_u8(void* index, long n, const unsigned char* x, const long* ids) {
+  GUARD(V(index)->add_with_ids_u8(n, x, ids))
+}
 int vlq_host_vlq_reserve_memory(void* index, long num_vecs) { GUARD(V(index)->reserveMemory((size_t)num_vecs)) }
 int vlq_host_vlq_set_train_iters(void* index, int niter) { GUARD(V(index)->cp_.niter = niter) }
 int vlq_host_vlq_get_codebooks(void* index, float* coarse, int* edge, float* edge_dist, float* lambda_cb, float* pq) {

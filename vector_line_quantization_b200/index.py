@@ -186,6 +186,19 @@ class GpuIndexIVFPQ(Index):
     def setListCap(self, cap):
         _call("vlq_host_vlq_set_list_cap", self.h, int(cap))
 
+    def add_with_ids_u8(self, x, ids=None):
+        """x: uint8 [n][d] (numpy or torch, host or device)"""
+        if _is_torch(x):
+            import torch
+
+            assert x.dtype == torch.uint8 and x.is_contiguous()
+            px = C.c_void_p(x.data_ptr())
+        else:
+            x = np.ascontiguousarray(x, np.uint8)
+            px = C.c_void_p(x.ctypes.data)
+        pi, ki, _ = _in(ids, np.int64)
+        _call("vlq_host_vlq_add_with_ids_u8", self.h, C.c_long(x.shape[0]), px, pi)
+
     def reserveMemory(self, num_vecs):
         _call("vlq_host_vlq_reserve_memory", self.h, C.c_long(int(num_vecs)))
 
