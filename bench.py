@@ -32,7 +32,8 @@ def parse():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--n", type=int, default=10_000_000, help="database vectors PER GPU")
+    ap.add_argument("--n", "--db-size", dest="n", type=int, default=10_000_000,
+                    help="database vectors PER GPU (use --db-size under torchrun: its parser treats --n as ambiguous)")
     ap.add_argument("--d", type=int, default=128)
     ap.add_argument("--nlist", type=int, default=65536)
     ap.add_argument("--nedge", type=int, default=32)
@@ -601,9 +602,11 @@ def run_b200(a):
             "scanned_entries_per_query": scanned_per_q, "parity_vs_oracle": parity,
             "host_api_matches_ops_bitwise": host_matches_ops,
         }
-        print(json.dumps(line))
+    else:
+        line = None
     if world > 1:
         dist.destroy_process_group()
+    return line
 
 
 def main():
@@ -611,7 +614,11 @@ def main():
     if a.impl == "reference":
         run_reference(a)
     else:
-        run_b200(a)
+        # libraries (NCCL's version banner, ...) print to fd 1: keep it clean for the ONE JSON line
+        with _StdoutToStderr():
+            line = run_b200(a)
+        if line is not None:
+            print(json.dumps(line), flush=True)
 
 
 if __name__ == "__main__":
