@@ -177,6 +177,9 @@ int vlq_coarse_select_lines(const float* D, int64_t nq, int64_t ldD, const float
  *          = ||q - ((1-l)c + l s) - p(code_i)||^2 - ||q||^2              (same value as the reference's formula)
  *     over the first min(len, cap) entries of each selected list; k smallest ascending, padded (FLT_MAX, -1).
  *     edge_d2 is indexed by list id (term5).  k <= VLQ_MAX_K, W <= VLQ_MAX_K.
+ *     list_len_hint: average list length of the index (entries / lists; 0 = unknown).  >= 24 selects the
+ *     warp-per-list walk (1B-scale lists), otherwise the flattened entry stream (lists of a few entries).  Results are
+ *     identical either way.
  *     workspace (optional, vlq_scan_topk_workspace_bytes): holds the term-3 tables of the batch, built by one
  *     persistent kernel with the PQ codebook in shared memory; with workspace == NULL every query CTA builds its own.
  * ---------------------------------------------------------------------------------------------------------------- */
@@ -184,7 +187,7 @@ size_t vlq_scan_topk_workspace_bytes(int64_t nq, int M);
 int vlq_scan_topk(const float* q, int64_t nq, int d, const float* pq, int M, const float* lambda_cb, int nL,
                   const int* line_list, const float* term1, const float* term6, const float* edge_d2, int W,
                   const int64_t* offsets, const uint8_t* codes, const uint8_t* lamq, const float* kappa,
-                  const int64_t* ids, int k, int cap, float* outD, int64_t* outI, void* workspace,
+                  const int64_t* ids, int k, int cap, int list_len_hint, float* outD, int64_t* outI, void* workspace,
                   size_t workspace_bytes, vlq_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------------------------------

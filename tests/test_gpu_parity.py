@@ -486,3 +486,22 @@ def test_large_encode_roundtrip_properties(ops, cuda):
     # querying with database vectors: the vector itself must be among its own candidates almost always
     hit = (I == torch.arange(256, device=cuda).unsqueeze(1)).any(dim=1).float().mean()
     assert float(hit) > 0.5
+
+
+@pytest.mark.parametrize("P,W,k,cap", [(16, 128, 10, 1024), (32, 1024, 200, 1024), (8, 64, 1024, 3)])
+def test_scan_modes_identical(ops, cuda, oracle, small_model, P, W, k, cap):
+    """the flattened-stream scan and the warp-per-list scan (1B-scale lists) return the same bits"""
+    import torch
+
+    m = small_model
+    gi = _gpu_index(ops, cuda, oracle, m, np.concatenate([m["xb"]] * 3))  # longer lists: every vector three times
+    q = T(m["xq"], cuda)
+    D = ops.l2_distances(q, gi["cent"], gi["cn"])
+    _, cid = ops.select_rows(D, P)
+    lst, t1, t6 = ops.select_lines(D, cid, gi["edge"], gi["ed2"], W)
+    args = (q, gi["pq"], gi["lcb"], lst, t1, t6, gi["ed2"].reshape(-1), gi["lists"], k, cap)
+    D0, I0 = ops.scan_topk(*args, list_len_hint=0)
+    D1, I1 = ops.scan_topk(*args, list_len_hint=100)
+    D2, I2 = ops.scan_topk(*args, list_len_hint=0, use_workspace=False)
+    assert torch.equal(D0, D1) and torch.equal(I0, I1)
+    assert torch.equal(D0, D2) and torch.equal(I0, I2)

@@ -258,7 +258,7 @@ struct CodeRegs {
 #pragma unroll
       for (int t = 0; t < M_T / 4; t++)
 #pragma unroll
-        for (int b = 0; b < 4; b++) acc += T3[(t * 4 + b) * 256 + ((w[t] >> (8 * b)) & 0xff)];
+        for (int b = 0; b < 4; b++) acc += T3[(t * 4 + b) * 256 + __byte_perm(w[t], 0, 0x4440 + b)];  // PRMT + LDS.X4 + FADD
     } else {
       for (int m = 0; m < M; m++) acc += T3[m * ksub + ptr[m]];
     }
@@ -266,7 +266,10 @@ struct CodeRegs {
   }
 };
 
-template <int M_T>
+// LONG = false: the selected lists are walked as ONE flattened entry stream (lists of a handful of entries keep all
+//               lanes busy);  LONG = true: every warp owns whole lists (slot w -> warp w % 8) and strides their entries,
+//               so the per-list scalars are warp-uniform and nothing has to be searched per entry.
+template <int M_T, bool LONG>
 __global__ void __launch_bounds__(Q_THREADS) scan_topk_kernel(ScanArgs a) {
   extern __shared__ __align__(16) unsigned char smem[];
   // smem: [topk keys S*8 + 16][T3 M*ksub f32][lambda nL f32][per line: start i64, prefix i32 (W+1), t1, t6, t5 f32]
@@ -289,7 +292,7 @@ __global__ void __launch_bounds__(Q_THREADS) scan_topk_kernel(ScanArgs a) {
   off += sizeof(float) * W;
   uint16_t* owner = reinterpret_cast<uint16_t*>(smem + off);  // [owner_cap] line slot of every stream position
 
-  sel.init(smem, a.k, a.sel_cap, Q_BATCH);
+  sel.init(smem, a.k, a.sel_cap, LONG ? 2 : Q_BATCH);
   const int64_t qi = blockIdx.x;
   const float* qv = a.q + qi * a.d;
 
@@ -348,30 +351,96 @@ __global__ void __launch_bounds__(Q_THREADS) scan_topk_kernel(ScanArgs a) {
   }
   __syncthreads();
   const int total = prefix[W];
-  const bool use_owner = total <= a.owner_cap;  // block-uniform
+  if (LONG) {
+    constexpr int NW = Q_THREADS / 32;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    int* rounds_s = reinterpret_cast<int*>(owner);  // scratch (the owner table is unused in this mode)
+    if (threadIdx.x == 0) *rounds_s = 0;
+    __syncthreads();
+    int mine = 0;  // 64-entry rounds this warp needs for its lists
+    for (int w = warp + NW * lane; w < W; w += NW * 32) mine += (prefix[w + 1] - prefix[w] + 63) >> 6;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) mine += __shfl_xor_sync(kFull, mine, o);
+    if (lane == 0) atomicMax(rounds_s, mine);
+    __syncthreads();
+    const int rounds = *rounds_s;
+    int li = warp, off_ = 0;
+    for (int r = 0; r < rounds; r++) {
+      bool any = false;
+      while (li < W && off_ >= prefix[li + 1] - prefix[li]) {  // warp-uniform: next non-exhausted list
+        li += NW;
+        off_ = 0;
+      }
+      if (li < W) {
+        const int p0 = prefix[li], len = prefix[li + 1] - p0;
+        const int64_t st = lstart[li];
+        const float t1 = lt1[li], t6 = lt6[li], t5 = lt5[li];
+        CodeRegs<M_T> cr[2];
+        uint8_t lq[2];
+        float kp[2];
+#pragma unroll
+        for (int u = 0; u < 2; u++) {
+          const int e = off_ + u * 32 + lane;
+          lq[u] = 0;
+          kp[u] = 0.f;
+          if (e < len) {
+            const int64_t ent = st + e;
+            cr[u].load(a.codes + ent * M);
+            lq[u] = a.lamq[ent];
+            kp[u] = a.kappa[ent];
+          }
+        }
+#pragma unroll
+        for (int u = 0; u < 2; u++) {
+          const int e = off_ + u * 32 + lane;
+          const bool valid = e < len;
+          float dist = 0.f;
+          if (valid) {
+            const float la = lcb[lq[u]];
+            const float base_d = t1 + la * t6 + (la * la - la) * t5;
+            dist = (kp[u] + cr[u].adc(T3, M, ksub)) + base_d;
+          }
+          any |= sel.offer_f(valid, dist, (uint32_t)(p0 + e));
+        }
+        off_ += 64;
+      }
+      sel.end_batch(any);
+    }
+  }
+  const bool use_owner = !LONG && total <= a.owner_cap;  // block-uniform
   if (use_owner) {  // each line writes its slot over its own range of stream positions (lists are short here)
     for (int w = threadIdx.x; w < W; w += Q_THREADS)
       for (int p = prefix[w]; p < prefix[w + 1]; p++) owner[p] = (uint16_t)w;
     __syncthreads();
   }
 
-  for (int base = 0; base < total; base += Q_BATCH * Q_THREADS) {
+  for (int base = 0; !LONG && base < total; base += Q_BATCH * Q_THREADS) {
     // phase A: which list / entry each stream position is; phase B: all global loads of the batch in flight;
     // phase C: arithmetic.  (Interleaving them serialises ~3 DRAM latencies per entry.)
+    // stream positions are warp-contiguous: warp w owns [base + 128 w, base + 128 w + 128), lane l the positions
+    // +l, +32+l, ...  One (warp-uniform) binary search finds the list of the warp's first position; every lane then
+    // walks forward from there -- 0-2 steps when lists are long.  Small batches use the owner table instead.
     int lo_[Q_BATCH];
     int64_t ent_[Q_BATCH];
+    const int wpos0 = base + (threadIdx.x >> 5) * (Q_BATCH * 32);
+    int wlo = 0;
+    if (!use_owner && wpos0 < total) {
+      int hi = W;
+      while (hi - wlo > 1) {  // largest w with prefix[w] <= wpos0
+        int mid = (wlo + hi) >> 1;
+        if (prefix[mid] <= wpos0) wlo = mid; else hi = mid;
+      }
+    }
 #pragma unroll
     for (int b = 0; b < Q_BATCH; b++) {
-      const int pos = base + b * Q_THREADS + threadIdx.x;
-      int lo = 0, hi = W;
+      const int pos = wpos0 + b * 32 + (threadIdx.x & 31);
+      int lo = wlo;
       if (pos < total) {
         if (use_owner) {
           lo = owner[pos];
         } else {
-          while (hi - lo > 1) {  // list of this stream position: largest w with prefix[w] <= pos
-            int mid = (lo + hi) >> 1;
-            if (prefix[mid] <= pos) lo = mid; else hi = mid;
-          }
+          while (lo + 1 < W && prefix[lo + 1] <= pos) lo++;
+          wlo = lo;  // positions of later sub-batches are larger: continue the walk from here
         }
       }
       lo_[b] = lo;
@@ -393,7 +462,7 @@ __global__ void __launch_bounds__(Q_THREADS) scan_topk_kernel(ScanArgs a) {
     bool any = false;
 #pragma unroll
     for (int b = 0; b < Q_BATCH; b++) {
-      const int pos = base + b * Q_THREADS + threadIdx.x;
+      const int pos = wpos0 + b * 32 + (threadIdx.x & 31);
       const bool valid = ent_[b] >= 0;
       float dist = 0.f;
       if (valid) {
@@ -464,6 +533,195 @@ term3_kernel(const float* __restrict__ q, int64_t nq, int d, const float* __rest
       out[m * 256 + threadIdx.x] = -2.f * ip;
     }
   }
+}
+
+// ------------------------------------------------------------------------------------------------ asynchronous scan
+// The 1B-scale variant of scan_topk_kernel (k <= 128): one CTA per query, but every WARP runs on its own -- it grabs the
+// next selected list from a shared counter, strides its entries (2 per lane per step, loads first), and keeps its own
+// exact top-k in a WarpSelect.  No block barrier between setup and the final merge, so the loads of eight independent
+// list walks per CTA are in flight at any time.  Same results as the other two modes (selection is exact and keys are
+// unique stream positions).
+template <int M_T>
+__global__ void __launch_bounds__(Q_THREADS) scan_async_kernel(ScanArgs a) {
+  extern __shared__ __align__(16) unsigned char smem[];
+  constexpr int NW = Q_THREADS / 32;
+  const int M = a.M, ksub = a.ksub, W = a.W;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  // smem: [block select (final merge)][NW x warp select][T3][lcb][lstart i64 W][prefix i32 W+1][t1 t6 t5 f32 W][misc]
+  size_t off = (select_smem_bytes(a.sel_cap) + 15) & ~size_t(15);
+  unsigned char* wsel = smem + off;
+  off += (size_t)NW * kWarpSelSmemBytes;
+  float* T3 = reinterpret_cast<float*>(smem + off);
+  off += sizeof(float) * M * ksub;
+  float* lcb = reinterpret_cast<float*>(smem + off);
+  off += sizeof(float) * ((a.nL + 3) & ~3);
+  int64_t* lstart = reinterpret_cast<int64_t*>(smem + off);
+  off += sizeof(int64_t) * W;
+  int* prefix = reinterpret_cast<int*>(smem + off);
+  off += sizeof(int) * ((W + 1 + 3) & ~3);
+  float* lt1 = reinterpret_cast<float*>(smem + off);
+  off += sizeof(float) * W;
+  float* lt6 = reinterpret_cast<float*>(smem + off);
+  off += sizeof(float) * W;
+  float* lt5 = reinterpret_cast<float*>(smem + off);
+  off += sizeof(float) * W;
+  int* misc = reinterpret_cast<int*>(smem + off);  // [0] next line, [1..NW] per-warp survivor counts
+
+  const int64_t qi = blockIdx.x;
+  {
+    const float4* src = reinterpret_cast<const float4*>(a.t3 + (size_t)qi * M * ksub);
+    float4* dst = reinterpret_cast<float4*>(T3);
+    for (int i = threadIdx.x; i < (M * ksub) / 4; i += Q_THREADS) dst[i] = src[i];
+  }
+  for (int i = threadIdx.x; i < a.nL; i += Q_THREADS) lcb[i] = a.lambda_cb[i];
+  for (int w = threadIdx.x; w < W; w += Q_THREADS) {  // line descriptors (lengths capped like IVFUtils.cu:87)
+    const int list = a.line_list[qi * W + w];
+    int len = 0;
+    int64_t st = 0;
+    float t5 = 0.f;
+    if (list >= 0) {
+      st = a.offsets[list];
+      int64_t l = a.offsets[list + 1] - st;
+      len = (int)(l < a.cap ? l : a.cap);
+      t5 = a.edge_d2[list];
+    }
+    lstart[w] = st;
+    prefix[w + 1] = len;
+    lt1[w] = a.term1[qi * W + w];
+    lt6[w] = a.term6[qi * W + w];
+    lt5[w] = t5;
+  }
+  if (threadIdx.x == 0) {
+    prefix[0] = 0;
+    misc[0] = 0;
+  }
+  __syncthreads();
+  if (threadIdx.x < kWarp) {  // inclusive scan of the lengths: stream position of every line (tie order of the results)
+    const int chunk = (W + kWarp - 1) / kWarp;
+    const int b = lane * chunk, e = min(W, b + chunk);
+    int s = 0;
+    for (int w = b; w < e; w++) s += prefix[w + 1];
+    int inc = s;
+#pragma unroll
+    for (int o = 1; o < kWarp; o <<= 1) {
+      int t = __shfl_up_sync(kFull, inc, o);
+      if (lane >= o) inc += t;
+    }
+    int run = inc - s;
+    for (int w = b; w < e; w++) {
+      run += prefix[w + 1];
+      prefix[w + 1] = run;
+    }
+  }
+  __syncthreads();
+
+  WarpSelect ws;
+  ws.init(wsel + (size_t)warp * kWarpSelSmemBytes, a.k);
+  // Software pipeline over 64-entry chunks (possibly of different lists): the loads of chunk i+1 are issued before the
+  // arithmetic of chunk i, so every warp keeps two chunks (~2.7 KB) in flight.
+  struct Chunk {
+    int p0, len, e0;
+    float t1, t6, t5;
+    CodeRegs<M_T> cr[2];
+    uint8_t lq[2];
+    float kp[2];
+    bool ok;
+  };
+  int cur_li = -1, cur_len = 0, cur_e0 = 0;  // warp-uniform walk state
+  auto fetch = [&](Chunk& c) {
+    cur_e0 += 64;
+    while (cur_li < W && cur_e0 >= cur_len) {  // next non-empty list from the shared counter
+      int li = 0;
+      if (lane == 0) li = atomicAdd(&misc[0], 1);
+      li = __shfl_sync(kFull, li, 0);
+      cur_li = li < W ? li : W;
+      cur_e0 = 0;
+      cur_len = cur_li < W ? prefix[cur_li + 1] - prefix[cur_li] : 0;
+    }
+    c.ok = cur_li < W;
+    if (!c.ok) return;
+    c.p0 = prefix[cur_li];
+    c.len = cur_len;
+    c.e0 = cur_e0;
+    c.t1 = lt1[cur_li];
+    c.t6 = lt6[cur_li];
+    c.t5 = lt5[cur_li];
+    const int64_t st = lstart[cur_li];
+#pragma unroll
+    for (int u = 0; u < 2; u++) {
+      const int e = cur_e0 + u * 32 + lane;
+      c.lq[u] = 0;
+      c.kp[u] = 0.f;
+      if (e < cur_len) {
+        const int64_t ent = st + e;
+        c.cr[u].load(a.codes + ent * M);
+        c.lq[u] = a.lamq[ent];
+        c.kp[u] = a.kappa[ent];
+      }
+    }
+  };
+  Chunk A, B;
+  fetch(A);
+  while (A.ok) {
+    fetch(B);
+#pragma unroll
+    for (int u = 0; u < 2; u++) {
+      const int e = A.e0 + u * 32 + lane;
+      const bool valid = e < A.len;
+      float dist = 0.f;
+      if (valid) {
+        const float la = lcb[A.lq[u]];
+        const float base_d = A.t1 + la * A.t6 + (la * la - la) * A.t5;
+        dist = (A.kp[u] + A.cr[u].adc(T3, M, ksub)) + base_d;
+      }
+      ws.offer(valid, dist, (uint32_t)(A.p0 + e));
+    }
+    A = B;
+  }
+  ws.compact();
+  if (lane == 0) misc[1 + warp] = ws.cnt;
+  __syncthreads();
+
+  // ---- merge the NW warp-local top-k sets
+  BlockSelect<Q_THREADS> sel;
+  sel.init(smem, a.k, a.sel_cap, 1);
+  for (int w = 0; w < NW; w++) {
+    const uint64_t* wk = reinterpret_cast<const uint64_t*>(wsel + (size_t)w * kWarpSelSmemBytes);
+    const int n = misc[1 + w];  // <= kWarpSelCap = Q_THREADS: one key per thread
+    const bool valid = (int)threadIdx.x < n;
+    const bool any = sel.offer(valid, valid ? wk[threadIdx.x] : kKeyInf);
+    sel.end_batch(any);
+  }
+  sel.finish();
+  for (int i = threadIdx.x; i < a.k; i += Q_THREADS) {
+    const uint64_t key = sel.keys[i];
+    float dv = FLT_MAX;
+    int64_t id = -1;
+    if (key != kKeyInf) {
+      const int pos = (int)key_payload(key);
+      int lo = 0, hi = W;
+      while (hi - lo > 1) {
+        int mid = (lo + hi) >> 1;
+        if (prefix[mid] <= pos) lo = mid; else hi = mid;
+      }
+      dv = key_val(key);
+      id = a.ids[lstart[lo] + (pos - prefix[lo])];
+    }
+    a.outD[qi * a.k + i] = dv;
+    a.outI[qi * a.k + i] = id;
+  }
+}
+
+static size_t scan_async_smem_bytes(int sel_cap, int M, int ksub, int nL, int W) {
+  size_t off = (select_smem_bytes(sel_cap) + 15) & ~size_t(15);
+  off += (size_t)(Q_THREADS / 32) * kWarpSelSmemBytes;
+  off += sizeof(float) * M * ksub;
+  off += sizeof(float) * ((nL + 3) & ~3);
+  off += sizeof(int64_t) * W;
+  off += sizeof(int) * ((W + 1 + 3) & ~3);
+  off += sizeof(float) * W * 3;
+  off += sizeof(int) * 16;
+  return off;
 }
 
 static size_t scan_smem_bytes(int sel_cap, int M, int ksub, int nL, int W, int owner_cap) {
@@ -579,7 +837,7 @@ size_t vlq_scan_topk_workspace_bytes(int64_t nq, int M) { return (size_t)(nq > 0
 int vlq_scan_topk(const float* q, int64_t nq, int d, const float* pq, int M, const float* lambda_cb, int nL,
                   const int* line_list, const float* term1, const float* term6, const float* edge_d2, int W,
                   const int64_t* offsets, const uint8_t* codes, const uint8_t* lamq, const float* kappa,
-                  const int64_t* ids, int k, int cap, float* outD, int64_t* outI, void* workspace,
+                  const int64_t* ids, int k, int cap, int list_len_hint, float* outD, int64_t* outI, void* workspace,
                   size_t workspace_bytes, vlq_stream_t stream) {
   if (nq > 0 && (!q || !pq || !lambda_cb || !line_list || !term1 || !term6 || !edge_d2 || !offsets || !outD || !outI))
     return VLQ_EINVAL;
@@ -604,19 +862,41 @@ int vlq_scan_topk(const float* q, int64_t nq, int d, const float* pq, int M, con
     a.t3 = t3;
   }
   a.owner_cap = (int)((long long)W * cap < 4096 ? (long long)W * cap : 4096);
+  const bool long_lists = list_len_hint >= 24;  // average list length of the index: warp-per-list pays off
+  if (long_lists && k <= kWarpSelMaxK && a.t3 != nullptr && (M * 256) % 4 == 0) {  // warp-autonomous scan
+    cudaStream_t st_ = as_stream(stream);
+    const int scap = select_capacity(k, Q_THREADS, 1, (long long)(Q_THREADS / 32) * k);  // <= k survivors per warp
+    a.sel_cap = scap;
+    const size_t smem_a = scan_async_smem_bytes(scap, M, a.ksub, nL, W);
+    const bool al16_ = (reinterpret_cast<uintptr_t>(codes) % 16) == 0;
+#define VLQ_ASYNC_LAUNCH(MT)                                                                                          \
+  do {                                                                                                                \
+    VLQ_CUDA_TRY(cudaFuncSetAttribute(scan_async_kernel<MT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_a)); \
+    VLQ_LAUNCH(scan_async_kernel<MT>, (unsigned)nq, Q_THREADS, smem_a, st_, a);                                       \
+  } while (0)
+    if (M == 16 && al16_) VLQ_ASYNC_LAUNCH(16);
+    else if (M == 8 && al16_) VLQ_ASYNC_LAUNCH(8);
+    else VLQ_ASYNC_LAUNCH(0);
+#undef VLQ_ASYNC_LAUNCH
+    return last_error();
+  }
+  if (long_lists) a.sel_cap = select_capacity(k, Q_THREADS, 2, (long long)W * cap);
   size_t smem = scan_smem_bytes(a.sel_cap, M, a.ksub, nL, W, a.owner_cap);
   cudaStream_t st = as_stream(stream);
   const bool al16 = (reinterpret_cast<uintptr_t>(codes) % 16) == 0;
+#define VLQ_SCAN_LAUNCH(MT, LG)                                                                                        \
+  do {                                                                                                                 \
+    VLQ_CUDA_TRY(cudaFuncSetAttribute(scan_topk_kernel<MT, LG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+    VLQ_LAUNCH((scan_topk_kernel<MT, LG>), (unsigned)nq, Q_THREADS, smem, st, a);                                      \
+  } while (0)
   if (M == 16 && al16) {
-    VLQ_CUDA_TRY(cudaFuncSetAttribute(scan_topk_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    VLQ_LAUNCH(scan_topk_kernel<16>, (unsigned)nq, Q_THREADS, smem, st, a);
+    if (long_lists) VLQ_SCAN_LAUNCH(16, true); else VLQ_SCAN_LAUNCH(16, false);
   } else if (M == 8 && al16) {
-    VLQ_CUDA_TRY(cudaFuncSetAttribute(scan_topk_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    VLQ_LAUNCH(scan_topk_kernel<8>, (unsigned)nq, Q_THREADS, smem, st, a);
+    if (long_lists) VLQ_SCAN_LAUNCH(8, true); else VLQ_SCAN_LAUNCH(8, false);
   } else {
-    VLQ_CUDA_TRY(cudaFuncSetAttribute(scan_topk_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    VLQ_LAUNCH(scan_topk_kernel<0>, (unsigned)nq, Q_THREADS, smem, st, a);
+    if (long_lists) VLQ_SCAN_LAUNCH(0, true); else VLQ_SCAN_LAUNCH(0, false);
   }
+#undef VLQ_SCAN_LAUNCH
   return last_error();
 }
 

@@ -281,4 +281,154 @@ struct BlockSelect {
   }
 };
 
+// ---------------------------------------------------------------------------------------------------------------------
+// Warp-scope twin of BlockSelect for k <= 128: one 256-key buffer + one 256-bin histogram per WARP in shared memory.
+// Appends are ballot-compacted (no atomics), the compaction is the same byte-wise radix select with __syncwarp()
+// instead of __syncthreads().  A warp that owns one of these never waits for another warp, which is what lets the
+// 1B-scale scan keep loads of many lists in flight (the block-wide barrier per batch of BlockSelect exposes one DRAM
+// round trip per batch).  The per-warp survivors are merged by a BlockSelect at the very end.
+constexpr int kWarpSelCap = 256;
+constexpr int kWarpSelMaxK = 128;
+constexpr int kWarpSelSmemBytes = kWarpSelCap * 8 + 256 * 4;  // keys | hist
+
+struct WarpSelect {
+  uint64_t* keys;  // [256]
+  int* hist;       // [256]
+  int cnt;         // keys in the buffer (warp-uniform)
+  int k;
+  uint64_t thr;
+  float thr_f;
+
+  __device__ void init(void* smem, int k_) {
+    keys = reinterpret_cast<uint64_t*>(smem);
+    hist = reinterpret_cast<int*>(keys + kWarpSelCap);
+    cnt = 0;
+    k = k_;
+    thr = kKeyInf;
+    thr_f = __int_as_float(0x7f800000);
+  }
+
+  // warp-collective: every lane offers at most one candidate
+  __device__ __forceinline__ void offer(bool valid, float v, uint32_t payload) {
+    bool take = valid && v <= thr_f;
+    uint64_t key = 0;
+    if (take) {
+      key = make_key(v, payload);
+      take = key < thr;
+    }
+    const unsigned m = __ballot_sync(kFull, take);
+    if (m) {
+      const int lane = threadIdx.x & 31;
+      if (take) keys[cnt + __popc(m & ((1u << lane) - 1))] = key;
+      cnt += __popc(m);
+      if (cnt > kWarpSelCap - 32) compact();
+    }
+  }
+
+  // warp-collective: keep the k smallest keys (unsorted) in keys[0..k), thr = k-th smallest
+  __device__ void compact() {
+    __syncwarp();
+    const int n = cnt;
+    if (n <= k) return;
+    const int lane = threadIdx.x & 31;
+    constexpr int ITEMS = kWarpSelCap / 32;
+    uint64_t mine[ITEMS];
+    unsigned dhi = 0, dlo = 0;
+    const uint64_t key0 = keys[0];
+#pragma unroll
+    for (int t = 0; t < ITEMS; t++) {
+      const int i = lane + 32 * t;
+      mine[t] = i < n ? keys[i] : kKeyInf;
+      if (i < n) {
+        const uint64_t x = mine[t] ^ key0;
+        dhi |= (unsigned)(x >> 32);
+        dlo |= (unsigned)x;
+      }
+    }
+    dhi = __reduce_or_sync(kFull, dhi);
+    dlo = __reduce_or_sync(kFull, dlo);
+    const uint64_t diff = ((uint64_t)dhi << 32) | dlo;
+    const int top = diff ? (63 - __clzll((long long)diff)) >> 3 : 0;
+    uint64_t prefix = top == 7 ? 0 : (key0 >> ((top + 1) * 8));
+    int need = k;
+    uint64_t kth = 0;
+    bool found = false;
+#pragma unroll 1
+    for (int pass = top; pass >= 0; pass--) {
+#pragma unroll
+      for (int j = 0; j < 8; j++) hist[lane * 8 + j] = 0;
+      __syncwarp();
+      const int shift = pass * 8;
+#pragma unroll
+      for (int t = 0; t < ITEMS; t++) {
+        const bool in = lane + 32 * t < n;
+        const bool match = in && (pass == 7 ? true : ((mine[t] >> (shift + 8)) == prefix));
+        if (match) atomicAdd(&hist[(int)((mine[t] >> shift) & 255)], 1);
+      }
+      __syncwarp();
+      int c[8], sum = 0;
+#pragma unroll
+      for (int j = 0; j < 8; j++) {
+        c[j] = hist[lane * 8 + j];
+        sum += c[j];
+      }
+      int inc = sum;
+#pragma unroll
+      for (int o = 1; o < kWarp; o <<= 1) {
+        const int t = __shfl_up_sync(kFull, inc, o);
+        if (lane >= o) inc += t;
+      }
+      int before = inc - sum;
+      const bool here = before < need && need <= inc;  // exactly one lane
+      int digit = 0, rem = 0, inbin = 0;
+      if (here) {
+#pragma unroll
+        for (int j = 0; j < 8; j++) {
+          if (need <= before + c[j]) {
+            digit = lane * 8 + j;
+            rem = need - before;
+            inbin = c[j];
+            break;
+          }
+          before += c[j];
+        }
+      }
+      const int src = __ffs(__ballot_sync(kFull, here)) - 1;
+      digit = __shfl_sync(kFull, digit, src);
+      need = __shfl_sync(kFull, rem, src);
+      inbin = __shfl_sync(kFull, inbin, src);
+      prefix = (prefix << 8) | (uint64_t)digit;
+      __syncwarp();
+      if (inbin == 1 && pass > 0) {  // the wanted key is the only one with this prefix
+        uint64_t cand = 0;
+        bool hit = false;
+#pragma unroll
+        for (int t = 0; t < ITEMS; t++)
+          if (lane + 32 * t < n && (mine[t] >> shift) == prefix) {
+            cand = mine[t];
+            hit = true;
+          }
+        const unsigned who = __ballot_sync(kFull, hit);
+        kth = __shfl_sync(kFull, cand, __ffs(who) - 1);
+        found = true;
+        break;
+      }
+    }
+    if (!found) kth = prefix;
+    // compaction from the register copies (all lanes hold their keys already)
+    int base = 0;
+#pragma unroll
+    for (int t = 0; t < ITEMS; t++) {
+      const bool keep = lane + 32 * t < n && mine[t] <= kth;
+      const unsigned m = __ballot_sync(kFull, keep);
+      if (keep) keys[base + __popc(m & ((1u << lane) - 1))] = mine[t];
+      base += __popc(m);
+    }
+    cnt = base;  // == k
+    thr = kth;
+    thr_f = key_val(kth);
+    __syncwarp();
+  }
+};
+
 }  // namespace vlq

@@ -337,7 +337,7 @@ void GpuIndexIVFPQ::search(Index::idx_t n, const float* x, Index::idx_t k, float
       VLQ_CALL(vlq_scan_topk(q, m, d, dPq_.as<float>(), M, dLambda_.as<float>(), nLambda_, lline, t1, t6,
                              dEdgeDist_.as<float>(), W, lOffsets_.as<int64_t>(), lCodes_.as<uint8_t>(),
                              lLamq_.as<uint8_t>(), lKappa_.as<float>(), lIds_.as<int64_t>(), (int)k, listCap_,
-                             outD.as<float>() + (size_t)s * k, outI.as<int64_t>() + (size_t)s * k, t3ws_.get(),
+                             (int)std::min<size_t>(nListed_ / ((size_t)nlist_ * numedge_), 1 << 20), outD.as<float>() + (size_t)s * k, outI.as<int64_t>() + (size_t)s * k, t3ws_.get(),
                              t3ws_.bytes(), st));
     }
     fromDevice(distances + (size_t)p0 * k, outD.get(), (size_t)pn * k * sizeof(float), st);

@@ -172,7 +172,8 @@ def select_lines(D, coarse_ids, edge, edge_d2, W):
 _scan_ws = {}
 
 
-def scan_topk(q, pq, lambda_cb, line_list, term1, term6, edge_d2, lists, k, cap=1024, use_workspace=True):
+def scan_topk(q, pq, lambda_cb, line_list, term1, term6, edge_d2, lists, k, cap=1024, use_workspace=True,
+              list_len_hint=None):
     """ADC scan of the selected lists fused with exact top-k (a13-a15): -> (D f32 [nq][k], I int64 [nq][k])"""
     q = _chk(q, torch.float32, "q")
     pq = _chk(pq, torch.float32, "pq")
@@ -181,6 +182,7 @@ def scan_topk(q, pq, lambda_cb, line_list, term1, term6, edge_d2, lists, k, cap=
     W = line_list.shape[1]
     outD = torch.empty((nq, k), dtype=torch.float32, device=q.device)
     outI = torch.empty((nq, k), dtype=torch.int64, device=q.device)
+    hint = list_len_hint if list_len_hint is not None else lists.ids.shape[0] // max(1, lists.offsets.shape[0] - 1)
     ws = None
     wsb = 0
     if use_workspace:  # term-3 tables of the batch (grow-only cache per device)
@@ -192,7 +194,7 @@ def scan_topk(q, pq, lambda_cb, line_list, term1, term6, edge_d2, lists, k, cap=
     _abi.call("vlq_scan_topk", _ptr(q), nq, d, _ptr(pq), M, _ptr(lambda_cb), lambda_cb.shape[0],
               _ptr(_chk(line_list, torch.int32, "line_list")), _ptr(term1), _ptr(term6), _ptr(edge_d2), W,
               _ptr(lists.offsets), _ptr(lists.codes), _ptr(lists.lamq), _ptr(lists.kappa), _ptr(lists.ids), k, cap,
-              _ptr(outD), _ptr(outI), _ptr(ws), wsb, _stream())
+              int(hint), _ptr(outD), _ptr(outI), _ptr(ws), wsb, _stream())
     return outD, outI
 
 
