@@ -664,17 +664,25 @@ __global__ void __launch_bounds__(Q_THREADS) scan_async_kernel(ScanArgs a) {
   fetch(A);
   while (A.ok) {
     fetch(B);
+    float dist[2];
+    bool pass = false;
 #pragma unroll
     for (int u = 0; u < 2; u++) {
       const int e = A.e0 + u * 32 + lane;
-      const bool valid = e < A.len;
-      float dist = 0.f;
-      if (valid) {
+      dist[u] = __int_as_float(0x7f800000);
+      if (e < A.len) {
         const float la = lcb[A.lq[u]];
         const float base_d = A.t1 + la * A.t6 + (la * la - la) * A.t5;
-        dist = (A.kp[u] + A.cr[u].adc(T3, M, ksub)) + base_d;
+        dist[u] = (A.kp[u] + A.cr[u].adc(T3, M, ksub)) + base_d;
+        pass |= dist[u] <= ws.thr_f;
       }
-      ws.offer(valid, dist, (uint32_t)(A.p0 + e));
+    }
+    if (__any_sync(kFull, pass)) {  // rare once the threshold has tightened
+#pragma unroll
+      for (int u = 0; u < 2; u++) {
+        const int e = A.e0 + u * 32 + lane;
+        ws.offer(e < A.len, dist[u], (uint32_t)(A.p0 + e));
+      }
     }
     A = B;
   }
