@@ -488,7 +488,8 @@ def test_large_encode_roundtrip_properties(ops, cuda):
     assert float(hit) > 0.5
 
 
-@pytest.mark.parametrize("P,W,k,cap", [(16, 128, 10, 1024), (32, 1024, 200, 1024), (8, 64, 1024, 3)])
+@pytest.mark.parametrize("P,W,k,cap", [(16, 128, 10, 1024), (32, 1024, 200, 1024), (8, 64, 1024, 3), (32, 1024, 100, 1024),
+                                       (32, 1024, 128, 5)])
 def test_scan_modes_identical(ops, cuda, oracle, small_model, P, W, k, cap):
     """the flattened-stream scan and the warp-per-list scan (1B-scale lists) return the same bits"""
     import torch
