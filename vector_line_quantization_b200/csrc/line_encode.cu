@@ -215,11 +215,17 @@ __global__ void __launch_bounds__(LE_THREADS, 1) line_encode_kernel(LineEncodeAr
             dis[c] = fmaf(df, df, dis[c]);
           }
         }
+        // lane-local arg-min on the floats (strict <: the lowest codeword index wins ties), one 64-bit key per lane
+        float bd = dis[0];
+        int bc = 0;
 #pragma unroll
-        for (int c = 0; c < 8; c++) {
-          const uint64_t key = make_key(dis[c], (uint32_t)(lane + 32 * c));
-          kc = key < kc ? key : kc;
+        for (int c = 1; c < 8; c++) {
+          if (dis[c] < bd) {
+            bd = dis[c];
+            bc = c;
+          }
         }
+        kc = make_key(bd, (uint32_t)(lane + 32 * bc));
       } else {
         for (int j = lane; j < ksub; j += kWarp) {
           const float* pp = a.pq + ((size_t)m * ksub + j) * dsub;

@@ -258,7 +258,7 @@ struct CodeRegs {
 #pragma unroll
       for (int t = 0; t < M_T / 4; t++)
 #pragma unroll
-        for (int b = 0; b < 4; b++) acc += T3[(t * 4 + b) * 256 + __byte_perm(w[t], 0, 0x4440 + b)];  // PRMT + LDS.X4 + FADD
+        for (int b = 0; b < 4; b++) acc += T3[(t * 4 + b) * 256 + ((w[t] >> (8 * b)) & 0xff)];
     } else {
       for (int m = 0; m < M; m++) acc += T3[m * ksub + ptr[m]];
     }
@@ -433,14 +433,20 @@ __global__ void __launch_bounds__(Q_THREADS) scan_topk_kernel(ScanArgs a) {
     }
 #pragma unroll
     for (int b = 0; b < Q_BATCH; b++) {
-      const int pos = wpos0 + b * 32 + (threadIdx.x & 31);
+      const int pos = use_owner ? base + b * Q_THREADS + (int)threadIdx.x : wpos0 + b * 32 + (int)(threadIdx.x & 31);
       int lo = wlo;
       if (pos < total) {
         if (use_owner) {
           lo = owner[pos];
-        } else {
+        } else if (total >= 16 * W) {  // long lists: a step or two forward from the warp's first list
           while (lo + 1 < W && prefix[lo + 1] <= pos) lo++;
           wlo = lo;  // positions of later sub-batches are larger: continue the walk from here
+        } else {  // many short lists per warp: bounded binary search, largest w with prefix[w] <= pos
+          int hi = W;
+          while (hi - lo > 1) {
+            const int mid = (lo + hi) >> 1;
+            if (prefix[mid] <= pos) lo = mid; else hi = mid;
+          }
         }
       }
       lo_[b] = lo;
@@ -462,7 +468,7 @@ __global__ void __launch_bounds__(Q_THREADS) scan_topk_kernel(ScanArgs a) {
     bool any = false;
 #pragma unroll
     for (int b = 0; b < Q_BATCH; b++) {
-      const int pos = wpos0 + b * 32 + (threadIdx.x & 31);
+      const int pos = use_owner ? base + b * Q_THREADS + (int)threadIdx.x : wpos0 + b * 32 + (int)(threadIdx.x & 31);
       const bool valid = ent_[b] >= 0;
       float dist = 0.f;
       if (valid) {
