@@ -68,6 +68,12 @@ size_t vlq_tc_cent_pack_bytes(int C, int d);
 int vlq_tc_pack_centroids(const float* cent, const float* cnorm, int C, int d, float scale, void* cent_pack,
                           vlq_stream_t stream);
 size_t vlq_l2_tc_workspace_bytes(int64_t n, int d, int C);
+/* vlq_l2_assign_tc flags (the add_xnorm argument): bit 0 = add ||x||^2 to out_dist, bit 1 = single-pass screen
+ * (experimental, needs out_dist == NULL): ONE hi.hi pass keeps best / second best per row; rows whose margin exceeds
+ * twice a rigorous error bound (2^-11 ||x|| max||c|| per rounded operand) have a proven arg-min, the others are
+ * gathered and re-run with the split-precision passes.  Same ids as the default path; currently slower. */
+#define VLQ_ASSIGN_ADD_XNORM 1
+#define VLQ_ASSIGN_SCREEN 2
 int vlq_l2_assign_tc(const float* x, int64_t n, int d, const void* cent_pack, float scale, int C, int add_xnorm,
                      int* out_ids, float* out_dist, void* workspace, size_t workspace_bytes, vlq_stream_t stream);
 /* bucket_min (nullable): [n][vlq_tc_num_buckets(C)], the minimum of every 32-column bucket of D, produced by the GEMM

@@ -104,3 +104,29 @@ def test_fused_coarse_select_equals_two_step(ops, cuda, nq, C, d, P, W, E):
     l1, a1, b1, cid1 = ops.coarse_select_lines(D, bm, C, P, edge, ed2, W, want_coarse=True)
     assert torch.equal(cid1, cid)
     assert torch.equal(l1, l0) and torch.equal(a1, a0) and torch.equal(b1, b0)
+
+
+@pytest.mark.parametrize("n,C,d,kind", [(300, 200, 128, "sift"), (5000, 4096, 96, "deep"), (3000, 65536, 128, "sift"),
+                                        (70000, 2048, 32, "sift"), (260, 130, 64, "deep")])
+def test_screened_assign_equals_split_passes(ops, cuda, n, C, d, kind):
+    """single-pass screen + fallback returns exactly the ids of the split-precision passes (which are checked against the
+    exact fp32 path above), including duplicated centroids (exact ties -> lowest id) and duplicated rows"""
+    import torch
+
+    x, c = _data(n, C, d, 3 * n + C, kind)
+    c[C // 2] = c[3]  # an exact tie between two centroids
+    x[5] = c[3] * 0.999
+    x[6] = x[5]
+    xt, ct = torch.from_numpy(x).to(cuda), torch.from_numpy(c).to(cuda)
+    pack = ops.CentPack(ct)
+    ids_s, _ = ops.l2_assign_tc(xt, pack, want_dist=False, screen=True)
+    ids_e, _ = ops.l2_assign_tc(xt, pack, want_dist=False, screen=False)
+    torch.cuda.synchronize()
+    ids_s, ids_e = ids_s.cpu().numpy(), ids_e.cpu().numpy()
+    bad = np.nonzero(ids_s != ids_e)[0]
+    x64, c64 = x.astype(np.float64), c.astype(np.float64)
+    for i in bad:  # a proven arg-min can only differ from the split passes where those are inside fp32 rounding
+        da, db = np.sum((x64[i] - c64[ids_s[i]]) ** 2), np.sum((x64[i] - c64[ids_e[i]]) ** 2)
+        assert da <= db * (1 + 1e-6) + 1e-9, (i, da, db)
+    assert len(bad) <= max(1, n // 5000)
+    assert ids_s[5] == 3 and ids_s[6] == 3  # ties resolve to the lowest id through the fallback
