@@ -506,3 +506,28 @@ def test_scan_modes_identical(ops, cuda, oracle, small_model, P, W, k, cap):
     D2, I2 = ops.scan_topk(*args, list_len_hint=0, use_workspace=False)
     assert torch.equal(D0, D1) and torch.equal(I0, I1)
     assert torch.equal(D0, D2) and torch.equal(I0, I2)
+
+
+def test_nan_vectors_are_skipped(ops, cuda, oracle, small_model):
+    """invalid (NaN) input rows get no centroid (-1) on both assignment paths and never reach the lists
+    (the reference drops them at add time, gpu/GpuIndexIVFPQ.cu:751-755)"""
+    import torch
+
+    m = small_model
+    x = m["xb"][:1000].copy()
+    x[7, 5] = np.nan
+    x[500, :] = np.nan
+    xt = T(x, cuda)
+    cent = T(m["cent"], cuda)
+    ids_simt, _ = ops.l2_assign(xt, cent)
+    ids_tc, _ = ops.l2_assign_tc(xt, ops.CentPack(cent), want_dist=False)
+    for ids in (N(ids_simt), N(ids_tc)):
+        assert ids[7] == -1 and ids[500] == -1 and (np.delete(ids, [7, 500]) >= 0).all()
+    enc = ops.line_encode(xt, ids_tc, cent, T(m["edge"], cuda), T(m["edge_d2"], cuda), T(m["lambda_cb"], cuda),
+                          T(m["pq"], cuda))
+    assert N(enc.list)[7] == -1 and N(enc.list)[500] == -1
+    lists = ops.build_lists(m["C"] * m["E"], m["M"], enc.list, enc.codes, enc.lamq, enc.kappa,
+                            torch.arange(1000, dtype=torch.int64, device=cuda))
+    assert int(lists.offsets[-1]) == 998
+    stored = set(N(lists.ids)[:998].tolist())
+    assert 7 not in stored and 500 not in stored and len(stored) == 998

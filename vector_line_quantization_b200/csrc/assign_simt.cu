@@ -208,17 +208,15 @@ l2_argmin_kernel(const float* __restrict__ x, int64_t n, int d, const float* __r
     }
     int64_t row = row0 + tile_row(ty, i);
     if (tx == 0 && row < n) {
-      out_ids[row] = (int)key_payload(b);
-      if (out_dist) {
-        float dv = key_val(b);
-        if (add_xnorm) {
-          const float* xr = x + row * d;
-          float xn = 0.f;
-          for (int t = 0; t < d; t++) xn = fmaf(xr[t], xr[t], xn);
-          dv += xn;
-        }
-        out_dist[row] = dv;
-      }
+      // a row containing NaN / Inf has no nearest centroid: id -1, the encoder then skips the vector like the reference
+      // does for invalid input (gpu/GpuIndexIVFPQ.cu:751-755); same behaviour as the tcgen05 path.  Decided from the
+      // row itself (the 64-bit key minimum is not a reliable NaN carrier).
+      const float* xr = x + row * d;
+      float xn = 0.f;
+      for (int t = 0; t < d; t++) xn = fmaf(xr[t], xr[t], xn);
+      const bool valid = xn < __int_as_float(0x7f800000);  // false for NaN and Inf
+      out_ids[row] = (valid && b != kKeyInf) ? (int)key_payload(b) : -1;
+      if (out_dist) out_dist[row] = valid ? key_val(b) + (add_xnorm ? xn : 0.f) : 3.402823466e+38f;
     }
   }
 }
