@@ -506,18 +506,19 @@ __global__ void __launch_bounds__(Q_THREADS) scan_topk_kernel(ScanArgs a) {
 // stage the PQ codebook once in shared memory (natural (m, j, t) layout, plain coalesced copy) and walk the queries;
 // thread j owns codeword j of every sub-quantizer, so the table rows are written coalesced.  Same fmaf chain (t
 // ascending) as the in-kernel build, hence bit-identical tables.
-__global__ void __launch_bounds__(Q_THREADS)
+constexpr int T3_THREADS = 256;  // one thread per codeword of a sub-quantizer (ksub = 256)
+__global__ void __launch_bounds__(T3_THREADS)
 term3_kernel(const float* __restrict__ q, int64_t nq, int d, const float* __restrict__ pq, int M, int dsub,
              float* __restrict__ t3) {
   extern __shared__ __align__(16) float t3s[];
   float* pqs = t3s;                          // [M][256][dsub]
   float* qs = t3s + (size_t)M * 256 * dsub;  // [d]
   const int total4 = (M * 256 * dsub) / 4;   // d % 4 == 0 is checked by the launcher
-  for (int i = threadIdx.x; i < total4; i += Q_THREADS)
+  for (int i = threadIdx.x; i < total4; i += T3_THREADS)
     reinterpret_cast<float4*>(pqs)[i] = reinterpret_cast<const float4*>(pq)[i];
   for (int64_t qi = blockIdx.x; qi < nq; qi += gridDim.x) {
     __syncthreads();
-    for (int j = threadIdx.x; j < d; j += Q_THREADS) qs[j] = q[qi * d + j];
+    for (int j = threadIdx.x; j < d; j += T3_THREADS) qs[j] = q[qi * d + j];
     __syncthreads();
     float* out = t3 + (size_t)qi * M * 256;
     int m = 0;
@@ -701,10 +702,13 @@ __global__ void __launch_bounds__(Q_THREADS) scan_async_kernel(ScanArgs a) {
   sel.init(smem, a.k, a.sel_cap, 1);
   for (int w = 0; w < NW; w++) {
     const uint64_t* wk = reinterpret_cast<const uint64_t*>(wsel + (size_t)w * kWarpSelSmemBytes);
-    const int n = misc[1 + w];  // <= kWarpSelCap = Q_THREADS: one key per thread
-    const bool valid = (int)threadIdx.x < n;
-    const bool any = sel.offer(valid, valid ? wk[threadIdx.x] : kKeyInf);
-    sel.end_batch(any);
+    const int n = misc[1 + w];  // <= k <= kWarpSelCap survivors of warp w
+    for (int i0 = 0; i0 < n; i0 += Q_THREADS) {  // n is block-uniform
+      const int i = i0 + (int)threadIdx.x;
+      const bool valid = i < n;
+      const bool any = sel.offer(valid, valid ? wk[i] : kKeyInf);
+      sel.end_batch(any);
+    }
   }
   sel.finish();
   for (int i = threadIdx.x; i < a.k; i += Q_THREADS) {
@@ -872,7 +876,7 @@ int vlq_scan_topk(const float* q, int64_t nq, int d, const float* pq, int M, con
     float* t3 = static_cast<float*>(workspace);
     VLQ_CUDA_TRY(cudaFuncSetAttribute(term3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pq_smem));
     const unsigned grid = (unsigned)(nq < 148 ? nq : 148);
-    VLQ_LAUNCH(term3_kernel, grid, Q_THREADS, pq_smem, as_stream(stream), q, nq, d, pq, M, a.dsub, t3);
+    VLQ_LAUNCH(term3_kernel, grid, T3_THREADS, pq_smem, as_stream(stream), q, nq, d, pq, M, a.dsub, t3);
     a.t3 = t3;
   }
   a.owner_cap = (int)((long long)W * cap < 4096 ? (long long)W * cap : 4096);
