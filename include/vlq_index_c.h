@@ -58,6 +58,15 @@ int vlq_host_vlq_read_codebook(void* index, const char* name);
 int vlq_host_vlq_write_db(void* index, const char* name);
 int vlq_host_vlq_read_db(void* index, const char* name, int pronum, int rank);
 
+/* dataset / matrix formats of the reference drivers (filehelper.cpp:106-345): TexMex .fvecs (kind 0) / .ivecs (1) /
+ * .bvecs (2), and the .umem/.imem layout (ASCII "num\ndim\n" header, payload at byte 20) */
+int vlq_host_vecs_header(const char* path, int elem_size, long* n, long* d);
+int vlq_host_vecs_read(const char* path, int kind, long start, long num, void* out); /* num == 0: to the end */
+int vlq_host_vecs_write(const char* path, int kind, const void* x, long n, long d);
+int vlq_host_umem_header(const char* path, long* num, long* dim);
+int vlq_host_umem_write(const char* path, long num, long dim, const void* ptr, int elem_size, long len, long offset);
+int vlq_host_umem_read(const char* path, void* ptr, int elem_size, long len, long offset);
+
 /* IndexProxy (replicas) / IndexShards (database shards); sub-indexes are borrowed */
 int vlq_host_proxy_new(void** out);
 int vlq_host_proxy_add_index(void* proxy, void* index);

@@ -5,15 +5,16 @@
 
 #include "GpuIndexIVFPQ.h"
 #include "IndexProxy.h"
+#include "filehelper.h"
 
 using namespace faiss;
 using namespace faiss::gpu;
 
 static thread_local std::string g_err;
 
-#define GUARD(body)                    \
+#define GUARD(...)                     \
   try {                                \
-    body;                              \
+    __VA_ARGS__;                       \
     return 0;                          \
   } catch (const std::exception& e) {  \
     g_err = e.what();                  \
@@ -149,6 +150,52 @@ int vlq_host_vlq_read_codebook(void* index, const char* name) { GUARD(V(index)->
 int vlq_host_vlq_write_db(void* index, const char* name) { GUARD(V(index)->writeDbToFile(name)) }
 int vlq_host_vlq_read_db(void* index, const char* name, int pronum, int rank) {
   GUARD(V(index)->readDbFromFile(name, pronum, rank))
+}
+
+/* dataset formats (reference filehelper.cpp) */
+int vlq_host_vecs_header(const char* path, int elem_size, long* n, long* d) {
+  GUARD({
+    size_t nn = 0, dd = 0;
+    vecs_header(path, (size_t)elem_size, &nn, &dd);
+    *n = (long)nn;
+    *d = (long)dd;
+  })
+}
+int vlq_host_vecs_read(const char* path, int kind, long start, long num, void* out) {
+  GUARD({
+    size_t n = 0, d = 0;
+    if (kind == 0) {
+      auto v = fvecs_read(path, &n, &d, (size_t)start, (size_t)num);
+      std::memcpy(out, v.data(), v.size() * sizeof(float));
+    } else if (kind == 1) {
+      auto v = ivecs_read(path, &n, &d, (size_t)start, (size_t)num);
+      std::memcpy(out, v.data(), v.size() * sizeof(int32_t));
+    } else {
+      auto v = bvecs_read(path, &n, &d, (size_t)start, (size_t)num);
+      std::memcpy(out, v.data(), v.size());
+    }
+  })
+}
+int vlq_host_vecs_write(const char* path, int kind, const void* x, long n, long d) {
+  GUARD({
+    if (kind == 0) fvecs_write(path, static_cast<const float*>(x), (size_t)n, (size_t)d);
+    else if (kind == 1) ivecs_write(path, static_cast<const int32_t*>(x), (size_t)n, (size_t)d);
+    else bvecs_write(path, static_cast<const uint8_t*>(x), (size_t)n, (size_t)d);
+  })
+}
+int vlq_host_umem_header(const char* path, long* num, long* dim) {
+  GUARD({
+    size_t a = 0, b = 0;
+    umem_header(path, &a, &b);
+    *num = (long)a;
+    *dim = (long)b;
+  })
+}
+int vlq_host_umem_write(const char* path, long num, long dim, const void* ptr, int elem_size, long len, long offset) {
+  GUARD(umem_write(path, (size_t)num, (size_t)dim, ptr, (size_t)elem_size, (size_t)len, (size_t)offset))
+}
+int vlq_host_umem_read(const char* path, void* ptr, int elem_size, long len, long offset) {
+  GUARD(umem_read(path, ptr, (size_t)elem_size, (size_t)len, (size_t)offset))
 }
 
 int vlq_host_proxy_new(void** out) { GUARD(*out = static_cast<Index*>(new IndexProxy())) }
