@@ -50,6 +50,8 @@ def parse():
     ap.add_argument("--no-tc", action="store_true", help="use the exact fp32 CUDA-core kernels for the coarse stage")
     ap.add_argument("--shape", default="sift", choices=["sift", "deep"], help="sift: d=128 uint8-valued; deep: d=96 unit-norm (use --d 96 --m 8)")
     ap.add_argument("--u8", action="store_true", help="e2e encode ingests uint8 host vectors (add_with_ids_u8), sift shape only")
+    ap.add_argument("--sweep", action="store_true",
+                    help="also report recall@1/10/100 and QPS over nprobe = 1..64 with w1 = 4*nprobe (BASELINE configs[2])")
     ap.add_argument("--quick", action="store_true", help="small sizes (for debugging the script itself)")
     a = ap.parse_args()
     if a.quick:
@@ -242,10 +244,18 @@ def _run_reference(a):
 
 
 def workload_config(a, n_gpus):
+    if a.shape == "deep":
+        cfg = "configs[2] (DEEP1B shape)"
+    elif a.u8 and a.n * n_gpus >= 1_000_000_000:
+        cfg = "configs[3] (SIFT1B shape, uint8 ingest)"
+    elif a.n == 10_000_000 and n_gpus == 1:
+        cfg = "configs[1]"
+    else:
+        cfg = "configs[1] geometry at another database size"
     return {
-        "workload": "BASELINE.json configs[1]: VLQ C=%d centroids x E=%d lines, PQ m=%d, nLambda=%d, d=%d, synthetic "
+        "workload": "BASELINE.json %s: VLQ C=%d centroids x E=%d lines, PQ m=%d, nLambda=%d, d=%d, synthetic "
                     "%s-shaped %d vectors per GPU; search nq=%d nprobe=%d w1=%d k=%d"
-                    % (a.nlist, a.nedge, a.m, a.nlambda, a.d, a.shape.upper(), a.n, a.nq, a.nprobe, a.w1, a.k),
+                    % (cfg, a.nlist, a.nedge, a.m, a.nlambda, a.d, a.shape.upper(), a.n, a.nq, a.nprobe, a.w1, a.k),
         "db_vectors_per_gpu": a.n, "db_vectors_total": a.n * n_gpus, "nlist": a.nlist, "nedge": a.nedge, "m": a.m,
         "nq": a.nq, "nprobe": a.nprobe, "w1": a.w1, "k": a.k,
         "parallelism": "id-range database shards, queries replicated, NCCL all-gather of per-shard top-k + merge kernel"
@@ -571,6 +581,22 @@ def run_b200(a):
     gt = gt_i.cpu().numpy()
     recall = {"R@1": data.recall_at(In, gt, 1), "R@10": data.recall_at(In, gt, 10), "R@100": data.recall_at(In, gt, min(100, k))}
 
+    # ---- recall / QPS over nprobe (BASELINE.json configs[2]: "recall@1/10/100 sweep over nprobe")
+    sweep = None
+    if a.sweep and world == 1:
+        sweep = []
+        for P_ in (1, 2, 4, 8, 16, 32, 64):
+            W_ = min(1024, 4 * P_)
+
+            def sw_step():
+                result["sw"] = ops.search(xq, cent, cn, edge, ed2, lcb, pq, lists, P_, W_, k, pack=pack)
+
+            ms_, _ = timed(sw_step, 3, 1)
+            Is = result["sw"][1].cpu().numpy()
+            sweep.append({"nprobe": P_, "w1": W_, "R@1": data.recall_at(Is, gt, 1), "R@10": data.recall_at(Is, gt, 10),
+                          "R@100": data.recall_at(Is, gt, min(100, k)), "qps": nq * 3 / (ms_ * 1e-3)})
+            log("sweep", sweep[-1])
+
     # ---- CPU baseline on rank 0 (N=1 only): oracle port against the same index + parity on the sample
     cpu_baseline, parity = None, None
     if rank == 0 and world == 1 and not a.no_cpu_baseline:
@@ -602,6 +628,8 @@ def run_b200(a):
             "scanned_entries_per_query": scanned_per_q, "parity_vs_oracle": parity,
             "host_api_matches_ops_bitwise": host_matches_ops,
         }
+        if sweep is not None:
+            line["recall_sweep"] = sweep
     else:
         line = None
     if world > 1:

@@ -11,9 +11,12 @@
 //  merge_topk_kernel   : one CTA per query over the [R][nq][k] all-gather layout.     [GpuIndexIVFPQ.cu:1467-1518]
 //  knn_graph           : tiled C x C coarse matrix + top-(E+1) + drop rank 0.        [GpuIndexFlat.cu:869-893]
 #include <cfloat>
+#include <cstdlib>
 
 #include "common.cuh"
 #include "topk.cuh"
+
+#include <type_traits>
 
 namespace vlq {
 
@@ -509,7 +512,7 @@ __global__ void __launch_bounds__(Q_THREADS) scan_topk_kernel(ScanArgs a) {
 constexpr int T3_THREADS = 256;  // one thread per codeword of a sub-quantizer (ksub = 256)
 __global__ void __launch_bounds__(T3_THREADS)
 term3_kernel(const float* __restrict__ q, int64_t nq, int d, const float* __restrict__ pq, int M, int dsub,
-             float* __restrict__ t3) {
+             float* __restrict__ t3, bool code_major) {
   extern __shared__ __align__(16) float t3s[];
   float* pqs = t3s;                          // [M][256][dsub]
   float* qs = t3s + (size_t)M * 256 * dsub;  // [d]
@@ -529,15 +532,20 @@ term3_kernel(const float* __restrict__ q, int64_t nq, int d, const float* __rest
         for (int u = 0; u < 4; u++)
           ip[u] = fmaf(qs[(m + u) * dsub + t], pqs[((size_t)(m + u) * 256 + threadIdx.x) * dsub + t], ip[u]);
       }
+      if (code_major) {  // [j][M]: the row of codeword j is what the bank-skewed scan copies (M % 4 == 0 there)
+        *reinterpret_cast<float4*>(out + (size_t)threadIdx.x * M + m) =
+            make_float4(-2.f * ip[0], -2.f * ip[1], -2.f * ip[2], -2.f * ip[3]);
+      } else {
 #pragma unroll
-      for (int u = 0; u < 4; u++) out[(m + u) * 256 + threadIdx.x] = -2.f * ip[u];
+        for (int u = 0; u < 4; u++) out[(m + u) * 256 + threadIdx.x] = -2.f * ip[u];
+      }
     }
     for (; m < M; m++) {
       const float* pp = pqs + ((size_t)m * 256 + threadIdx.x) * dsub;
       const float* qm = qs + m * dsub;
       float ip = 0.f;
       for (int t = 0; t < dsub; t++) ip = fmaf(qm[t], pp[t], ip);
-      out[m * 256 + threadIdx.x] = -2.f * ip;
+      out[code_major ? (size_t)threadIdx.x * M + m : (size_t)m * 256 + threadIdx.x] = -2.f * ip;
     }
   }
 }
@@ -557,19 +565,83 @@ struct __align__(16) LineDesc {
   int pad;
 };
 
+// SKEW (M = 16 or 8): bank-conflict-free lookups.  With the plain [m][256] tables the 32 lanes of a warp read 32 random
+// words of one table: ~2.2 shared-memory wavefronts per lookup, and ncu shows the L1/shared data path at 91 % -- that,
+// not HBM, bounds the scan.  Here lane l works on sub-quantizer (s + l) % M at step s, and the tables are stored
+// code-major with a 64-word row: word c of row `code` holds T3[c % M][code] for c < 31 + M.  Lane l reads word
+// M*(l/M) + l%M + s of row code: the 32 lanes always hit 32 different banks whatever their codes are, the row stride of
+// 256 bytes turns "extract byte, scale, add lane offset" into ONE byte-permute, and the step offset is an immediate.
+// The lane rotates the code bytes of its entry once (12 ALU ops for M = 16).  Price: the M terms are summed in a
+// lane-dependent order, so a distance can differ from the other scan modes in the last ulp.  64 KB of tables per query:
+// 12 warps per CTA, two CTAs per SM; the block select of the final merge reuses the table space.
+constexpr int AQ_THREADS_SKEW = 384;
+constexpr int kSkewRowWords = 64;
+
 template <int M_T>
-__global__ void __launch_bounds__(Q_THREADS) scan_async_kernel(ScanArgs a) {
+struct SkewCodes {
+  uint32_t w[M_T / 4];  // as loaded; rotated only when scored, so that the load stays asynchronous
+  __device__ __forceinline__ void load(const uint8_t* __restrict__ p) {
+    if (M_T == 16) {
+      const uint4 c = ld_nc_v4(p);
+      w[0] = c.x; w[1] = c.y; w[M_T / 4 - 2] = c.z; w[M_T / 4 - 1] = c.w;
+    } else {
+      const uint2 c = ld_nc_v2(p);
+      w[0] = c.x; w[M_T / 4 - 1] = c.y;
+    }
+  }
+  // a1/a2: bits of (lane % M_T) / 4 (word rotation), selb: byte funnel selector of (lane % M_T) % 4;
+  // tbl: skewed tables (bytes), lofs: 4 * (M_T*(lane/M_T) + lane%M_T) < 256
+  __device__ __forceinline__ float adc(const unsigned char* __restrict__ tbl, uint32_t lofs, bool a1, bool a2,
+                                       uint32_t selb) const {
+    uint32_t r[M_T / 4];
+    if (M_T == 16) {
+      uint32_t w0 = w[0], w1 = w[1], w2 = w[M_T / 4 - 2], w3 = w[M_T / 4 - 1];
+      if (a1) { const uint32_t t = w0; w0 = w1; w1 = w2; w2 = w3; w3 = t; }
+      if (a2) { uint32_t t = w0; w0 = w2; w2 = t; t = w1; w1 = w3; w3 = t; }
+      r[0] = __byte_perm(w0, w1, selb);
+      r[1] = __byte_perm(w1, w2, selb);
+      r[M_T / 4 - 2] = __byte_perm(w2, w3, selb);
+      r[M_T / 4 - 1] = __byte_perm(w3, w0, selb);
+    } else {
+      uint32_t w0 = w[0], w1 = w[M_T / 4 - 1];
+      if (a1) { const uint32_t t = w0; w0 = w1; w1 = t; }
+      r[0] = __byte_perm(w0, w1, selb);
+      r[M_T / 4 - 1] = __byte_perm(w1, w0, selb);
+    }
+    float acc = 0.f;
+#pragma unroll
+    for (int s = 0; s < M_T; s++) {
+      const uint32_t o = __byte_perm(r[s >> 2], lofs, 0x5504 | ((s & 3) << 4));  // code << 8 | lofs
+      acc += *reinterpret_cast<const float*>(tbl + o + 4 * s);
+    }
+    return acc;
+  }
+};
+
+template <int M_T, bool SKEW>
+__global__ void __launch_bounds__(SKEW ? AQ_THREADS_SKEW : Q_THREADS, SKEW ? 2 : 1) scan_async_kernel(ScanArgs a) {
   extern __shared__ __align__(16) unsigned char smem[];
-  constexpr int NW = Q_THREADS / 32;
+  constexpr int NT = SKEW ? AQ_THREADS_SKEW : Q_THREADS;
+  constexpr int NW = NT / 32;
+  constexpr int MS = M_T ? M_T : 4;  // only used when SKEW
   const int M = a.M, ksub = a.ksub, W = a.W;
   const int MM = M_T ? M_T : M;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  // smem: [block select (final merge)][NW x warp select][T3][lcb][LineDesc W][misc]
-  size_t off = (select_smem_bytes(a.sel_cap) + 15) & ~size_t(15);
+  // smem: [tables | block select of the final merge (SKEW: same space)][NW x warp select][lcb][LineDesc W][misc]
+  const size_t sel_bytes = (select_smem_bytes(a.sel_cap) + 15) & ~size_t(15);
+  const size_t tbl_bytes = SKEW ? sizeof(float) * 256 * kSkewRowWords : sizeof(float) * M * ksub;
+  size_t off = 0;
+  float* T3;
+  if (SKEW) {
+    T3 = reinterpret_cast<float*>(smem);
+    off = sel_bytes > tbl_bytes ? sel_bytes : tbl_bytes;
+  } else {
+    off = sel_bytes;
+    T3 = reinterpret_cast<float*>(smem + off);
+    off += tbl_bytes;
+  }
   unsigned char* wsel = smem + off;
   off += (size_t)NW * kWarpSelSmemBytes;
-  float* T3 = reinterpret_cast<float*>(smem + off);
-  off += sizeof(float) * M * ksub;
   float* lcb = reinterpret_cast<float*>(smem + off);
   off += sizeof(float) * ((a.nL + 3) & ~3);
   LineDesc* desc = reinterpret_cast<LineDesc*>(smem + off);
@@ -577,13 +649,22 @@ __global__ void __launch_bounds__(Q_THREADS) scan_async_kernel(ScanArgs a) {
   int* misc = reinterpret_cast<int*>(smem + off);  // [0] next line, [1..NW] per-warp survivor counts
 
   const int64_t qi = blockIdx.x;
-  {
+  if (SKEW) {  // a.t3 is code-major here: row `code` = M consecutive floats
+    // word c of row `code` = src[code*M + c % M]: whole float4s, (31 + M + 3) / 4 of them per row
+    const float4* src4 = reinterpret_cast<const float4*>(a.t3 + (size_t)qi * M * ksub);
+    float4* dst4 = reinterpret_cast<float4*>(T3);
+    constexpr int Q4 = (31 + MS + 3) / 4, S4 = MS / 4;
+    for (int i = threadIdx.x; i < 256 * Q4; i += NT) {
+      const int code = i / Q4, q4 = i % Q4;
+      dst4[code * (kSkewRowWords / 4) + q4] = src4[code * S4 + (q4 & (S4 - 1))];
+    }
+  } else {
     const float4* src = reinterpret_cast<const float4*>(a.t3 + (size_t)qi * M * ksub);
     float4* dst = reinterpret_cast<float4*>(T3);
-    for (int i = threadIdx.x; i < (M * ksub) / 4; i += Q_THREADS) dst[i] = src[i];
+    for (int i = threadIdx.x; i < (M * ksub) / 4; i += NT) dst[i] = src[i];
   }
-  for (int i = threadIdx.x; i < a.nL; i += Q_THREADS) lcb[i] = a.lambda_cb[i];
-  for (int w = threadIdx.x; w < W; w += Q_THREADS) {
+  for (int i = threadIdx.x; i < a.nL; i += NT) lcb[i] = a.lambda_cb[i];
+  for (int w = threadIdx.x; w < W; w += NT) {
     const int list = a.line_list[qi * W + w];
     LineDesc dsc;
     dsc.st = 0;
@@ -627,14 +708,21 @@ __global__ void __launch_bounds__(Q_THREADS) scan_async_kernel(ScanArgs a) {
   // Software pipeline over 64-entry chunks (possibly of different lists): the loads of chunk i+1 are issued before the
   // arithmetic of chunk i, so every warp keeps two chunks (~2.7 KB) in flight.  (Unrolling by two so that the buffers
   // alternate roles instead of being copied measured 25-40 % slower: the loop body no longer fits the instruction cache.)
+  using Codes = typename std::conditional<SKEW, SkewCodes<MS>, CodeRegs<M_T>>::type;
   struct Chunk {
     int p0, nrem;  // stream position of the chunk's first entry, entries of the list left from there
     float t1, t6, t5;
-    CodeRegs<M_T> cr[2];
+    Codes cr[2];
     uint32_t lq[2];
     float kp[2];
     bool ok;
   };
+  // per-lane constants of the skewed lookups
+  const int lp = lane & (MS - 1);
+  const bool rot_a1 = ((lp >> 2) & 1) != 0, rot_a2 = ((lp >> 2) & 2) != 0;
+  const uint32_t rot_selb = 0x3210u + 0x1111u * (uint32_t)(lp & 3);
+  const uint32_t lofs = 4u * (uint32_t)(MS * (lane / MS) + lp);
+  const unsigned char* tblc = reinterpret_cast<const unsigned char*>(T3);
   LineDesc cur;  // warp-uniform walk state
   cur.len = 0;
   int cur_e0 = 0;
@@ -694,7 +782,10 @@ __global__ void __launch_bounds__(Q_THREADS) scan_async_kernel(ScanArgs a) {
       if (u * 32 + lane < c.nrem) {
         const float la = lcb[c.lq[u]];
         const float base_d = c.t1 + la * c.t6 + (la * la - la) * c.t5;
-        dist[u] = (c.kp[u] + c.cr[u].adc(T3, M, ksub)) + base_d;
+        float adc;
+        if constexpr (SKEW) adc = c.cr[u].adc(tblc, lofs, rot_a1, rot_a2, rot_selb);
+        else adc = c.cr[u].adc(T3, M, ksub);
+        dist[u] = (c.kp[u] + adc) + base_d;
         pass |= dist[u] <= ws.thr_f;
       }
     }
@@ -717,12 +808,12 @@ __global__ void __launch_bounds__(Q_THREADS) scan_async_kernel(ScanArgs a) {
   __syncthreads();
 
   // ---- merge the NW warp-local top-k sets
-  BlockSelect<Q_THREADS> sel;
+  BlockSelect<NT> sel;
   sel.init(smem, a.k, a.sel_cap, 1);
   for (int w = 0; w < NW; w++) {
     const uint64_t* wk = reinterpret_cast<const uint64_t*>(wsel + (size_t)w * kWarpSelSmemBytes);
     const int n = misc[1 + w];  // <= k <= kWarpSelCap survivors of warp w
-    for (int i0 = 0; i0 < n; i0 += Q_THREADS) {  // n is block-uniform
+    for (int i0 = 0; i0 < n; i0 += NT) {  // n is block-uniform
       const int i = i0 + (int)threadIdx.x;
       const bool valid = i < n;
       const bool any = sel.offer(valid, valid ? wk[i] : kKeyInf);
@@ -730,7 +821,7 @@ __global__ void __launch_bounds__(Q_THREADS) scan_async_kernel(ScanArgs a) {
     }
   }
   sel.finish();
-  for (int i = threadIdx.x; i < a.k; i += Q_THREADS) {
+  for (int i = threadIdx.x; i < a.k; i += NT) {
     const uint64_t key = sel.keys[i];
     float dv = FLT_MAX;
     int64_t id = -1;
@@ -749,10 +840,11 @@ __global__ void __launch_bounds__(Q_THREADS) scan_async_kernel(ScanArgs a) {
   }
 }
 
-static size_t scan_async_smem_bytes(int sel_cap, int M, int ksub, int nL, int W) {
-  size_t off = (select_smem_bytes(sel_cap) + 15) & ~size_t(15);
-  off += (size_t)(Q_THREADS / 32) * kWarpSelSmemBytes;
-  off += sizeof(float) * M * ksub;
+static size_t scan_async_smem_bytes(int sel_cap, int M, int ksub, int nL, int W, bool skew) {
+  const size_t sel_bytes = (select_smem_bytes(sel_cap) + 15) & ~size_t(15);
+  const size_t tbl_bytes = skew ? sizeof(float) * 256 * kSkewRowWords : sizeof(float) * M * ksub;
+  size_t off = skew ? (sel_bytes > tbl_bytes ? sel_bytes : tbl_bytes) : sel_bytes + tbl_bytes;
+  off += (size_t)((skew ? AQ_THREADS_SKEW : Q_THREADS) / 32) * kWarpSelSmemBytes;
   off += sizeof(float) * ((nL + 3) & ~3);
   off += sizeof(LineDesc) * W;
   off += sizeof(int) * 16;
@@ -888,37 +980,49 @@ int vlq_scan_topk(const float* q, int64_t nq, int d, const float* pq, int M, con
   a.t3 = nullptr;
   const size_t t3_bytes = (size_t)nq * M * 256 * sizeof(float);
   const size_t pq_smem = ((size_t)M * 256 * a.dsub + d) * sizeof(float);
-  if (workspace && workspace_bytes >= t3_bytes && pq_smem <= 200 * 1024 && d % 4 == 0 &&
-      ((reinterpret_cast<uintptr_t>(workspace) | reinterpret_cast<uintptr_t>(pq)) & 15) == 0) {
+  const bool long_lists = list_len_hint >= 24;  // average list length of the index: warp-per-list pays off
+  const bool al16 = (reinterpret_cast<uintptr_t>(codes) % 16) == 0;
+  const bool have_t3 = workspace && workspace_bytes >= t3_bytes && pq_smem <= 200 * 1024 && d % 4 == 0 &&
+                       ((reinterpret_cast<uintptr_t>(workspace) | reinterpret_cast<uintptr_t>(pq)) & 15) == 0;
+  const bool use_async = long_lists && k <= kWarpSelMaxK && have_t3 && (M * 256) % 4 == 0;  // warp-autonomous scan
+  // bank-skewed tables pay off once the lists are long enough to amortise the 64 KB table fill and the four extra
+  // warps per query (measured on the C2 geometry, average list length -> speed-up over the plain tables:
+  // 48 -> 0.94x, 60 -> 1.13x, 72 -> 1.15x, 95 -> 1.18x, 143 -> 1.23x, 477 -> 1.26x)
+  static const int skew_min_len = [] {
+    const char* e = getenv("VLQ_SCAN_SKEW_MIN_LEN");  // tuning knob
+    return e ? atoi(e) : 56;
+  }();
+  const bool skew = use_async && al16 && (M == 16 || M == 8) && list_len_hint >= skew_min_len;
+  if (have_t3) {
     float* t3 = static_cast<float*>(workspace);
     VLQ_CUDA_TRY(cudaFuncSetAttribute(term3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pq_smem));
     const unsigned grid = (unsigned)(nq < 148 ? nq : 148);
-    VLQ_LAUNCH(term3_kernel, grid, T3_THREADS, pq_smem, as_stream(stream), q, nq, d, pq, M, a.dsub, t3);
+    VLQ_LAUNCH(term3_kernel, grid, T3_THREADS, pq_smem, as_stream(stream), q, nq, d, pq, M, a.dsub, t3, skew);
     a.t3 = t3;
   }
   a.owner_cap = (int)((long long)W * cap < 4096 ? (long long)W * cap : 4096);
-  const bool long_lists = list_len_hint >= 24;  // average list length of the index: warp-per-list pays off
-  if (long_lists && k <= kWarpSelMaxK && a.t3 != nullptr && (M * 256) % 4 == 0) {  // warp-autonomous scan
+  if (use_async) {
     cudaStream_t st_ = as_stream(stream);
-    const int scap = select_capacity(k, Q_THREADS, 1, (long long)(Q_THREADS / 32) * k);  // <= k survivors per warp
+    const int nt = skew ? AQ_THREADS_SKEW : Q_THREADS;
+    const int scap = select_capacity(k, nt, 1, (long long)(nt / 32) * k);  // <= k survivors per warp
     a.sel_cap = scap;
-    const size_t smem_a = scan_async_smem_bytes(scap, M, a.ksub, nL, W);
-    const bool al16_ = (reinterpret_cast<uintptr_t>(codes) % 16) == 0;
-#define VLQ_ASYNC_LAUNCH(MT)                                                                                          \
+    const size_t smem_a = scan_async_smem_bytes(scap, M, a.ksub, nL, W, skew);
+#define VLQ_ASYNC_LAUNCH(MT, SK)                                                                                      \
   do {                                                                                                                \
-    VLQ_CUDA_TRY(cudaFuncSetAttribute(scan_async_kernel<MT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_a)); \
-    VLQ_LAUNCH(scan_async_kernel<MT>, (unsigned)nq, Q_THREADS, smem_a, st_, a);                                       \
+    VLQ_CUDA_TRY(cudaFuncSetAttribute(scan_async_kernel<MT, SK>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_a)); \
+    VLQ_LAUNCH((scan_async_kernel<MT, SK>), (unsigned)nq, nt, smem_a, st_, a);                                        \
   } while (0)
-    if (M == 16 && al16_) VLQ_ASYNC_LAUNCH(16);
-    else if (M == 8 && al16_) VLQ_ASYNC_LAUNCH(8);
-    else VLQ_ASYNC_LAUNCH(0);
+    if (skew && M == 16) VLQ_ASYNC_LAUNCH(16, true);
+    else if (skew) VLQ_ASYNC_LAUNCH(8, true);
+    else if (M == 16 && al16) VLQ_ASYNC_LAUNCH(16, false);
+    else if (M == 8 && al16) VLQ_ASYNC_LAUNCH(8, false);
+    else VLQ_ASYNC_LAUNCH(0, false);
 #undef VLQ_ASYNC_LAUNCH
     return last_error();
   }
   if (long_lists) a.sel_cap = select_capacity(k, Q_THREADS, 2, (long long)W * cap);
   size_t smem = scan_smem_bytes(a.sel_cap, M, a.ksub, nL, W, a.owner_cap);
   cudaStream_t st = as_stream(stream);
-  const bool al16 = (reinterpret_cast<uintptr_t>(codes) % 16) == 0;
 #define VLQ_SCAN_LAUNCH(MT, LG)                                                                                        \
   do {                                                                                                                 \
     VLQ_CUDA_TRY(cudaFuncSetAttribute(scan_topk_kernel<MT, LG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
