@@ -550,6 +550,65 @@ term3_kernel(const float* __restrict__ q, int64_t nq, int d, const float* __rest
   }
 }
 
+// Register-resident variant for the two production shapes (M x dsub = 16 x 8 and 8 x 12): thread j keeps codeword j of
+// EVERY sub-quantizer in registers (d floats) for the whole launch, so a query costs d fused multiply-adds per thread,
+// d/4 broadcast 16-byte reads of the query from shared memory and M coalesced stores -- no shared-memory traffic for the
+// codebook at all (the shared-memory version above reads it with an 8-way bank conflict: stride dsub words).
+// Same fmaf chains (t ascending from 0), hence the same bits.
+template <int M_T, int DSUB>
+__global__ void __launch_bounds__(T3_THREADS, 1)
+term3_reg_kernel(const float* __restrict__ q, int64_t nq, const float* __restrict__ pq, float* __restrict__ t3,
+                 bool code_major) {
+  constexpr int D = M_T * DSUB;
+  __shared__ __align__(16) float qs[2][D];
+  float p[D];
+#pragma unroll
+  for (int m = 0; m < M_T; m++) {
+    const float4* src = reinterpret_cast<const float4*>(pq + ((size_t)m * 256 + threadIdx.x) * DSUB);
+#pragma unroll
+    for (int t4 = 0; t4 < DSUB / 4; t4++) {
+      const float4 v = src[t4];
+      p[m * DSUB + t4 * 4 + 0] = v.x;
+      p[m * DSUB + t4 * 4 + 1] = v.y;
+      p[m * DSUB + t4 * 4 + 2] = v.z;
+      p[m * DSUB + t4 * 4 + 3] = v.w;
+    }
+  }
+  int buf = 0;
+  if ((int64_t)blockIdx.x < nq && threadIdx.x < D) qs[0][threadIdx.x] = q[(int64_t)blockIdx.x * D + threadIdx.x];
+  __syncthreads();
+  for (int64_t qi = blockIdx.x; qi < nq; qi += gridDim.x) {
+    const int64_t nxt = qi + gridDim.x;  // the next query is staged while this one is computed: one barrier per query
+    if (nxt < nq && threadIdx.x < D) qs[buf ^ 1][threadIdx.x] = q[nxt * D + threadIdx.x];
+    float* out = t3 + (size_t)qi * M_T * 256;
+    const float4* q4 = reinterpret_cast<const float4*>(qs[buf]);
+    float res[M_T];
+#pragma unroll
+    for (int m = 0; m < M_T; m++) {
+      float ip = 0.f;
+#pragma unroll
+      for (int t4 = 0; t4 < DSUB / 4; t4++) {
+        const float4 qv = q4[(m * DSUB) / 4 + t4];
+        ip = fmaf(qv.x, p[m * DSUB + t4 * 4 + 0], ip);
+        ip = fmaf(qv.y, p[m * DSUB + t4 * 4 + 1], ip);
+        ip = fmaf(qv.z, p[m * DSUB + t4 * 4 + 2], ip);
+        ip = fmaf(qv.w, p[m * DSUB + t4 * 4 + 3], ip);
+      }
+      res[m] = -2.f * ip;
+    }
+    if (code_major) {
+#pragma unroll
+      for (int m = 0; m < M_T; m += 4)
+        *reinterpret_cast<float4*>(out + (size_t)threadIdx.x * M_T + m) = make_float4(res[m], res[m + 1], res[m + 2], res[m + 3]);
+    } else {
+#pragma unroll
+      for (int m = 0; m < M_T; m++) out[m * 256 + threadIdx.x] = res[m];
+    }
+    __syncthreads();
+    buf ^= 1;
+  }
+}
+
 // ------------------------------------------------------------------------------------------------ asynchronous scan
 // The 1B-scale variant of scan_topk_kernel (k <= 128): one CTA per query, but every WARP runs on its own -- it grabs the
 // next selected list from a shared counter, strides its entries (2 per lane per step, loads first), and keeps its own
@@ -995,9 +1054,15 @@ int vlq_scan_topk(const float* q, int64_t nq, int d, const float* pq, int M, con
   const bool skew = use_async && al16 && (M == 16 || M == 8) && list_len_hint >= skew_min_len;
   if (have_t3) {
     float* t3 = static_cast<float*>(workspace);
-    VLQ_CUDA_TRY(cudaFuncSetAttribute(term3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pq_smem));
     const unsigned grid = (unsigned)(nq < 148 ? nq : 148);
-    VLQ_LAUNCH(term3_kernel, grid, T3_THREADS, pq_smem, as_stream(stream), q, nq, d, pq, M, a.dsub, t3, skew);
+    if (M == 16 && a.dsub == 8) {
+      VLQ_LAUNCH((term3_reg_kernel<16, 8>), grid, T3_THREADS, 0, as_stream(stream), q, nq, pq, t3, skew);
+    } else if (M == 8 && a.dsub == 12) {
+      VLQ_LAUNCH((term3_reg_kernel<8, 12>), grid, T3_THREADS, 0, as_stream(stream), q, nq, pq, t3, skew);
+    } else {
+      VLQ_CUDA_TRY(cudaFuncSetAttribute(term3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pq_smem));
+      VLQ_LAUNCH(term3_kernel, grid, T3_THREADS, pq_smem, as_stream(stream), q, nq, d, pq, M, a.dsub, t3, skew);
+    }
     a.t3 = t3;
   }
   a.owner_cap = (int)((long long)W * cap < 4096 ? (long long)W * cap : 4096);
