@@ -113,22 +113,31 @@ coarse_select_lines_kernel(const float* __restrict__ D, int64_t ldD, const float
   // ---- 1: P smallest bucket minima
   const int Pb = P < nb ? P : nb;
   sel.init(smem, Pb, cap, Q_BATCH);
-  for (int base = 0; base < nb; base += Q_BATCH * Q_THREADS) {
-    float v[Q_BATCH];
-#pragma unroll
-    for (int b = 0; b < Q_BATCH; b++) {
-      const int j = base + b * Q_THREADS + threadIdx.x;
-      v[b] = j < nb ? bq[j] : 0.f;
-    }
-    bool any = false;
-#pragma unroll
-    for (int b = 0; b < Q_BATCH; b++) {
-      const int j = base + b * Q_THREADS + threadIdx.x;
-      any |= sel.offer_f(j < nb, v[b], (uint32_t)j);
-    }
-    sel.end_batch(any);
+  bool direct = false;
+  if (nb <= cap) {  // block-uniform: every candidate fits the buffer, see BlockSelect::put
+    bool bad = false;
+    for (int j = threadIdx.x; j < nb; j += Q_THREADS) bad |= sel.put(j, true, bq[j], (uint32_t)j);
+    direct = sel.placed(nb, bad);
+    if (!direct) sel.init(smem, Pb, cap, Q_BATCH);
   }
-  sel.finish();
+  if (!direct) {
+    for (int base = 0; base < nb; base += Q_BATCH * Q_THREADS) {
+      float v[Q_BATCH];
+#pragma unroll
+      for (int b = 0; b < Q_BATCH; b++) {
+        const int j = base + b * Q_THREADS + threadIdx.x;
+        v[b] = j < nb ? bq[j] : 0.f;
+      }
+      bool any = false;
+#pragma unroll
+      for (int b = 0; b < Q_BATCH; b++) {
+        const int j = base + b * Q_THREADS + threadIdx.x;
+        any |= sel.offer_f(j < nb, v[b], (uint32_t)j);
+      }
+      sel.end_batch(any);
+    }
+  }
+  sel.finish(false);  // only the set of buckets matters
   for (int i = threadIdx.x; i < Pb; i += Q_THREADS) {
     const uint64_t key = sel.keys[i];
     bk_s[i] = key != kKeyInf ? (int)key_payload(key) : -1;
@@ -138,27 +147,44 @@ coarse_select_lines_kernel(const float* __restrict__ D, int64_t ldD, const float
   const int Pk = P < C ? P : C;
   sel.init(smem, Pk, cap, Q_BATCH);
   const int ncand = Pb * 32;
-  for (int base = 0; base < ncand; base += Q_BATCH * Q_THREADS) {
-    float v[Q_BATCH];
-    int col[Q_BATCH];
-#pragma unroll
-    for (int b = 0; b < Q_BATCH; b++) {
-      const int i = base + b * Q_THREADS + threadIdx.x;
-      col[b] = -1;
-      v[b] = 0.f;
-      if (i < ncand) {
-        const int bk = bk_s[i >> 5];
-        const int c = bk * 32 + (i & 31);
-        if (bk >= 0 && c < C) {
-          col[b] = c;
-          v[b] = Dq[c];
-        }
-      }
+  auto cand2 = [&](int i, int& col, float& v) {  // candidate i: column (i & 31) of bucket slot i >> 5
+    col = -1;
+    v = 0.f;
+    const int bk = bk_s[i >> 5];
+    const int c = bk * 32 + (i & 31);
+    if (bk >= 0 && c < C) {
+      col = c;
+      v = Dq[c];
     }
-    bool any = false;
+  };
+  direct = false;
+  if (ncand <= cap) {
+    bool bad = false;
+    for (int i = threadIdx.x; i < ncand; i += Q_THREADS) {
+      int col;
+      float v;
+      cand2(i, col, v);
+      bad |= sel.put(i, col >= 0, v, (uint32_t)col);
+    }
+    direct = sel.placed(ncand, bad);
+    if (!direct) sel.init(smem, Pk, cap, Q_BATCH);
+  }
+  if (!direct) {
+    for (int base = 0; base < ncand; base += Q_BATCH * Q_THREADS) {
+      float v[Q_BATCH];
+      int col[Q_BATCH];
 #pragma unroll
-    for (int b = 0; b < Q_BATCH; b++) any |= sel.offer_f(col[b] >= 0, v[b], (uint32_t)col[b]);
-    sel.end_batch(any);
+      for (int b = 0; b < Q_BATCH; b++) {
+        const int i = base + b * Q_THREADS + threadIdx.x;
+        col[b] = -1;
+        v[b] = 0.f;
+        if (i < ncand) cand2(i, col[b], v[b]);
+      }
+      bool any = false;
+#pragma unroll
+      for (int b = 0; b < Q_BATCH; b++) any |= sel.offer_f(col[b] >= 0, v[b], (uint32_t)col[b]);
+      sel.end_batch(any);
+    }
   }
   sel.finish();
   for (int i = threadIdx.x; i < P; i += Q_THREADS) {
@@ -171,28 +197,44 @@ coarse_select_lines_kernel(const float* __restrict__ D, int64_t ldD, const float
   // ---- 3: the W best of the P*E lines (BroadcastSum.cu:505-552)
   sel.init(smem, W, cap, Q_BATCH);
   const int num = P * E;
-  for (int base = 0; base < num; base += Q_BATCH * Q_THREADS) {
-    bool any = false;
-#pragma unroll
-    for (int b = 0; b < Q_BATCH; b++) {
-      const int i = base + b * Q_THREADS + threadIdx.x;
-      bool valid = i < num;
-      float score = 0.f;
-      if (valid) {
-        const int c = cq_s[ed.div(i)];
-        valid = c >= 0;
-        if (valid) {
-          const int e = ed.mod(i);
-          const int s = edge[(int64_t)c * E + e];
-          const float a2 = Dq[s], b2 = Dq[c], c2 = edge_d2[(int64_t)c * E + e];
-          float v = __fsub_rn(a2, b2);
-          v = __fsub_rn(v, c2);
-          score = (v > 0.f) ? b2 : __fsub_rn(b2, __fdiv_rn(__fmul_rn(__fmul_rn(0.25f, v), v), c2));
-        }
-      }
-      any |= sel.offer_f(valid, score, (uint32_t)i);
+  auto cand3 = [&](int i, bool& valid, float& score) {  // line i = (centroid slot i / E, edge i % E)
+    score = 0.f;
+    const int c = cq_s[ed.div(i)];
+    valid = c >= 0;
+    if (valid) {
+      const int e = ed.mod(i);
+      const int s = edge[(int64_t)c * E + e];
+      const float a2 = Dq[s], b2 = Dq[c], c2 = edge_d2[(int64_t)c * E + e];
+      float v = __fsub_rn(a2, b2);
+      v = __fsub_rn(v, c2);
+      score = (v > 0.f) ? b2 : __fsub_rn(b2, __fdiv_rn(__fmul_rn(__fmul_rn(0.25f, v), v), c2));
     }
-    sel.end_batch(any);
+  };
+  direct = false;
+  if (num <= cap) {
+    bool bad = false;
+    for (int i = threadIdx.x; i < num; i += Q_THREADS) {
+      bool valid;
+      float score;
+      cand3(i, valid, score);
+      bad |= sel.put(i, valid, score, (uint32_t)i);
+    }
+    direct = sel.placed(num, bad);
+    if (!direct) sel.init(smem, W, cap, Q_BATCH);
+  }
+  if (!direct) {
+    for (int base = 0; base < num; base += Q_BATCH * Q_THREADS) {
+      bool any = false;
+#pragma unroll
+      for (int b = 0; b < Q_BATCH; b++) {
+        const int i = base + b * Q_THREADS + threadIdx.x;
+        bool valid = false;
+        float score = 0.f;
+        if (i < num) cand3(i, valid, score);
+        any |= sel.offer_f(valid, score, (uint32_t)i);
+      }
+      sel.end_batch(any);
+    }
   }
   sel.finish();
   for (int w = threadIdx.x; w < W; w += Q_THREADS) {

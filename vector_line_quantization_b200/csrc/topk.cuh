@@ -121,6 +121,24 @@ struct BlockSelect {
     }
     return false;
   }
+  // ---- direct placement: when ALL candidates are known up front and fit the buffer (total <= cap) every thread stores
+  // its candidates at their own index -- no atomics, no per-batch barriers -- and one radix select in finish() does the
+  // rest.  put() for every index in [0, total), then placed(total); NaN values must be offered as invalid.  Invalid
+  // slots hold kKeyInf; placed() reports whether there were any (they would defeat the byte-skipping of the radix
+  // select), in which case the caller re-runs the selection through offer_f()/end_batch() after a fresh init().
+  __device__ __forceinline__ bool put(int idx, bool valid, float v, uint32_t payload) {
+    valid = valid && v == v;
+    keys[idx] = valid ? make_key(v, payload) : kKeyInf;
+    return !valid;
+  }
+  __device__ __forceinline__ bool placed(int total, bool any_invalid) {
+    const bool bad = __syncthreads_or(any_invalid) != 0;
+    if (threadIdx.x == 0) meta[0] = total;
+    fill = total;
+    __syncthreads();
+    return !bad;
+  }
+
   // collective; `any` = this thread appended at least one key in the batch
   __device__ __forceinline__ void end_batch(bool any) {
     fill += batch * __syncthreads_count(any);  // barrier + identical conservative count in every thread
@@ -248,13 +266,14 @@ struct BlockSelect {
   }
 
   // collective: afterwards keys[0..k) hold the k smallest keys ascending, padded with kKeyInf
-  __device__ void finish() {
+  __device__ void finish(bool sorted = true) {
     compact();
     const int n = meta[0] < k ? meta[0] : k;
     int S = next_pow2(k);  // S <= cap because cap >= k + batch*THREADS and cap is a power of two
     if (S < 32) S = 32;
     for (int i = n + threadIdx.x; i < S; i += THREADS) keys[i] = kKeyInf;
     __syncthreads();
+    if (!sorted) return;  // the caller only needs the SET of the k smallest keys
     if (S <= 64) {  // one warp sorts in registers (no barriers per step); measured slower than the block network for S >= 128
       if (threadIdx.x < kWarp) {
         if (S == 32) warp_bitonic_sort<1>(keys);
