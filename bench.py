@@ -389,12 +389,37 @@ def run_b200(a):
     gD = torch.empty((world, nq, k), dtype=torch.float32, device=dev) if world > 1 else None
     gI = torch.empty((world, nq, k), dtype=torch.int64, device=dev) if world > 1 else None
 
-    def step(q):
+    def step_nccl(q):
         D, I = ops.search(q, cent, cn, edge, ed2, lcb, pq, lists, P, W, k, pack=pack)
         if world > 1:
             sharding.gather_topk(D, I, gD, gI)
             D, I = ops.merge_topk(gD, gI)
         return D, I
+
+    # exchange step: peer-memory gather fused into the merge kernel (default) or NCCL all-gather + merge kernel
+    exchange = "none"
+    px = None
+    if world > 1:
+        exchange = "nccl all-gather + merge kernel"
+        if os.environ.get("VLQ_EXCHANGE", "peer") == "peer":
+            try:
+                px = sharding.PeerExchange(nq, k, dev)
+                exchange = "merge kernel reading the shards' results from peer memory over NVLink (one device barrier)"
+            except Exception as exc:  # symmetric memory unavailable on this box: the NCCL path is the same result
+                log("peer-memory exchange unavailable (%s: %s); using NCCL" % (type(exc).__name__, exc))
+                px = None
+
+    def step_peer(q):
+        ops.search(q, cent, cn, edge, ed2, lcb, pq, lists, P, W, k, pack=pack, out=px.local_out())
+        return px.merge()
+
+    step = step_peer if px is not None else step_nccl
+    if px is not None:  # both exchanges must return the same bits
+        Dn, In = step_nccl(xq)
+        Dp, Ip = step_peer(xq)
+        torch.cuda.synchronize()
+        assert torch.equal(Dn, Dp) and torch.equal(In, Ip), "peer-memory exchange differs from the NCCL exchange"
+        log("peer-memory exchange == NCCL exchange (bitwise)")
 
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
 
@@ -614,7 +639,7 @@ def run_b200(a):
             "metric": "vlq_search_qps", "value": qps * world, "unit": "queries/s" if world == 1 else "shard-queries/s",
             "n_gpus": world, "steps": a.steps, "warmup": a.warmup, "ms_per_step": total_ms / a.steps,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32 (coarse GEMM: split-fp16 x3 tcgen05, fp32 accumulate)" if use_tc else "f32", "data": "synthetic",
-            "config": workload_config(a, world), "merged_qps": qps,
+            "config": dict(workload_config(a, world), exchange=exchange), "merged_qps": qps,
             "e2e": {"value": e2e_qps * world, "unit": "queries/s" if world == 1 else "shard-queries/s",
                     "h2d_bytes_per_step": nq * d * 4, "d2h_bytes_per_step": nq * k * 12, "merged_qps": e2e_qps},
             "gpu_launches": launches, "roofline": roof, "cpu_baseline": cpu_baseline, "clocks": clk, "recall": recall,

@@ -197,11 +197,19 @@ int vlq_scan_topk(const float* q, int64_t nq, int d, const float* pq, int M, con
                   size_t workspace_bytes, vlq_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------------------------------
- * a16 shard merge: k smallest of R*k candidates per query; D, I are [R][nq][k] (the all-gather layout).
+ * a16 shard merge: k smallest of R*k candidates per query; D, I are [R][nq][k] (the all-gather layout); shards with
+ *     fewer than k results pad with (FLT_MAX, -1), as vlq_scan_topk does.
  *     replaces GpuIndexIVFPQ::merge / mergekernel, gpu/GpuIndexIVFPQ.cu:1467-1591 (CPU twin MetaIndexes.cpp:290-347).
  * ---------------------------------------------------------------------------------------------------------------- */
 int vlq_merge_topk(const float* D, const int64_t* I, int R, int64_t nq, int k, float* outD, int64_t* outI,
                    vlq_stream_t stream);
+/* Same merge with the gather fused in: shard r's (nq,k) results are read where they were produced, from
+ * peer_bufs[r] + d_offset_bytes (f32 distances) and + i_offset_bytes (int64 ids).  peer_bufs is a DEVICE array of R
+ * device pointers; entries may point into the memory of other GPUs of the NVLink domain (peer-mapped), which turns the
+ * MPI_Gather + mergekernel pair of gpu/test/sift1b16_query.cpp / GpuIndexIVFPQ.cu:1467-1591 into one kernel of P2P
+ * loads.  The caller orders it after the producers (a cross-GPU barrier); results are identical to vlq_merge_topk. */
+int vlq_merge_topk_peers(const void* const* peer_bufs, size_t d_offset_bytes, size_t i_offset_bytes, int R, int64_t nq,
+                         int k, float* outD, int64_t* outI, vlq_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------------------------------
  * f1 (next row) k-means centroid update on the device: deterministic per-centroid mean in row order + the

@@ -391,6 +391,32 @@ def test_merge_topk_exact(ops, cuda, oracle, R, nq, k):
     assert np.array_equal(N(oI), wI)
 
 
+@pytest.mark.parametrize("R,nq,k", [(2, 10, 1), (8, 33, 100), (4, 7, 1024)])
+def test_merge_topk_peers_equals_gathered(ops, cuda, R, nq, k):
+    """gather fused into the merge (vlq_merge_topk_peers): shard r's results are read from its own buffer through a
+    device array of pointers (peer-mapped symmetric memory in the multi-GPU run; R separate allocations here)"""
+    import torch
+
+    g = torch.Generator(device="cpu").manual_seed(R * 7 + k)
+    D = torch.sort(torch.rand(R, nq, k, generator=g), dim=2).values
+    I = torch.randint(0, 1 << 40, (R, nq, k), generator=g)
+    D[0, :, k // 2:] = torch.finfo(torch.float32).max
+    I[0, :, k // 2:] = -1
+    D, I = D.to(cuda), I.to(cuda)
+    wD, wI = ops.merge_topk(D, I)
+    i_off = (nq * k * 4 + 15) // 16 * 16
+    base = 256  # the results sit at an offset inside each buffer (double-buffer slot)
+    bufs = []
+    for r in range(R):
+        b = torch.zeros(base + i_off + nq * k * 8, dtype=torch.uint8, device=cuda)
+        b[base:base + 4 * nq * k].view(torch.float32).copy_(D[r].reshape(-1))
+        b[base + i_off:base + i_off + 8 * nq * k].view(torch.int64).copy_(I[r].reshape(-1))
+        bufs.append(b)
+    ptrs = torch.tensor([b.data_ptr() for b in bufs], dtype=torch.int64, device=cuda)
+    oD, oI = ops.merge_topk_peers(ptrs.data_ptr(), base, base + i_off, R, nq, k, device=cuda)
+    assert torch.equal(oD, wD) and torch.equal(oI, wI)
+
+
 def test_sharded_search_equals_single(ops, cuda, oracle, small_model):
     """id-range shards + merge == one index, exact up to ties"""
     m = small_model

@@ -964,29 +964,50 @@ static size_t scan_smem_bytes(int sel_cap, int M, int ksub, int nL, int W, int o
 }
 
 // ------------------------------------------------------------------------------------------------ shard merge
+// `peers` != nullptr: shard r's results are read from peers[r] + d_off / + i_off -- buffers that live on the OTHER GPUs of
+// the NVLink domain (peer-mapped symmetric memory), so the gather of the exchange step happens inside this kernel as
+// plain P2P loads instead of a separate collective.
 __global__ void __launch_bounds__(Q_THREADS)
-merge_topk_kernel(const float* __restrict__ D, const int64_t* __restrict__ I, int R, int64_t nq, int k, int cap,
-                  float* __restrict__ outD, int64_t* __restrict__ outI) {
+merge_topk_kernel(const float* __restrict__ D, const int64_t* __restrict__ I, const unsigned char* const* __restrict__ peers,
+                  size_t d_off, size_t i_off, int R, int64_t nq, int k, int cap, float* __restrict__ outD,
+                  int64_t* __restrict__ outI) {
   extern __shared__ __align__(16) unsigned char smem[];
   BlockSelect<Q_THREADS> sel;
   sel.init(smem, k, cap, Q_BATCH);
   const int64_t q = blockIdx.x;
   const int num = R * k;
-  for (int base = 0; base < num; base += Q_BATCH * Q_THREADS) {
-    bool any = false;
+  auto d_of = [&](int rank) {
+    return peers ? reinterpret_cast<const float*>(peers[rank] + d_off) + q * k : D + ((int64_t)rank * nq + q) * k;
+  };
+  auto i_of = [&](int rank) {
+    return peers ? reinterpret_cast<const int64_t*>(peers[rank] + i_off) + q * k : I + ((int64_t)rank * nq + q) * k;
+  };
+  // Only the distances are read here (4 of the 12 bytes per candidate); the ids of the k winners are fetched at the end.
+  // Padding entries carry (FLT_MAX, -1): they lose against every real entry, and where one is selected the output is
+  // the same (FLT_MAX, -1) an empty slot gets.
+  bool direct = false;
+  if (num <= cap) {  // every candidate fits the buffer: no atomics, no per-batch barriers (BlockSelect::put)
+    bool bad = false;
+    for (int i = threadIdx.x; i < num; i += Q_THREADS) bad |= sel.put(i, true, d_of(i / k)[i % k], (uint32_t)i);
+    direct = sel.placed(num, bad);
+    if (!direct) sel.init(smem, k, cap, Q_BATCH);
+  }
+  if (!direct) {
+    for (int base = 0; base < num; base += Q_BATCH * Q_THREADS) {
+      float v[Q_BATCH];
 #pragma unroll
-    for (int b = 0; b < Q_BATCH; b++) {
-      const int i = base + b * Q_THREADS + threadIdx.x;
-      bool valid = i < num;
-      float v = 0.f;
-      if (valid) {
-        const int rank = i / k, pos = i % k;
-        v = D[((int64_t)rank * nq + q) * k + pos];
-        valid = I[((int64_t)rank * nq + q) * k + pos] >= 0;  // padding entries never win
+      for (int b = 0; b < Q_BATCH; b++) {  // loads of the whole batch first: remote reads are NVLink round trips
+        const int i = base + b * Q_THREADS + threadIdx.x;
+        v[b] = i < num ? d_of(i / k)[i % k] : 0.f;
       }
-      any |= sel.offer_f(valid, v, (uint32_t)i);
+      bool any = false;
+#pragma unroll
+      for (int b = 0; b < Q_BATCH; b++) {
+        const int i = base + b * Q_THREADS + threadIdx.x;
+        any |= sel.offer_f(i < num, v[b], (uint32_t)i);
+      }
+      sel.end_batch(any);
     }
-    sel.end_batch(any);
   }
   sel.finish();
   for (int i = threadIdx.x; i < k; i += Q_THREADS) {
@@ -996,7 +1017,7 @@ merge_topk_kernel(const float* __restrict__ D, const int64_t* __restrict__ I, in
     if (key != kKeyInf) {
       const int fi = (int)key_payload(key);
       dv = key_val(key);
-      id = I[((int64_t)(fi / k) * nq + q) * k + (fi % k)];
+      id = i_of(fi / k)[fi % k];
     }
     outD[q * k + i] = dv;
     outI[q * k + i] = id;
@@ -1153,7 +1174,21 @@ int vlq_merge_topk(const float* D, const int64_t* I, int R, int64_t nq, int k, f
   if (!D || !I || !outD || !outI) return VLQ_EINVAL;
   const int cap = select_capacity(k, Q_THREADS, Q_BATCH, (long long)R * k);
   const size_t smem = select_smem_bytes(cap);
-  VLQ_LAUNCH(merge_topk_kernel, (unsigned)nq, Q_THREADS, smem, as_stream(stream), D, I, R, nq, k, cap, outD, outI);
+  VLQ_LAUNCH(merge_topk_kernel, (unsigned)nq, Q_THREADS, smem, as_stream(stream), D, I,
+             (const unsigned char* const*)nullptr, (size_t)0, (size_t)0, R, nq, k, cap, outD, outI);
+  return last_error();
+}
+
+int vlq_merge_topk_peers(const void* const* peer_bufs, size_t d_offset_bytes, size_t i_offset_bytes, int R, int64_t nq,
+                         int k, float* outD, int64_t* outI, vlq_stream_t stream) {
+  if (R <= 0 || nq < 0 || k <= 0 || k > VLQ_MAX_K || d_offset_bytes % 4 != 0 || i_offset_bytes % 8 != 0) return VLQ_EINVAL;
+  if (nq == 0) return VLQ_OK;
+  if (!peer_bufs || !outD || !outI) return VLQ_EINVAL;
+  const int cap = select_capacity(k, Q_THREADS, Q_BATCH, (long long)R * k);
+  const size_t smem = select_smem_bytes(cap);
+  VLQ_LAUNCH(merge_topk_kernel, (unsigned)nq, Q_THREADS, smem, as_stream(stream), (const float*)nullptr,
+             (const int64_t*)nullptr, reinterpret_cast<const unsigned char* const*>(peer_bufs), d_offset_bytes,
+             i_offset_bytes, R, nq, k, cap, outD, outI);
   return last_error();
 }
 

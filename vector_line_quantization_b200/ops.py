@@ -173,15 +173,19 @@ _scan_ws = {}
 
 
 def scan_topk(q, pq, lambda_cb, line_list, term1, term6, edge_d2, lists, k, cap=1024, use_workspace=True,
-              list_len_hint=None):
+              list_len_hint=None, out=None):
     """ADC scan of the selected lists fused with exact top-k (a13-a15): -> (D f32 [nq][k], I int64 [nq][k])"""
     q = _chk(q, torch.float32, "q")
     pq = _chk(pq, torch.float32, "pq")
     nq, d = q.shape
     M = pq.shape[0]
     W = line_list.shape[1]
-    outD = torch.empty((nq, k), dtype=torch.float32, device=q.device)
-    outI = torch.empty((nq, k), dtype=torch.int64, device=q.device)
+    if out is not None:  # contiguous (nq, k) f32 / int64 destinations (e.g. row slices of the caller's result arrays)
+        outD, outI = _chk(out[0], torch.float32, "out D"), _chk(out[1], torch.int64, "out I")
+        assert outD.shape == (nq, k) and outI.shape == (nq, k)
+    else:
+        outD = torch.empty((nq, k), dtype=torch.float32, device=q.device)
+        outI = torch.empty((nq, k), dtype=torch.int64, device=q.device)
     hint = list_len_hint if list_len_hint is not None else lists.ids.shape[0] // max(1, lists.offsets.shape[0] - 1)
     ws = None
     wsb = 0
@@ -209,6 +213,15 @@ def merge_topk(D, I):
     return outD, outI
 
 
+def merge_topk_peers(peer_ptrs_dev, d_off, i_off, R, nq, k, out=None, device=None):
+    """shard merge with the gather fused in (a16): peer_ptrs_dev = device address of an array of R buffer pointers
+    (symmetric memory), each buffer holding [D f32 (nq,k)] at d_off and [I int64 (nq,k)] at i_off"""
+    if out is None:
+        out = (torch.empty((nq, k), dtype=torch.float32, device=device), torch.empty((nq, k), dtype=torch.int64, device=device))
+    _abi.call("vlq_merge_topk_peers", int(peer_ptrs_dev), d_off, i_off, R, nq, k, _ptr(out[0]), _ptr(out[1]), _stream())
+    return out
+
+
 def km_update(x, assign, k):
     """k-means mean step, deterministic row order (f1): -> (centroids f32 [k][d], counts int32 [k])"""
     x = _chk(x, torch.float32, "x")
@@ -222,14 +235,17 @@ def km_update(x, assign, k):
     return cent, counts
 
 
-def search(q, cent, cnorm, edge, edge_d2, lambda_cb, pq, lists, P, W, k, cap=1024, tile=4096, pack=None):
+def search(q, cent, cnorm, edge, edge_d2, lambda_cb, pq, lists, P, W, k, cap=1024, tile=4096, pack=None, out=None):
     """Full query path on resident tensors (a11-a15), tiled over queries so the coarse matrix stays L2-sized.
     pack (a CentPack) routes the coarse distances through the tcgen05 kernel."""
     nq = q.shape[0]
     C = cent.shape[0]
     P = min(P, C)
-    outD = torch.empty((nq, k), dtype=torch.float32, device=q.device)
-    outI = torch.empty((nq, k), dtype=torch.int64, device=q.device)
+    if out is not None:
+        outD, outI = out
+    else:
+        outD = torch.empty((nq, k), dtype=torch.float32, device=q.device)
+        outI = torch.empty((nq, k), dtype=torch.int64, device=q.device)
     Dbuf = torch.empty((min(tile, nq), C), dtype=torch.float32, device=q.device)
     bbuf = torch.empty((min(tile, nq), num_buckets(C)), dtype=torch.float32, device=q.device) if pack is not None else None
     ed2_flat = edge_d2.reshape(-1)
@@ -243,9 +259,7 @@ def search(q, cent, cnorm, edge, edge_d2, lambda_cb, pq, lists, P, W, k, cap=102
             D = l2_distances(qt, cent, cnorm, out=Dbuf[: e - s])
             _, cid = select_rows(D, P)
             lst, t1, t6 = select_lines(D, cid, edge, edge_d2, W)
-        d_, i_ = scan_topk(qt, pq, lambda_cb, lst, t1, t6, ed2_flat, lists, k, cap)
-        outD[s:e] = d_
-        outI[s:e] = i_
+        scan_topk(qt, pq, lambda_cb, lst, t1, t6, ed2_flat, lists, k, cap, out=(outD[s:e], outI[s:e]))
     return outD, outI
 
 
