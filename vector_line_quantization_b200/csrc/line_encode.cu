@@ -57,14 +57,23 @@ __device__ __forceinline__ void warp_transpose_reduce32(float (&v)[32], int lane
   }
 }
 
+// A warp takes LE_V consecutive vectors at a time.  Phase A (per vector): line stage, lambda byte, residual -> per-warp
+// shared memory.  Phase B (the LE_V vectors together): PQ encode -- every codeword component read from shared memory is
+// used for LE_V vectors, which cuts the shared-memory instructions per multiply-add by LE_V (the loop was LSU-bound:
+// one LDS per FSUB+FFMA pair).  Phase C (per vector): kappa and the outputs.  The arithmetic of every vector is
+// unchanged (same operation order), so the results do not depend on the grouping.
+constexpr int LE_V = 4;
+
 template <int NPL>
 __global__ void __launch_bounds__(LE_THREADS, 1) line_encode_kernel(LineEncodeArgs a) {
   extern __shared__ __align__(16) float smem[];
-  // layout: [pq transposed: M*dsub*ksub floats (optional)] [per-warp r: LE_WARPS*d] [per-warp codes: LE_WARPS*64 bytes]
+  // layout: [pq transposed: M*dsub*ksub floats (optional)] [per-warp r: LE_WARPS*LE_V*d] [per-warp scalars]
+  //         [per-warp codes: LE_WARPS*LE_V*64 bytes]
   const int d = a.d, E = a.E, M = a.M, ksub = a.ksub, dsub = a.dsub;
   float* pqs = smem;
   float* rbuf = smem + (a.pq_in_smem ? (size_t)M * dsub * ksub : 0);
-  uint8_t* cbuf = reinterpret_cast<uint8_t*>(rbuf + (size_t)LE_WARPS * d);
+  int* sbuf = reinterpret_cast<int*>(rbuf + (size_t)LE_WARPS * LE_V * d);  // per warp, per vector: A, s, lq, lh
+  uint8_t* cbuf = reinterpret_cast<uint8_t*>(sbuf + LE_WARPS * LE_V * 4);
   const int warp = threadIdx.x / kWarp, lane = threadIdx.x % kWarp;
   const bool encode = a.lambda_cb != nullptr;
 
@@ -80,189 +89,236 @@ __global__ void __launch_bounds__(LE_THREADS, 1) line_encode_kernel(LineEncodeAr
   }
   __syncthreads();
 
-  float* r_s = rbuf + (size_t)warp * d;
-  uint8_t* code_s = cbuf + warp * 64;
+  float* r_w = rbuf + (size_t)warp * LE_V * d;
+  int* sc_w = sbuf + warp * LE_V * 4;
+  uint8_t* code_w = cbuf + warp * LE_V * 64;
 
-  for (int64_t i = (int64_t)blockIdx.x * LE_WARPS + warp; i < a.n; i += (int64_t)gridDim.x * LE_WARPS) {
-    float xv[NPL];
-    const float* xr = a.x + i * d;
+  for (int64_t i0 = ((int64_t)blockIdx.x * LE_WARPS + warp) * LE_V; i0 < a.n;
+       i0 += (int64_t)gridDim.x * LE_WARPS * LE_V) {
+    // ------------------------------------------------------------------ phase A: line stage, lambda byte, residual
+#pragma unroll 1
+    for (int v = 0; v < LE_V; v++) {
+      const int64_t i = i0 + v;
+      float* r_s = r_w + v * d;
+      if (lane == 0) sc_w[v * 4] = -1;
+      if (i >= a.n) continue;  // warp-uniform
+      float xv[NPL];
+      const float* xr = a.x + i * d;
 #pragma unroll
-    for (int t = 0; t < NPL; t++) {
-      int j = lane + 32 * t;
-      xv[t] = j < d ? xr[j] : 0.f;
-    }
-    const int A = a.assign[i];
-    if (A < 0) {  // invalid vector (NaN input): the reference skips it (GpuIndexIVFPQ.cu:751-755)
-      if (lane == 0) {
-        a.out_list[i] = -1;
-        if (a.out_lambda) a.out_lambda[i] = 0.f;
+      for (int t = 0; t < NPL; t++) {
+        int j = lane + 32 * t;
+        xv[t] = j < d ? xr[j] : 0.f;
       }
-      continue;
-    }
-    const float* cA = a.cent + (int64_t)A * d;
-    float cAv[NPL];
-    float bp = 0.f;
-#pragma unroll
-    for (int t = 0; t < NPL; t++) {
-      int j = lane + 32 * t;
-      cAv[t] = j < d ? cA[j] : 0.f;
-      float df = xv[t] - cAv[t];
-      bp = fmaf(df, df, bp);
-    }
-    const float b = warp_sum(bp);
-
-    // lane e (+32) owns edge e
-    int my_s[2] = {0, 0};
-    float my_a[2] = {0.f, 0.f};
-    float my_c2[2] = {1.f, 1.f};
-#pragma unroll
-    for (int h = 0; h < 2; h++) {
-      int e = lane + 32 * h;
-      if (e < E) {
-        my_s[h] = a.edge[(int64_t)A * E + e];
-        my_c2[h] = a.edge_d2[(int64_t)A * E + e];
-      }
-    }
-    for (int g = 0; g * 32 < E; g++) {  // 32 edges at a time: lane-private partial sums, one transposed reduction
-      float part[32];
-#pragma unroll
-      for (int ee = 0; ee < 32; ee++) {
-        const int e = g * 32 + ee;
-        const int s = __shfl_sync(kFull, my_s[g], ee);  // edges beyond E read centroid 0 (result unused)
-        const float* cs = a.cent + (int64_t)(e < E ? s : 0) * d;
-        float ap = 0.f;
-#pragma unroll
-        for (int t = 0; t < NPL; t++) {
-          int j = lane + 32 * t;
-          float cv = j < d ? cs[j] : 0.f;
-          float df = xv[t] - cv;
-          ap = fmaf(df, df, ap);
+      const int A = a.assign[i];
+      if (A < 0) {  // invalid vector (NaN input): the reference skips it (GpuIndexIVFPQ.cu:751-755)
+        if (lane == 0) {
+          a.out_list[i] = -1;
+          if (a.out_lambda) a.out_lambda[i] = 0.f;
         }
-        part[ee] = ap;
+        continue;
       }
-      warp_transpose_reduce32(part, lane);
-      my_a[g] = part[0];
-    }
-    uint64_t kv = kKeyInf, ka = kKeyInf;
-    float my_lam[2];
+      const float* cA = a.cent + (int64_t)A * d;
+      float cAv[NPL];
+      float bp = 0.f;
 #pragma unroll
-    for (int h = 0; h < 2; h++) {
-      int e = lane + 32 * h;
-      float v = my_a[h] - b - my_c2[h];
-      float lam = -0.5f * v / my_c2[h];                                 // project()
-      float q2 = __fadd_rn(__fadd_rn(b, __fmul_rn(__fmul_rn(lam, lam), my_c2[h])), __fmul_rn(lam, v));  // dist2()
-      my_lam[h] = lam;
-      if (e < E) {
-        uint64_t key = make_key(q2, (uint32_t)e);
-        ka = key < ka ? key : ka;
-        if (lam >= 0.f && lam <= 1.f) kv = key < kv ? key : kv;
+      for (int t = 0; t < NPL; t++) {
+        int j = lane + 32 * t;
+        cAv[t] = j < d ? cA[j] : 0.f;
+        float df = xv[t] - cAv[t];
+        bp = fmaf(df, df, bp);
       }
-    }
-    kv = warp_min_u64(kv);
-    ka = warp_min_u64(ka);
-    const uint64_t kbest = kv != kKeyInf ? kv : ka;
-    const int ebest = (int)key_payload(kbest);
-    const float lam = __shfl_sync(kFull, my_lam[ebest >> 5], ebest & 31);
-    const int sbest = __shfl_sync(kFull, my_s[ebest >> 5], ebest & 31);
-    if (lane == 0) {
-      a.out_list[i] = A * E + ebest;
-      if (a.out_lambda) a.out_lambda[i] = lam;
+      const float b = warp_sum(bp);
+
+      // lane e (+32) owns edge e
+      int my_s[2] = {0, 0};
+      float my_a[2] = {0.f, 0.f};
+      float my_c2[2] = {1.f, 1.f};
+#pragma unroll
+      for (int h = 0; h < 2; h++) {
+        int e = lane + 32 * h;
+        if (e < E) {
+          my_s[h] = a.edge[(int64_t)A * E + e];
+          my_c2[h] = a.edge_d2[(int64_t)A * E + e];
+        }
+      }
+      for (int g = 0; g * 32 < E; g++) {  // 32 edges at a time: lane-private partial sums, one transposed reduction
+        float part[32];
+#pragma unroll
+        for (int ee = 0; ee < 32; ee++) {
+          const int e = g * 32 + ee;
+          const int s = __shfl_sync(kFull, my_s[g], ee);  // edges beyond E read centroid 0 (result unused)
+          const float* cs = a.cent + (int64_t)(e < E ? s : 0) * d;
+          float ap = 0.f;
+#pragma unroll
+          for (int t = 0; t < NPL; t++) {
+            int j = lane + 32 * t;
+            float cv = j < d ? cs[j] : 0.f;
+            float df = xv[t] - cv;
+            ap = fmaf(df, df, ap);
+          }
+          part[ee] = ap;
+        }
+        warp_transpose_reduce32(part, lane);
+        my_a[g] = part[0];
+      }
+      uint64_t kv = kKeyInf, ka = kKeyInf;
+      float my_lam[2];
+#pragma unroll
+      for (int h = 0; h < 2; h++) {
+        int e = lane + 32 * h;
+        float vv = my_a[h] - b - my_c2[h];
+        float lam = -0.5f * vv / my_c2[h];                                 // project()
+        float q2 = __fadd_rn(__fadd_rn(b, __fmul_rn(__fmul_rn(lam, lam), my_c2[h])), __fmul_rn(lam, vv));  // dist2()
+        my_lam[h] = lam;
+        if (e < E) {
+          uint64_t key = make_key(q2, (uint32_t)e);
+          ka = key < ka ? key : ka;
+          if (lam >= 0.f && lam <= 1.f) kv = key < kv ? key : kv;
+        }
+      }
+      kv = warp_min_u64(kv);
+      ka = warp_min_u64(ka);
+      const uint64_t kbest = kv != kKeyInf ? kv : ka;
+      const int ebest = (int)key_payload(kbest);
+      const float lam = __shfl_sync(kFull, my_lam[ebest >> 5], ebest & 31);
+      const int sbest = __shfl_sync(kFull, my_s[ebest >> 5], ebest & 31);
+      if (lane == 0) {
+        a.out_list[i] = A * E + ebest;
+        if (a.out_lambda) a.out_lambda[i] = lam;
+      }
+      if (!encode) continue;
+
+      // ---- lambda quantiser: argmin_j (lam - cb[j])^2, lowest j on ties
+      uint64_t kl = kKeyInf;
+      for (int j = lane; j < a.nL; j += kWarp) {
+        float t = lam - a.lambda_cb[j];
+        uint64_t key = make_key(__fmul_rn(t, t), (uint32_t)j);
+        kl = key < kl ? key : kl;
+      }
+      kl = warp_min_u64(kl);
+      const int lq = (int)key_payload(kl);
+      const float lh = a.lambda_cb[lq];
+
+      // ---- residual -> per-warp shared memory for the sub-space walk
+      const float* cs = a.cent + (int64_t)sbest * d;
+      const float oml = 1.f - lh;
+#pragma unroll
+      for (int t = 0; t < NPL; t++) {
+        int j = lane + 32 * t;
+        float sv = j < d ? cs[j] : 0.f;
+        const float anc = __fadd_rn(__fmul_rn(oml, cAv[t]), __fmul_rn(lh, sv));
+        float rv = __fsub_rn(xv[t], anc);
+        if (j < d) {
+          r_s[j] = rv;
+          if (a.out_residual) a.out_residual[i * d + j] = rv;
+        }
+      }
+      if (lane == 0) {
+        sc_w[v * 4 + 0] = A;
+        sc_w[v * 4 + 1] = sbest;
+        sc_w[v * 4 + 2] = lq;
+        sc_w[v * 4 + 3] = __float_as_int(lh);
+      }
     }
     if (!encode) continue;
-
-    // ---- lambda quantiser: argmin_j (lam - cb[j])^2, lowest j on ties
-    uint64_t kl = kKeyInf;
-    for (int j = lane; j < a.nL; j += kWarp) {
-      float t = lam - a.lambda_cb[j];
-      uint64_t key = make_key(__fmul_rn(t, t), (uint32_t)j);
-      kl = key < kl ? key : kl;
-    }
-    kl = warp_min_u64(kl);
-    const int lq = (int)key_payload(kl);
-    const float lh = a.lambda_cb[lq];
-
-    // ---- residual (kept in registers + a per-warp smem copy for the sub-space walk)
-    const float* cs = a.cent + (int64_t)sbest * d;
-    float anc[NPL];
-    const float oml = 1.f - lh;
-    __syncwarp();
-#pragma unroll
-    for (int t = 0; t < NPL; t++) {
-      int j = lane + 32 * t;
-      float sv = j < d ? cs[j] : 0.f;
-      anc[t] = __fadd_rn(__fmul_rn(oml, cAv[t]), __fmul_rn(lh, sv));
-      float rv = __fsub_rn(xv[t], anc[t]);
-      if (j < d) {
-        r_s[j] = rv;
-        if (a.out_residual) a.out_residual[i * d + j] = rv;
-      }
-    }
     __syncwarp();
 
-    // ---- PQ encode: lane owns codewords lane + 32c; distances accumulate over t in order (ProductQuantizer.cpp:311-336)
+    // ------------------------------------------------------------------ phase B: PQ encode of the LE_V vectors.  Lane
+    // owns codewords lane + 32c; distances accumulate over t in order (ProductQuantizer.cpp:311-336).
     for (int m = 0; m < M; m++) {
-      uint64_t kc = kKeyInf;
+      uint64_t kc[LE_V];
       if (a.pq_in_smem && ksub == 256) {
-        float dis[8];
+        float dis[LE_V][8];
 #pragma unroll
-        for (int c = 0; c < 8; c++) dis[c] = 0.f;
+        for (int v = 0; v < LE_V; v++)
+#pragma unroll
+          for (int c = 0; c < 8; c++) dis[v][c] = 0.f;
         const float* pp = pqs + (size_t)m * dsub * ksub + lane;
         for (int t = 0; t < dsub; t++) {
-          const float rt = r_s[m * dsub + t];
+          float pc[8];
 #pragma unroll
-          for (int c = 0; c < 8; c++) {
-            const float df = rt - pp[t * ksub + 32 * c];
-            dis[c] = fmaf(df, df, dis[c]);
+          for (int c = 0; c < 8; c++) pc[c] = pp[t * ksub + 32 * c];
+#pragma unroll
+          for (int v = 0; v < LE_V; v++) {
+            const float rt = r_w[v * d + m * dsub + t];
+#pragma unroll
+            for (int c = 0; c < 8; c++) {
+              const float df = rt - pc[c];
+              dis[v][c] = fmaf(df, df, dis[v][c]);
+            }
           }
         }
         // lane-local arg-min on the floats (strict <: the lowest codeword index wins ties), one 64-bit key per lane
-        float bd = dis[0];
-        int bc = 0;
 #pragma unroll
-        for (int c = 1; c < 8; c++) {
-          if (dis[c] < bd) {
-            bd = dis[c];
-            bc = c;
+        for (int v = 0; v < LE_V; v++) {
+          float bd = dis[v][0];
+          int bc = 0;
+#pragma unroll
+          for (int c = 1; c < 8; c++) {
+            if (dis[v][c] < bd) {
+              bd = dis[v][c];
+              bc = c;
+            }
           }
+          kc[v] = make_key(bd, (uint32_t)(lane + 32 * bc));
         }
-        kc = make_key(bd, (uint32_t)(lane + 32 * bc));
       } else {
-        for (int j = lane; j < ksub; j += kWarp) {
-          const float* pp = a.pq + ((size_t)m * ksub + j) * dsub;
-          float dis = 0.f;
-          for (int t = 0; t < dsub; t++) {
-            const float df = r_s[m * dsub + t] - pp[t];
-            dis = fmaf(df, df, dis);
+#pragma unroll
+        for (int v = 0; v < LE_V; v++) {
+          kc[v] = kKeyInf;
+          for (int j = lane; j < ksub; j += kWarp) {
+            const float* pp = a.pq + ((size_t)m * ksub + j) * dsub;
+            float dis = 0.f;
+            for (int t = 0; t < dsub; t++) {
+              const float df = r_w[v * d + m * dsub + t] - pp[t];
+              dis = fmaf(df, df, dis);
+            }
+            const uint64_t key = make_key(dis, (uint32_t)j);
+            kc[v] = key < kc[v] ? key : kc[v];
           }
-          const uint64_t key = make_key(dis, (uint32_t)j);
-          kc = key < kc ? key : kc;
         }
       }
-      kc = warp_min_u64(kc);
-      if (lane == 0) code_s[m] = (uint8_t)key_payload(kc);
+#pragma unroll
+      for (int v = 0; v < LE_V; v++) {
+        kc[v] = warp_min_u64(kc[v]);
+        if (lane == 0) code_w[v * 64 + m] = (uint8_t)key_payload(kc[v]);
+      }
     }
     __syncwarp();
 
-    // ---- kappa = ||p||^2 + 2 anchor.p
-    float kp = 0.f;
+    // ------------------------------------------------------------------ phase C: kappa = ||p||^2 + 2 anchor.p, outputs
+#pragma unroll 1
+    for (int v = 0; v < LE_V; v++) {
+      const int A = sc_w[v * 4 + 0];
+      if (A < 0) continue;  // beyond n, or an invalid vector
+      const int64_t i = i0 + v;
+      const int sbest = sc_w[v * 4 + 1], lq = sc_w[v * 4 + 2];
+      const float lh = __int_as_float(sc_w[v * 4 + 3]);
+      const float oml = 1.f - lh;
+      const float* cA = a.cent + (int64_t)A * d;
+      const float* cs = a.cent + (int64_t)sbest * d;
+      const uint8_t* code_s = code_w + v * 64;
+      float kp = 0.f;
 #pragma unroll
-    for (int t = 0; t < NPL; t++) {
-      int j = lane + 32 * t;
-      if (j < d) {
-        int m = j / dsub, tt = j % dsub;
-        int code = code_s[m];
-        float pv = a.pq_in_smem ? pqs[(size_t)(m * dsub + tt) * ksub + code] : a.pq[((size_t)m * ksub + code) * dsub + tt];
-        kp = fmaf(pv, pv, kp);
-        kp = fmaf(2.f * anc[t], pv, kp);
+      for (int t = 0; t < NPL; t++) {
+        int j = lane + 32 * t;
+        if (j < d) {
+          const float anc = __fadd_rn(__fmul_rn(oml, cA[j]), __fmul_rn(lh, cs[j]));  // same bits as in phase A
+          int m = j / dsub, tt = j % dsub;
+          int code = code_s[m];
+          float pv = a.pq_in_smem ? pqs[(size_t)(m * dsub + tt) * ksub + code] : a.pq[((size_t)m * ksub + code) * dsub + tt];
+          kp = fmaf(pv, pv, kp);
+          kp = fmaf(2.f * anc, pv, kp);
+        }
       }
+      kp = warp_sum(kp);
+      if (lane == 0) {
+        if (a.out_lamq) a.out_lamq[i] = (uint8_t)lq;
+        if (a.out_kappa) a.out_kappa[i] = kp;
+      }
+      if (a.out_codes)
+        for (int m = lane; m < M; m += kWarp) a.out_codes[i * M + m] = code_s[m];
     }
-    kp = warp_sum(kp);
-    if (lane == 0) {
-      if (a.out_lamq) a.out_lamq[i] = (uint8_t)lq;
-      if (a.out_kappa) a.out_kappa[i] = kp;
-    }
-    if (a.out_codes)
-      for (int m = lane; m < M; m += kWarp) a.out_codes[i * M + m] = code_s[m];
     __syncwarp();
   }
 }
@@ -366,13 +422,13 @@ extern "C" int vlq_line_encode(const float* x, int64_t n, int d, const int* assi
   }
   if (n == 0) return VLQ_OK;
   size_t pq_bytes = lambda_cb ? (size_t)M * a.dsub * ksub * sizeof(float) : 0;
-  size_t tail = (size_t)LE_WARPS * d * sizeof(float) + LE_WARPS * 64;
+  size_t tail = (size_t)LE_WARPS * LE_V * (d * sizeof(float) + 4 * sizeof(int) + 64);
   a.pq_in_smem = (lambda_cb && pq_bytes + tail <= 200 * 1024) ? 1 : 0;
   size_t smem = (a.pq_in_smem ? pq_bytes : 0) + tail;
   int dev = 0, sms = 148;
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-  int64_t need = div_up(n, LE_WARPS);
+  int64_t need = div_up(n, LE_WARPS * LE_V);
   unsigned grid = (unsigned)(need < sms ? need : sms);
   const int npl = (d + 31) / 32;
   cudaStream_t st = as_stream(stream);
