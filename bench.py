@@ -586,20 +586,41 @@ def run_b200(a):
     hbm_peak = peaks.get("hbm_gbs", 6650.0)
     tc_peak = peaks.get("bf16_tflops", 1590.0)
     peak_src = "measured (MEASURED_PEAKS.json, burst: kernel timed alone)" if peaks else "fallback (B200_PROFILING.md)"
+    # ncu-measured DRAM traffic per launch of each stage's kernel (profiles/r01_traffic.json, written by
+    # tools/ncu_traffic.py from the committed `ncu --set full` capture of this workload); null when absent
+    traffic = {}
+    try:
+        tj = json.load(open(os.path.join(ROOT, "profiles", "r01_traffic.json")))
+        if tj.get("db_vectors_per_gpu") == a.n and tj.get("nq") == nq:
+            traffic = tj.get("bytes_per_launch", {})
+    except Exception:
+        pass
+
+    def stage_roofline(name):
+        """algorithmic work of one launch of the stage over its measured launch time"""
+        if not st_cnt.get(name):
+            return None
+        ms = st_ms[name] / st_cnt[name]
+        rows = nq / st_cnt[name]
+        if name == "scan_topk":  # SURVEY 8d: codes + lambda of every scanned entry, ids of the k winners
+            r = {"bound": "hbm", "achieved": rows * (scanned_per_q * (M + 1) + k * 8) / (ms * 1e-3) / 1e9,
+                 "peak": hbm_peak, "unit": "GB/s"}
+        elif name == "coarse_select_lines":  # bucket minima + P 128-byte lines of D + P*E gathers + W outputs
+            nbk = ops.num_buckets(C)
+            r = {"bound": "hbm", "achieved": rows * (nbk * 4 + P * 128 + P * E * 4 + W * 12) / (ms * 1e-3) / 1e9,
+                 "peak": hbm_peak, "unit": "GB/s"}
+        elif name in ("select_rows", "select_lines"):  # the whole row of D is read
+            r = {"bound": "hbm", "achieved": rows * C * 4.0 / (ms * 1e-3) / 1e9, "peak": hbm_peak, "unit": "GB/s"}
+        else:  # coarse distance tile: the GEMM is cheap next to writing 4*C bytes of distances (+ bucket minima) per query
+            r = {"bound": "hbm", "achieved": rows * (C * 4.0 + (ops.num_buckets(C) * 4 if use_tc else 0)) / (ms * 1e-3) / 1e9,
+                 "peak": hbm_peak, "unit": "GB/s", "tensor_tflops": rows * 2.0 * C * d / (ms * 1e-3) / 1e12}
+        r.update(frac=r["achieved"] / r["peak"], traffic=traffic.get(name), kernel=name, ms_per_launch=ms)
+        return r
+
     dominant = max(st_ms, key=st_ms.get)
-    per_launch_ms = st_ms[dominant] / max(1, st_cnt[dominant])
-    rows_per_launch = nq / max(1, st_cnt[dominant])
-    if dominant == "scan_topk":
-        alg = rows_per_launch * (scanned_per_q * (M + 1) + k * 8)
-        roof = {"bound": "hbm", "achieved": alg / (per_launch_ms * 1e-3) / 1e9, "peak": hbm_peak, "unit": "GB/s"}
-    elif dominant in ("select_rows", "select_lines", "coarse_select_lines"):
-        alg = rows_per_launch * C * 4.0
-        roof = {"bound": "hbm", "achieved": alg / (per_launch_ms * 1e-3) / 1e9, "peak": hbm_peak, "unit": "GB/s"}
-    else:
-        flops = rows_per_launch * 2.0 * C * d
-        roof = {"bound": "tensor", "achieved": flops / (per_launch_ms * 1e-3) / 1e12, "peak": tc_peak, "unit": "TFLOP/s"}
-    roof.update(frac=roof["achieved"] / roof["peak"], traffic=None, kernel=dominant, peak_source=peak_src,
-                ms_per_launch=per_launch_ms, stage_ms_per_step=st_ms)
+    roof = stage_roofline(dominant)
+    roof.update(peak_source=peak_src, stage_ms_per_step=st_ms,
+                stages=[r for r in (stage_roofline(n_) for n_ in st_ms if n_ != dominant) if r])
 
     # ---- recall (R@r of the true 1-NN, gpu/test/sift1b_query.cpp:334-347)
     In = I.cpu().numpy()
