@@ -244,6 +244,8 @@ int vlq_pointer_is_device(const void* ptr); /* 1 device, 0 host, <0 error */
 int vlq_stream_create(vlq_stream_t* stream);
 int vlq_stream_destroy(vlq_stream_t stream);
 int vlq_stream_synchronize(vlq_stream_t stream);
+/* work enqueued on `waiter` after this call starts only when everything enqueued on `producer` so far has finished */
+int vlq_stream_wait(vlq_stream_t waiter, vlq_stream_t producer);
 
 #ifdef __cplusplus
 }

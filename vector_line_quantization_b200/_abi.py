@@ -67,6 +67,7 @@ SIGNATURES = {
     "vlq_stream_create": (_i, [C.POINTER(_p)]),
     "vlq_stream_destroy": (_i, [_p]),
     "vlq_stream_synchronize": (_i, [_p]),
+    "vlq_stream_wait": (_i, [_p, _p]),
 }
 
 

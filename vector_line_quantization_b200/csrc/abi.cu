@@ -72,5 +72,14 @@ int vlq_stream_create(vlq_stream_t* stream) {
 }
 int vlq_stream_destroy(vlq_stream_t stream) { return (int)cudaStreamDestroy(vlq::as_stream(stream)); }
 int vlq_stream_synchronize(vlq_stream_t stream) { return (int)cudaStreamSynchronize(vlq::as_stream(stream)); }
+int vlq_stream_wait(vlq_stream_t waiter, vlq_stream_t producer) {
+  cudaEvent_t ev;
+  cudaError_t e = cudaEventCreateWithFlags(&ev, cudaEventDisableTiming);
+  if (e != cudaSuccess) return (int)e;
+  e = cudaEventRecord(ev, vlq::as_stream(producer));
+  if (e == cudaSuccess) e = cudaStreamWaitEvent(vlq::as_stream(waiter), ev, 0);
+  cudaEventDestroy(ev);  // released once the recorded work has completed
+  return (int)e;
+}
 
 }  // extern "C"

@@ -316,14 +316,34 @@ void GpuIndexIVFPQ::search(Index::idx_t n, const float* x, Index::idx_t k, float
   float* t6 = t1 + (size_t)tile * W;
   float* bmin = t6 + (size_t)tile * W;
   t3ws_.reserve(vlq_scan_topk_workspace_bytes(tile, M));
+  // Host buffers: the queries of tile i+1 go up and the results of tile i-1 come down on the copy stream while tile i is
+  // computed (cross-stream order by vlq_stream_wait); device buffers are used in place.
+  vlq_stream_t cs = resources_->getAsyncCopyStream();
+  const bool xOnDevice = vlq_pointer_is_device(x) == 1;
+  const bool dOnDevice = vlq_pointer_is_device(distances) == 1, lOnDevice = vlq_pointer_is_device(labels) == 1;
   for (Index::idx_t p0 = 0; p0 < n; p0 += page) {
     const Index::idx_t pn = std::min(page, n - p0);
-    const float* dx = static_cast<const float*>(toDevice(x + (size_t)p0 * d, (size_t)pn * d * sizeof(float), xin, st));
+    const float* xp = x + (size_t)p0 * d;
+    const float* dx = xp;
+    if (!xOnDevice) {
+      xin.reserve((size_t)pn * d * sizeof(float));
+      dx = xin.as<float>();
+      VLQ_CALL(vlq_stream_wait(cs, st));  // the staging buffer may still be read by the previous page / call
+      VLQ_CALL(vlq_memcpy_h2d(xin.get(), xp, (size_t)std::min(tile, pn) * d * sizeof(float), cs));
+    }
     outD.reserve((size_t)pn * k * sizeof(float));
     outI.reserve((size_t)pn * k * sizeof(int64_t));
     for (Index::idx_t s = 0; s < pn; s += tile) {
       const Index::idx_t m = std::min(tile, pn - s);
       const float* q = dx + (size_t)s * d;
+      if (!xOnDevice) {
+        VLQ_CALL(vlq_stream_wait(st, cs));  // this tile's queries have arrived
+        if (s + tile < pn) {
+          const Index::idx_t m2 = std::min(tile, pn - s - tile);
+          VLQ_CALL(vlq_memcpy_h2d(xin.as<float>() + (size_t)(s + tile) * d, xp + (size_t)(s + tile) * d,
+                                  (size_t)m2 * d * sizeof(float), cs));
+        }
+      }
       if (tc) {  // tensor-core GEMM emits bucket minima; top-P and the line selection are one fused kernel
         quantizer_->distancesDevice(q, m, dmat.as<float>(), nlist_, bmin);
         VLQ_CALL(vlq_coarse_select_lines(dmat.as<float>(), m, nlist_, bmin, nb, nlist_, P, dEdge_.as<int>(),
@@ -334,14 +354,25 @@ void GpuIndexIVFPQ::search(Index::idx_t n, const float* x, Index::idx_t k, float
         VLQ_CALL(vlq_select_lines(dmat.as<float>(), m, nlist_, cidx, P, dEdge_.as<int>(), dEdgeDist_.as<float>(),
                                   numedge_, W, lline, t1, t6, st));
       }
+      float* oD = outD.as<float>() + (size_t)s * k;
+      int64_t* oI = outI.as<int64_t>() + (size_t)s * k;
       VLQ_CALL(vlq_scan_topk(q, m, d, dPq_.as<float>(), M, dLambda_.as<float>(), nLambda_, lline, t1, t6,
                              dEdgeDist_.as<float>(), W, lOffsets_.as<int64_t>(), lCodes_.as<uint8_t>(),
                              lLamq_.as<uint8_t>(), lKappa_.as<float>(), lIds_.as<int64_t>(), (int)k, listCap_,
-                             (int)std::min<size_t>(nListed_ / ((size_t)nlist_ * numedge_), 1 << 20), outD.as<float>() + (size_t)s * k, outI.as<int64_t>() + (size_t)s * k, t3ws_.get(),
+                             (int)std::min<size_t>(nListed_ / ((size_t)nlist_ * numedge_), 1 << 20), oD, oI, t3ws_.get(),
                              t3ws_.bytes(), st));
+      float* hD = distances + (size_t)(p0 + s) * k;
+      Index::idx_t* hI = labels + (size_t)(p0 + s) * k;
+      if (dOnDevice && lOnDevice) {
+        VLQ_CALL(vlq_memcpy_d2d(hD, oD, (size_t)m * k * sizeof(float), st));
+        VLQ_CALL(vlq_memcpy_d2d(hI, oI, (size_t)m * k * sizeof(int64_t), st));
+      } else {
+        VLQ_CALL(vlq_stream_wait(cs, st));  // results of this tile are complete
+        fromDevice(hD, oD, (size_t)m * k * sizeof(float), cs);
+        fromDevice(hI, oI, (size_t)m * k * sizeof(int64_t), cs);
+      }
     }
-    fromDevice(distances + (size_t)p0 * k, outD.get(), (size_t)pn * k * sizeof(float), st);
-    fromDevice(labels + (size_t)p0 * k, outI.get(), (size_t)pn * k * sizeof(int64_t), st);
+    VLQ_CALL(vlq_stream_synchronize(cs));
     resources_->syncDefaultStream();
   }
 }
