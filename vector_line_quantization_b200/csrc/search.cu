@@ -821,8 +821,12 @@ __global__ void __launch_bounds__(SKEW ? AQ_THREADS_SKEW : Q_THREADS, SKEW ? 2 :
   // per-lane constants of the skewed lookups
   const int lp = lane & (MS - 1);
   const bool rot_a1 = ((lp >> 2) & 1) != 0, rot_a2 = ((lp >> 2) & 2) != 0;
-  const uint32_t rot_selb = 0x3210u + 0x1111u * (uint32_t)(lp & 3);
-  const uint32_t lofs = 4u * (uint32_t)(MS * (lane / MS) + lp);
+  uint32_t rot_selb = 0x3210u + 0x1111u * (uint32_t)(lp & 3);
+  uint32_t lofs = 4u * (uint32_t)(MS * (lane / MS) + lp);
+  if (SKEW) {  // keep the two per-lane constants in registers: the compiler otherwise recomputes them in every chunk
+    asm volatile("" : "+r"(rot_selb));
+    asm volatile("" : "+r"(lofs));
+  }
   const unsigned char* tblc = reinterpret_cast<const unsigned char*>(T3);
   LineDesc cur;  // warp-uniform walk state
   cur.len = 0;
