@@ -58,6 +58,10 @@ int vlq_host_vlq_read_codebook(void* index, const char* name);
 int vlq_host_vlq_write_db(void* index, const char* name);
 int vlq_host_vlq_read_db(void* index, const char* name, int pronum, int rank);
 
+/* the permutation Clustering::train subsamples and initialises with (rand_perm, utils.cpp:307-317, on the glibc random_r
+ * generator of utils.cpp:135-160): host-only, exposed so that CPU tests can pin it against the reference library */
+int vlq_host_rand_perm(int* perm, long n, long seed);
+
 /* dataset / matrix formats of the reference drivers (filehelper.cpp:106-345): TexMex .fvecs (kind 0) / .ivecs (1) /
  * .bvecs (2), and the .umem/.imem layout (ASCII "num\ndim\n" header, payload at byte 20) */
 int vlq_host_vecs_header(const char* path, int elem_size, long* n, long* d);

@@ -1,4 +1,4 @@
-"""Dataset formats of the reference drivers (reference filehelper.cpp:106-345), through the C++ host layer.
+"""Host-layer logic that runs without a GPU: dataset formats of the reference drivers (reference filehelper.cpp:106-345), through the C++ host layer.
 CPU-only: the files are written by numpy in the documented layout and read back through the library, and vice versa."""
 import numpy as np
 import pytest
@@ -72,3 +72,21 @@ def test_imem_and_u8(tmp_path):
     np.testing.assert_array_equal(fh.readUint8(q, 16, 2, offset=1), codes[1:3])
     with pytest.raises(FaissException):
         fh.readInt(p, 4, 11)                           # short read
+
+
+# ------------------------------------------------------------------------------------------------ host k-means RNG
+@pytest.mark.parametrize("n,seed", [(1, 1234), (10, 1234), (1000, 1235), (65536, 7)])
+def test_host_rand_perm_matches_reference(n, seed):
+    """host/Clustering.cpp rand_perm (the subsampling / initialisation order of the device k-means) against the
+    reference library's rand_perm (utils.cpp:307-317) and the oracle restatement"""
+    import ctypes as C
+
+    from oracle import pyoracle as po
+    from vector_line_quantization_b200.index import _call
+
+    perm = np.empty(n, dtype=np.int32)
+    _call("vlq_host_rand_perm", C.c_void_p(perm.ctypes.data), C.c_long(n), C.c_long(seed))
+    assert sorted(perm.tolist()) == list(range(n))
+    np.testing.assert_array_equal(perm, po.rand_perm(n, seed))
+    if po.ref_available():
+        np.testing.assert_array_equal(perm, po.ref_rand_perm(n, seed))

@@ -3,6 +3,7 @@
 #include <cstring>
 #include <string>
 
+#include "Clustering.h"
 #include "GpuIndexIVFPQ.h"
 #include "IndexProxy.h"
 #include "filehelper.h"
@@ -151,6 +152,9 @@ int vlq_host_vlq_write_db(void* index, const char* name) { GUARD(V(index)->write
 int vlq_host_vlq_read_db(void* index, const char* name, int pronum, int rank) {
   GUARD(V(index)->readDbFromFile(name, pronum, rank))
 }
+
+/* host-side pieces of k-means that never touch the GPU (reference utils.cpp:135-160,307-317) */
+int vlq_host_rand_perm(int* perm, long n, long seed) { GUARD(rand_perm(perm, (size_t)n, seed)) }
 
 /* dataset formats (reference filehelper.cpp) */
 int vlq_host_vecs_header(const char* path, int elem_size, long* n, long* d) {
