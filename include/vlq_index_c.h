@@ -17,6 +17,7 @@ const char* vlq_host_last_error(void);
 /* StandardGpuResources */
 int vlq_host_resources_new(int device, void** out);
 int vlq_host_resources_free(void* res);
+int vlq_host_resources_sync(void* res); /* wait for the resource's default stream (syncDefaultStream) */
 
 /* any index handle (flat, VLQ, proxy, shards): the faiss::Index virtual API */
 int vlq_host_index_free(void* index);
@@ -31,6 +32,10 @@ int vlq_host_index_is_trained(void* index);
 /* GpuIndexFlatL2 + its VLQ helper surface */
 int vlq_host_flat_new(void* res, int d, int use_tensor_cores, void** out);
 int vlq_host_flat_assign(void* flat, long n, const float* x, int* labels);
+int vlq_host_flat_search_int(void* flat, long n, const float* x, long k, float* distances, int* labels); /* searchInt */
+/* assign1Base: device pointers only; line id (assign2 = A*numedge + e) and float lambda of every row */
+int vlq_host_flat_assign1_base(void* flat, long n, const float* d_input, const int* d_assign1, int* d_assign2,
+                               float* d_lambdaf, const int* d_edge, const float* d_edge_dist, int numedge);
 int vlq_host_flat_build_graph(void* flat, int nedge, float* distances, int* labels);
 
 /* Clustering::train over a GpuIndexFlatL2 assigner */

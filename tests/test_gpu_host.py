@@ -57,6 +57,32 @@ def test_flat_accepts_device_pointers(vi, res, cuda):
     assert Dd.is_cuda and np.array_equal(Id.cpu().numpy(), Ih) and np.array_equal(Dd.cpu().numpy(), Dh)
 
 
+def test_flat_search_int_and_assign1_base(vi, res, cuda, oracle):
+    """searchInt == search with int labels; assign1Base (device pointers) == the oracle's line stage"""
+    import torch
+
+    from vector_line_quantization_b200 import data
+
+    cent = data.sift_like(512, seed=5)
+    x = data.sift_like(700, seed=6)
+    flat = vi.GpuIndexFlatL2(res, 128)
+    flat.add(cent)
+    D, I = flat.search(x[:50], 7)
+    Di, Ii = flat.searchInt(x[:50], 7)
+    assert Ii.dtype == np.int32 and np.array_equal(Ii, I) and np.array_equal(Di, D)
+    E = 16
+    edge, ed2 = oracle.knn_graph(cent, E)
+    A = oracle.l2_topk(x, cent, 1)[1][:, 0].astype(np.int32)
+    a2, lam = flat.assign1Base(torch.from_numpy(x).to(cuda), torch.from_numpy(A).to(cuda),
+                               torch.from_numpy(edge).to(cuda), torch.from_numpy(ed2).to(cuda))
+    lo, lamo = oracle.line_stage(x, A, cent, edge, ed2)[:2]
+    assert (a2.cpu().numpy() == lo).mean() > 0.995
+    same = a2.cpu().numpy() == lo
+    np.testing.assert_allclose(lam.cpu().numpy()[same], lamo[same], rtol=1e-3, atol=1e-4)
+    with pytest.raises(vi.FaissException):
+        flat.assign1Base(torch.from_numpy(x), torch.from_numpy(A), torch.from_numpy(edge), torch.from_numpy(ed2))
+
+
 def test_kmeans_matches_oracle(vi, res, oracle):
     from vector_line_quantization_b200 import data
 

@@ -144,6 +144,16 @@ void GpuIndexFlat::distancesDevice(const float* dx, Index::idx_t n, float* dD, I
 }
 
 void GpuIndexFlat::search(Index::idx_t n, const float* x, Index::idx_t k, float* distances, Index::idx_t* labels) const {
+  searchCore_(n, x, k, distances, labels, nullptr);
+}
+
+// same search, int labels (reference searchInt, gpu/GpuIndexFlat.cu:299-372)
+void GpuIndexFlat::searchInt(Index::idx_t n, const float* x, Index::idx_t k, float* distances, int* labels) const {
+  searchCore_(n, x, k, distances, nullptr, labels);
+}
+
+void GpuIndexFlat::searchCore_(Index::idx_t n, const float* x, Index::idx_t k, float* distances, Index::idx_t* labels,
+                               int* intLabels) const {
   VLQ_THROW_IF_NOT_MSG(k >= 1 && k <= VLQ_MAX_K, "k must be in [1, 1024]");
   VLQ_THROW_IF_NOT_MSG(ntotal > 0, "index is empty");
   if (n == 0) return;
@@ -169,9 +179,12 @@ void GpuIndexFlat::search(Index::idx_t n, const float* x, Index::idx_t k, float*
       VLQ_CALL(vlq_select_rows(dmat.as<float>(), m, (int)ntotal, ntotal, (int)k, xn.as<float>(), outv.as<float>(),
                                outi.as<int>(), st));
     }
-    VLQ_CALL(vlq_i32_to_i64(outi.as<int>(), (int64_t)m * k, outl.as<int64_t>(), st));
     fromDevice(distances + (size_t)s * k, outv.get(), (size_t)m * k * sizeof(float), st);
-    fromDevice(labels + (size_t)s * k, outl.get(), (size_t)m * k * sizeof(int64_t), st);
+    if (labels) {
+      VLQ_CALL(vlq_i32_to_i64(outi.as<int>(), (int64_t)m * k, outl.as<int64_t>(), st));
+      fromDevice(labels + (size_t)s * k, outl.get(), (size_t)m * k * sizeof(int64_t), st);
+    }
+    if (intLabels) fromDevice(intLabels + (size_t)s * k, outi.get(), (size_t)m * k * sizeof(int), st);
     resources_->syncDefaultStream();
   }
 }
@@ -220,6 +233,19 @@ void GpuIndexFlat::assign1(Index::idx_t n, int dd, const float* x, int* assign, 
   fromDevice(assign1, ol.get(), ol.bytes(), st);
   fromDevice(lamdaf, of.get(), of.bytes(), st);
   resources_->syncDefaultStream();
+}
+
+// the device-resident core of assign1 (reference assign1Base takes device Tensors, gpu/GpuIndexFlat.cu:756-807): every
+// pointer is a device pointer, nothing is copied or synchronised
+void GpuIndexFlat::assign1Base(Index::idx_t n, const float* dInput, const int* dAssign1, int* dAssign2, float* dLambdaf,
+                               const int* dEdgeInfo, const float* dEdgeDistInfo, int numedge, int /*k*/) const {
+  if (n == 0) return;
+  VLQ_THROW_IF_NOT_MSG(vlq_pointer_is_device(dInput) == 1 && vlq_pointer_is_device(dAssign2) == 1,
+                       "assign1Base works on device memory (use assign1 for host pointers)");
+  DeviceScope scope(config_.device);
+  VLQ_CALL(vlq_line_encode(dInput, n, d, dAssign1, vecs_.as<float>(), dEdgeInfo, dEdgeDistInfo, numedge, nullptr, 0,
+                           nullptr, 0, dAssign2, dLambdaf, nullptr, nullptr, nullptr, nullptr,
+                           resources_->getDefaultStream()));
 }
 
 void GpuIndexFlat::assignLambda(int n, float* lambdaf, uint8_t* lambda, float* lambdaInfo, int nlambda) const {

@@ -32,6 +32,8 @@ class GpuIndexFlat : public faiss::Index {
   size_t getNumVecs() const { return (size_t)ntotal; }
 
   // ---- VLQ surface of the reference (gpu/GpuIndexFlat.h:75-143); host or device pointers
+  /// search with int labels (reference searchInt, gpu/GpuIndexFlat.cu:299-372)
+  void searchInt(Index::idx_t n, const float* x, Index::idx_t k, float* distances, int* labels) const;
   /// nearest stored vector per row as int labels (reference assignFlat, gpu/GpuIndexFlat.cu:894-900); k must be 1
   void assignFlat(Index::idx_t n, const float* x, int* labels, Index::idx_t k = 1);
   /// kNN graph of the stored vectors: the k = nedge nearest OTHER vectors (rank 0 dropped) (gpu/GpuIndexFlat.cu:375-429)
@@ -40,6 +42,9 @@ class GpuIndexFlat : public faiss::Index {
   void assign1(Index::idx_t n, int d, const float* x, int* assign, int* assign1, float* lamdaf, int* edgeinfo,
                float* edgedistinfo, int nlist, int numedge, int k = 1) const;
   /// lambda -> uint8 code against the 1-D codebook (gpu/GpuIndexFlat.cu:702-752)
+  /// device-pointer core of assign1 (reference assign1Base, gpu/GpuIndexFlat.cu:756-807; raw pointers instead of Tensors)
+  void assign1Base(Index::idx_t n, const float* dInput, const int* dAssign1, int* dAssign2, float* dLambdaf,
+                   const int* dEdgeInfo, const float* dEdgeDistInfo, int numedge, int k = 1) const;
   void assignLambda(int n, float* lambdaf, uint8_t* lambda, float* lambdaInfo, int nlambda) const;
   /// r = x - ((1-l) c_A + l c_s) with l = lambdaInfo[lambda]; assign holds A*numedge + e (gpu/GpuIndexFlat.cu:1194-1258)
   void compute_residual(Index::idx_t n, const float* x, float* residual, int* edgeInfo, uint8_t* lambda,
@@ -60,6 +65,8 @@ class GpuIndexFlat : public faiss::Index {
 
  private:
   void refreshDerived_();
+  void searchCore_(Index::idx_t n, const float* x, Index::idx_t k, float* distances, Index::idx_t* labels,
+                   int* intLabels) const;
 
   GpuResources* resources_;
   GpuIndexFlatConfig config_;

@@ -43,6 +43,7 @@ const char* vlq_host_last_error(void) { return g_err.c_str(); }
 
 int vlq_host_resources_new(int device, void** out) { GUARD(*out = new StandardGpuResources(device)) }
 int vlq_host_resources_free(void* res) { GUARD(delete static_cast<StandardGpuResources*>(res)) }
+int vlq_host_resources_sync(void* res) { GUARD(static_cast<GpuResources*>(res)->syncDefaultStream()) }
 
 int vlq_host_index_free(void* index) { GUARD(delete I(index)) }
 int vlq_host_index_train(void* index, long n, const float* x) { GUARD(I(index)->train(n, x)) }
@@ -66,6 +67,13 @@ int vlq_host_flat_new(void* res, int d, int use_tensor_cores, void** out) {
   })
 }
 int vlq_host_flat_assign(void* flat, long n, const float* x, int* labels) { GUARD(F(flat)->assignFlat(n, x, labels, 1)) }
+int vlq_host_flat_search_int(void* flat, long n, const float* x, long k, float* distances, int* labels) {
+  GUARD(F(flat)->searchInt(n, x, k, distances, labels))
+}
+int vlq_host_flat_assign1_base(void* flat, long n, const float* d_input, const int* d_assign1, int* d_assign2,
+                               float* d_lambdaf, const int* d_edge, const float* d_edge_dist, int numedge) {
+  GUARD(F(flat)->assign1Base(n, d_input, d_assign1, d_assign2, d_lambdaf, d_edge, d_edge_dist, numedge))
+}
 int vlq_host_flat_build_graph(void* flat, int nedge, float* distances, int* labels) {
   GUARD(F(flat)->buildGraph(F(flat)->ntotal, nedge, distances, labels))
 }

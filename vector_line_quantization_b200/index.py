@@ -65,6 +65,9 @@ class StandardGpuResources:
         _call("vlq_host_resources_new", int(device), C.byref(self.h))
         self.device = device
 
+    def sync(self):
+        _call("vlq_host_resources_sync", self.h)
+
     def __del__(self):
         try:
             if self.h:
@@ -144,6 +147,29 @@ class GpuIndexFlatL2(Index):
         out = np.empty(x.shape[0], np.int32)
         _call("vlq_host_flat_assign", self.h, C.c_long(x.shape[0]), p, C.c_void_p(out.ctypes.data))
         return out
+
+    def searchInt(self, x, k):
+        """search with int32 labels (reference GpuIndexFlat::searchInt)"""
+        p, keep, _ = _in(x, np.float32)
+        n = x.shape[0]
+        D = np.empty((n, k), np.float32)
+        I = np.empty((n, k), np.int32)
+        _call("vlq_host_flat_search_int", self.h, C.c_long(n), p, C.c_long(k), C.c_void_p(D.ctypes.data),
+              C.c_void_p(I.ctypes.data))
+        return D, I
+
+    def assign1Base(self, x, assign, edge, edge_d2):
+        """device-pointer line stage (reference assign1Base): torch CUDA tensors in, (assign2 int32, lambda f32) out"""
+        import torch
+
+        n = x.shape[0]
+        a2 = torch.empty(n, dtype=torch.int32, device=x.device)
+        lam = torch.empty(n, dtype=torch.float32, device=x.device)
+        _call("vlq_host_flat_assign1_base", self.h, C.c_long(n), C.c_void_p(x.data_ptr()), C.c_void_p(assign.data_ptr()),
+              C.c_void_p(a2.data_ptr()), C.c_void_p(lam.data_ptr()), C.c_void_p(edge.data_ptr()),
+              C.c_void_p(edge_d2.data_ptr()), edge.shape[1])
+        self.res.sync()
+        return a2, lam
 
     def buildGraph(self, nedge):
         n = self.ntotal
