@@ -32,6 +32,7 @@ int vlq_host_index_is_trained(void* index);
 /* GpuIndexFlatL2 + its VLQ helper surface */
 int vlq_host_flat_new(void* res, int d, int use_tensor_cores, void** out);
 int vlq_host_flat_assign(void* flat, long n, const float* x, int* labels);
+int vlq_host_index_reconstruct_n(void* index, long i0, long ni, float* recons); /* Index::reconstruct_n; throws (-1) where undecodable */
 int vlq_host_flat_search_int(void* flat, long n, const float* x, long k, float* distances, int* labels); /* searchInt */
 /* assign1Base: device pointers only; line id (assign2 = A*numedge + e) and float lambda of every row */
 int vlq_host_flat_assign1_base(void* flat, long n, const float* d_input, const int* d_assign1, int* d_assign2,

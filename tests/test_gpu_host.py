@@ -37,6 +37,10 @@ def test_flat_search_matches_oracle(vi, res, oracle):
             assert (I == Io).mean() > 0.995
             np.testing.assert_allclose(D, Do, rtol=2e-4, atol=1.0)
         assert np.array_equal(flat.assign(xq), oracle.l2_topk(xq, xb, 1)[1][:, 0])
+    np.testing.assert_array_equal(flat.reconstruct_n(2990, 20), xb[2990:3010])  # rows of both adds, in order
+    np.testing.assert_array_equal(flat.reconstruct(4999), xb[4999])
+    with pytest.raises(vi.FaissException):
+        flat.reconstruct_n(4990, 20)
     with pytest.raises(vi.FaissException):
         flat.search(xq, 2000)  # k <= 1024
     flat.reset()

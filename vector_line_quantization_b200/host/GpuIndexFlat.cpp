@@ -74,6 +74,17 @@ void GpuIndexFlat::reset() {
   pack_.release();
 }
 
+void GpuIndexFlat::reconstruct(Index::idx_t key, float* out) const { reconstruct_n(key, 1, out); }
+
+void GpuIndexFlat::reconstruct_n(Index::idx_t i0, Index::idx_t num, float* out) const {
+  VLQ_THROW_IF_NOT_MSG(i0 >= 0 && num >= 0 && i0 + num <= ntotal, "reconstruct: rows out of range");
+  if (num == 0) return;
+  DeviceScope scope(config_.device);
+  vlq_stream_t st = resources_->getDefaultStream();
+  fromDevice(out, vecs_.as<float>() + (size_t)i0 * d, (size_t)num * d * sizeof(float), st);
+  resources_->syncDefaultStream();
+}
+
 void GpuIndexFlat::add(Index::idx_t n, const float* x) {
   if (n == 0) return;
   VLQ_THROW_IF_NOT_MSG(n > 0 && x, "invalid add arguments");

@@ -32,6 +32,9 @@ class GpuIndexFlat : public faiss::Index {
   size_t getNumVecs() const { return (size_t)ntotal; }
 
   // ---- VLQ surface of the reference (gpu/GpuIndexFlat.h:75-143); host or device pointers
+  /// stored rows back to host or device memory (reference gpu/GpuIndexFlat.h:196-204)
+  void reconstruct(Index::idx_t key, float* out) const override;
+  void reconstruct_n(Index::idx_t i0, Index::idx_t num, float* out) const override;
   /// search with int labels (reference searchInt, gpu/GpuIndexFlat.cu:299-372)
   void searchInt(Index::idx_t n, const float* x, Index::idx_t k, float* distances, int* labels) const;
   /// nearest stored vector per row as int labels (reference assignFlat, gpu/GpuIndexFlat.cu:894-900); k must be 1

@@ -52,6 +52,13 @@ struct Index {
   virtual void search(idx_t n, const float* x, idx_t k, float* distances, idx_t* labels) const = 0;
   virtual void reset() = 0;
 
+  /// stored vector `key` (reference Index.h:157; indexes that cannot decode throw, Index.cpp:49-51)
+  virtual void reconstruct(idx_t /*key*/, float* /*recons*/) const { VLQ_THROW_MSG("reconstruct not implemented for this type of index"); }
+  /// stored vectors [i0, i0 + ni) (reference Index.cpp:54-59: one reconstruct per row unless overridden)
+  virtual void reconstruct_n(idx_t i0, idx_t ni, float* recons) const {
+    for (idx_t i = 0; i < ni; i++) reconstruct(i0 + i, recons + i * d);
+  }
+
   /// labels of the k nearest neighbours (= search without the distances; reference Index.cpp:23-29)
   void assign(idx_t n, const float* x, idx_t* labels, idx_t k = 1);
 };

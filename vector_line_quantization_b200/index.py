@@ -136,7 +136,18 @@ class Index:
             pass
 
 
+def _reconstruct_n(self, i0, ni):
+    out = np.empty((ni, self.d), np.float32)
+    _call("vlq_host_index_reconstruct_n", self.h, C.c_long(i0), C.c_long(ni), C.c_void_p(out.ctypes.data))
+    return out
+
+
 class GpuIndexFlatL2(Index):
+    reconstruct_n = _reconstruct_n
+
+    def reconstruct(self, key):
+        return _reconstruct_n(self, key, 1)[0]
+
     def __init__(self, res, d, use_tensor_cores=True):
         super().__init__(d)
         self.res = res
