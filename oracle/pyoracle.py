@@ -219,6 +219,19 @@ def merge_topk(D, I):
     return oD, oI
 
 
+def imi_search(x, cent, k):
+    """IMI coarse quantizer (next row f3): cent = (M, ksub, dsub) sub-space codebooks -> (D [n][k], cell labels [n][k])"""
+    x = _c(x, _f32)
+    cent = _c(cent, _f32)
+    n, d = x.shape
+    M, ksub, _ = cent.shape
+    D = np.empty((n, k), _f32)
+    I = np.empty((n, k), _i64)
+    lib().vlqo_imi_search(_p(x, c_float_p), C.c_long(n), d, _p(cent, c_float_p), M, ksub, k, _p(D, c_float_p),
+                          _p(I, c_long_p))
+    return D, I
+
+
 def decode_distance(q, c, s, lam, pq, code):
     pq = _c(pq, _f32)
     M, ksub, _ = pq.shape
@@ -306,6 +319,21 @@ def ref_pq_compute_codes(x, pq, nbits=8):
     codes = np.empty((n, M), _u8)
     ref().ref_pq_compute_codes(d, M, nbits, _p(pq, c_float_p), C.c_long(n), _p(x, c_float_p), _p(codes, c_u8_p))
     return codes
+
+
+def ref_imi_search(x, cent, k):
+    """the reference's MultiIndexQuantizer::search on the same sub-space codebooks"""
+    x = _c(x, _f32)
+    cent = _c(cent, _f32)
+    n, d = x.shape
+    M, ksub, _ = cent.shape
+    nbits = int(round(np.log2(ksub)))
+    assert 1 << nbits == ksub
+    D = np.empty((n, k), _f32)
+    I = np.empty((n, k), _i64)
+    ref().ref_imi_search(d, M, nbits, _p(cent, c_float_p), C.c_long(n), _p(x, c_float_p), C.c_long(k),
+                         _p(D, c_float_p), _p(I, c_long_p))
+    return D, I
 
 
 def ref_heap_topk(vals, k):

@@ -18,6 +18,7 @@
 #include "Heap.h"
 #include "IndexFlat.h"
 #include "IndexIVFPQ.h"
+#include "IndexPQ.h"
 #include "MetaIndexes.h"
 #include "ProductQuantizer.h"
 #include "utils.h"
@@ -153,4 +154,15 @@ void ref_shards_flat_search(int d, int nshard, const long* shard_sizes, const fl
   for (auto* f : subs) delete f;
 }
 
+
+// MultiIndexQuantizer::search (IndexPQ.cpp:813-855) on given sub-space codebooks (M, 2^nbits, d/M): the IMI coarse
+// quantizer of the sift1b_imi_pq baselines (next row f3)
+void ref_imi_search(int d, int M, int nbits, const float* centroids, long n, const float* x, long k, float* D, long* I) {
+  MultiIndexQuantizer miq(d, M, nbits);
+  memcpy(miq.pq.centroids.data(), centroids, sizeof(float) * miq.pq.centroids.size());
+  miq.is_trained = true;
+  miq.ntotal = 1;
+  for (int m = 0; m < M; m++) miq.ntotal *= miq.pq.ksub;
+  miq.search(n, x, k, D, I);
+}
 }  // extern "C"

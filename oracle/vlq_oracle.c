@@ -534,3 +534,147 @@ double vlqo_decode_distance(const float* q, int d, const float* c, const float* 
   }
   return acc - qn;
 }
+
+/* ------------------------------------------------------------------------------------------------------------------
+ * IMI coarse quantizer (next row f3): see vlq_oracle.h.  Follows IndexPQ.cpp:813-855 / 636-778.
+ * ---------------------------------------------------------------------------------------------------------------- */
+typedef struct {
+  float sum;
+  long pos; /* sum_m t_m * ksub^m, t_m = rank in the sorted table of sub-space m */
+} imi_node_t;
+
+static inline int imi_less(const imi_node_t* a, const imi_node_t* b) {
+  return a->sum < b->sum || (a->sum == b->sum && a->pos < b->pos);
+}
+static void imi_heap_push(imi_node_t* h, int* n, imi_node_t v) {
+  int i = (*n)++;
+  while (i > 0) {
+    int p = (i - 1) / 2;
+    if (!imi_less(&v, &h[p])) break;
+    h[i] = h[p];
+    i = p;
+  }
+  h[i] = v;
+}
+static imi_node_t imi_heap_pop(imi_node_t* h, int* n) {
+  imi_node_t top = h[0], v = h[--(*n)];
+  int i = 0;
+  for (;;) {
+    int c = 2 * i + 1;
+    if (c >= *n) break;
+    if (c + 1 < *n && imi_less(&h[c + 1], &h[c])) c++;
+    if (!imi_less(&h[c], &v)) break;
+    h[i] = h[c];
+    i = c;
+  }
+  h[i] = v;
+  return top;
+}
+/* open-addressing set of visited grid positions */
+static int imi_seen_add(long* set, int cap, long pos) {
+  unsigned long hsh = (unsigned long)pos * 0x9E3779B97F4A7C15ul;
+  int i = (int)(hsh % (unsigned long)cap);
+  while (set[i] != -1) {
+    if (set[i] == pos) return 0;
+    i = i + 1 == cap ? 0 : i + 1;
+  }
+  set[i] = pos;
+  return 1;
+}
+typedef struct {
+  float v;
+  int j;
+} imi_ent_t;
+static int imi_ent_cmp(const void* a, const void* b) {
+  const imi_ent_t *x = (const imi_ent_t*)a, *y = (const imi_ent_t*)b;
+  if (x->v < y->v) return -1;
+  if (x->v > y->v) return 1;
+  return x->j - y->j;
+}
+
+void vlqo_imi_search(const float* x, long n, int d, const float* cent, int M, int ksub, int k, float* D, long* I) {
+  const int dsub = d / M;
+#pragma omp parallel
+  {
+    float* tab = (float*)malloc(sizeof(float) * (size_t)M * ksub);
+    imi_ent_t* srt = (imi_ent_t*)malloc(sizeof(imi_ent_t) * (size_t)M * ksub);
+    const int hcap = k * M + M + 1, scap = 4 * (k * M + M) + 7;
+    imi_node_t* heap = (imi_node_t*)malloc(sizeof(imi_node_t) * hcap);
+    long* seen = (long*)malloc(sizeof(long) * scap);
+#pragma omp for
+    for (long i = 0; i < n; i++) {
+      const float* xi = x + i * d;
+      for (int m = 0; m < M; m++) /* ProductQuantizer::compute_distance_table, direct differences */
+        for (int j = 0; j < ksub; j++) tab[(size_t)m * ksub + j] = l2sqr8(xi + m * dsub, cent + ((size_t)m * ksub + j) * dsub, dsub);
+      if (k == 1) { /* IndexPQ.cpp:823-846 */
+        float dis = 0.f;
+        long label = 0, w = 1;
+        for (int m = 0; m < M; m++) {
+          float vmin = HUGE_VALF;
+          long lmin = -1;
+          for (int j = 0; j < ksub; j++)
+            if (tab[(size_t)m * ksub + j] < vmin) {
+              vmin = tab[(size_t)m * ksub + j];
+              lmin = j;
+            }
+          dis += vmin;
+          label += lmin * w;
+          w *= ksub;
+        }
+        D[i] = dis;
+        I[i] = label;
+        continue;
+      }
+      for (int m = 0; m < M; m++) {
+        for (int j = 0; j < ksub; j++) {
+          srt[(size_t)m * ksub + j].v = tab[(size_t)m * ksub + j];
+          srt[(size_t)m * ksub + j].j = j;
+        }
+        qsort(srt + (size_t)m * ksub, ksub, sizeof(imi_ent_t), imi_ent_cmp);
+      }
+      int hn = 0;
+      for (int t = 0; t < scap; t++) seen[t] = -1;
+      imi_node_t first = {0.f, 0};
+      for (int m = 0; m < M; m++) first.sum += srt[(size_t)m * ksub].v;
+      imi_heap_push(heap, &hn, first);
+      imi_seen_add(seen, scap, 0);
+      for (int r = 0; r < k; r++) {
+        if (hn == 0) { /* fewer than k cells exist */
+          D[i * k + r] = FLT_MAX;
+          I[i * k + r] = -1;
+          continue;
+        }
+        imi_node_t cur = imi_heap_pop(heap, &hn);
+        long label = 0, w = 1, pp = cur.pos;
+        for (int m = 0; m < M; m++) { /* grid position -> cell label through the sort permutations */
+          int t = (int)(pp % ksub);
+          pp /= ksub;
+          label += (long)srt[(size_t)m * ksub + t].j * w;
+          w *= ksub;
+        }
+        D[i * k + r] = cur.sum;
+        I[i * k + r] = label;
+        w = 1;
+        pp = cur.pos;
+        for (int m = 0; m < M; m++) { /* followers: one step along every axis (MinSumK::enqueue_follower) */
+          int t = (int)(pp % ksub);
+          pp /= ksub;
+          if (t + 1 < ksub) {
+            long npos = cur.pos + w;
+            if (imi_seen_add(seen, scap, npos)) {
+              imi_node_t nx;
+              nx.pos = npos;
+              nx.sum = cur.sum + (srt[(size_t)m * ksub + t + 1].v - srt[(size_t)m * ksub + t].v); /* sum + get_diff */
+              imi_heap_push(heap, &hn, nx);
+            }
+          }
+          w *= ksub;
+        }
+      }
+    }
+    free(tab);
+    free(srt);
+    free(heap);
+    free(seen);
+  }
+}

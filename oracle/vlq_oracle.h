@@ -86,6 +86,14 @@ void vlqo_merge_topk(const float* D, const long* I, int R, long nq, int k, float
 double vlqo_decode_distance(const float* q, int d, const float* c, const float* s, float l, const float* pq, int M,
                             int ksub, const uint8_t* code);
 
+/* ---- the inverted multi-index coarse quantizer of BASELINE configs[4].
+ * MultiIndexQuantizer::search (IndexPQ.cpp:813-855): per sub-space tables ||x_m - c_mj||^2
+ * (ProductQuantizer.cpp:410-462), then the k cells with the smallest table sums, ascending; cell label =
+ * sum_m j_m * ksub^m.  k == 1: per-sub-space arg-min (first minimum).  k > 1: best-first walk of the M-dimensional grid
+ * of the sorted tables (the multi-sequence algorithm; reference MinSumK, IndexPQ.cpp:636-778).  cent = (M, ksub, dsub).
+ * Order among cells with EQUAL sums is unspecified in the reference (heap order); here: by position in the sorted grid. */
+void vlqo_imi_search(const float* x, long n, int d, const float* cent, int M, int ksub, int k, float* D, long* I);
+
 #ifdef __cplusplus
 }
 #endif
