@@ -31,7 +31,10 @@ def parse():
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
-    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference", "imipq"],
+                    help="b200: this framework; reference: the CPU arm of the same metric; imipq: the reference's IMI-PQ "
+                         "CPU baseline index of BASELINE configs[4] on a bounded sample (host cores only, its own metric)")
+    ap.add_argument("--imi-bits", type=int, default=10, help="--impl imipq: bits per coarse sub-quantizer (2^(2*bits) cells)")
     ap.add_argument("--n", "--db-size", dest="n", type=int, default=10_000_000,
                     help="database vectors PER GPU (use --db-size under torchrun: its parser treats --n as ambiguous)")
     ap.add_argument("--d", type=int, default=128)
@@ -164,6 +167,51 @@ def run_reference(a):
         return
     with _StdoutToStderr():
         line = _run_reference(a)
+    print(json.dumps(line))
+
+
+def run_imipq(a):
+    """--impl imipq: BASELINE configs[4]'s baseline -- MultiIndexQuantizer(d, 2, bits) + IndexIVFPQ, the UNMODIFIED reference
+    CPU classes (tests/sift1b_imi_pq.cpp:216-236 through oracle/_ref) -- on a bounded sample of the synthetic SIFT-shaped
+    workload, with the same recall definition as the VLQ runs.  Host cores only; reported beside, not against, the GPU."""
+    with _StdoutToStderr():
+        from oracle import pyoracle as po
+        from vector_line_quantization_b200 import data
+
+        d, M, k = a.d, a.m, a.k
+        nb = min(a.n, 1_000_000)
+        nt = min(nb, 200_000)
+        nq = min(a.nq, 2000)
+        xt = data.sift_like(nt, d=d, kc=a.kc, seed=1)
+        xb = data.sift_like(nb, d=d, kc=a.kc, seed=2)
+        xq = data.sift_like(nq, d=d, kc=a.kc, seed=3)
+        t0 = time.time()
+        idx = po.RefIMIPQ(d, a.imi_bits, M)
+        idx.train(xt)
+        t_train = time.time() - t0
+        t0 = time.time()
+        idx.add(xb)
+        t_add = time.time() - t0
+        gt = po.ref_flat_search(xb, xq, 1)[1][:, 0]
+        sweep = []
+        for nprobe in (8, 64, 512):
+            idx.search(xq[:64], k, nprobe)
+            t0 = time.time()
+            D, I = idx.search(xq, k, nprobe)
+            dt = time.time() - t0
+            sweep.append({"nprobe": nprobe, "qps": nq / dt, "R@1": data.recall_at(I, gt, 1),
+                          "R@10": data.recall_at(I, gt, 10), "R@100": data.recall_at(I, gt, min(100, k))})
+            print("[bench] imipq", sweep[-1], file=sys.stderr, flush=True)
+        mid = sweep[1]
+        line = {"impl": "imipq", "metric": "imipq_search_qps", "value": mid["qps"], "unit": "queries/s",
+                "higher_is_better": True, "data": "synthetic", "dtype": "f32",
+                "config": {"workload": "BASELINE.json configs[4] baseline, bounded sample: reference IMI-PQ "
+                                       "(MultiIndexQuantizer(d,2,%d) + IndexIVFPQ m=%d) on %d synthetic SIFT-shaped "
+                                       "vectors, %d queries, k=%d" % (a.imi_bits, M, nb, nq, k),
+                           "cells": 1 << (2 * a.imi_bits), "bytes_per_vector": M, "db_vectors": nb, "nq": nq},
+                "cpu_baseline": {"value": mid["qps"], "unit": "queries/s", "cores": po.ref_num_threads(), "kind": "reference",
+                                 "sample": "nprobe 64 of the sweep below"},
+                "sweep": sweep, "train_s": t_train, "add_vec_per_s": nb / t_add}
     print(json.dumps(line))
 
 
@@ -687,6 +735,9 @@ def main():
     a = parse()
     if a.impl == "reference":
         run_reference(a)
+    elif a.impl == "imipq":
+        if int(os.environ.get("RANK", "0")) == 0:
+            run_imipq(a)
     else:
         # libraries (NCCL's version banner, ...) print to fd 1: keep it clean for the ONE JSON line
         with _StdoutToStderr():

@@ -336,6 +336,41 @@ def ref_imi_search(x, cent, k):
     return D, I
 
 
+class RefIMIPQ:
+    """the reference's IMI-PQ baseline index (tests/sift1b_imi_pq.cpp:216-236): MultiIndexQuantizer(d, 2, nbits_coarse)
+    + IndexIVFPQ(2^(2 nbits_coarse) lists, M bytes per code), all reference CPU code"""
+
+    def __init__(self, d, nbits_coarse, M, nbits=8):
+        r = ref()
+        r.ref_imipq_new.restype = C.c_void_p
+        self.d = d
+        self.h = C.c_void_p(r.ref_imipq_new(d, nbits_coarse, M, nbits))
+
+    def train(self, x):
+        x = _c(x, _f32)
+        ref().ref_imipq_train(self.h, C.c_long(x.shape[0]), _p(x, c_float_p))
+
+    def add(self, x):
+        x = _c(x, _f32)
+        ref().ref_imipq_add(self.h, C.c_long(x.shape[0]), _p(x, c_float_p))
+
+    def search(self, xq, k, nprobe):
+        xq = _c(xq, _f32)
+        D = np.empty((xq.shape[0], k), _f32)
+        I = np.empty((xq.shape[0], k), _i64)
+        ref().ref_imipq_search(self.h, C.c_long(xq.shape[0]), _p(xq, c_float_p), C.c_long(k), C.c_long(nprobe),
+                               _p(D, c_float_p), _p(I, c_long_p))
+        return D, I
+
+    def __del__(self):
+        try:
+            if self.h:
+                ref().ref_imipq_free(self.h)
+                self.h = None
+        except Exception:
+            pass
+
+
 def ref_heap_topk(vals, k):
     vals = _c(vals, _f32)
     n, m = vals.shape

@@ -165,4 +165,31 @@ void ref_imi_search(int d, int M, int nbits, const float* centroids, long n, con
   for (int m = 0; m < M; m++) miq.ntotal *= miq.pq.ksub;
   miq.search(n, x, k, D, I);
 }
+
+// ---- the IMI-PQ baseline index of tests/sift1b_imi_pq.cpp:216-236 (BASELINE configs[4]): MultiIndexQuantizer(d, 2, nbits_coarse)
+// as coarse quantizer of an IndexIVFPQ with 2^(2*nbits_coarse) lists, quantizer_trains_alone = true
+struct RefIMIPQ {
+  MultiIndexQuantizer* miq;
+  IndexIVFPQ* index;
+};
+void* ref_imipq_new(int d, int nbits_coarse, int M, int nbits) {
+  RefIMIPQ* h = new RefIMIPQ;
+  h->miq = new MultiIndexQuantizer(d, 2, nbits_coarse);
+  h->index = new IndexIVFPQ(h->miq, d, (size_t)1 << (2 * nbits_coarse), M, nbits);
+  h->index->quantizer_trains_alone = true;
+  return h;
+}
+void ref_imipq_train(void* hv, long n, const float* x) { ((RefIMIPQ*)hv)->index->train(n, x); }
+void ref_imipq_add(void* hv, long n, const float* x) { ((RefIMIPQ*)hv)->index->add(n, x); }
+void ref_imipq_search(void* hv, long nq, const float* xq, long k, long nprobe, float* D, long* I) {
+  RefIMIPQ* h = (RefIMIPQ*)hv;
+  h->index->nprobe = nprobe;
+  h->index->search(nq, xq, k, D, I);
+}
+void ref_imipq_free(void* hv) {
+  RefIMIPQ* h = (RefIMIPQ*)hv;
+  delete h->index;
+  delete h->miq;
+  delete h;
+}
 }  // extern "C"

@@ -186,3 +186,24 @@ def test_imi_search_matches_multi_index_quantizer(ref, d, M, nbits, k):
         np.testing.assert_allclose(udr, D[i][:n_u], rtol=3e-5, atol=2e-6)
         assert np.mean(ur == I[i][:n_u]) > 0.97
         assert k - n_u <= max(2, k // 50)  # duplicates are rare
+
+
+def test_reference_imipq_baseline_index(ref):
+    """the IMI-PQ baseline of BASELINE configs[4] (tests/sift1b_imi_pq.cpp) builds and searches through the reference's
+    own classes: exact-duplicate queries find themselves, results ascend, recall grows with nprobe"""
+    rng = np.random.RandomState(4)
+    d = 32
+    xt = rng.rand(4000, d).astype(np.float32)
+    xb = rng.rand(3000, d).astype(np.float32)
+    xq = xb[:100] + rng.normal(0, 0.01, (100, d)).astype(np.float32)
+    idx = ref.RefIMIPQ(d, 4, 8)  # 2 x 2^4 coarse codebooks = 256 cells, 8 bytes per code
+    idx.train(xt)
+    idx.add(xb)
+    gt = ref.l2_topk(xq, xb, 1)[1][:, 0]
+    rec = []
+    for nprobe in (1, 8, 64):
+        D, I = idx.search(xq, 10, nprobe)
+        for i in range(100):
+            assert np.all(np.diff(D[i][I[i] >= 0]) >= 0)
+        rec.append(np.mean([gt[i] in I[i] for i in range(100)]))
+    assert rec[0] <= rec[1] <= rec[2] and rec[2] > 0.5
