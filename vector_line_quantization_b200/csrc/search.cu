@@ -1,15 +1,20 @@
-// Query-time kernels (SURVEY.md 8a rows a4, a12, a13-a15, a16).
+// Query-time kernels (SURVEY.md 8a rows a4, a11-a16).
 //
-//  select_lines_kernel : one CTA per query; scores the P*E lines of the probed centroids from the coarse matrix D and
-//                        keeps the W best (exact block top-k).                      [BroadcastSum.cu:477-560]
-//  scan_topk_kernel    : one CTA per query; builds the per-query term3 table (-2 q_m.p_mj) in shared memory, walks
-//                        the selected lists as ONE flattened entry stream (so 5-entry lists and 1000-entry lists
-//                        use the lanes equally), 16-byte code loads, distance from the per-entry kappa and the
-//                        per-line scalars, fused exact top-k -- no intermediate distance array, no term2 tables.
-//                                                                                   [PQScanMultiPassPrecomputed.cu:675-881,
-//                                                                                    IVFUtils*.cu]
-//  merge_topk_kernel   : one CTA per query over the [R][nq][k] all-gather layout.     [GpuIndexIVFPQ.cu:1467-1518]
-//  knn_graph           : tiled C x C coarse matrix + top-(E+1) + drop rank 0.        [GpuIndexFlat.cu:869-893]
+//  select_lines_kernel        : one CTA per query; scores the P*E lines of the probed centroids from the coarse matrix D
+//                               and keeps the W best (exact block top-k).                 [BroadcastSum.cu:477-560]
+//  coarse_select_lines_kernel : the same fused with the exact top-P (through 32-column bucket minima of D).
+//                                                                        [Distance.cu:233-383, L2Select.cu:124-165]
+//  term3_reg_kernel / term3_kernel : per-query tables -2 q_m.p_mj for a batch of queries.     [IVFPQ.cu:1398-1432]
+//  scan_topk_kernel<M, LONG>  : one CTA per query, block-synchronous; LONG = false walks the selected lists as ONE
+//                               flattened entry stream (5-entry and 1000-entry lists use the lanes equally), LONG = true
+//                               gives every warp whole lists.  16-byte code loads, distance from the per-entry kappa
+//                               and the per-line scalars, fused exact top-k -- no intermediate distance array, no
+//                               term-2 tables.                 [PQScanMultiPassPrecomputed.cu:675-881, IVFUtils*.cu]
+//  scan_async_kernel<M, SKEW> : warp-autonomous scan for long lists (own top-k per warp, software-pipelined chunks);
+//                               SKEW = bank-conflict-free table layout (see the comment above the kernel).
+//  merge_topk_kernel          : one CTA per query over the [R][nq][k] all-gather layout, or gathering the shards'
+//                               results itself from peer-mapped memory.                 [GpuIndexIVFPQ.cu:1467-1518]
+//  knn_graph                  : tiled C x C coarse matrix + top-(E+1) + drop rank 0.     [GpuIndexFlat.cu:869-893]
 #include <cfloat>
 #include <cstdlib>
 
