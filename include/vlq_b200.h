@@ -60,20 +60,16 @@ int vlq_l2_assign(const float* x, int64_t n, int d, const float* cent, const flo
  *     Supported when vlq_tc_supported(d, C): d a multiple of 32, 32 <= d <= 128.  Other shapes use the exact fp32
  *     CUDA-core entry points above (the host layer dispatches; both are CUDA, there is no CPU path).
  *     cent_pack is produced once per codebook by vlq_tc_pack_centroids (packed fp16 tiles + padded ||c||^2);
- *     `scale` must be the same power of two in the pack call and the query calls: choose it so that
- *     max|c|*scale is about 2^9 (inputs up to 2^15/scale stay finite in fp16).
+ *     `scale` (the same power of two in the pack call and the query calls) scales the CENTROIDS: choose it so that
+ *     max|c|*scale is about 2^9.  Vectors / queries are scaled per row by their own power of two inside the call
+ *     (max|x_row| -> [2^8, 2^9)), so inputs of any magnitude stay inside fp16's range.
  * ---------------------------------------------------------------------------------------------------------------- */
 int vlq_tc_supported(int d, int C);
 size_t vlq_tc_cent_pack_bytes(int C, int d);
 int vlq_tc_pack_centroids(const float* cent, const float* cnorm, int C, int d, float scale, void* cent_pack,
                           vlq_stream_t stream);
 size_t vlq_l2_tc_workspace_bytes(int64_t n, int d, int C);
-/* vlq_l2_assign_tc flags (the add_xnorm argument): bit 0 = add ||x||^2 to out_dist, bit 1 = single-pass screen
- * (experimental, needs out_dist == NULL): ONE hi.hi pass keeps best / second best per row; rows whose margin exceeds
- * twice a rigorous error bound (2^-11 ||x|| max||c|| per rounded operand) have a proven arg-min, the others are
- * gathered and re-run with the split-precision passes.  Same ids as the default path; currently slower. */
-#define VLQ_ASSIGN_ADD_XNORM 1
-#define VLQ_ASSIGN_SCREEN 2
+/* add_xnorm != 0: out_dist gets ||x||^2 added (true squared distance) */
 int vlq_l2_assign_tc(const float* x, int64_t n, int d, const void* cent_pack, float scale, int C, int add_xnorm,
                      int* out_ids, float* out_dist, void* workspace, size_t workspace_bytes, vlq_stream_t stream);
 /* bucket_min (nullable): [n][vlq_tc_num_buckets(C)], the minimum of every 32-column bucket of D, produced by the GEMM

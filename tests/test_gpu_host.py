@@ -111,7 +111,7 @@ def _build(vi, res, m, xb, chunks=2):
     return idx
 
 
-def test_vlq_index_matches_oracle(vi, res, oracle, small_model):
+def test_vlq_index_matches_oracle(vi, res, oracle, small_model, tmp_path):
     m = small_model
     idx = _build(vi, res, m, m["xb"], chunks=3)
     assert idx.ntotal == len(m["xb"])
@@ -129,18 +129,50 @@ def test_vlq_index_matches_oracle(vi, res, oracle, small_model):
             continue
         assert (codes == enc["codes"][want]).mean() > 0.99 and (las == enc["lamq"][want]).mean() > 0.99
     assert mism <= 2
-    idx.setNumProbes(16)
-    idx.w1_ = 128
-    D, I = idx.search(m["xq"], 20)
-    Do, Io = oracle.search(m["xq"], m["cent"], m["edge"], m["edge_d2"], m["lambda_cb"], m["pq"], off,
-                           enc["codes"][perm], enc["lamq"][perm], perm.astype(np.int64), P=16, W=128, k=20)
-    assert (I == Io).mean() > 0.98
-    qn = (m["xq"].astype(np.float64) ** 2).sum(1, keepdims=True)
-    same = I == Io
-    assert np.all(np.abs(D - Do)[same] <= 1e-4 * (np.abs(Do) + qn)[same])
+    # search: the oracle gets the index exactly as the device stored it (dumped through the reference's .db* files), so
+    # only the query path differs; every differing id must be a float64 near-tie (tests/parity_util.py)
+    _search_vs_oracle_same_index(idx, oracle, m, m["xq"], 16, 128, 20, tmp_path)
 
 
-def test_vlq_train_on_device(vi, res, oracle, small_model):
+def _dump_index(idx, m, tmp_path):
+    """(offsets, list-major codes / lambda bytes / ids, per-id entry tables) of the device index, via writeDbToFile"""
+    name = str(tmp_path / "dump")
+    idx.writeDbToFile(name)
+    M, nl = m["M"], m["C"] * m["E"]
+    counts = np.fromfile(name + ".dbcount", dtype=np.int32)
+    assert len(counts) == nl
+    ids = np.fromfile(name + ".dbIdx", dtype=np.int64)
+    codes = np.fromfile(name + ".dbcodes", dtype=np.uint8).reshape(-1, M)
+    las = np.fromfile(name + ".dblas", dtype=np.uint8)
+    off = np.zeros(nl + 1, np.int64)
+    off[1:] = np.cumsum(counts)
+    n = int(ids.max()) + 1
+    e_list = np.full(n, -1, np.int32)
+    e_list[ids] = np.repeat(np.arange(nl, dtype=np.int32), counts)
+    e_lamq = np.zeros(n, np.uint8)
+    e_lamq[ids] = las
+    e_codes = np.zeros((n, M), np.uint8)
+    e_codes[ids] = codes
+    return off, codes, las, ids, e_list, e_lamq, e_codes
+
+
+def _search_vs_oracle_same_index(idx, oracle, m, xq, P, W, k, tmp_path, model=None):
+    from tests.parity_util import check_topk
+
+    mm = m if model is None else model
+    off, codes, las, ids, e_list, e_lamq, e_codes = _dump_index(idx, m, tmp_path)
+    idx.setNumProbes(P)
+    idx.w1_ = W
+    D, I = idx.search(xq, k)
+    Do, Io, _, lines, _ = oracle.search(xq, mm["cent"], mm["edge"], mm["edge_d2"], mm["lambda_cb"], mm["pq"], off, codes,
+                                        las, ids, P=P, W=W, k=k, want_debug=True)
+    # a query whose line set could differ (line-score near-tie) shows up as an unexplained id; none is tolerated here
+    # beyond what check_topk proves to be distance near-ties
+    check_topk(D, I, Do, Io, xq, mm, e_list, e_lamq, e_codes)
+    return I, Io
+
+
+def test_vlq_train_on_device(vi, res, oracle, small_model, tmp_path):
     """train() end to end on the device; quality must match the oracle-trained model (same algorithm, same seeds)"""
     from vector_line_quantization_b200 import data
 
@@ -158,17 +190,16 @@ def test_vlq_train_on_device(vi, res, oracle, small_model):
     eo, _ = oracle.knn_graph(cb["cent"], m["E"])
     assert (cb["edge"] == eo).mean() > 0.999
     idx.add(m["xb"])
-    idx.setNumProbes(32)
-    idx.w1_ = 256
-    _, I = idx.search(m["xq"], 100)
-    _, gt = oracle.l2_topk(m["xq"], m["xb"], 1)
-    r_gpu = data.recall_at(I, gt[:, 0], 100)
-    enc = oracle.encode_all(m["xb"], m["cent"], m["edge"], m["edge_d2"], m["lambda_cb"], m["pq"])
-    off, perm = oracle.build_lists(enc["list"], m["C"] * m["E"])
-    _, Io = oracle.search(m["xq"], m["cent"], m["edge"], m["edge_d2"], m["lambda_cb"], m["pq"], off, enc["codes"][perm],
-                          enc["lamq"][perm], perm.astype(np.int64), P=32, W=256, k=100)
-    r_cpu = data.recall_at(Io, gt[:, 0], 100)
-    assert r_gpu > 0.8 and abs(r_gpu - r_cpu) < 0.08, (r_gpu, r_cpu)
+    # recall (gpu/test/sift1b_query.cpp:334-347) against the oracle on the SAME index (device-trained codebooks, device-
+    # stored lists): within 0.1 pt (north_star) on 2000 queries -- in fact the results are identical up to near-ties
+    xq = data.sift_like(2000, kc=512, seed=4)
+    cbm = dict(cent=cb["cent"], edge=cb["edge"], edge_d2=cb["edge_d2"], lambda_cb=cb["lambda_cb"], pq=cb["pq"])
+    I, Io = _search_vs_oracle_same_index(idx, oracle, m, xq, 32, 256, 100, tmp_path, model=cbm)
+    _, gt = oracle.l2_topk(xq, m["xb"], 1)
+    for r in (1, 10, 100):
+        r_gpu, r_cpu = data.recall_at(I, gt[:, 0], r), data.recall_at(Io, gt[:, 0], r)
+        assert abs(r_gpu - r_cpu) <= 0.001, (r, r_gpu, r_cpu)
+    assert data.recall_at(I, gt[:, 0], 100) > 0.8  # and the device-trained model is as good as the oracle-trained one
 
 
 def test_file_formats_roundtrip_and_rank_slices(vi, res, small_model, tmp_path):

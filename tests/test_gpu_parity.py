@@ -297,30 +297,27 @@ def _oracle_index(oracle, m, lst, lamq, codes):
 @pytest.mark.parametrize("P,W,k,cap", [(16, 128, 10, 1024), (32, 256, 100, 1024), (8, 1024, 1024, 1024),
                                        (16, 64, 50, 2), (1, 1, 1, 1024)])
 def test_search_matches_oracle(ops, cuda, oracle, small_model, P, W, k, cap):
-    """same index on both sides: the device-encoded lists are handed to the oracle, so only the query path differs"""
+    """same index on both sides: the device-encoded lists are handed to the oracle, so only the query path differs.
+    Every id that differs from the oracle's is verified as a near-tie in float64 (tests/parity_util.py); more
+    geometries and every scan kernel: tests/test_gpu_search_parity.py"""
+    from tests.parity_util import check_lines, check_topk
+
     m = small_model
     gi = _gpu_index(ops, cuda, oracle, m, m["xb"])
     enc = gi["enc"]
-    off, codes_l, lamq_l, ids_l = _oracle_index(oracle, m, N(enc.list), N(enc.lamq), N(enc.codes))
+    e_list, e_lamq, e_codes = N(enc.list), N(enc.lamq), N(enc.codes)
+    off, codes_l, lamq_l, ids_l = _oracle_index(oracle, m, e_list, e_lamq, e_codes)
     assert np.array_equal(N(gi["lists"].offsets), off) and np.array_equal(N(gi["lists"].ids), ids_l)
-    D, I = ops.search(T(m["xq"], cuda), gi["cent"], gi["cn"], gi["edge"], gi["ed2"], gi["lcb"], gi["pq"], gi["lists"],
-                      P, W, k, cap)
+    q = T(m["xq"], cuda)
+    D, I = ops.search(q, gi["cent"], gi["cn"], gi["edge"], gi["ed2"], gi["lcb"], gi["pq"], gi["lists"], P, W, k, cap)
     Do, Io, _, lines, _ = oracle.search(m["xq"], m["cent"], m["edge"], m["edge_d2"], m["lambda_cb"], m["pq"], off,
                                         codes_l, lamq_l, ids_l, P=P, W=W, k=k, cap=cap, want_debug=True)
-    D, I = N(D), N(I)
-    assert np.array_equal(I < 0, Io < 0)  # same padding
-    valid = Io >= 0
-    fmax = np.finfo(np.float32).max
-    assert np.all(D[~valid] == fmax) and np.all(Do[~valid] == fmax)
-    qn = np.sum(m["xq"].astype(np.float64) ** 2, axis=1, keepdims=True) * np.ones_like(D)
-    # distances are ||q-y||^2 - ||q||^2: tolerance relative to the magnitudes that were cancelled
-    assert np.all(np.abs(D[valid] - Do[valid]) <= REL_DIST * (np.abs(Do[valid]) + qn[valid]))
-    assert (I[valid] == Io[valid]).mean() > 0.99
-    assert np.all(np.diff(D, axis=1) >= 0)
-    # rank-insensitive: the returned id sets agree
-    rows = [i for i in range(len(I)) if valid[i].any()]  # P=W=1 can land on an empty list: nothing to compare there
-    agree = np.mean([len(set(I[i][valid[i]]) & set(Io[i][valid[i]])) / valid[i].sum() for i in rows])
-    assert agree > 0.995
+    Dm = ops.l2_distances(q, gi["cent"], gi["cn"])
+    _, cid = ops.select_rows(Dm, P)
+    lst, _, _ = ops.select_lines(Dm, cid, gi["edge"], gi["ed2"], W)
+    same_lines = check_lines(N(lst), lines, m["xq"], m)
+    ndiff, nexempt = check_topk(N(D), N(I), Do, Io, m["xq"], m, e_list, e_lamq, e_codes, same_lines)
+    assert nexempt <= 2
 
 
 def test_search_golden(ops, cuda, g):
@@ -368,10 +365,17 @@ def test_select_lines_matches_oracle(ops, cuda, oracle, small_model):
     _, _, coarse, lines, _ = oracle.search(m["xq"], m["cent"], m["edge"], m["edge_d2"], m["lambda_cb"], m["pq"], off,
                                            np.zeros((0, m["M"]), np.uint8), np.zeros(0, np.uint8),
                                            np.zeros(0, np.int64), P=P, W=W, k=1, want_debug=True)
-    assert (N(cid) == coarse).mean() > 0.995
-    assert (N(lst) == lines).mean() > 0.98
-    agree = np.mean([len(set(a) & set(b)) / W for a, b in zip(N(lst), lines)])
-    assert agree > 0.99
+    from tests.parity_util import Model64, check_lines
+
+    m64 = Model64(m)
+    cidn = N(cid)
+    qi, r = np.nonzero(cidn != coarse)  # top-P differences must be near-ties of the coarse distance (float64)
+    if len(qi):
+        q64 = m["xq"].astype(np.float64)[qi]
+        dg, do = m64.coarse(q64, cidn[qi, r]), m64.coarse(q64, coarse[qi, r])
+        assert np.all(np.abs(dg - do) <= REL_TIE * (np.abs(do) + (q64 ** 2).sum(1)))
+    same = check_lines(N(lst), lines, m["xq"], m64)  # every differing line is a near-tie of the float64 line score
+    assert same.sum() >= len(same) - 2
 
 
 # ------------------------------------------------------------------------------------------------ merge (a16)

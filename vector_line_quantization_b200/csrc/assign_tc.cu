@@ -137,55 +137,95 @@ __device__ __forceinline__ uint64_t make_desc(uint32_t smem_addr) {
 constexpr uint32_t kIdesc = (1u << 4) | ((uint32_t)(TILE_ROWS >> 3) << 17) | ((uint32_t)(TILE_ROWS >> 4) << 24);
 
 // ------------------------------------------------------------------------------------------------------ pack kernel
-// fp32 [rows][d] -> packed fp16 hi/lo tiles, values pre-multiplied by `scale` (a power of two: exact).
-// Rows in [rows, rows_padded) are written as zeros.
+// fp32 [rows][d] -> packed fp16 hi/lo tiles.  Rows in [rows, rows_padded) are written as zeros.
+// Scaling (always a power of two, hence exact):
+//   * centroids (row_inv == nullptr): the caller's fixed `scale` for the whole codebook, chosen from max|c|;
+//   * vectors / queries (row_inv != nullptr): a PER-ROW scale 2^e with max|x_row| * 2^e in [2^8, 2^9), so no input can
+//     overflow fp16 (65504) or lose its lo part to underflow, whatever its magnitude relative to the centroids;
+//     row_inv[row] = 2^-e is folded back in by the GEMM epilogue.  Non-finite rows keep scale 1: their products are
+//     NaN / inf and the row gets label -1, as on the exact fp32 path.
 // lo_flags (nullable): lo_flags[row / 256] is set when any lo part of that 256-row block is non-zero; blocks whose rows
 // are exactly representable in fp16 (e.g. uint8-valued SIFT data) let the MMA issuer skip the x_lo.c_hi pass.
-__global__ void pack_rows_kernel(const float* __restrict__ x, int64_t rows, int64_t rows_padded, int d, float scale,
-                                 uint8_t* __restrict__ out, int* __restrict__ lo_flags, const int* __restrict__ n_dev) {
-  if (n_dev) {  // row count produced on the device (rows flagged by the screen pass)
-    rows = *n_dev;
-    rows_padded = (rows + TILE_ROWS * ROW_TILES - 1) / (TILE_ROWS * ROW_TILES) * (TILE_ROWS * ROW_TILES);
-  }
+constexpr int PACK_ROWS = 32;      // rows per CTA iteration
+constexpr int PACK_THREADS = 256;  // d / 8 <= 16 groups per row: at most two groups per thread and iteration
+
+__global__ void __launch_bounds__(PACK_THREADS)
+pack_rows_kernel(const float* __restrict__ x, int64_t rows, int64_t rows_padded, int d, float scale,
+                 uint8_t* __restrict__ out, int* __restrict__ lo_flags, float* __restrict__ row_inv) {
+  __shared__ unsigned rmax[PACK_ROWS];
   const int g8 = d / 8;  // 8-element groups per row
   const int nkb = d / KB;
-  int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  const int64_t total = rows_padded * g8;
-  for (; idx < total; idx += (int64_t)gridDim.x * blockDim.x) {
-    const int64_t row = idx / g8;
-    const int kg8 = (int)(idx % g8);
-    float v[8];
-    if (row < rows) {
-      const float4* p = reinterpret_cast<const float4*>(x + row * d + kg8 * 8);
-      float4 a = p[0], b = p[1];
-      v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
-    } else {
+  const int items = PACK_ROWS * g8;  // <= 512
+  for (int64_t row0 = (int64_t)blockIdx.x * PACK_ROWS; row0 < rows_padded; row0 += (int64_t)gridDim.x * PACK_ROWS) {
+    if (threadIdx.x < PACK_ROWS) rmax[threadIdx.x] = 0;
+    __syncthreads();
+    float v[2][8];
 #pragma unroll
-      for (int t = 0; t < 8; t++) v[t] = 0.f;
-    }
-    __align__(16) __half hi[8];
-    __align__(16) __half lo[8];
-    bool lo_nz = false;
+    for (int u = 0; u < 2; u++) {
+      const int it = threadIdx.x + u * PACK_THREADS;
+      const int r = it / g8, kg8 = it % g8;
+      const int64_t row = row0 + r;
+      unsigned mx = 0;
+      if (it < items && row < rows) {
+        const float4* p = reinterpret_cast<const float4*>(x + row * d + kg8 * 8);
+        const float4 a = p[0], b = p[1];
+        v[u][0] = a.x; v[u][1] = a.y; v[u][2] = a.z; v[u][3] = a.w;
+        v[u][4] = b.x; v[u][5] = b.y; v[u][6] = b.z; v[u][7] = b.w;
 #pragma unroll
-    for (int t = 0; t < 8; t++) {
-      const float s = v[t] * scale;
-      const __half h = __float2half_rn(s);
-      hi[t] = h;
-      const float rem = s - __half2float(h);
-      lo[t] = __float2half_rn(rem);
-      lo_nz |= rem != 0.f;
+        for (int t = 0; t < 8; t++) mx = max(mx, __float_as_uint(v[u][t]) & 0x7fffffffu);  // |v| orders like its bits; NaN > inf
+      } else {
+#pragma unroll
+        for (int t = 0; t < 8; t++) v[u][t] = 0.f;
+      }
+      if (row_inv && mx) atomicMax(&rmax[r], mx);
     }
-    if (lo_flags && lo_nz) {
-      int* f = lo_flags + row / (TILE_ROWS * ROW_TILES);
-      if (*reinterpret_cast<volatile int*>(f) == 0) atomicOr(f, 1);
+    __syncthreads();
+#pragma unroll
+    for (int u = 0; u < 2; u++) {
+      const int it = threadIdx.x + u * PACK_THREADS;
+      if (it >= items) break;
+      const int r = it / g8, kg8 = it % g8;
+      const int64_t row = row0 + r;
+      if (row >= rows_padded) break;
+      float sc = scale;
+      if (row_inv) {
+        const unsigned e = rmax[r] >> 23;  // biased exponent of max|x_row| (0: zero / subnormal row, 255: inf or NaN)
+        sc = 1.f;
+        float inv = 1.f;
+        if (e >= 1 && e <= 254) {
+          unsigned se = 262u - e;  // 2^(8 - (e - 127))
+          se = se > 254u ? 254u : se;
+          sc = __uint_as_float(se << 23);
+          inv = __uint_as_float((254u - se) << 23);  // 2^-(se - 127); se = 254 -> 2^-127 is subnormal: exact all the same
+          if (se == 254u) inv = 0x1.0p-127f;
+        }
+        if (kg8 == 0 && row < rows) row_inv[row] = inv;
+      }
+      __align__(16) __half hi[8];
+      __align__(16) __half lo[8];
+      bool lo_nz = false;
+#pragma unroll
+      for (int t = 0; t < 8; t++) {
+        const float s = v[u][t] * sc;
+        const __half h = __float2half_rn(s);
+        hi[t] = h;
+        const float rem = s - __half2float(h);
+        lo[t] = __float2half_rn(rem);
+        lo_nz |= rem != 0.f;
+      }
+      if (lo_flags && lo_nz) {
+        int* f = lo_flags + row / (TILE_ROWS * ROW_TILES);
+        if (*reinterpret_cast<volatile int*>(f) == 0) atomicOr(f, 1);
+      }
+      const int64_t tile = row / TILE_ROWS;
+      const int rr = (int)(row % TILE_ROWS);
+      const int kb = kg8 / (KB / 8), kg = kg8 % (KB / 8);
+      const int64_t base = (tile * 2) * (int64_t)nkb * TILE_KB_BYTES;
+      const int64_t inner = (int64_t)kb * TILE_KB_BYTES + (rr / 8) * 512 + kg * 128 + (rr % 8) * 16;
+      *reinterpret_cast<uint4*>(out + base + inner) = *reinterpret_cast<const uint4*>(hi);
+      *reinterpret_cast<uint4*>(out + base + (int64_t)nkb * TILE_KB_BYTES + inner) = *reinterpret_cast<const uint4*>(lo);
     }
-    const int64_t tile = row / TILE_ROWS;
-    const int rr = (int)(row % TILE_ROWS);
-    const int kb = kg8 / (KB / 8), kg = kg8 % (KB / 8);
-    const int64_t base = (tile * 2) * (int64_t)nkb * TILE_KB_BYTES;
-    const int64_t inner = (int64_t)kb * TILE_KB_BYTES + (rr / 8) * 512 + kg * 128 + (rr % 8) * 16;
-    *reinterpret_cast<uint4*>(out + base + inner) = *reinterpret_cast<const uint4*>(hi);
-    *reinterpret_cast<uint4*>(out + base + (int64_t)nkb * TILE_KB_BYTES + inner) = *reinterpret_cast<const uint4*>(lo);
+    __syncthreads();
   }
 }
 
@@ -206,16 +246,15 @@ struct Params {
   int n_ctiles;            // Cpad / 128
   int csplit;              // work item = (row block, centroid split)
   int tiles_per_split;
-  float m2s;               // -2 / scale^2
+  float m2s;               // -2 / scale of the centroids
+  const float* row_inv;    // [n] 1 / (per-row scale of the vectors), see pack_rows_kernel
   unsigned long long* keys;  // mode 0: [n] packed (ordered distance << 32 | centroid)
   float* D;                // mode 1: [n][ldD]
   int64_t ldD;
   float* bmin;             // mode 1 (nullable): [n][n_ctiles*4] minimum of every 32-column bucket of D
-  float4* screen;          // mode 2: [n][2*csplit] (best, bits(best id), second best, -) of one single-pass sweep
-  const int* n_dev;        // optional: number of valid rows lives on the device (fallback launches of the screen path)
 };
 
-template <int MODE>  // 0 = fused arg-min, 1 = store the distance tile, 2 = single-pass screen (best + second best)
+template <int MODE>  // 0 = fused arg-min, 1 = store the distance tile
 __global__ void __launch_bounds__(THREADS, 1) l2_tc_kernel(const Params p) {
   extern __shared__ __align__(1024) uint8_t smem[];
   const int nkb = p.d / KB;
@@ -260,9 +299,8 @@ __global__ void __launch_bounds__(THREADS, 1) l2_tc_kernel(const Params p) {
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
-  const int64_t n_rows = p.n_dev ? (int64_t)*p.n_dev : p.n;
-  const int n_row_blocks = p.n_dev ? (int)((n_rows + TILE_ROWS * ROW_TILES - 1) / (TILE_ROWS * ROW_TILES)) : p.n_row_blocks;
-  const int n_items = n_row_blocks * p.csplit;
+  const int64_t n_rows = p.n;
+  const int n_items = p.n_row_blocks * p.csplit;
 
   if (warp == 0) {
     // ===================================================================== producer
@@ -283,11 +321,10 @@ __global__ void __launch_bounds__(THREADS, 1) l2_tc_kernel(const Params p) {
           const uint8_t* bsrc = p.b_pack + (int64_t)t * a_tile_bytes;
           for (int kb = 0; kb < nkb; kb++) {
             mbar_wait(&empty[stage], phase ^ 1);
-            mbar_arrive_expect_tx(&full[stage], (MODE == 2 ? 1 : 2) * TILE_KB_BYTES);
+            mbar_arrive_expect_tx(&full[stage], 2 * TILE_KB_BYTES);
             uint8_t* dst = b_s + stage * 2 * TILE_KB_BYTES;
             bulk_g2s(dst, bsrc + (int64_t)kb * TILE_KB_BYTES, TILE_KB_BYTES, &full[stage]);                       // hi
-            if (MODE != 2)
-              bulk_g2s(dst + TILE_KB_BYTES, bsrc + (int64_t)(nkb + kb) * TILE_KB_BYTES, TILE_KB_BYTES, &full[stage]);  // lo
+            bulk_g2s(dst + TILE_KB_BYTES, bsrc + (int64_t)(nkb + kb) * TILE_KB_BYTES, TILE_KB_BYTES, &full[stage]);  // lo
             if (++stage == STAGES) {
               stage = 0;
               phase ^= 1;
@@ -305,7 +342,7 @@ __global__ void __launch_bounds__(THREADS, 1) l2_tc_kernel(const Params p) {
       const int t1 = min(p.n_ctiles, t0 + p.tiles_per_split);
       mbar_wait(a_full, item_phase);
       tc_fence_after();
-      const int npass = MODE == 2 ? 1 : ((p.a_lo_flags[item / p.csplit] != 0) ? 3 : 2);  // warp-uniform
+      const int npass = (p.a_lo_flags[item / p.csplit] != 0) ? 3 : 2;  // warp-uniform
       for (int t = t0; t < t1; t++) {
         mbar_wait(&t_empty[acc_buf], acc_phase ^ 1);
         tc_fence_after();
@@ -364,13 +401,14 @@ __global__ void __launch_bounds__(THREADS, 1) l2_tc_kernel(const Params p) {
       const int rb = item / p.csplit, cs = item % p.csplit;
       const int t0 = cs * p.tiles_per_split;
       const int t1 = min(p.n_ctiles, t0 + p.tiles_per_split);
-      float best[ROW_TILES], second[ROW_TILES];
+      float best[ROW_TILES], m2s[ROW_TILES];
       int bidx[ROW_TILES];
 #pragma unroll
       for (int r = 0; r < ROW_TILES; r++) {
         best[r] = __int_as_float(0x7f800000);
-        second[r] = __int_as_float(0x7f800000);
         bidx[r] = 0x7fffffff;
+        const int64_t row = ((int64_t)rb * ROW_TILES + r) * TILE_ROWS + row_in_tile;
+        m2s[r] = p.m2s * (row < n_rows ? p.row_inv[row] : 1.f);  // -2 / (centroid scale * this row's scale): exact
       }
       float cn_next = (et < TILE_ROWS && t0 < t1) ? p.cnorm_pad[t0 * TILE_ROWS + et] : 0.f;
       for (int t = t0; t < t1; t++) {
@@ -400,24 +438,10 @@ __global__ void __launch_bounds__(THREADS, 1) l2_tc_kernel(const Params p) {
             if (MODE == 0) {
 #pragma unroll
               for (int i = 0; i < 32; i++) {
-                const float dv = fmaf(__uint_as_float(v[c][i]), p.m2s, cn[c * 32 + i]);
+                const float dv = fmaf(__uint_as_float(v[c][i]), m2s[r], cn[c * 32 + i]);
                 if (dv < best[r]) {
                   best[r] = dv;
                   bidx[r] = col0 + i;
-                }
-              }
-            } else if (MODE == 2) {
-#pragma unroll
-              for (int i = 0; i < 32; i++) {
-                const float dv = fmaf(__uint_as_float(v[c][i]), p.m2s, cn[c * 32 + i]);
-                if (dv < second[r]) {  // rare after the first few tiles
-                  if (dv < best[r]) {
-                    second[r] = best[r];
-                    best[r] = dv;
-                    bidx[r] = col0 + i;
-                  } else {
-                    second[r] = dv;
-                  }
                 }
               }
             } else {
@@ -430,10 +454,10 @@ __global__ void __launch_bounds__(THREADS, 1) l2_tc_kernel(const Params p) {
 #pragma unroll
               for (int i = 0; i < 32; i += 4) {
                 float4 o;
-                o.x = fmaf(__uint_as_float(v[c][i + 0]), p.m2s, cn[c * 32 + i + 0]);
-                o.y = fmaf(__uint_as_float(v[c][i + 1]), p.m2s, cn[c * 32 + i + 1]);
-                o.z = fmaf(__uint_as_float(v[c][i + 2]), p.m2s, cn[c * 32 + i + 2]);
-                o.w = fmaf(__uint_as_float(v[c][i + 3]), p.m2s, cn[c * 32 + i + 3]);
+                o.x = fmaf(__uint_as_float(v[c][i + 0]), m2s[r], cn[c * 32 + i + 0]);
+                o.y = fmaf(__uint_as_float(v[c][i + 1]), m2s[r], cn[c * 32 + i + 1]);
+                o.z = fmaf(__uint_as_float(v[c][i + 2]), m2s[r], cn[c * 32 + i + 2]);
+                o.w = fmaf(__uint_as_float(v[c][i + 3]), m2s[r], cn[c * 32 + i + 3]);
                 mn = fminf(fminf(mn, fminf(o.x, o.y)), fminf(o.z, o.w));
                 srow[i >> 2] = o;
               }
@@ -479,15 +503,6 @@ __global__ void __launch_bounds__(THREADS, 1) l2_tc_kernel(const Params p) {
             atomicMin(&p.keys[row], make_key(best[r], (uint32_t)bidx[r]));
         }
       }
-      if (MODE == 2) {  // one record per (row, writer); screen_finalize_kernel merges the writers
-#pragma unroll
-        for (int r = 0; r < ROW_TILES; r++) {
-          const int64_t row = ((int64_t)rb * ROW_TILES + r) * TILE_ROWS + row_in_tile;
-          if (row < n_rows)
-            p.screen[row * (2 * p.csplit) + cs * 2 + col_half] =
-                make_float4(best[r], __int_as_float(bidx[r]), second[r], 0.f);
-        }
-      }
     }
   }
 
@@ -496,79 +511,6 @@ __global__ void __launch_bounds__(THREADS, 1) l2_tc_kernel(const Params p) {
   if (warp == 1) {
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)TMEM_COLS)
                  : "memory");
-  }
-}
-
-// max_j ||c_j|| (for the error bound of the single-pass screen); cn2max holds the float bits of max ||c||^2
-__global__ void cnorm_max_kernel(const float* __restrict__ cnorm, int C, unsigned* __restrict__ cn2max) {
-  unsigned m = 0;
-  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < C; i += gridDim.x * blockDim.x)
-    m = max(m, __float_as_uint(fmaxf(cnorm[i], 0.f)));  // non-negative floats order like their bits
-  m = __reduce_max_sync(kFull, m);
-  if ((threadIdx.x & 31) == 0) atomicMax(cn2max, m);
-}
-
-// Screen verdict, one warp per row: merge the writers' (best, id, second best); the single-pass arg-min is PROVABLY
-// the exact arg-min when  second - best > 2 eps,  eps = 2 * kappa * ||x|| * max||c||  bounds the error of one
-// fp16 x fp16 -> fp32 product sum (kappa = 2^-11 per rounded operand; x_hi is exact for blocks with lo == 0).
-// Rows inside the bound are appended to the fallback list and re-run with the split-precision passes.
-__global__ void screen_finalize_kernel(const float4* __restrict__ screen, int writers, const float* __restrict__ x,
-                                       int64_t n, int d, const int* __restrict__ lo_flags,
-                                       const unsigned* __restrict__ cn2max, int* __restrict__ out_ids,
-                                       int* __restrict__ flagged, int* __restrict__ n_flagged) {
-  const int64_t row = (int64_t)blockIdx.x * (blockDim.x / kWarp) + threadIdx.x / kWarp;
-  if (row >= n) return;
-  const int lane = threadIdx.x % kWarp;
-  float xn = 0.f;
-  for (int j = lane; j < d; j += kWarp) {
-    const float v = x[row * d + j];
-    xn = fmaf(v, v, xn);
-  }
-  xn = warp_sum(xn);
-  // merge: global best (lowest id on ties), and the smallest value among everything else
-  uint64_t kb = kKeyInf;
-  float others = __int_as_float(0x7f800000);
-  for (int w = lane; w < writers; w += kWarp) {
-    const float4 r = screen[row * writers + w];
-    kb = min(kb, make_key(r.x, (uint32_t)__float_as_int(r.y)));
-    others = fminf(others, r.z);
-  }
-  const uint64_t kbest = warp_min_u64(kb);
-  for (int w = lane; w < writers; w += kWarp) {  // the bests of the writers that did not win are "others" too
-    const float4 r = screen[row * writers + w];
-    if (make_key(r.x, (uint32_t)__float_as_int(r.y)) != kbest) others = fminf(others, r.x);
-  }
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) others = fminf(others, __shfl_xor_sync(kFull, others, o));
-  if (lane == 0) {
-    const float kappa = lo_flags[row / (TILE_ROWS * ROW_TILES)] ? 0x1.0p-10f * 1.0005f : 0x1.0p-11f;
-    const float eps = 2.2f * kappa * sqrtf(xn) * sqrtf(__uint_as_float(*cn2max)) + 1e-30f;  // 10 % slack (fp32 accumulation)
-    const float best = key_val(kbest);
-    const bool safe = (others - best) > 2.f * eps;  // NaN / inf rows are never "safe"
-    if (safe) {
-      out_ids[row] = (int)key_payload(kbest);
-    } else {
-      flagged[atomicAdd(n_flagged, 1)] = (int)row;
-    }
-  }
-}
-
-__global__ void gather_flagged_kernel(const float* __restrict__ x, int d, const int* __restrict__ flagged,
-                                      const int* __restrict__ n_flagged, float* __restrict__ dst) {
-  const int n = *n_flagged;
-  const int lane = threadIdx.x % kWarp;
-  for (int i = blockIdx.x * (blockDim.x / kWarp) + threadIdx.x / kWarp; i < n; i += gridDim.x * (blockDim.x / kWarp)) {
-    const float* s = x + (int64_t)flagged[i] * d;
-    for (int j = lane; j < d; j += kWarp) dst[(int64_t)i * d + j] = s[j];
-  }
-}
-
-__global__ void scatter_keys_kernel(const unsigned long long* __restrict__ keys, const int* __restrict__ flagged,
-                                    const int* __restrict__ n_flagged, int* __restrict__ out_ids) {
-  const int n = *n_flagged;
-  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
-    const unsigned long long k = keys[i];
-    out_ids[flagged[i]] = k != kKeyInf ? (int)key_payload(k) : -1;
   }
 }
 
@@ -639,7 +581,11 @@ int vlq_tc_supported(int d, int C) { return tc::supported(d, C) ? 1 : 0; }
 size_t vlq_tc_cent_pack_bytes(int C, int d) {
   if (!tc::supported(d, C)) return 0;
   const int64_t Cpad = div_up(C, tc::TILE_ROWS) * tc::TILE_ROWS;
-  return tc::align256((size_t)tc::packed_bytes(Cpad, d)) + tc::align256(sizeof(float) * Cpad) + 256;  // + max ||c||^2
+  return tc::align256((size_t)tc::packed_bytes(Cpad, d)) + tc::align256(sizeof(float) * Cpad);
+}
+
+static unsigned pack_grid(int64_t rows_padded) {
+  return (unsigned)std::min<int64_t>(div_up(rows_padded, tc::PACK_ROWS), (int64_t)tc::num_sms() * 8);
 }
 
 int vlq_tc_pack_centroids(const float* cent, const float* cnorm, int C, int d, float scale, void* cent_pack,
@@ -649,14 +595,10 @@ int vlq_tc_pack_centroids(const float* cent, const float* cnorm, int C, int d, f
   if ((reinterpret_cast<uintptr_t>(cent) & 15) || (reinterpret_cast<uintptr_t>(cent_pack) & 15)) return VLQ_EINVAL;
   const int64_t Cpad = div_up(C, tc::TILE_ROWS) * tc::TILE_ROWS;
   cudaStream_t st = as_stream(stream);
-  const int64_t total = Cpad * (d / 8);
-  VLQ_LAUNCH(tc::pack_rows_kernel, (unsigned)std::min<int64_t>(div_up(total, 256), 148 * 16), 256, 0, st, cent,
-             (int64_t)C, Cpad, d, scale, static_cast<uint8_t*>(cent_pack), (int*)nullptr, (const int*)nullptr);
+  VLQ_LAUNCH(tc::pack_rows_kernel, pack_grid(Cpad), tc::PACK_THREADS, 0, st, cent, (int64_t)C, Cpad, d, scale,
+             static_cast<uint8_t*>(cent_pack), (int*)nullptr, (float*)nullptr);
   float* cn_pad = reinterpret_cast<float*>(static_cast<uint8_t*>(cent_pack) + tc::align256((size_t)tc::packed_bytes(Cpad, d)));
   VLQ_LAUNCH(tc::pad_cnorm_kernel, (unsigned)div_up(Cpad, 256), 256, 0, st, cnorm, C, (int)Cpad, cn_pad);
-  unsigned* cn2max = reinterpret_cast<unsigned*>(reinterpret_cast<uint8_t*>(cn_pad) + tc::align256(sizeof(float) * Cpad));
-  VLQ_CUDA_TRY(cudaMemsetAsync(cn2max, 0, sizeof(unsigned), st));
-  VLQ_LAUNCH(tc::cnorm_max_kernel, 64, 256, 0, st, cnorm, C, cn2max);
   return last_error();
 }
 
@@ -664,12 +606,8 @@ size_t vlq_l2_tc_workspace_bytes(int64_t n, int d, int C) {
   if (!tc::supported(d, C) || n < 0) return 0;
   const int64_t rows = n < tc::CHUNK_ROWS ? n : tc::CHUNK_ROWS;
   const int64_t rpad = div_up(rows, tc::TILE_ROWS * tc::ROW_TILES) * tc::TILE_ROWS * tc::ROW_TILES;
-  const size_t screen_entries = (size_t)std::max<int64_t>(2 * rows, 2 * 256 * 148);
   return tc::align256((size_t)tc::packed_bytes(rpad, d)) + tc::align256(sizeof(unsigned long long) * rows) +
-         tc::align256(sizeof(float) * rows) + tc::align256(sizeof(int) * (rpad / (tc::TILE_ROWS * tc::ROW_TILES))) +
-         /* single-pass screen: records, fallback list + counter, gathered rows */
-         tc::align256(sizeof(float4) * screen_entries) + tc::align256(sizeof(int) * rows) + 256 +
-         tc::align256(sizeof(float) * (size_t)rows * d) + 256;
+         2 * tc::align256(sizeof(float) * rows) + tc::align256(sizeof(int) * (rpad / (tc::TILE_ROWS * tc::ROW_TILES))) + 256;
 }
 
 static int tc_run(int mode, const float* x, int64_t n, int d, const void* cent_pack, float scale, int C, int add_xnorm,
@@ -694,29 +632,17 @@ static int tc_run(int mode, const float* x, int64_t n, int d, const void* cent_p
   uint8_t* a_pack = ws;
   unsigned long long* keys = reinterpret_cast<unsigned long long*>(ws + tc::align256((size_t)tc::packed_bytes(cpad_rows, d)));
   float* xnorm = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(keys) + tc::align256(sizeof(unsigned long long) * chunk));
-  int* lo_flags = reinterpret_cast<int*>(reinterpret_cast<uint8_t*>(xnorm) + tc::align256(sizeof(float) * chunk));
-  const size_t screen_entries = (size_t)std::max<int64_t>(2 * chunk, 2 * 256 * 148);
-  float4* screen_buf = reinterpret_cast<float4*>(reinterpret_cast<uint8_t*>(lo_flags) +
-                                                 tc::align256(sizeof(int) * (cpad_rows / (tc::TILE_ROWS * tc::ROW_TILES))));
-  int* flagged = reinterpret_cast<int*>(reinterpret_cast<uint8_t*>(screen_buf) + tc::align256(sizeof(float4) * screen_entries));
-  int* n_flagged = reinterpret_cast<int*>(reinterpret_cast<uint8_t*>(flagged) + tc::align256(sizeof(int) * chunk));
-  float* fx = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(n_flagged) + 256);
-  const unsigned* cn2max = reinterpret_cast<const unsigned*>(reinterpret_cast<const uint8_t*>(cn_pad) + tc::align256(sizeof(float) * Cpad));
+  float* row_inv = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(xnorm) + tc::align256(sizeof(float) * chunk));
+  int* lo_flags = reinterpret_cast<int*>(reinterpret_cast<uint8_t*>(row_inv) + tc::align256(sizeof(float) * chunk));
   const bool add_xn = (add_xnorm & 1) != 0;
-  // single-pass screen + exact fallback (opt-in, VLQ_ASSIGN_SCREEN): only when no distances are requested (the screen
-  // proves the arg-min, it does not produce fp32-grade values).  Measured on B200 (C = 65536, d = 128, 14 % of the
-  // rows flagged): 12.6 ms per 256 Ki rows against 6.2 ms for the two split passes -- with a single MMA pass per tile
-  // the per-element epilogue (FFMA + best/second update) becomes the bottleneck, so it is NOT the default.
-  const bool screen = mode == 0 && (add_xnorm & 2) != 0 && out_dist == nullptr && C >= 2;
   const int sms = tc::num_sms();
   for (int64_t r0 = 0; r0 < n; r0 += chunk) {
     const int64_t rows = (n - r0) < chunk ? (n - r0) : chunk;
     const int64_t rpad = div_up(rows, tc::TILE_ROWS * tc::ROW_TILES) * tc::TILE_ROWS * tc::ROW_TILES;
-    const int64_t total = rpad * (d / 8);
     const int nblocks = (int)(rpad / (tc::TILE_ROWS * tc::ROW_TILES));
     VLQ_CUDA_TRY(cudaMemsetAsync(lo_flags, 0, sizeof(int) * nblocks, st));
-    VLQ_LAUNCH(tc::pack_rows_kernel, (unsigned)std::min<int64_t>(div_up(total, 256), 148 * 16), 256, 0, st,
-               x + r0 * d, rows, rpad, d, scale, a_pack, lo_flags, (const int*)nullptr);
+    VLQ_LAUNCH(tc::pack_rows_kernel, pack_grid(rpad), tc::PACK_THREADS, 0, st, x + r0 * d, rows, rpad, d, 1.f, a_pack,
+               lo_flags, row_inv);
     tc::Params p{};
     p.a_pack = a_pack;
     p.b_pack = b_pack;
@@ -725,7 +651,7 @@ static int tc_run(int mode, const float* x, int64_t n, int d, const void* cent_p
     p.n = rows;
     p.C = C;
     p.d = d;
-    p.n_row_blocks = (int)(rpad / (tc::TILE_ROWS * tc::ROW_TILES));
+    p.n_row_blocks = nblocks;
     p.n_ctiles = (int)(Cpad / tc::TILE_ROWS);
     // few row blocks (query batches): split the centroid sweep so that every SM has work
     int csplit = 1;
@@ -736,41 +662,14 @@ static int tc_run(int mode, const float* x, int64_t n, int d, const void* cent_p
     }
     p.tiles_per_split = (int)div_up(p.n_ctiles, csplit);
     p.csplit = (int)div_up(p.n_ctiles, p.tiles_per_split);
-    p.m2s = -2.f / (scale * scale);
+    p.m2s = -2.f / scale;
+    p.row_inv = row_inv;
     p.keys = keys;
     p.D = mode == 1 ? D + r0 * ldD : nullptr;
     p.ldD = ldD;
     p.bmin = (mode == 1 && bmin) ? bmin + r0 * (int64_t)(Cpad / 32) : nullptr;
     int rc;
-    if (screen) {
-      // (1) one hi.hi sweep keeping best / second best per row
-      p.screen = screen_buf;
-      rc = tc::launch<2>(p, st);
-      if (rc) return rc;
-      // (2) verdict per row: proven arg-mins are final, the rest go to the fallback list
-      VLQ_CUDA_TRY(cudaMemsetAsync(n_flagged, 0, sizeof(int), st));
-      VLQ_LAUNCH(tc::screen_finalize_kernel, (unsigned)div_up(rows, 8), 256, 0, st, screen_buf, 2 * p.csplit, x + r0 * d,
-                 rows, d, lo_flags, cn2max, out_ids + r0, flagged, n_flagged);
-      // (3) fallback: the flagged rows, gathered, through the split-precision passes (row count stays on the device)
-      VLQ_LAUNCH(tc::gather_flagged_kernel, 148 * 8, 256, 0, st, x + r0 * d, d, flagged, n_flagged, fx);
-      VLQ_CUDA_TRY(cudaMemsetAsync(lo_flags, 0, sizeof(int) * nblocks, st));
-      VLQ_LAUNCH(tc::pack_rows_kernel, (unsigned)std::min<int64_t>(div_up(total, 256), 148 * 16), 256, 0, st, fx, rows,
-                 rpad, d, scale, a_pack, lo_flags, (const int*)n_flagged);
-      VLQ_CUDA_TRY(cudaMemsetAsync(keys, 0xff, sizeof(unsigned long long) * rows, st));
-      tc::Params p2 = p;
-      p2.n_dev = n_flagged;
-      p2.csplit = 1;
-      p2.tiles_per_split = p.n_ctiles;
-      rc = tc::launch<0>(p2, st);
-      if (rc) return rc;
-      VLQ_LAUNCH(tc::scatter_keys_kernel, 148 * 4, 256, 0, st, keys, flagged, n_flagged, out_ids + r0);
-      if (getenv("VLQ_DEBUG_SCREEN")) {  // diagnostics only (synchronises): fraction of rows that needed the fallback
-        int nf = 0;
-        cudaMemcpyAsync(&nf, n_flagged, sizeof(int), cudaMemcpyDeviceToHost, st);
-        cudaStreamSynchronize(st);
-        fprintf(stderr, "[vlq] screen: %d of %lld rows flagged (%.2f%%)\n", nf, (long long)rows, 100.0 * nf / rows);
-      }
-    } else if (mode == 0) {
+    if (mode == 0) {
       VLQ_CUDA_TRY(cudaMemsetAsync(keys, 0xff, sizeof(unsigned long long) * rows, st));
       rc = tc::launch<0>(p, st);
       if (rc) return rc;

@@ -292,16 +292,15 @@ class CentPack:
         return self._ws
 
 
-def l2_assign_tc(x, pack, add_xnorm=True, want_dist=True, screen=False):
-    """nearest centroid per row on the tensor cores (a2): -> (ids int32 [n], dist f32 [n] or None).
-    screen=True (needs want_dist=False) selects the experimental single-pass screen + exact fallback."""
+def l2_assign_tc(x, pack, add_xnorm=True, want_dist=True):
+    """nearest centroid per row on the tensor cores (a2): -> (ids int32 [n], dist f32 [n] or None)"""
     x = _chk(x, torch.float32, "x")
     n, d = x.shape
     ids = torch.empty(n, dtype=torch.int32, device=x.device)
     dist = torch.empty(n, dtype=torch.float32, device=x.device) if want_dist else None
     ws = pack.workspace(n)
     _abi.call("vlq_l2_assign_tc", _ptr(x), n, d, _ptr(pack.buf), pack.scale, pack.C,
-              (1 if add_xnorm else 0) | (2 if screen else 0), _ptr(ids),
+              1 if add_xnorm else 0, _ptr(ids),
               _ptr(dist), _ptr(ws), ws.numel(), _stream())
     return ids, dist
 
