@@ -208,6 +208,27 @@ def search(q, cent, edge, edge_d2, lambda_cb, pq, offsets, codes, lamq, ids, P, 
     return D, I
 
 
+def scan_lines(q, cent, edge, edge_d2, lambda_cb, pq, offsets, codes, lamq, ids, lines, k, cap=1024, T2=None):
+    """the scan half of search() on a given line choice: lines [nq][W] list ids in rank order (-1 padded)"""
+    q = _c(q, _f32)
+    cent = _c(cent, _f32)
+    lines = _c(lines, _i32)
+    nq, d = q.shape
+    W = lines.shape[1]
+    M, ksub, _ = pq.shape
+    D = np.empty((nq, k), _f32)
+    I = np.empty((nq, k), _i64)
+    if T2 is not None:
+        T2 = _c(T2, _f32)
+    lib().vlqo_scan_lines(_p(q, c_float_p), C.c_long(nq), d, _p(cent, c_float_p), C.c_long(cent.shape[0]),
+                          _p(_c(edge, _i32), c_int_p), _p(_c(edge_d2, _f32), c_float_p), edge.shape[1],
+                          _p(_c(lambda_cb, _f32), c_float_p), len(lambda_cb), _p(_c(pq, _f32), c_float_p), M, ksub,
+                          _p(T2, c_float_p), _p(_c(offsets, _i64), c_long_p), _p(_c(codes, _u8), c_u8_p),
+                          _p(_c(lamq, _u8), c_u8_p), _p(_c(ids, _i64), c_long_p), _p(lines, c_int_p), W, k, cap,
+                          _p(D, c_float_p), _p(I, c_long_p))
+    return D, I
+
+
 def merge_topk(D, I):
     """D, I: [R][nq][k]"""
     D = _c(D, _f32)

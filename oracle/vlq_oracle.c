@@ -366,10 +366,14 @@ void vlqo_term2(const float* cent, long C, int d, const float* pq, int M, int ks
 /* ---------------------------------------------------------------------------------------------------------------
  * Search (a11-a15).
  * ------------------------------------------------------------------------------------------------------------- */
-void vlqo_search(const float* q, long nq, int d, const float* cent, long C, const int* edge, const float* edge_d2,
-                 int E, const float* lambda_cb, int nL, const float* pq, int M, int ksub, const float* T2_in,
-                 const long* offsets, const uint8_t* codes, const uint8_t* lamq, const long* ids, int P, int W, int k,
-                 int cap, float* outD, long* outI, int* out_coarse, int* out_lines, long* out_nscanned) {
+/* in_lines == NULL: the whole query path.  in_lines != NULL ([nq][W] list ids, -1 padded at the end): the coarse top-P
+ * and the line selection are skipped and exactly these lines are scanned, in this order (test infrastructure: lets a
+ * test compare the scan of another implementation's line choice when that choice differs by a line-score near-tie). */
+static void search_impl(const float* q, long nq, int d, const float* cent, long C, const int* edge, const float* edge_d2,
+                        int E, const float* lambda_cb, int nL, const float* pq, int M, int ksub, const float* T2_in,
+                        const long* offsets, const uint8_t* codes, const uint8_t* lamq, const long* ids, int P, int W, int k,
+                        int cap, float* outD, long* outI, int* out_coarse, int* out_lines, long* out_nscanned,
+                        const int* in_lines) {
   (void)nL;
   int dsub = d / M;
   if (P > C) P = (int)C;
@@ -390,6 +394,8 @@ void vlqo_search(const float* q, long nq, int d, const float* cent, long C, cons
     cand_t* cbuf = (cand_t*)malloc(sizeof(cand_t) * (P + 1));
     cand_t* lbuf = (cand_t*)malloc(sizeof(cand_t) * (W + 1));
     cand_t* kbuf = (cand_t*)malloc(sizeof(cand_t) * (k + 1));
+    long* lc = (long*)malloc(sizeof(long) * W); /* centroid and edge of every selected line */
+    int* le = (int*)malloc(sizeof(int) * W);
     float* T3 = (float*)malloc(sizeof(float) * M * ksub);
     float* t23 = (float*)malloc(sizeof(float) * M * ksub);
     float* t4 = (float*)malloc(sizeof(float) * M * ksub);
@@ -400,13 +406,13 @@ void vlqo_search(const float* q, long nq, int d, const float* cent, long C, cons
       int ccnt = 0;
       for (long j = 0; j < C; j++) {
         D[j] = cn[j] - 2.f * dot8(qv, cent + j * d, d);
-        topk_push(cbuf, &ccnt, P, D[j], j);
+        if (!in_lines) topk_push(cbuf, &ccnt, P, D[j], j);
       }
       if (out_coarse)
         for (int p = 0; p < P; p++) out_coarse[qi * P + p] = p < ccnt ? (int)cbuf[p].i : -1;
       /* line scoring over the P*E lines, flat index i = p*E + e (BroadcastSum.cu:505-520) */
       int lcnt = 0;
-      for (int p = 0; p < ccnt; p++) {
+      for (int p = 0; !in_lines && p < ccnt; p++) {
         long c = cbuf[p].i;
         for (int e = 0; e < E; e++) {
           long s = edge[c * E + e];
@@ -415,6 +421,18 @@ void vlqo_search(const float* q, long nq, int d, const float* cent, long C, cons
           v -= c2;
           float score = (v > 0) ? b2 : (b2 - 0.25f * v * v / c2);
           topk_push(lbuf, &lcnt, W, score, (long)p * E + e);
+        }
+      }
+      if (in_lines) {
+        for (int w = 0; w < W && in_lines[qi * W + w] >= 0; w++) {
+          lc[w] = in_lines[qi * W + w] / E;
+          le[w] = in_lines[qi * W + w] % E;
+          lcnt = w + 1;
+        }
+      } else {
+        for (int w = 0; w < lcnt; w++) {
+          lc[w] = cbuf[lbuf[w].i / E].i;
+          le[w] = (int)(lbuf[w].i % E);
         }
       }
       /* term3 = -2 q_m . p_mj (IVFPQ.cu:1409-1432) */
@@ -432,8 +450,8 @@ void vlqo_search(const float* q, long nq, int d, const float* cent, long C, cons
           if (out_lines) out_lines[qi * W + w] = -1;
           continue;
         }
-        int p = (int)(lbuf[w].i / E), e = (int)(lbuf[w].i % E);
-        long c = cbuf[p].i;
+        int e = le[w];
+        long c = lc[w];
         long s = edge[c * E + e];
         long list = c * E + e; /* BroadcastSum.cu:552 */
         if (out_lines) out_lines[qi * W + w] = (int)list;
@@ -476,8 +494,7 @@ void vlqo_search(const float* q, long nq, int d, const float* cent, long C, cons
           outI[qi * k + r] = -1;
         }
         for (int w = 0; w < lcnt; w++) {
-          int p = (int)(lbuf[w].i / E), e = (int)(lbuf[w].i % E);
-          long list = cbuf[p].i * E + e;
+          long list = lc[w] * E + le[w];
           long len = offsets[list + 1] - offsets[list];
           long limit = len < cap ? len : cap;
           for (int r = 0; r < kcnt; r++)
@@ -493,12 +510,30 @@ void vlqo_search(const float* q, long nq, int d, const float* cent, long C, cons
     free(cbuf);
     free(lbuf);
     free(kbuf);
+    free(lc);
+    free(le);
     free(T3);
     free(t23);
     free(t4);
   }
   free(cn);
   free(T2own);
+}
+
+void vlqo_search(const float* q, long nq, int d, const float* cent, long C, const int* edge, const float* edge_d2,
+                 int E, const float* lambda_cb, int nL, const float* pq, int M, int ksub, const float* T2_in,
+                 const long* offsets, const uint8_t* codes, const uint8_t* lamq, const long* ids, int P, int W, int k,
+                 int cap, float* outD, long* outI, int* out_coarse, int* out_lines, long* out_nscanned) {
+  search_impl(q, nq, d, cent, C, edge, edge_d2, E, lambda_cb, nL, pq, M, ksub, T2_in, offsets, codes, lamq, ids, P, W, k,
+              cap, outD, outI, out_coarse, out_lines, out_nscanned, NULL);
+}
+
+void vlqo_scan_lines(const float* q, long nq, int d, const float* cent, long C, const int* edge, const float* edge_d2,
+                     int E, const float* lambda_cb, int nL, const float* pq, int M, int ksub, const float* T2_in,
+                     const long* offsets, const uint8_t* codes, const uint8_t* lamq, const long* ids,
+                     const int* lines, int W, int k, int cap, float* outD, long* outI) {
+  search_impl(q, nq, d, cent, C, edge, edge_d2, E, lambda_cb, nL, pq, M, ksub, T2_in, offsets, codes, lamq, ids, 1, W, k,
+              cap, outD, outI, NULL, NULL, NULL, lines);
 }
 
 void vlqo_merge_topk(const float* D, const long* I, int R, long nq, int k, float* outD, long* outI) {

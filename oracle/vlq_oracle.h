@@ -78,6 +78,14 @@ void vlqo_search(const float* q, long nq, int d, const float* cent, long C, cons
                  const long* offsets, const uint8_t* codes, const uint8_t* lamq, const long* ids, int P, int W, int k,
                  int cap, float* outD, long* outI, int* out_coarse, int* out_lines, long* out_nscanned);
 
+/* The scan half of vlqo_search on a GIVEN line choice: lines [nq][W] list ids in rank order, -1 padded at the end
+ * (term1 / term6 / term5 are recomputed from the codebooks).  Test infrastructure for implementations whose line
+ * selection differs from the oracle's by a verified line-score near-tie. */
+void vlqo_scan_lines(const float* q, long nq, int d, const float* cent, long C, const int* edge, const float* edge_d2,
+                     int E, const float* lambda_cb, int nL, const float* pq, int M, int ksub, const float* T2,
+                     const long* offsets, const uint8_t* codes, const uint8_t* lamq, const long* ids,
+                     const int* lines, int W, int k, int cap, float* outD, long* outI);
+
 /* Shard merge: k smallest of the R*k candidates per query, [rank][nq][k] in, ties by (rank,pos)
  * (gpu/GpuIndexIVFPQ.cu:1467-1518; CPU twin MetaIndexes.cpp:290-347). */
 void vlqo_merge_topk(const float* D, const long* I, int R, long nq, int k, float* outD, long* outI);

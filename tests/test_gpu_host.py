@@ -157,7 +157,7 @@ def _dump_index(idx, m, tmp_path):
 
 
 def _search_vs_oracle_same_index(idx, oracle, m, xq, P, W, k, tmp_path, model=None):
-    from tests.parity_util import check_topk
+    from tests.parity_util import check_lines, check_topk
 
     mm = m if model is None else model
     off, codes, las, ids, e_list, e_lamq, e_codes = _dump_index(idx, m, tmp_path)
@@ -166,10 +166,28 @@ def _search_vs_oracle_same_index(idx, oracle, m, xq, P, W, k, tmp_path, model=No
     D, I = idx.search(xq, k)
     Do, Io, _, lines, _ = oracle.search(xq, mm["cent"], mm["edge"], mm["edge_d2"], mm["lambda_cb"], mm["pq"], off, codes,
                                         las, ids, P=P, W=W, k=k, want_debug=True)
-    # a query whose line set could differ (line-score near-tie) shows up as an unexplained id; none is tolerated here
-    # beyond what check_topk proves to be distance near-ties
-    check_topk(D, I, Do, Io, xq, mm, e_list, e_lamq, e_codes)
-    return I, Io
+    # the line lists the device path selected (same kernels through the operator layer): every difference from the
+    # oracle's choice is verified as a float64 line-score near-tie, and the top-k is compared with the oracle's scan of
+    # exactly these lines
+    import torch
+
+    from vector_line_quantization_b200 import ops
+
+    dev = torch.device("cuda:0")
+    t = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(dev)  # noqa: E731
+    cent = t(mm["cent"])
+    pack = ops.CentPack(cent)
+    qd = t(xq)
+    bm = torch.empty((len(xq), ops.num_buckets(m["C"])), dtype=torch.float32, device=dev)
+    Dm = ops.l2_distances_tc(qd, pack, bucket_min=bm)
+    lst, _, _ = ops.coarse_select_lines(Dm, bm, m["C"], min(P, m["C"]), t(mm["edge"]), t(mm["edge_d2"]), W)
+    same_lines = check_lines(lst.cpu().numpy(), lines, xq, mm)
+    # strict for every query: against the oracle's scan of the device's own line choice
+    Dl, Il = oracle.scan_lines(xq, mm["cent"], mm["edge"], mm["edge_d2"], mm["lambda_cb"], mm["pq"], off, codes, las, ids,
+                               lst.cpu().numpy(), k)
+    check_topk(D, I, Dl, Il, xq, mm, e_list, e_lamq, e_codes)
+    check_topk(D, I, Do, Io, xq, mm, e_list, e_lamq, e_codes, same_lines)
+    return I, Il
 
 
 def test_vlq_train_on_device(vi, res, oracle, small_model, tmp_path):

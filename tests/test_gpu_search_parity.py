@@ -136,19 +136,26 @@ def test_query_path_vs_oracle_near_tie_verified(ops, cuda, oracle, models, name,
     Do, Io, coarse_ref, lines_ref, _ = _oracle_search(oracle, m, gi, P, W, k, cap)
     q, cid, lst, t1, t6 = _coarse_and_lines(ops, cuda, m, gi, P, W, route)
     _check_coarse(N(cid), coarse_ref, m["xq"], gi["m64"])
+    # (1) the line lists: every rank that differs from the oracle's is a float64 line-score near-tie (the two directions of
+    #     one graph edge score identically in exact arithmetic, so such ties are common at the W boundary)
     same_lines = check_lines(N(lst), lines_ref, m["xq"], gi["m64"])
-    assert same_lines.sum() >= len(same_lines) - max(1, len(same_lines) // 16)
+    # (2) the scan, for ALL queries, against the oracle's scan of the SAME line choice (no query is exempt); where the
+    #     line sets agree that is the oracle's own full search
+    perm = gi["perm"]
+    Dl, Il = oracle.scan_lines(m["xq"], m["cent"], m["edge"], m["edge_d2"], m["lambda_cb"], m["pq"], gi["off"],
+                               gi["e_codes"][perm], gi["e_lamq"][perm], perm.astype(np.int64), N(lst), k, cap)
+    same_order = (N(lst) == lines_ref).all(axis=1)
+    assert np.array_equal(Dl[same_order], Do[same_order]) and np.array_equal(Il[same_order], Io[same_order])
     ed2f = gi["ed2"].reshape(-1)
     avg_len = len(gi["perm"]) / (m["C"] * m["E"])
     # every scan kernel the dispatcher can choose, each against the oracle directly:
-    #   hint 0 flattened stream; 30 warp-autonomous (k <= 128) or warp-per-list; 100 bank-skewed / TMA-staged (M = 8, 16)
+    #   hint 0 flattened stream; 30 warp-autonomous (k <= 128) or warp-per-list; 100 bank-skewed TMA-staged stream (M = 8, 16)
     for hint in (0, 30, 100, int(avg_len)):
         D, I = ops.scan_topk(q, gi["pq"], gi["lcb"], lst, t1, t6, ed2f, gi["lists"], k, cap, list_len_hint=hint)
-        ndiff, nex = check_topk(N(D), N(I), Do, Io, m["xq"], gi["m64"], gi["e_list"], gi["e_lamq"], gi["e_codes"],
-                                same_lines)
-        assert nex <= max(1, len(same_lines) // 16)
+        check_topk(N(D), N(I), Dl, Il, m["xq"], gi["m64"], gi["e_list"], gi["e_lamq"], gi["e_codes"])
+        check_topk(N(D), N(I), Do, Io, m["xq"], gi["m64"], gi["e_list"], gi["e_lamq"], gi["e_codes"], same_lines)
     D, I = ops.scan_topk(q, gi["pq"], gi["lcb"], lst, t1, t6, ed2f, gi["lists"], k, cap, use_workspace=False)
-    check_topk(N(D), N(I), Do, Io, m["xq"], gi["m64"], gi["e_list"], gi["e_lamq"], gi["e_codes"], same_lines)
+    check_topk(N(D), N(I), Dl, Il, m["xq"], gi["m64"], gi["e_list"], gi["e_lamq"], gi["e_codes"])
 
 
 @pytest.mark.parametrize("name", ["c2_small", "deep_d96_m8", "e64_l256", "long_lists_m16"])

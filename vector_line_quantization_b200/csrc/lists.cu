@@ -1,4 +1,5 @@
 // Inverted-list construction on the device.
+// (Stored layout: the M code bytes of the entry at list position pos are rotated by pos mod M, see scan.cuh.)
 //
 // The reference keeps one growable array per list and appends on the host with a hash map and per-byte copies
 // (gpu/GpuIndexIVFPQ.cu:741-905, gpu/impl/InvertedListAppend.cu:20-120).  Here the lists are one CSR slab
@@ -9,7 +10,7 @@
 //   3. scatter of the new entry ordinals with a per-list cursor (arbitrary order inside a list) ...
 //   4. ... made deterministic: each list segment is sorted by ordinal = arrival order (what push_back gives)
 //   5. old entries are copied to their new place; new entries are gathered behind them.
-#include "common.cuh"
+#include "scan.cuh"
 
 namespace vlq {
 
@@ -181,6 +182,27 @@ seg_sort_kernel(const int64_t* __restrict__ new_base, int64_t nlists, uint32_t* 
   }
 }
 
+// canonical code (arrival order arrays) -> stored code of the entry at list position pos: stored[j] = code[(j + pos) mod M]
+__device__ __forceinline__ void store_code_rotated(uint8_t* dst, const uint8_t* src, int M, int64_t pos) {
+  if (M == 16) {
+    const uint4 c = *reinterpret_cast<const uint4*>(src);
+    uint32_t w[4] = {c.x, c.y, c.z, c.w};
+    rot16(w, (int)(pos & 15));
+    *reinterpret_cast<uint4*>(dst) = make_uint4(w[0], w[1], w[2], w[3]);
+  } else if (M == 8) {
+    const uint2 c = *reinterpret_cast<const uint2*>(src);
+    uint32_t w[2] = {c.x, c.y};
+    rot8(w, (int)(pos & 7));
+    *reinterpret_cast<uint2*>(dst) = make_uint2(w[0], w[1]);
+  } else {
+    int j = (int)(pos % M);
+    for (int t = 0; t < M; t++) {
+      dst[t] = src[j];
+      j = j + 1 == M ? 0 : j + 1;
+    }
+  }
+}
+
 __device__ __forceinline__ void copy_code(uint8_t* dst, const uint8_t* src, int M) {
   if (M == 16) {
     *reinterpret_cast<uint4*>(dst) = *reinterpret_cast<const uint4*>(src);
@@ -216,8 +238,9 @@ __global__ void gather_new_kernel(const uint32_t* __restrict__ perm, int64_t nli
     uint32_t s = perm[j];
     int l = new_list[s];
     int64_t old_len = old_offsets ? old_offsets[l + 1] - old_offsets[l] : 0;
-    int64_t o = out_offsets[l] + old_len + (j - new_base[l]);
-    copy_code(dst.codes + o * M, src.codes + (int64_t)s * M, M);
+    const int64_t pos = old_len + (j - new_base[l]);  // position inside the list
+    int64_t o = out_offsets[l] + pos;
+    store_code_rotated(dst.codes + o * M, src.codes + (int64_t)s * M, M, pos);
     dst.lamq[o] = src.lamq[s];
     dst.kappa[o] = src.kappa[s];
     dst.ids[o] = src.ids[s];
@@ -284,13 +307,14 @@ __global__ void recompute_kappa_kernel(int64_t n, int64_t nlists, const int64_t*
     }
     const int A = (int)(lo / E);
     const int s = edge[lo];
+    const int rot = (int)((i - offsets[lo]) % M);  // stored[j] = code[(j + pos) mod M]
     const float lh = lambda_cb[lamq[i]];
     const float oml = 1.f - lh;
     float kp = 0.f;
     for (int j = lane; j < d; j += kWarp) {
       const float anc = __fadd_rn(__fmul_rn(oml, cent[(int64_t)A * d + j]), __fmul_rn(lh, cent[(int64_t)s * d + j]));
       const int m = j / dsub, tt = j % dsub;
-      const float pv = pq[((size_t)m * 256 + codes[i * M + m]) * dsub + tt];
+      const float pv = pq[((size_t)m * 256 + codes[i * M + (m - rot + M) % M]) * dsub + tt];
       kp = fmaf(pv, pv, kp);
       kp = fmaf(2.f * anc, pv, kp);
     }

@@ -18,7 +18,7 @@
 #include <cfloat>
 #include <cstdlib>
 
-#include "common.cuh"
+#include "scan.cuh"
 #include "topk.cuh"
 
 #include <type_traits>
@@ -261,56 +261,50 @@ coarse_select_lines_kernel(const float* __restrict__ D, int64_t ldD, const float
 }
 
 // ------------------------------------------------------------------------------------------------ scan + top-k
-struct ScanArgs {
-  const float* q;
-  int d;
-  const float* pq;
-  int M, ksub, dsub;
-  const float* lambda_cb;
-  int nL;
-  const int* line_list;
-  const float* term1;
-  const float* term6;
-  const float* edge_d2;
-  int W;
-  const int64_t* offsets;
-  const uint8_t* codes;
-  const uint8_t* lamq;
-  const float* kappa;
-  const int64_t* ids;
-  int k, cap;
-  int sel_cap;
-  int owner_cap;    // stream positions covered by the shared-memory owner table (0 = always binary search)
-  const float* t3;  // optional precomputed term-3 tables [nq][M*ksub] (term3_kernel); nullptr = build in the kernel
-  float* outD;
-  int64_t* outI;
-};
-
 // PQ codes of one entry held in registers (16-byte / 8-byte vector loads for M = 16 / 8; byte loads otherwise)
+// `pos` = position of the entry inside its list: the stored bytes are rotated by pos mod M (scan.cuh) and adc() sums the
+// sub-quantizers in canonical order m = 0..M-1, the order of the reference and of the oracle.
 template <int M_T>
 struct CodeRegs {
   uint32_t w[M_T == 16 ? 4 : (M_T == 8 ? 2 : 1)];
   const uint8_t* ptr;
-  __device__ __forceinline__ void load(const uint8_t* __restrict__ code_ptr) {
-    if (M_T == 16) {
+  int rot;
+  __device__ __forceinline__ void load(const uint8_t* __restrict__ code_ptr, int pos) {
+    if constexpr (M_T == 16) {
       const uint4 c = ld_nc_v4(code_ptr);
       w[0] = c.x; w[1] = c.y; w[2] = c.z; w[3] = c.w;
-    } else if (M_T == 8) {
+      rot = (16 - (pos & 15)) & 15;
+    } else if constexpr (M_T == 8) {
       const uint2 c = ld_nc_v2(code_ptr);
       w[0] = c.x; w[1] = c.y;
+      rot = (8 - (pos & 7)) & 7;
     } else {
       ptr = code_ptr;
+      rot = pos;
     }
   }
   __device__ __forceinline__ float adc(const float* __restrict__ T3, int M, int ksub) const {
     float acc = 0.f;
-    if (M_T == 16 || M_T == 8) {
+    if constexpr (M_T == 16) {
+      uint32_t r[4] = {w[0], w[1], w[2], w[3]};
+      rot16(r, rot);
 #pragma unroll
-      for (int t = 0; t < M_T / 4; t++)
+      for (int t = 0; t < 4; t++)
 #pragma unroll
-        for (int b = 0; b < 4; b++) acc += T3[(t * 4 + b) * 256 + ((w[t] >> (8 * b)) & 0xff)];
+        for (int b = 0; b < 4; b++) acc += T3[(t * 4 + b) * 256 + ((r[t] >> (8 * b)) & 0xff)];
+    } else if constexpr (M_T == 8) {
+      uint32_t r[2] = {w[0], w[1]};
+      rot8(r, rot);
+#pragma unroll
+      for (int t = 0; t < 2; t++)
+#pragma unroll
+        for (int b = 0; b < 4; b++) acc += T3[(t * 4 + b) * 256 + ((r[t] >> (8 * b)) & 0xff)];
     } else {
-      for (int m = 0; m < M; m++) acc += T3[m * ksub + ptr[m]];
+      int j = (M - rot % M) % M;  // stored[j] = code[(j + pos) mod M]  =>  code[m] = stored[(m - pos) mod M]
+      for (int m = 0; m < M; m++) {
+        acc += T3[m * ksub + ptr[j]];
+        j = j + 1 == M ? 0 : j + 1;
+      }
     }
     return acc;
   }
@@ -435,7 +429,7 @@ __global__ void __launch_bounds__(Q_THREADS) scan_topk_kernel(ScanArgs a) {
           kp[u] = 0.f;
           if (e < len) {
             const int64_t ent = st + e;
-            cr[u].load(a.codes + ent * M);
+            cr[u].load(a.codes + ent * M, e);
             lq[u] = a.lamq[ent];
             kp[u] = a.kappa[ent];
           }
@@ -471,6 +465,7 @@ __global__ void __launch_bounds__(Q_THREADS) scan_topk_kernel(ScanArgs a) {
     // +l, +32+l, ...  One (warp-uniform) binary search finds the list of the warp's first position; every lane then
     // walks forward from there -- 0-2 steps when lists are long.  Small batches use the owner table instead.
     int lo_[Q_BATCH];
+    int pos_[Q_BATCH];  // position inside the list (code rotation)
     int64_t ent_[Q_BATCH];
     const int wpos0 = base + (threadIdx.x >> 5) * (Q_BATCH * 32);
     int wlo = 0;
@@ -500,7 +495,8 @@ __global__ void __launch_bounds__(Q_THREADS) scan_topk_kernel(ScanArgs a) {
         }
       }
       lo_[b] = lo;
-      ent_[b] = pos < total ? lstart[lo] + (pos - prefix[lo]) : -1;
+      pos_[b] = pos < total ? pos - prefix[lo] : 0;
+      ent_[b] = pos < total ? lstart[lo] + pos_[b] : -1;
     }
     CodeRegs<M_T> cr[Q_BATCH];
     uint8_t lq[Q_BATCH];
@@ -510,7 +506,7 @@ __global__ void __launch_bounds__(Q_THREADS) scan_topk_kernel(ScanArgs a) {
       lq[b] = 0;
       kp[b] = 0.f;
       if (ent_[b] >= 0) {
-        cr[b].load(a.codes + ent_[b] * M);
+        cr[b].load(a.codes + ent_[b] * M, pos_[b]);
         lq[b] = a.lamq[ent_[b]];
         kp[b] = a.kappa[ent_[b]];
       }
@@ -677,47 +673,32 @@ struct __align__(16) LineDesc {
 // code-major with a 64-word row: word c of row `code` holds T3[c % M][code] for c < 31 + M.  Lane l reads word
 // M*(l/M) + l%M + s of row code: the 32 lanes always hit 32 different banks whatever their codes are, the row stride of
 // 256 bytes turns "extract byte, scale, add lane offset" into ONE byte-permute, and the step offset is an immediate.
-// The lane rotates the code bytes of its entry once (12 ALU ops for M = 16).  Price: the M terms are summed in a
-// lane-dependent order, so a distance can differ from the other scan modes in the last ulp.  64 KB of tables per query:
+// The lists store the code bytes pre-rotated by the position inside the list (scan.cuh), so the lane needs no byte
+// shuffling of its own.  Price: the M terms are summed in a lane-dependent order, so a distance can differ from the other scan modes in the last ulp.  64 KB of tables per query:
 // 12 warps per CTA, two CTAs per SM; the block select of the final merge reuses the table space.
 constexpr int AQ_THREADS_SKEW = 384;
 constexpr int kSkewRowWords = 64;
 
 template <int M_T>
 struct SkewCodes {
-  uint32_t w[M_T / 4];  // as loaded; rotated only when scored, so that the load stays asynchronous
-  __device__ __forceinline__ void load(const uint8_t* __restrict__ p) {
-    if (M_T == 16) {
+  uint32_t w[M_T / 4];
+  __device__ __forceinline__ void load(const uint8_t* __restrict__ p, int /*pos*/) {
+    if constexpr (M_T == 16) {
       const uint4 c = ld_nc_v4(p);
-      w[0] = c.x; w[1] = c.y; w[M_T / 4 - 2] = c.z; w[M_T / 4 - 1] = c.w;
+      w[0] = c.x; w[1] = c.y; w[2] = c.z; w[3] = c.w;
     } else {
       const uint2 c = ld_nc_v2(p);
-      w[0] = c.x; w[M_T / 4 - 1] = c.y;
+      w[0] = c.x; w[1] = c.y;
     }
   }
-  // a1/a2: bits of (lane % M_T) / 4 (word rotation), selb: byte funnel selector of (lane % M_T) % 4;
-  // tbl: skewed tables (bytes), lofs: 4 * (M_T*(lane/M_T) + lane%M_T) < 256
-  __device__ __forceinline__ float adc(const unsigned char* __restrict__ tbl, uint32_t lofs, bool a1, bool a2,
-                                       uint32_t selb) const {
-    uint32_t r[M_T / 4];
-    if (M_T == 16) {
-      uint32_t w0 = w[0], w1 = w[1], w2 = w[M_T / 4 - 2], w3 = w[M_T / 4 - 1];
-      if (a1) { const uint32_t t = w0; w0 = w1; w1 = w2; w2 = w3; w3 = t; }
-      if (a2) { uint32_t t = w0; w0 = w2; w2 = t; t = w1; w1 = w3; w3 = t; }
-      r[0] = __byte_perm(w0, w1, selb);
-      r[1] = __byte_perm(w1, w2, selb);
-      r[M_T / 4 - 2] = __byte_perm(w2, w3, selb);
-      r[M_T / 4 - 1] = __byte_perm(w3, w0, selb);
-    } else {
-      uint32_t w0 = w[0], w1 = w[M_T / 4 - 1];
-      if (a1) { const uint32_t t = w0; w0 = w1; w1 = t; }
-      r[0] = __byte_perm(w0, w1, selb);
-      r[M_T / 4 - 1] = __byte_perm(w1, w0, selb);
-    }
+  // The lists store the code bytes of the entry at position pos rotated by pos mod M (scan.cuh); a chunk starts at a
+  // multiple of 64 inside its list, so lane l holds entries with pos mod M == l mod M and byte s of the stored code is
+  // the byte of sub-quantizer (s + l) mod M.  tbl: skewed tables (bytes), lofs = 4 * lane.
+  __device__ __forceinline__ float adc(const unsigned char* __restrict__ tbl, uint32_t lofs) const {
     float acc = 0.f;
 #pragma unroll
     for (int s = 0; s < M_T; s++) {
-      const uint32_t o = __byte_perm(r[s >> 2], lofs, 0x5504 | ((s & 3) << 4));  // code << 8 | lofs
+      const uint32_t o = __byte_perm(w[s >> 2], lofs, 0x5504 | ((s & 3) << 4));  // code << 8 | lofs
       acc += *reinterpret_cast<const float*>(tbl + o + 4 * s);
     }
     return acc;
@@ -823,15 +804,7 @@ __global__ void __launch_bounds__(SKEW ? AQ_THREADS_SKEW : Q_THREADS, SKEW ? 2 :
     float kp[2];
     bool ok;
   };
-  // per-lane constants of the skewed lookups
-  const int lp = lane & (MS - 1);
-  const bool rot_a1 = ((lp >> 2) & 1) != 0, rot_a2 = ((lp >> 2) & 2) != 0;
-  uint32_t rot_selb = 0x3210u + 0x1111u * (uint32_t)(lp & 3);
-  uint32_t lofs = 4u * (uint32_t)(MS * (lane / MS) + lp);
-  if (SKEW) {  // keep the two per-lane constants in registers: the compiler otherwise recomputes them in every chunk
-    asm volatile("" : "+r"(rot_selb));
-    asm volatile("" : "+r"(lofs));
-  }
+  const uint32_t lofs = 4u * (uint32_t)lane;  // column of the lane in the skewed table rows
   const unsigned char* tblc = reinterpret_cast<const unsigned char*>(T3);
   LineDesc cur;  // warp-uniform walk state
   cur.len = 0;
@@ -877,7 +850,7 @@ __global__ void __launch_bounds__(SKEW ? AQ_THREADS_SKEW : Q_THREADS, SKEW ? 2 :
       c.lq[u] = 0;
       c.kp[u] = 0.f;
       if ((int)i < c.nrem) {
-        c.cr[u].load(cb + i * (unsigned)MM);
+        c.cr[u].load(cb + i * (unsigned)MM, cur_e0 + (int)i);
         c.lq[u] = lb[i];
         c.kp[u] = kb[i];
       }
@@ -893,7 +866,7 @@ __global__ void __launch_bounds__(SKEW ? AQ_THREADS_SKEW : Q_THREADS, SKEW ? 2 :
         const float la = lcb[c.lq[u]];
         const float base_d = c.t1 + la * c.t6 + (la * la - la) * c.t5;
         float adc;
-        if constexpr (SKEW) adc = c.cr[u].adc(tblc, lofs, rot_a1, rot_a2, rot_selb);
+        if constexpr (SKEW) adc = c.cr[u].adc(tblc, lofs);
         else adc = c.cr[u].adc(T3, M, ksub);
         dist[u] = (c.kp[u] + adc) + base_d;
         pass |= dist[u] <= ws.thr_f;
@@ -1090,7 +1063,8 @@ int vlq_coarse_select_lines(const float* D, int64_t nq, int64_t ldD, const float
   return last_error();
 }
 
-size_t vlq_scan_topk_workspace_bytes(int64_t nq, int M) { return (size_t)(nq > 0 ? nq : 0) * M * 256 * sizeof(float); }
+// term-3 tables of the batch + the query counter of the streaming scan
+size_t vlq_scan_topk_workspace_bytes(int64_t nq, int M) { return (size_t)(nq > 0 ? nq : 0) * M * 256 * sizeof(float) + 256; }
 
 int vlq_scan_topk(const float* q, int64_t nq, int d, const float* pq, int M, const float* lambda_cb, int nL,
                   const int* line_list, const float* term1, const float* term6, const float* edge_d2, int W,
@@ -1113,7 +1087,7 @@ int vlq_scan_topk(const float* q, int64_t nq, int d, const float* pq, int M, con
   const size_t pq_smem = ((size_t)M * 256 * a.dsub + d) * sizeof(float);
   const bool long_lists = list_len_hint >= 24;  // average list length of the index: warp-per-list pays off
   const bool al16 = (reinterpret_cast<uintptr_t>(codes) % 16) == 0;
-  const bool have_t3 = workspace && workspace_bytes >= t3_bytes && pq_smem <= 200 * 1024 && d % 4 == 0 &&
+  const bool have_t3 = workspace && workspace_bytes >= t3_bytes + 256 && pq_smem <= 200 * 1024 && d % 4 == 0 &&
                        ((reinterpret_cast<uintptr_t>(workspace) | reinterpret_cast<uintptr_t>(pq)) & 15) == 0;
   const bool use_async = long_lists && k <= kWarpSelMaxK && have_t3 && (M * 256) % 4 == 0;  // warp-autonomous scan
   // bank-skewed tables pay off once the lists are long enough to amortise the 64 KB table fill and the four extra
@@ -1123,7 +1097,19 @@ int vlq_scan_topk(const float* q, int64_t nq, int d, const float* pq, int M, con
     const char* e = getenv("VLQ_SCAN_SKEW_MIN_LEN");  // tuning knob
     return e ? atoi(e) : 56;
   }();
-  const bool skew = use_async && al16 && (M == 16 || M == 8) && list_len_hint >= skew_min_len;
+  // which long-list kernel: "stream" (default) = TMA-staged producer / consumer ring, any k (scan_stream.cu);
+  // "skew" = the register-pipelined warp-autonomous kernel below (k <= 128); both use the bank-skewed tables
+  static const int long_kernel = [] {
+    const char* e = getenv("VLQ_SCAN_KERNEL");
+    return (e && e[0] == 's' && e[1] == 'k') ? 1 : 0;
+  }();
+  bool use_stream = false;
+  if (long_lists && have_t3 && list_len_hint >= skew_min_len && long_kernel == 0) {
+    ScanArgs probe = a;
+    probe.t3 = static_cast<float*>(workspace);
+    use_stream = scan_stream_supported(probe);
+  }
+  const bool skew = use_stream || (use_async && al16 && (M == 16 || M == 8) && list_len_hint >= skew_min_len);
   if (have_t3) {
     float* t3 = static_cast<float*>(workspace);
     const unsigned grid = (unsigned)(nq < 148 ? nq : 148);
@@ -1138,6 +1124,10 @@ int vlq_scan_topk(const float* q, int64_t nq, int d, const float* pq, int M, con
     a.t3 = t3;
   }
   a.owner_cap = (int)((long long)W * cap < 4096 ? (long long)W * cap : 4096);
+  if (use_stream) {
+    int* counter = reinterpret_cast<int*>(static_cast<unsigned char*>(workspace) + ((t3_bytes + 15) & ~size_t(15)));
+    return launch_scan_stream(a, nq, counter, as_stream(stream));
+  }
   if (use_async) {
     cudaStream_t st_ = as_stream(stream);
     const int nt = skew ? AQ_THREADS_SKEW : Q_THREADS;

@@ -75,8 +75,33 @@ __device__ __forceinline__ void warp_bitonic_sort(uint64_t* keys) {
   for (int r = 0; r < R; r++) keys[lane + 32 * r] = v[r];
 }
 
-template <int THREADS>
+// BAR = 0: the whole CTA takes part (__syncthreads).  BAR > 0: the selection is run by the first THREADS threads of the
+// CTA only, synchronised through named barrier BAR (the streaming scan keeps its TMA producer warp out of it).
+template <int THREADS, int BAR = 0>
 struct BlockSelect {
+  static __device__ __forceinline__ void bsync() {
+    if constexpr (BAR == 0) __syncthreads();
+    else asm volatile("bar.sync %0, %1;" ::"n"(BAR), "n"(THREADS) : "memory");
+  }
+  static __device__ __forceinline__ int bsync_count(bool p) {
+    if constexpr (BAR == 0) {
+      return __syncthreads_count(p);
+    } else {
+      int r;
+      asm volatile(
+          "{\n\t"
+          ".reg .pred q;\n\t"
+          "setp.ne.b32 q, %3, 0;\n\t"
+          "bar.red.popc.u32 %0, %1, %2, q;\n\t"
+          "}"
+          : "=r"(r)
+          : "n"(BAR), "n"(THREADS), "r"((int)p)
+          : "memory");
+      return r;
+    }
+  }
+  static __device__ __forceinline__ bool bsync_or(bool p) { return bsync_count(p) != 0; }
+
   uint64_t* keys;  // [cap]
   int* hist;       // [256]
   int* meta;       // [0] append cursor, [1] chosen digit, [2] remaining rank
@@ -97,7 +122,20 @@ struct BlockSelect {
     thr = kKeyInf;
     thr_f = __int_as_float(0x7f800000);
     if (threadIdx.x == 0) meta[0] = 0;
-    __syncthreads();
+    bsync();
+  }
+
+  // adopt a buffer (same layout as init) that other code has filled: meta[0] holds the number of keys in keys[0..)
+  __device__ void attach(void* smem, int k_, int cap_) {
+    k = k_;
+    cap = cap_;
+    batch = 1;
+    keys = reinterpret_cast<uint64_t*>(smem);
+    hist = reinterpret_cast<int*>(keys + cap);
+    meta = hist + 256;
+    fill = cap;
+    thr = kKeyInf;
+    thr_f = __int_as_float(0x7f800000);
   }
 
   // non-collective part of a batch: call up to `batch` times per thread, then end_batch() once (collective)
@@ -132,26 +170,26 @@ struct BlockSelect {
     return !valid;
   }
   __device__ __forceinline__ bool placed(int total, bool any_invalid) {
-    const bool bad = __syncthreads_or(any_invalid) != 0;
+    const bool bad = bsync_or(any_invalid);
     if (threadIdx.x == 0) meta[0] = total;
     fill = total;
-    __syncthreads();
+    bsync();
     return !bad;
   }
 
   // collective; `any` = this thread appended at least one key in the batch
   __device__ __forceinline__ void end_batch(bool any) {
-    fill += batch * __syncthreads_count(any);  // barrier + identical conservative count in every thread
+    fill += batch * bsync_count(any);  // barrier + identical conservative count in every thread
     if (fill > cap - batch * THREADS) compact();
   }
 
   // collective: keep the k smallest keys of keys[0..n) (unsorted) in keys[0..k), thr = k-th smallest
   __device__ void compact() {
-    __syncthreads();
+    bsync();
     const int n = meta[0];
     if (n <= k) {  // nothing to drop; the conservative counter was too pessimistic
       fill = n;
-      __syncthreads();
+      bsync();
       return;
     }
     // ---- radix select of the k-th smallest key, most significant byte first.
@@ -168,14 +206,14 @@ struct BlockSelect {
     dhi = __reduce_or_sync(kFull, dhi);
     dlo = __reduce_or_sync(kFull, dlo);
     if (threadIdx.x < 2) hist[threadIdx.x] = 0;
-    __syncthreads();
+    bsync();
     if ((threadIdx.x & 31) == 0) {
       if (dhi) atomicOr(reinterpret_cast<unsigned*>(&hist[0]), dhi);
       if (dlo) atomicOr(reinterpret_cast<unsigned*>(&hist[1]), dlo);
     }
-    __syncthreads();
+    bsync();
     const uint64_t diff = ((uint64_t)(unsigned)hist[0] << 32) | (unsigned)hist[1];
-    __syncthreads();
+    bsync();
     const int top = diff ? (63 - __clzll((long long)diff)) >> 3 : 0;  // most significant byte that varies
     uint64_t prefix = top == 7 ? 0 : (key0 >> ((top + 1) * 8));
     int need = k;  // rank (1-based) of the wanted key among the keys matching `prefix`
@@ -186,14 +224,14 @@ struct BlockSelect {
       hist[threadIdx.x & 255] = 0;
       if (THREADS < 256)
         for (int j = threadIdx.x; j < 256; j += THREADS) hist[j] = 0;
-      __syncthreads();
+      bsync();
       const int shift = pass * 8;
       for (int i = threadIdx.x; i < n; i += THREADS) {
         const uint64_t key = keys[i];
         const bool match = pass == 7 ? true : ((key >> (shift + 8)) == prefix);
         if (match) atomicAdd(&hist[(int)((key >> shift) & 255)], 1);
       }
-      __syncthreads();
+      bsync();
       if (threadIdx.x < kWarp) {  // lane l owns bins [8l, 8l+8)
         const int lane = threadIdx.x;
         int c[8], s = 0;
@@ -222,7 +260,7 @@ struct BlockSelect {
           }
         }
       }
-      __syncthreads();
+      bsync();
       prefix = (prefix << 8) | (uint64_t)meta[1];
       need = meta[2];
       const int in_bin = meta[3];
@@ -231,10 +269,10 @@ struct BlockSelect {
           const uint64_t key = keys[i];
           if ((key >> shift) == prefix) *reinterpret_cast<uint64_t*>(hist) = key;
         }
-        __syncthreads();
+        bsync();
         kth = *reinterpret_cast<uint64_t*>(hist);
         found = true;
-        __syncthreads();
+        bsync();
         break;
       }
     }
@@ -248,9 +286,9 @@ struct BlockSelect {
       const int i = threadIdx.x + t * THREADS;
       mine[t] = i < n ? keys[i] : kKeyInf;
     }
-    __syncthreads();
+    bsync();
     if (threadIdx.x == 0) meta[0] = 0;
-    __syncthreads();
+    bsync();
 #pragma unroll
     for (int t = 0; t < kSelMaxItems; t++) {
       if (t * THREADS >= n) break;
@@ -262,7 +300,7 @@ struct BlockSelect {
     thr = kth;
     thr_f = key_val(kth);
     fill = k;
-    __syncthreads();
+    bsync();
   }
 
   // collective: afterwards keys[0..k) hold the k smallest keys ascending, padded with kKeyInf
@@ -272,14 +310,14 @@ struct BlockSelect {
     int S = next_pow2(k);  // S <= cap because cap >= k + batch*THREADS and cap is a power of two
     if (S < 32) S = 32;
     for (int i = n + threadIdx.x; i < S; i += THREADS) keys[i] = kKeyInf;
-    __syncthreads();
+    bsync();
     if (!sorted) return;  // the caller only needs the SET of the k smallest keys
     if (S <= 64) {  // one warp sorts in registers (no barriers per step); measured slower than the block network for S >= 128
       if (threadIdx.x < kWarp) {
         if (S == 32) warp_bitonic_sort<1>(keys);
         else warp_bitonic_sort<2>(keys);
       }
-      __syncthreads();
+      bsync();
       return;
     }
     for (int k2 = 2; k2 <= S; k2 <<= 1) {
@@ -294,7 +332,7 @@ struct BlockSelect {
             keys[l] = a;
           }
         }
-        __syncthreads();
+        bsync();
       }
     }
   }

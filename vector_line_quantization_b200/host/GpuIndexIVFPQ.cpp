@@ -388,6 +388,18 @@ int GpuIndexIVFPQ::getListLength(int listId) const {
   return (int)(o[1] - o[0]);
 }
 
+// Device lists keep the M code bytes of the entry at list position pos rotated by pos mod M (csrc/scan.cuh):
+// stored[j] = code[(j + pos) mod M].  The accessors and the .dbcodes files use the canonical order.
+static void rotateListCodes(uint8_t* codes, size_t len, int M, bool toStored) {
+  std::vector<uint8_t> tmp(M);
+  for (size_t pos = 0; pos < len; pos++) {
+    uint8_t* c = codes + pos * M;
+    const int r = (int)(pos % M);
+    for (int j = 0; j < M; j++) tmp[j] = toStored ? c[(j + r) % M] : c[(j - r + M) % M];
+    std::memcpy(c, tmp.data(), M);
+  }
+}
+
 template <typename T>
 static std::vector<T> fetchList(const DeviceBuffer& offsets, const DeviceBuffer& data, int listId, size_t per,
                                 GpuResources* res) {
@@ -406,7 +418,9 @@ std::vector<unsigned char> GpuIndexIVFPQ::getListCodes(int listId) const {
   VLQ_THROW_IF_NOT(listId >= 0 && listId < nlist_ * numedge_);
   DeviceScope scope(ivfConfig_.device);
   commit_();
-  return fetchList<unsigned char>(lOffsets_, lCodes_, listId, subQuantizers_, resources_);
+  std::vector<unsigned char> codes = fetchList<unsigned char>(lOffsets_, lCodes_, listId, subQuantizers_, resources_);
+  rotateListCodes(codes.data(), codes.size() / subQuantizers_, subQuantizers_, false);
+  return codes;
 }
 std::vector<unsigned char> GpuIndexIVFPQ::getListLambdas(int listId) const {
   VLQ_THROW_IF_NOT(listId >= 0 && listId < nlist_ * numedge_);
@@ -487,7 +501,10 @@ void GpuIndexIVFPQ::writeDbToFile(const std::string& name) {  // .dbIdx .dbcodes
   }
   resources_->syncDefaultStream();
   std::vector<int> counts(L);
-  for (size_t l = 0; l < L; l++) counts[l] = (int)(off[l + 1] - off[l]);
+  for (size_t l = 0; l < L; l++) {
+    counts[l] = (int)(off[l + 1] - off[l]);
+    rotateListCodes(codes.data() + (size_t)off[l] * subQuantizers_, (size_t)counts[l], subQuantizers_, false);
+  }
   std::ofstream fi((name + ".dbIdx").c_str(), std::ofstream::binary), fc((name + ".dbcodes").c_str(), std::ofstream::binary),
       fn((name + ".dbcount").c_str(), std::ofstream::binary), fl((name + ".dblas").c_str(), std::ofstream::binary);
   VLQ_THROW_IF_NOT_MSG(fi.good() && fc.good() && fn.good() && fl.good(), "cannot open database files for writing");
@@ -512,8 +529,12 @@ void GpuIndexIVFPQ::installLists_(const std::vector<int>& counts, const std::vec
   lKappa_.resize(std::max<size_t>(1, tot) * sizeof(float));
   lIds_.resize(std::max<size_t>(1, tot) * sizeof(int64_t));
   VLQ_CALL(vlq_memcpy_h2d(lOffsets_.get(), off.data(), off.size() * sizeof(int64_t), st));
+  std::vector<uint8_t> stored;  // outlives the copy (freed after the stream sync below)
   if (tot) {
-    VLQ_CALL(vlq_memcpy_h2d(lCodes_.get(), codes.data(), codes.size(), st));
+    stored = codes;
+    for (size_t l = 0; l < L; l++)
+      rotateListCodes(stored.data() + (size_t)off[l] * subQuantizers_, (size_t)counts[l], subQuantizers_, true);
+    VLQ_CALL(vlq_memcpy_h2d(lCodes_.get(), stored.data(), stored.size(), st));
     VLQ_CALL(vlq_memcpy_h2d(lLamq_.get(), las.data(), tot, st));
     VLQ_CALL(vlq_memcpy_h2d(lIds_.get(), ids.data(), tot * sizeof(int64_t), st));
     VLQ_CALL(vlq_recompute_kappa((int64_t)tot, (int64_t)L, lOffsets_.as<int64_t>(), lCodes_.as<uint8_t>(),

@@ -154,6 +154,18 @@ def build_lists(nlists, M, new_list, new_codes, new_lamq, new_kappa, new_ids, ol
     return out
 
 
+def rotate_codes(offsets, codes, inverse=False):
+    """canonical list-major codes [n][M] -> the stored layout (or back with inverse=True): the entry at position pos of
+    its list keeps stored[j] = code[(j + pos) mod M] (csrc/scan.cuh).  Plumbing for callers that assemble Lists by hand
+    (tests, fixtures); vlq_build_lists produces the stored layout itself."""
+    n, M = codes.shape
+    lens = offsets[1:] - offsets[:-1]
+    pos = torch.arange(n, device=codes.device) - torch.repeat_interleave(offsets[:-1], lens)[:n]
+    j = torch.arange(M, device=codes.device).unsqueeze(0)
+    idx = (j + (-pos if inverse else pos).unsqueeze(1)) % M
+    return torch.gather(codes, 1, idx).contiguous()
+
+
 def select_lines(D, coarse_ids, edge, edge_d2, W):
     """query-time line selection (a12): -> (list int32 [nq][W], term1, term6 f32 [nq][W])"""
     D = _chk(D, torch.float32, "D")
