@@ -28,6 +28,7 @@
 //
 // Streamed per entry: M + 1 + 4 bytes (codes, lambda byte, kappa); SURVEY 8d counts M + 1 of them as algorithmic.
 #include <cfloat>
+#include <cstdlib>
 
 #include "scan.cuh"
 #include "topk.cuh"
@@ -268,7 +269,9 @@ __device__ __forceinline__ void shared_offer(uint64_t* keys, int* hist, int* met
   }
 }
 
-template <int MS, int NC>
+// PROBE: the consumers release every chunk without scoring it (results are meaningless): measures what the producer /
+// TMA / HBM side can deliver for this access pattern, the ceiling of the real kernel (tools/bench_scan.py).
+template <int MS, int NC, bool PROBE>
 __global__ void __launch_bounds__((NC + 1) * 32, 1) scan_stream_kernel(ScanArgs a, int64_t nq, int* work_counter,
                                                                         Layout L) {
   extern __shared__ __align__(128) unsigned char smem[];
@@ -446,7 +449,10 @@ __global__ void __launch_bounds__((NC + 1) * 32, 1) scan_stream_kernel(ScanArgs 
     mbar_wait(&full[slot], use & 1);
     const int4 m0 = reinterpret_cast<const int4*>(cmeta + slot)[0];
     const int4 m1 = reinterpret_cast<const int4*>(cmeta + slot)[1];
-    if (m0.x == KIND_DATA) {
+    if (PROBE && m0.x == KIND_DATA) {
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&empty[slot]);
+    } else if (m0.x == KIND_DATA) {
       const unsigned char* sp = ring + (size_t)slot * L.slot_bytes;
       const int n = m0.y;
       const unsigned char* cp = sp + (m0.w & 0xff);
@@ -574,9 +580,15 @@ template <int MS, int NC>
 static int launch_t(const ScanArgs& a, int64_t nq, int* counter, cudaStream_t st) {
   const Layout L = make_layout(MS, a.W, smem_optin());
   if (L.nslot < 2 * NC + 32) return VLQ_EUNSUPPORTED;
-  VLQ_CUDA_TRY(cudaFuncSetAttribute(scan_stream_kernel<MS, NC>, cudaFuncAttributeMaxDynamicSharedMemorySize, L.total));
   const unsigned grid = (unsigned)(nq < sm_count() ? nq : sm_count());
-  VLQ_LAUNCH((scan_stream_kernel<MS, NC>), grid, (NC + 1) * 32, (size_t)L.total, st, a, nq, counter, L);
+  static const bool probe = getenv("VLQ_SCAN_PROBE") != nullptr;  // measurement aid, see the kernel
+  if (probe) {
+    VLQ_CUDA_TRY(cudaFuncSetAttribute(scan_stream_kernel<MS, NC, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, L.total));
+    VLQ_LAUNCH((scan_stream_kernel<MS, NC, true>), grid, (NC + 1) * 32, (size_t)L.total, st, a, nq, counter, L);
+    return last_error();
+  }
+  VLQ_CUDA_TRY(cudaFuncSetAttribute(scan_stream_kernel<MS, NC, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, L.total));
+  VLQ_LAUNCH((scan_stream_kernel<MS, NC, false>), grid, (NC + 1) * 32, (size_t)L.total, st, a, nq, counter, L);
   return last_error();
 }
 

@@ -160,7 +160,9 @@ def rotate_codes(offsets, codes, inverse=False):
     (tests, fixtures); vlq_build_lists produces the stored layout itself."""
     n, M = codes.shape
     lens = offsets[1:] - offsets[:-1]
-    pos = torch.arange(n, device=codes.device) - torch.repeat_interleave(offsets[:-1], lens)[:n]
+    live = int(offsets[-1])  # rows beyond the last list (skipped vectors) are left as they are
+    pos = torch.zeros(n, dtype=torch.int64, device=codes.device)
+    pos[:live] = torch.arange(live, device=codes.device) - torch.repeat_interleave(offsets[:-1], lens)
     j = torch.arange(M, device=codes.device).unsqueeze(0)
     idx = (j + (-pos if inverse else pos).unsqueeze(1)) % M
     return torch.gather(codes, 1, idx).contiguous()
