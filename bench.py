@@ -697,7 +697,8 @@ def run_b200(a):
         from oracle import pyoracle as po  # checker / baseline only
 
         mh = {key: model[key].cpu().numpy() for key in ("cent", "edge", "edge_d2", "lambda_cb", "pq")}
-        lh = (lists.offsets.cpu().numpy(), lists.codes.cpu().numpy(), lists.lamq.cpu().numpy(), lists.ids.cpu().numpy())
+        lh = (lists.offsets.cpu().numpy(), ops.rotate_codes(lists.offsets, lists.codes, inverse=True).cpu().numpy(),
+              lists.lamq.cpu().numpy(), lists.ids.cpu().numpy())  # canonical code order for the oracle
         cpu_baseline, parity = cpu_search_baseline(po, mh, lh, xq.cpu().numpy(), P, W, k, a.cpu_seconds,
                                                    (D.cpu().numpy(), In))
 

@@ -540,10 +540,13 @@ def test_scan_modes_identical(ops, cuda, oracle, small_model, P, W, k, cap):
     D0, I0 = ops.scan_topk(*args, list_len_hint=0)
     D1, I1 = ops.scan_topk(*args, list_len_hint=100)
     D2, I2 = ops.scan_topk(*args, list_len_hint=0, use_workspace=False)
+    D3, I3 = ops.scan_topk(*args, list_len_hint=400)  # the long-list kernel (scan_long.cu): same arithmetic as hint 100
     assert torch.equal(D0, D2) and torch.equal(I0, I2)
     if gi["pq"].shape[0] not in (8, 16):  # the block-synchronous list scan: same summation order, same bits
         assert torch.equal(D0, D1) and torch.equal(I0, I1)
         return
+    if k <= 128:  # both bank-skewed kernels ran: same lane-dependent summation order, same bits
+        assert torch.equal(D1, D3) and torch.equal(I1, I3)
     # the bank-skewed streaming scan sums the M table terms in a lane-dependent order: last-ulp differences, so ids
     # may only differ where two candidates are closer than that
     D0n, D1n, I0n, I1n = N(D0), N(D1), N(I0), N(I1)
@@ -561,7 +564,7 @@ def test_scan_modes_identical(ops, cuda, oracle, small_model, P, W, k, cap):
 
 @pytest.mark.parametrize("M,d,k", [(16, 128, 100), (8, 96, 100), (8, 64, 10), (4, 32, 50), (16, 64, 128)])
 def test_scan_modes_random_index(ops, cuda, M, d, k):
-    """flattened-stream scan vs the warp-autonomous scans (plain tables: hint 30; bank-skewed tables: hint 100, M = 8/16)
+    """flattened-stream scan vs the warp-autonomous scans (plain tables: hint 30; bank-skewed tables: hint 100 and the long-list kernel: hint 400, M = 8/16)
     on a random index with lists of 0..400 entries: same top-k up to last-ulp distance differences"""
     import torch
 
@@ -586,7 +589,7 @@ def test_scan_modes_random_index(ops, cuda, M, d, k):
     ed2 = (torch.rand(nlist, generator=g) * 4 + 0.5).to(cuda)
     args = (q, pq, lcb, line, t1, t6, ed2, lists, k, 1024)
     D0, I0 = ops.scan_topk(*args, list_len_hint=0)
-    for hint in (30, 100):
+    for hint in (30, 100, 400):  # warp-autonomous plain tables / bank-skewed tables / long-list kernel (scan_long.cu)
         D1, I1 = ops.scan_topk(*args, list_len_hint=hint)
         if hint == 30 or M not in (8, 16):
             assert torch.equal(D0, D1) and torch.equal(I0, I1)

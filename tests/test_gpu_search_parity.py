@@ -1,7 +1,7 @@
 """Query path (a11-a15) against the oracle with PER-MISMATCH near-tie verification in float64 (tests/parity_util.py):
 no fraction-based bars.  Geometries: SIFT-shaped d=128 / M=16 / E=32 (C2), DEEP-shaped d=96 / M=8 (C3), the 64-edge,
 256-level graphs of the 1B drivers (gpu/test/sift1b16_query.cpp:252-254), and indexes with >= 100-entry lists on which
-every scan kernel (flattened stream, warp-per-list, warp-autonomous, bank-skewed, TMA-staged) is compared with the oracle
+every scan kernel (flattened stream, warp-per-list, warp-autonomous, bank-skewed, long-list) is compared with the oracle
 directly.  Both coarse routes: exact fp32 CUDA-core kernels and the tcgen05 route (fused top-P + line selection).
 """
 import numpy as np
@@ -149,8 +149,9 @@ def test_query_path_vs_oracle_near_tie_verified(ops, cuda, oracle, models, name,
     ed2f = gi["ed2"].reshape(-1)
     avg_len = len(gi["perm"]) / (m["C"] * m["E"])
     # every scan kernel the dispatcher can choose, each against the oracle directly:
-    #   hint 0 flattened stream; 30 warp-autonomous (k <= 128) or warp-per-list; 100 bank-skewed TMA-staged stream (M = 8, 16)
-    for hint in (0, 30, 100, int(avg_len)):
+    #   hint 0 flattened stream; 30 warp-autonomous (k <= 128) or warp-per-list; 100 bank-skewed (M = 8, 16);
+    #   400 the long-list kernel of scan_long.cu (M = 8, 16)
+    for hint in (0, 30, 100, 400, int(avg_len)):
         D, I = ops.scan_topk(q, gi["pq"], gi["lcb"], lst, t1, t6, ed2f, gi["lists"], k, cap, list_len_hint=hint)
         check_topk(N(D), N(I), Dl, Il, m["xq"], gi["m64"], gi["e_list"], gi["e_lamq"], gi["e_codes"])
         check_topk(N(D), N(I), Do, Io, m["xq"], gi["m64"], gi["e_list"], gi["e_lamq"], gi["e_codes"], same_lines)

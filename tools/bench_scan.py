@@ -4,8 +4,9 @@ encode): times vlq_scan_topk alone, tile by tile, with CUDA events, and reports 
 peak ((M + 1) bytes per scanned entry + 8 k bytes per query).
 
   python tools/bench_scan.py [--entries 1e9] [--nlists 2097152] [--m 16] [--nq 10000] [--w1 256] [--k 100]
-  VLQ_SCAN_KERNEL=skew  python tools/bench_scan.py ...   # the register-pipelined warp-autonomous kernel
-  VLQ_SCAN_PROBE=1      python tools/bench_scan.py ...   # producer / TMA ceiling of the streaming kernel (no scoring)
+  VLQ_SCAN_KERNEL=skew|long python tools/bench_scan.py ...   # force the register-pipelined warp-autonomous kernel /
+                                                             # the long-list kernel (default: chosen by list length)
+  VLQ_SCAN_LOOK=n VLQ_SCAN_EPL=2|3|4 VLQ_SCAN_LPT=0|1        # tuning knobs of the long-list kernel (scan_long.cu)
 
 List lengths are Poisson around entries/nlists with a Gamma(4) spread and queries pick lists size-biased (dense regions
 attract both vectors and queries, as in the real index: 193 k scanned entries per query at 1 B vs 256 x 477 = 122 k).
@@ -105,7 +106,7 @@ def main():
     streamed = nq * scanned * (M + 5)
     chk = int(outI.clamp_min(0).sum()) & 0xffffffff
     print(json.dumps({
-        "kernel": os.environ.get("VLQ_SCAN_KERNEL", "stream") + ("+probe" if os.environ.get("VLQ_SCAN_PROBE") else ""),
+        "kernel": os.environ.get("VLQ_SCAN_KERNEL", "auto"),
         "entries": int(lists.ids.shape[0]), "avg_len": lists.ids.shape[0] / a.nlists, "M": M, "nq": nq, "w1": W, "k": k,
         "scanned_per_query": scanned, "ms_mean": mean, "ms_best": best,
         "algorithmic_GBs": alg / (mean * 1e-3) / 1e9, "streamed_GBs": streamed / (mean * 1e-3) / 1e9,

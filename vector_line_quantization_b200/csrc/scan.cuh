@@ -1,5 +1,5 @@
-// Declarations shared by the scan kernels (search.cu: block-synchronous and warp-autonomous scans; scan_stream.cu: the
-// TMA-staged streaming scan for 1B-scale lists).
+// Declarations shared by the scan kernels (search.cu: block-synchronous and warp-autonomous scans; scan_long.cu: the
+// long-list scan for 1B-scale list densities).
 #pragma once
 #include "common.cuh"
 
@@ -56,9 +56,9 @@ __device__ __forceinline__ void rot8(uint32_t (&w)[2], int r) {  // out[j] = in[
   w[1] = __byte_perm(w1, w0, selb);
 }
 
-// TMA-staged streaming scan (scan_stream.cu).  Returns VLQ_EUNSUPPORTED when the configuration does not fit (the caller
-// then uses the kernels of search.cu); `counter` is a zero-initialised int in the workspace (dynamic query queue).
-int launch_scan_stream(const ScanArgs& a, int64_t nq, int* counter, cudaStream_t st);
-bool scan_stream_supported(const ScanArgs& a);
+// Long-list scan with TMA bulk prefetch into L2 (scan_long.cu): one CTA per query, four entries per lane.  Returns
+// VLQ_EUNSUPPORTED when the configuration does not fit (the caller then uses the kernels of search.cu).
+int launch_scan_long(const ScanArgs& a, int64_t nq, cudaStream_t st);
+bool scan_long_supported(const ScanArgs& a);
 
 }  // namespace vlq

@@ -314,7 +314,7 @@ struct CodeRegs {
 //               lanes busy);  LONG = true: every warp owns whole lists (slot w -> warp w % 8) and strides their entries,
 //               so the per-list scalars are warp-uniform and nothing has to be searched per entry.
 template <int M_T, bool LONG>
-__global__ void __launch_bounds__(Q_THREADS) scan_topk_kernel(ScanArgs a) {
+__global__ void __launch_bounds__(Q_THREADS, M_T == 16 ? 3 : 2) scan_topk_kernel(ScanArgs a) {  // 3 CTAs per SM: <= 80 registers
   extern __shared__ __align__(16) unsigned char smem[];
   // smem: [topk keys S*8 + 16][T3 M*ksub f32][lambda nL f32][per line: start i64, prefix i32 (W+1), t1, t6, t5 f32]
   const int M = a.M, ksub = a.ksub, dsub = a.dsub, W = a.W;
@@ -1063,7 +1063,7 @@ int vlq_coarse_select_lines(const float* D, int64_t nq, int64_t ldD, const float
   return last_error();
 }
 
-// term-3 tables of the batch + the query counter of the streaming scan
+// term-3 tables of the batch (+ 256 spare bytes)
 size_t vlq_scan_topk_workspace_bytes(int64_t nq, int M) { return (size_t)(nq > 0 ? nq : 0) * M * 256 * sizeof(float) + 256; }
 
 int vlq_scan_topk(const float* q, int64_t nq, int d, const float* pq, int M, const float* lambda_cb, int nL,
@@ -1097,19 +1097,28 @@ int vlq_scan_topk(const float* q, int64_t nq, int d, const float* pq, int M, con
     const char* e = getenv("VLQ_SCAN_SKEW_MIN_LEN");  // tuning knob
     return e ? atoi(e) : 56;
   }();
-  // which long-list kernel: "stream" (default) = TMA-staged producer / consumer ring, any k (scan_stream.cu);
-  // "skew" = the register-pipelined warp-autonomous kernel below (k <= 128); both use the bank-skewed tables
+  // which long-list kernel: scan_long.cu (four entries per lane behind TMA bulk prefetches into L2, any k) for lists of
+  // >= long_min_len entries on average, else the register-pipelined warp-autonomous kernel below (k <= 128).  Both use
+  // the bank-skewed tables.  Measured, ms per 10 k queries (long / skew): 60 entries per list 2.63 / 2.40,
+  // 477 entries per list 7.54 / 8.35.  VLQ_SCAN_KERNEL=skew | long forces one of them (tests, tools/bench_scan.py).
   static const int long_kernel = [] {
     const char* e = getenv("VLQ_SCAN_KERNEL");
-    return (e && e[0] == 's' && e[1] == 'k') ? 1 : 0;
+    if (e && e[0] == 's') return 1;
+    if (e && e[0] == 'l') return 2;
+    return 0;
   }();
-  bool use_stream = false;
-  if (long_lists && have_t3 && list_len_hint >= skew_min_len && long_kernel == 0) {
+  static const int long_min_len = [] {
+    const char* e = getenv("VLQ_SCAN_LONG_MIN_LEN");
+    return e ? atoi(e) : 160;
+  }();
+  bool use_long = false;
+  if (long_lists && have_t3 && list_len_hint >= skew_min_len && long_kernel != 1 &&
+      (long_kernel == 2 || list_len_hint >= long_min_len || k > kWarpSelMaxK)) {
     ScanArgs probe = a;
     probe.t3 = static_cast<float*>(workspace);
-    use_stream = scan_stream_supported(probe);
+    use_long = scan_long_supported(probe);
   }
-  const bool skew = use_stream || (use_async && al16 && (M == 16 || M == 8) && list_len_hint >= skew_min_len);
+  const bool skew = use_long || (use_async && al16 && (M == 16 || M == 8) && list_len_hint >= skew_min_len);
   if (have_t3) {
     float* t3 = static_cast<float*>(workspace);
     const unsigned grid = (unsigned)(nq < 148 ? nq : 148);
@@ -1124,10 +1133,7 @@ int vlq_scan_topk(const float* q, int64_t nq, int d, const float* pq, int M, con
     a.t3 = t3;
   }
   a.owner_cap = (int)((long long)W * cap < 4096 ? (long long)W * cap : 4096);
-  if (use_stream) {
-    int* counter = reinterpret_cast<int*>(static_cast<unsigned char*>(workspace) + ((t3_bytes + 15) & ~size_t(15)));
-    return launch_scan_stream(a, nq, counter, as_stream(stream));
-  }
+  if (use_long) return launch_scan_long(a, nq, as_stream(stream));
   if (use_async) {
     cudaStream_t st_ = as_stream(stream);
     const int nt = skew ? AQ_THREADS_SKEW : Q_THREADS;

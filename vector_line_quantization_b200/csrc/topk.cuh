@@ -488,4 +488,157 @@ struct WarpSelect {
   }
 };
 
+
+// ---------------------------------------------------------------------------------------------------------------------
+// ONE candidate buffer per CTA shared by autonomous warps (the long-list scans): slots are reserved with an atomicAdd,
+// and the warp whose reservation crosses the capacity compacts the buffer alone (radix select of the k smallest) while
+// the others keep scanning.  One threshold per query: ~k ln(n/k) insertions in total instead of that per warp.  The
+// buffer has the BlockSelect layout (keys | hist[256] | meta[8]) so that BlockSelect::attach + finish ends the query.
+constexpr int kSharedSelCap = 2048;
+__device__ __forceinline__ int ld_volatile(const int* p) { return *reinterpret_cast<const volatile int*>(p); }
+
+// k smallest of keys[0..n) by ONE warp: byte-wise radix select (same scheme as WarpSelect::compact, keys streamed from
+// shared memory), then an in-place stable partition.  Returns the k-th smallest key; keys[0..k) hold the survivors.
+__device__ inline uint64_t warp_select_smem(uint64_t* keys, int n, int k, int* hist) {
+  const int lane = threadIdx.x & 31;
+  const uint64_t key0 = keys[0];
+  unsigned dhi = 0, dlo = 0;
+  for (int i = lane; i < n; i += 32) {
+    const uint64_t x = keys[i] ^ key0;
+    dhi |= (unsigned)(x >> 32);
+    dlo |= (unsigned)x;
+  }
+  dhi = __reduce_or_sync(kFull, dhi);
+  dlo = __reduce_or_sync(kFull, dlo);
+  const uint64_t diff = ((uint64_t)dhi << 32) | dlo;
+  const int top = diff ? (63 - __clzll((long long)diff)) >> 3 : 0;
+  uint64_t prefix = top == 7 ? 0 : (key0 >> ((top + 1) * 8));
+  int need = k;
+  uint64_t kth = 0;
+  bool found = false;
+#pragma unroll 1
+  for (int pass = top; pass >= 0; pass--) {
+#pragma unroll
+    for (int j = 0; j < 8; j++) hist[lane * 8 + j] = 0;
+    __syncwarp();
+    const int shift = pass * 8;
+    for (int i = lane; i < n; i += 32) {
+      const uint64_t key = keys[i];
+      const bool match = pass == 7 ? true : ((key >> (shift + 8)) == prefix);
+      if (match) atomicAdd(&hist[(int)((key >> shift) & 255)], 1);
+    }
+    __syncwarp();
+    int c[8], sum = 0;
+#pragma unroll
+    for (int j = 0; j < 8; j++) {
+      c[j] = hist[lane * 8 + j];
+      sum += c[j];
+    }
+    int inc = sum;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const int t = __shfl_up_sync(kFull, inc, o);
+      if (lane >= o) inc += t;
+    }
+    int before = inc - sum;
+    const bool here = before < need && need <= inc;  // exactly one lane
+    int digit = 0, rem = 0, inbin = 0;
+    if (here) {
+#pragma unroll
+      for (int j = 0; j < 8; j++) {
+        if (need <= before + c[j]) {
+          digit = lane * 8 + j;
+          rem = need - before;
+          inbin = c[j];
+          break;
+        }
+        before += c[j];
+      }
+    }
+    const int src = __ffs(__ballot_sync(kFull, here)) - 1;
+    digit = __shfl_sync(kFull, digit, src);
+    need = __shfl_sync(kFull, rem, src);
+    inbin = __shfl_sync(kFull, inbin, src);
+    prefix = (prefix << 8) | (uint64_t)digit;
+    __syncwarp();
+    if (inbin == 1 && pass > 0) {  // the wanted key is the only one with this prefix
+      uint64_t cand = 0;
+      bool hit = false;
+      for (int i = lane; i < n; i += 32) {
+        const uint64_t key = keys[i];
+        if ((key >> shift) == prefix) {
+          cand = key;
+          hit = true;
+        }
+      }
+      const unsigned who = __ballot_sync(kFull, hit);
+      kth = __shfl_sync(kFull, cand, __ffs(who) - 1);
+      found = true;
+      break;
+    }
+  }
+  if (!found) kth = prefix;
+  int base = 0;  // in-place partition: writes never pass the reads (base <= i0)
+  for (int i0 = 0; i0 < n; i0 += 32) {
+    const int i = i0 + lane;
+    const uint64_t key = i < n ? keys[i] : kKeyInf;
+    const bool keep = i < n && key <= kth;
+    const unsigned m = __ballot_sync(kFull, keep);
+    __syncwarp();
+    if (keep) keys[base + __popc(m & ((1u << lane) - 1))] = key;
+    base += __popc(m);
+    __syncwarp();
+  }
+  return kth;
+}
+
+// meta words of the shared selection (BlockSelect uses [0..3]: [0] is the append cursor)
+constexpr int META_COMMITTED = 4;
+constexpr int META_THR = 5;
+
+// warp-collective: lanes with take == true append their key
+__device__ __forceinline__ void shared_offer(uint64_t* keys, int* hist, int* meta, int k, bool valid, float dist,
+                                             uint32_t payload, int lane) {
+  for (;;) {
+    const float thr = __int_as_float(ld_volatile(&meta[META_THR]));
+    const bool take = valid && dist <= thr;
+    const unsigned m = __ballot_sync(kFull, take);
+    if (!m) return;
+    const int n = __popc(m);
+    int base = 0;
+    if (lane == 0) base = atomicAdd(&meta[0], n);
+    base = __shfl_sync(kFull, base, 0);
+    if (base + n <= kSharedSelCap) {
+      if (take) keys[base + __popc(m & ((1u << lane) - 1))] = make_key(dist, payload);
+      __syncwarp();
+      if (lane == 0) {
+        __threadfence_block();
+        atomicAdd(&meta[META_COMMITTED], n);
+      }
+      return;
+    }
+    if (base <= kSharedSelCap) {
+      // this warp's reservation crossed the capacity: slots [0, base) belong to other warps' appends.  Wait until they
+      // are all written, keep the k smallest, publish the new threshold and reopen the buffer.
+      while (ld_volatile(&meta[META_COMMITTED]) != base) __nanosleep(64);
+      __threadfence_block();
+      int kept = base;
+      if (base > k) {
+        const uint64_t kth = warp_select_smem(keys, base, k, hist);
+        kept = k;
+        if (lane == 0) *reinterpret_cast<volatile int*>(&meta[META_THR]) = __float_as_int(key_val(kth));
+      }
+      __syncwarp();
+      if (lane == 0) {
+        *reinterpret_cast<volatile int*>(&meta[META_COMMITTED]) = kept;
+        __threadfence_block();
+        atomicExch(&meta[0], kept);
+      }
+      __syncwarp();
+    } else {
+      while (ld_volatile(&meta[0]) > kSharedSelCap) __nanosleep(128);  // closed for compaction
+    }
+  }
+}
+
 }  // namespace vlq
