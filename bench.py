@@ -7,9 +7,11 @@
                                                                   ProductQuantizer from oracle/_ref) for the stock
                                                                   pieces + the oracle port for the VLQ-only search
 
-A "step" is one pass of the search hot path (coarse top-P -> line selection -> ADC scan + top-k [-> all-gather +
-merge for N>1]) over one batch of nq queries.  `value` is timed with the inputs resident in HBM; `e2e` goes through
-host (pinned) buffers with the H2D / D2H copies inside the timed region.  Prints ONE JSON line on rank 0.
+A "step" is one pass of the search hot path (coarse top-P -> line selection -> ADC scan + top-k [-> line exchange +
+peer merge for N>1]) over one batch of nq queries.  `value` (queries/s, merged, at every N) is timed with the inputs
+resident in HBM; `e2e` goes through host (pinned) buffers with the H2D / D2H copies inside the timed region.
+N > 1 is STRONG scaling by default: the same --n vector database is sharded N ways (--scaling weak keeps --n vectors
+per GPU instead).  Prints ONE JSON line on rank 0.
 """
 import argparse
 import json
@@ -46,7 +48,12 @@ def parse():
     ap.add_argument("--nprobe", type=int, default=64)
     ap.add_argument("--w1", type=int, default=256)
     ap.add_argument("--k", type=int, default=100)
-    ap.add_argument("--train-iters", type=int, default=4, help="coarse k-means iterations in the (untimed) setup")
+    ap.add_argument("--train-iters", type=int, default=10, help="coarse k-means iterations in the (untimed) setup "
+                    "(the reference's default, gpu/GpuIndexIVF.cu:50)")
+    ap.add_argument("--scaling", default=None, choices=["strong", "weak"],
+                    help="N > 1: strong (default) = the --n database sharded N ways; weak = --n vectors per GPU")
+    ap.add_argument("--no-c4-stage", action="store_true",
+                    help="skip the extra scan measurement at BASELINE configs[3] list density (1 B synthetic entries)")
     ap.add_argument("--kc", type=int, default=1 << 18, help="mixture components of the synthetic generator")
     ap.add_argument("--cpu-seconds", type=float, default=15.0, help="CPU-baseline budget in the default arm")
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -116,7 +123,7 @@ class ClockSampler:
 
 
 # ------------------------------------------------------------------------------------------------------- CPU arm
-def cpu_search_baseline(po, model, lists_host, xq, P, W, k, budget_s, gpu_result=None):
+def cpu_search_baseline(po, model, lists_host, xq, P, W, k, budget_s, gpu_result=None, gt=None, recall_at=None):
     """Times the oracle port of the VLQ search (the reference has no CPU VLQ) on a bounded sample of the queries,
     against the SAME index.  Returns the cpu_baseline object (+ a parity summary against the GPU results)."""
     T2 = po.term2(model["cent"], model["pq"])  # the reference precomputes this at train time (IVFPQ.cu:599-684)
@@ -143,6 +150,13 @@ def cpu_search_baseline(po, model, lists_host, xq, P, W, k, budget_s, gpu_result
         rel = np.abs(gD - D)[valid] / (np.abs(D) + qn)[valid]
         parity = {"queries": ns, "id_match": float((gI == I)[I >= 0].mean()), "max_rel_dist_err": float(rel.max()),
                   "set_overlap": float(np.mean([len(set(a) & set(b)) / max(1, len(set(b))) for a, b in zip(gI, I)]))}
+        if gt is not None:  # recall of both sides on the SAME queries of the SAME index (north_star: within 0.1 pt)
+            rg = {"R@%d" % r: recall_at(gI, gt[:ns], min(r, k)) for r in (1, 10, 100)}
+            ro = {"R@%d" % r: recall_at(I, gt[:ns], min(r, k)) for r in (1, 10, 100)}
+            parity["recall_gpu"] = rg
+            parity["recall_oracle"] = ro
+            parity["recall_max_abs_delta"] = max(abs(rg[key] - ro[key]) for key in rg)
+            parity["recall_within_0.001"] = parity["recall_max_abs_delta"] <= 1e-3
     return out, parity
 
 
@@ -160,11 +174,25 @@ class _StdoutToStderr:
         os.close(self.saved)
 
 
+def _all_host_cores():
+    """torchrun exports OMP_NUM_THREADS=1 to its workers; the CPU arms use every core of the box (must run before the
+    OpenMP runtime of the oracle / reference libraries is loaded)"""
+    n = os.cpu_count() or 1
+    try:
+        n = len(os.sched_getaffinity(0))
+    except Exception:
+        pass
+    for key in ("OMP_NUM_THREADS", "OPENBLAS_NUM_THREADS", "MKL_NUM_THREADS"):
+        os.environ[key] = str(n)
+    return n
+
+
 def run_reference(a):
     """--impl reference: everything on the host cores; no CUDA library is loaded."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
+    _all_host_cores()
     with _StdoutToStderr():
         line = _run_reference(a)
     print(json.dumps(line))
@@ -216,6 +244,10 @@ def run_imipq(a):
 
 
 def _run_reference(a):
+    """CPU arm on the SAME configuration as ours: the index has C x E lists and a.n entries (same list density, so a
+    query scans as many entries as on the GPU).  Only `enc` vectors are really encoded on the CPU (the reference encodes
+    ~10 k vectors/s on 16 cores); the a.n-entry index is that encoded sample tiled a.n / enc times with fresh ids --
+    every list is as long as in the full database and the scan touches a.n-entry arrays."""
     from oracle import pyoracle as po
     from vector_line_quantization_b200 import data
 
@@ -223,9 +255,10 @@ def _run_reference(a):
     ncores = po.num_threads()
     C, E, M, d = a.nlist, a.nedge, a.m, a.d
     t_setup = time.time()
-    nb = min(a.n, 100_000)  # bounded sample of the database (see `sample`)
+    enc = min(a.n, 500_000)
+    reps = max(1, a.n // enc)
     xt = data.sift_like(max(C, 32768), d=d, kc=min(a.kc, 1 << 16), seed=1)
-    xb = data.sift_like(nb, d=d, kc=min(a.kc, 1 << 16), seed=2)
+    xb = data.sift_like(enc, d=d, kc=min(a.kc, 1 << 16), seed=2)
     xq = data.sift_like(a.nq, d=d, kc=min(a.kc, 1 << 16), seed=3)
     # codebooks: untimed setup.  CPU k-means at C=2^16 takes ~1 h on 8 cores, so centroids are a random sample of the
     # training rows (search / encode cost does not depend on centroid quality); everything else follows the train path.
@@ -244,7 +277,7 @@ def _run_reference(a):
     r2 = po.residual(x2, lst2, po.lambda_quantize(lam2, lcb), lcb, cent, edge)
     pq = po.ref_pq_train(r2, M) if have_ref else np.stack(
         [po.kmeans(r2[:, m * (d // M):(m + 1) * (d // M)], 256, niter=10)[0] for m in range(M)])
-    # encode the database sample (timed: the CPU encode rate)
+    # encode the sample (timed: the CPU encode rate)
     t0 = time.time()
     if have_ref:
         A = po.ref_flat_search(cent, xb, 1)[1][:, 0].astype(np.int32)  # IndexFlatL2::search, the CPU twin of a2
@@ -254,10 +287,15 @@ def _run_reference(a):
     lamq = po.lambda_quantize(lam, lcb)
     r = po.residual(xb, lst, lamq, lcb, cent, edge)
     codes = po.ref_pq_compute_codes(r, pq) if have_ref else po.pq_encode(r, pq)
-    off, perm = po.build_lists(lst, C * E)
     t_enc = time.time() - t0
+    # the a.n-entry index: the encoded sample `reps` times over (ids i + j * enc)
+    lst_all = np.tile(lst, reps)
+    off, perm = po.build_lists(lst_all, C * E)
+    src = perm % enc
     T2 = po.term2(cent, pq)
-    args = (cent, edge, ed2, lcb, pq, off, codes[perm], lamq[perm], perm.astype(np.int64))
+    args = (cent, edge, ed2, lcb, pq, off, codes[src], lamq[src], perm.astype(np.int64))
+    nb = int(lst_all.shape[0])
+    del lst_all
     t_setup = time.time() - t_setup
     # steps: each a bounded sample of the nq-query batch, sized for ~4 s
     probe = min(a.nq, max(2 * ncores, 16))
@@ -274,40 +312,48 @@ def _run_reference(a):
         times.append(time.time() - t0)
     tot = sum(times)
     qps = ns * a.steps / tot
-    sample = ("%d of %d queries per step against a %d-vector sample of the %d-vector database (same C/E/M geometry; "
-              "centroids = random training rows, no CPU k-means); stock pieces by the reference CPU library = %s"
-              % (ns, a.nq, nb, a.n, have_ref))
+    sample = ("%d of %d queries per step against a %d-entry index with the configuration's C x E = %d lists (same list "
+              "density as the %d-vector database): %d vectors encoded on the CPU, tiled %d x with fresh ids; centroids = "
+              "random training rows (no CPU k-means at C = %d); stock pieces by the reference CPU library = %s"
+              % (ns, a.nq, nb, C * E, a.n, enc, reps, C, have_ref))
+    cfg = workload_config(a, 1)
+    cfg["db_vectors_searched"] = nb
+    cfg["db_vectors_encoded_on_cpu"] = enc
     line = {
         "impl": "reference", "metric": "vlq_search_qps", "value": qps, "unit": "queries/s", "n_gpus": a.gpus,
         "steps": a.steps, "warmup": a.warmup, "ms_per_step": 1e3 * tot / a.steps, "higher_is_better": True,
-        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": workload_config(a, a.gpus),
+        "scaling": "strong" if a.gpus > 1 and a.scaling != "weak" else "weak", "vs_baseline": None, "dtype": "f32",
+        "data": "synthetic", "config": cfg,
         "cpu_baseline": {"value": qps, "unit": "queries/s", "cores": ncores, "kind": "port", "sample": sample},
         "e2e": {"value": qps, "unit": "queries/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-        "encode": {"value": nb / t_enc / 1e6, "unit": "Mvec/s", "kind": "reference" if have_ref else "port",
-                   "sample": "%d vectors: IndexFlatL2 assign + oracle line stage + ProductQuantizer::compute_codes" % nb},
+        "encode": {"value": enc / t_enc / 1e6, "unit": "Mvec/s", "kind": "reference" if have_ref else "port",
+                   "sample": "%d vectors: IndexFlatL2 assign + oracle line stage + ProductQuantizer::compute_codes" % enc},
         "setup_s": t_setup,
     }
     return line
 
 
 def workload_config(a, n_gpus):
+    strong = n_gpus > 1 and a.scaling != "weak"
+    total = a.n if (strong or n_gpus == 1) else a.n * n_gpus
+    per_gpu = a.n // n_gpus if strong else a.n
     if a.shape == "deep":
         cfg = "configs[2] (DEEP1B shape)"
-    elif a.u8 and a.n * n_gpus >= 1_000_000_000:
+    elif a.u8 and total >= 1_000_000_000:
         cfg = "configs[3] (SIFT1B shape, uint8 ingest)"
-    elif a.n == 10_000_000 and n_gpus == 1:
+    elif total == 10_000_000:
         cfg = "configs[1]"
     else:
         cfg = "configs[1] geometry at another database size"
     return {
         "workload": "BASELINE.json %s: VLQ C=%d centroids x E=%d lines, PQ m=%d, nLambda=%d, d=%d, synthetic "
-                    "%s-shaped %d vectors per GPU; search nq=%d nprobe=%d w1=%d k=%d"
-                    % (cfg, a.nlist, a.nedge, a.m, a.nlambda, a.d, a.shape.upper(), a.n, a.nq, a.nprobe, a.w1, a.k),
-        "db_vectors_per_gpu": a.n, "db_vectors_total": a.n * n_gpus, "nlist": a.nlist, "nedge": a.nedge, "m": a.m,
-        "nq": a.nq, "nprobe": a.nprobe, "w1": a.w1, "k": a.k,
-        "parallelism": "id-range database shards, queries replicated, NCCL all-gather of per-shard top-k + merge kernel"
-        if n_gpus > 1 else "single GPU",
+                    "%s-shaped %d vectors in total (%d per GPU); search nq=%d nprobe=%d w1=%d k=%d"
+                    % (cfg, a.nlist, a.nedge, a.m, a.nlambda, a.d, a.shape.upper(), total, per_gpu, a.nq, a.nprobe, a.w1, a.k),
+        "db_vectors_per_gpu": per_gpu, "db_vectors_total": total, "nlist": a.nlist, "nedge": a.nedge, "m": a.m,
+        "nq": a.nq, "nprobe": a.nprobe, "w1": a.w1, "k": a.k, "train_iters": a.train_iters,
+        "parallelism": ("id-range database shards (%s scaling); coarse stage split by queries, line lists exchanged "
+                        "through peer-mapped memory, every shard scans all queries, per-shard top-k merged by query slice "
+                        "over NVLink" % ("strong" if strong else "weak")) if n_gpus > 1 else "single GPU",
         "l2": "an L2-sized (256 MiB) buffer is overwritten between timed steps",
     }
 
@@ -329,6 +375,10 @@ def run_b200(a):
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
     C, E, M, d, P, W, k, nq = a.nlist, a.nedge, a.m, a.d, a.nprobe, a.w1, a.k, a.nq
+    strong = world > 1 and a.scaling != "weak"
+    n_total = a.n if (strong or world == 1) else a.n * world
+    id0, id1 = sharding.shard_range(n_total, world, rank)  # this rank's rows of the global database
+    n_loc = id1 - id0
 
     def log(*s):
         if rank == 0:
@@ -341,7 +391,7 @@ def run_b200(a):
 
     # ---- setup (untimed): codebooks trained on the device; identical on all ranks (rank 0 broadcasts)
     t0 = time.time()
-    nt = min(C * 64, 4 * a.n)
+    nt = min(C * 64, 4 * n_total)
     gen = data.SyntheticGen(a.shape, d=d, kc=a.kc, device=dev)
     xt = torch.cat([gen.chunk(7000 + i, min(1 << 20, nt - i * (1 << 20))) for i in range((nt + (1 << 20) - 1) >> 20)])
     model = train.train_vlq(xt, C, E, M, a.nlambda, niter=a.train_iters, pq_niter=10, exact_perm=False)
@@ -365,10 +415,15 @@ def run_b200(a):
     #      outside the timed events.
     chunk = 1 << 20
 
-    def db_chunk(s):  # rows [s, s + chunk) of this rank's shard
-        return gen.chunk((1000 + rank) * 1000003 + s // chunk, min(chunk, a.n - s))
+    def db_chunk(s):  # rows [s, s + chunk) of this rank's shard = rows id0 + s ... of the GLOBAL database, which is
+        # generated in 1 Mi-row blocks (the same database for every N: a shard boundary may fall inside a block)
+        g0, g1 = id0 + s, min(id1, id0 + s + chunk)
+        parts_ = []
+        for c in range(g0 // chunk, (g1 - 1) // chunk + 1):
+            blk = gen.chunk(1000003 + c, min(chunk, n_total - c * chunk))
+            parts_.append(blk[max(g0 - c * chunk, 0):min(g1 - c * chunk, blk.shape[0])])
+        return parts_[0] if len(parts_) == 1 else torch.cat(parts_)
 
-    id0 = rank * a.n
     lists = None
     barrier()
     prof = os.environ.get("VLQ_PROFILE", "")  # ncu --profile-from-start off: wrap one region in cudaProfilerStart/Stop
@@ -377,7 +432,7 @@ def run_b200(a):
     n_before = ops.launch_count()
     evs = []
     parts = []
-    for s in range(0, a.n, chunk):
+    for s in range(0, n_loc, chunk):
         x = db_chunk(s)
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
@@ -389,7 +444,7 @@ def run_b200(a):
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     new_list = torch.cat([p.list for p in parts])
-    ids = torch.arange(id0, id0 + a.n, dtype=torch.int64, device=dev)
+    ids = torch.arange(id0, id1, dtype=torch.int64, device=dev)
     lists = ops.build_lists(C * E, M, new_list, torch.cat([p.codes for p in parts]), torch.cat([p.lamq for p in parts]),
                             torch.cat([p.kappa for p in parts]), ids)
     e1.record()
@@ -404,15 +459,16 @@ def run_b200(a):
     enc_launches = ops.launch_count() - n_before
     del parts, new_list, ids
     torch.cuda.empty_cache()
-    log("encoded %d vectors/GPU in %.1f ms" % (a.n, enc_ms))
+    log("encoded %d vectors/GPU in %.1f ms" % (n_loc, enc_ms))
+    n_loc_sum = n_total  # vectors encoded by all ranks together
 
     # ---- queries + exact ground truth (brute force over every shard, for recall)
     xq = gen.chunk(3, nq)
     gt_d = torch.full((nq,), float("inf"), device=dev)
     gt_i = torch.full((nq,), -1, dtype=torch.int64, device=dev)
     gchunk = 1 << 18
-    exact_gt = a.n <= 20_000_000  # beyond that the brute force runs on the tensor-core kernel (fp32-grade)
-    for s0 in range(0, a.n, chunk):
+    exact_gt = n_total <= 20_000_000  # beyond that the brute force runs on the tensor-core kernel (fp32-grade)
+    for s0 in range(0, n_loc, chunk):
         xc = db_chunk(s0)
         for s in range(0, xc.shape[0], gchunk):  # "centroids" = a database slice; argmin per query = exact 1-NN in the slice
             sl = xc[s:s + gchunk]
@@ -434,40 +490,52 @@ def run_b200(a):
         gt_i = si.gather(0, best)[0]
 
     # ---- the step
+    #  N = 1: the product's C++ API, GpuIndexIVFPQ::search with DEVICE pointers (built further down: `hidx`)
+    #  N > 1: query-split coarse stage -> line exchange through peer-mapped memory -> every shard scans all queries ->
+    #         peer merge by query slice (sharding.QuerySplitSearch); NCCL all-gather + merge kernel when symmetric
+    #         memory is unavailable
     gD = torch.empty((world, nq, k), dtype=torch.float32, device=dev) if world > 1 else None
     gI = torch.empty((world, nq, k), dtype=torch.int64, device=dev) if world > 1 else None
 
+    def ops_search(q):  # the whole query path on this rank's lists through the C-ABI (ops = ctypes bindings)
+        return ops.search(q, cent, cn, edge, ed2, lcb, pq, lists, P, W, k, pack=pack)
+
     def step_nccl(q):
-        D, I = ops.search(q, cent, cn, edge, ed2, lcb, pq, lists, P, W, k, pack=pack)
+        D, I = ops_search(q)
         if world > 1:
             sharding.gather_topk(D, I, gD, gI)
             D, I = ops.merge_topk(gD, gI)
         return D, I
 
-    # exchange step: peer-memory gather fused into the merge kernel (default) or NCCL all-gather + merge kernel
     exchange = "none"
-    px = None
+    qss = None
     if world > 1:
-        exchange = "nccl all-gather + merge kernel"
+        exchange = "replicated coarse stage, nccl all-gather of the per-shard top-k + merge kernel"
         if os.environ.get("VLQ_EXCHANGE", "peer") == "peer":
             try:
-                px = sharding.PeerExchange(nq, k, dev)
-                exchange = "merge kernel reading the shards' results from peer memory over NVLink (one device barrier)"
+                qss = sharding.QuerySplitSearch(nq, k, W, dev)
+                exchange = ("coarse stage split by queries; (list, term1, term6) pulled from the peers' symmetric memory "
+                            "over NVLink; per-shard top-k merged by query slice straight from peer memory (two device barriers)")
             except Exception as exc:  # symmetric memory unavailable on this box: the NCCL path is the same result
                 log("peer-memory exchange unavailable (%s: %s); using NCCL" % (type(exc).__name__, exc))
-                px = None
+                qss = None
 
-    def step_peer(q):
-        ops.search(q, cent, cn, edge, ed2, lcb, pq, lists, P, W, k, pack=pack, out=px.local_out())
-        return px.merge()
+    def coarse_fn(qs, out):
+        return ops.coarse_lines(qs, cent, cn, edge, ed2, P, W, pack=pack, out=out)
 
-    step = step_peer if px is not None else step_nccl
-    if px is not None:  # both exchanges must return the same bits
+    def scan_fn(q, lines, out):
+        return ops.scan_lines(q, pq, lcb, lines, ed2, lists, k, out=out)
+
+    def step_peer(q):  # -> (D, I) of this rank's query slice
+        return qss.search(q, coarse_fn, scan_fn)
+
+    if qss is not None:  # the query-split exchange must return the same bits as the NCCL exchange
         Dn, In = step_nccl(xq)
         Dp, Ip = step_peer(xq)
         torch.cuda.synchronize()
-        assert torch.equal(Dn, Dp) and torch.equal(In, Ip), "peer-memory exchange differs from the NCCL exchange"
-        log("peer-memory exchange == NCCL exchange (bitwise)")
+        qs0, qs1 = qss.my_slice()
+        assert torch.equal(Dn[qs0:qs1], Dp) and torch.equal(In[qs0:qs1], Ip), "query-split exchange differs from the NCCL exchange"
+        log("query-split peer exchange == NCCL exchange (bitwise)")
 
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
 
@@ -491,21 +559,6 @@ def run_b200(a):
             dist.all_reduce(ms, op=dist.ReduceOp.MAX)
         return float(ms), launches
 
-    clocks = ClockSampler(local)
-    clocks.start()
-    time.sleep(0.5)  # let nvidia-smi come up: the timed region is only tens of milliseconds long
-    result = {}
-
-    def dev_step():
-        result["DI"] = step(xq)
-
-    if prof == "search":
-        torch.cuda.profiler.start()
-    total_ms, launches = timed(dev_step, a.steps, a.warmup)
-    if prof == "search":
-        torch.cuda.profiler.stop()
-    D, I = result["DI"]
-
     # ---- e2e: the reference-facing API (C++ host layer: GpuIndexIVFPQ::add_with_ids / ::search) with HOST buffers;
     #      the host->device copy of the inputs and the device->host copy of the results are inside the timed region
     from vector_line_quantization_b200 import index as vi
@@ -515,14 +568,14 @@ def run_b200(a):
     hidx.setCodebooks(*(model[key].cpu().numpy() for key in ("cent", "edge", "edge_d2", "lambda_cb", "pq")))
     hidx.setNumProbes(P)
     hidx.w1_ = W
-    hidx.reserveMemory(a.n)  # GpuIndexIVFPQ::reserveMemory, as the reference drivers do before a bulk load
+    hidx.reserveMemory(n_loc)  # GpuIndexIVFPQ::reserveMemory, as the reference drivers do before a bulk load
     add_chunk = 2 * chunk  # the reference drivers ingest 2 M vectors per add (gpu/test/sift1b_createdb.cpp:276-289)
     use_u8 = a.u8 and a.shape == "sift"
-    hx = torch.empty((min(add_chunk, a.n), d), dtype=torch.uint8 if use_u8 else torch.float32).pin_memory()
-    hids = torch.empty(min(add_chunk, a.n), dtype=torch.int64).pin_memory()
+    hx = torch.empty((min(add_chunk, n_loc), d), dtype=torch.uint8 if use_u8 else torch.float32).pin_memory()
+    hids = torch.empty(min(add_chunk, n_loc), dtype=torch.int64).pin_memory()
     enc_e2e_s = 0.0
-    for s in range(0, a.n, add_chunk):
-        m_ = min(add_chunk, a.n - s)
+    for s in range(0, n_loc, add_chunk):
+        m_ = min(add_chunk, n_loc - s)
         for s2 in range(s, s + m_, chunk):  # staging the synthetic rows on the host is not part of the timed region
             xc = db_chunk(s2)
             hx[s2 - s:s2 - s + xc.shape[0]].copy_(xc.to(torch.uint8) if use_u8 else xc)
@@ -545,25 +598,64 @@ def run_b200(a):
     del hx
     torch.cuda.empty_cache()
 
+    # ---- `value`: device-resident step
+    dD = torch.empty((nq, k), dtype=torch.float32, device=dev)
+    dI = torch.empty((nq, k), dtype=torch.int64, device=dev)
+    clocks = ClockSampler(local)
+    clocks.start()
+    time.sleep(0.5)  # let nvidia-smi come up: the timed region is only tens of milliseconds long
+    result = {}
+
+    def dev_step():
+        if world == 1:
+            hidx.search(xq, k, out=(dD, dI))  # GpuIndexIVFPQ::search, device pointers in and out
+            result["DI"] = (dD, dI)
+        elif qss is not None:
+            result["DI"] = step_peer(xq)
+        else:
+            result["DI"] = step_nccl(xq)
+
+    if prof == "search":
+        torch.cuda.profiler.start()
+    total_ms, launches = timed(dev_step, a.steps, a.warmup)
+    if prof == "search":
+        torch.cuda.profiler.stop()
+    D, I = result["DI"]
+    if world > 1 and qss is not None:  # assemble the distributed result (outside the timed region) for recall / parity
+        qsl = [qss.q0[r + 1] - qss.q0[r] for r in range(world)]
+        if len(set(qsl)) == 1:
+            fullD = torch.empty((nq, k), dtype=torch.float32, device=dev)
+            fullI = torch.empty((nq, k), dtype=torch.int64, device=dev)
+            dist.all_gather_into_tensor(fullD, D.contiguous())
+            dist.all_gather_into_tensor(fullI, I.contiguous())
+            D, I = fullD, fullI
+        else:
+            D, I = step_nccl(xq)
+    ops_matches = None
+    if world == 1:  # the C++ API and the C-ABI tile loop of ops.search must agree bit for bit
+        Do_, Io_ = ops_search(xq)
+        ops_matches = bool(torch.equal(Do_, D) and torch.equal(Io_, I))
+
     hq = torch.empty((nq, d), dtype=torch.float32).pin_memory()
     hq.copy_(xq.cpu())
     hD = torch.empty((nq, k), dtype=torch.float32).pin_memory()
     hI = torch.empty((nq, k), dtype=torch.int64).pin_memory()
     dq = torch.empty_like(xq)
-    dD = torch.empty((nq, k), dtype=torch.float32, device=dev)
-    dI = torch.empty((nq, k), dtype=torch.int64, device=dev)
+    qs0, qs1 = (qss.my_slice() if qss is not None else (0, nq))
 
     def e2e_step():
         if world == 1:
             hidx.search(hq, k, out=(hD, hI))  # host pointers straight through the C++ API
-        else:
+        else:  # every rank uploads the query batch (the scan needs all of it) and downloads its slice of the result
             dq.copy_(hq, non_blocking=True)
-            torch.cuda.current_stream().synchronize()
-            hidx.search(dq, k, out=(dD, dI))
-            sharding.gather_topk(dD, dI, gD, gI)
-            D_, I_ = ops.merge_topk(gD, gI)
-            hD.copy_(D_, non_blocking=True)
-            hI.copy_(I_, non_blocking=True)
+            if qss is not None:
+                D_, I_ = step_peer(dq)
+                hD[qs0:qs1].copy_(D_, non_blocking=True)
+                hI[qs0:qs1].copy_(I_, non_blocking=True)
+            else:
+                D_, I_ = step_nccl(dq)
+                hD.copy_(D_, non_blocking=True)
+                hI.copy_(I_, non_blocking=True)
             torch.cuda.synchronize()
 
     for _ in range(a.warmup):
@@ -577,7 +669,9 @@ def run_b200(a):
     if world > 1:
         dist.all_reduce(e2e_t, op=dist.ReduceOp.MAX)
     e2e_ms = float(e2e_t) * 1e3
-    host_matches_ops = bool((hI.to(dev) == I).all()) and bool((hD.to(dev) == D).all())
+    host_matches_ops = bool((hI[qs0:qs1].to(dev) == I[qs0:qs1]).all()) and bool((hD[qs0:qs1].to(dev) == D[qs0:qs1]).all())
+    if ops_matches is not None:
+        host_matches_ops = host_matches_ops and ops_matches
     clk = clocks.stop()  # sampled across the device-timed steps and the e2e steps
 
     # ---- per-stage device times of one step (CUDA events on the launching stream) -> roofline of the dominant kernel
@@ -634,15 +728,9 @@ def run_b200(a):
     hbm_peak = peaks.get("hbm_gbs", 6650.0)
     tc_peak = peaks.get("bf16_tflops", 1590.0)
     peak_src = "measured (MEASURED_PEAKS.json, burst: kernel timed alone)" if peaks else "fallback (B200_PROFILING.md)"
-    # ncu-measured DRAM traffic per launch of each stage's kernel (profiles/r01_traffic.json, written by
-    # tools/ncu_traffic.py from the committed `ncu --set full` capture of this workload); null when absent
+    # DRAM traffic per launch comes from an `ncu --set full` capture of the same command (profiles/, tools/ncu_traffic.py);
+    # it is not measurable inside this run, so the line carries null and the committed summaries carry the numbers
     traffic = {}
-    try:
-        tj = json.load(open(os.path.join(ROOT, "profiles", "r01_traffic.json")))
-        if tj.get("db_vectors_per_gpu") == a.n and tj.get("nq") == nq:
-            traffic = tj.get("bytes_per_launch", {})
-    except Exception:
-        pass
 
     def stage_roofline(name):
         """algorithmic work of one launch of the stage over its measured launch time"""
@@ -700,29 +788,102 @@ def run_b200(a):
         lh = (lists.offsets.cpu().numpy(), ops.rotate_codes(lists.offsets, lists.codes, inverse=True).cpu().numpy(),
               lists.lamq.cpu().numpy(), lists.ids.cpu().numpy())  # canonical code order for the oracle
         cpu_baseline, parity = cpu_search_baseline(po, mh, lh, xq.cpu().numpy(), P, W, k, a.cpu_seconds,
-                                                   (D.cpu().numpy(), In))
+                                                   (D.cpu().numpy(), In), gt=gt, recall_at=data.recall_at)
+    # ---- N > 1: the merged result against the oracle's search of the UNION of the shards (sub-sample of the queries)
+    if world > 1 and n_total <= 20_000_000 and not a.no_cpu_baseline:
+        canon = ops.rotate_codes(lists.offsets, lists.codes, inverse=True)
+        lens_r = (lists.offsets[1:] - lists.offsets[:-1]).to(torch.int32)
+        szs = [torch.zeros(1, dtype=torch.int64, device=dev) for _ in range(world)]
+        dist.all_gather(szs, torch.tensor([n_loc], dtype=torch.int64, device=dev))
+        szs = [int(x) for x in szs]
+        mx = max(szs)
+
+        def gather_rows(t):  # ragged all-gather of per-entry arrays (padded to the largest shard)
+            pad = torch.zeros((mx,) + tuple(t.shape[1:]), dtype=t.dtype, device=dev)
+            pad[: t.shape[0]] = t
+            outs = [torch.empty_like(pad) for _ in range(world)]
+            dist.all_gather(outs, pad)
+            return [o[:n_].cpu().numpy() for o, n_ in zip(outs, szs)]
+
+        all_lens = [torch.empty_like(lens_r) for _ in range(world)]
+        dist.all_gather(all_lens, lens_r)
+        g_codes, g_lamq, g_ids = gather_rows(canon), gather_rows(lists.lamq), gather_rows(lists.ids)
+        if rank == 0:
+            from oracle import pyoracle as po  # checker only
+
+            lens_np = [x.cpu().numpy().astype(np.int64) for x in all_lens]
+            tot_len = sum(lens_np)
+            off_u = np.zeros(C * E + 1, dtype=np.int64)
+            off_u[1:] = np.cumsum(tot_len)
+            nU = int(off_u[-1])
+            codes_u = np.empty((nU, M), dtype=np.uint8)
+            lamq_u = np.empty(nU, dtype=np.uint8)
+            ids_u = np.empty(nU, dtype=np.int64)
+            cur = off_u[:-1].copy()
+            for r in range(world):  # list-major union, shard order inside a list (= ascending ids: what one index holds)
+                offr = np.zeros(C * E + 1, dtype=np.int64)
+                offr[1:] = np.cumsum(lens_np[r])
+                dst = np.repeat(cur - offr[:-1], lens_np[r]) + np.arange(szs[r])
+                codes_u[dst], lamq_u[dst], ids_u[dst] = g_codes[r], g_lamq[r], g_ids[r]
+                cur += lens_np[r]
+            mh = {key: model[key].cpu().numpy() for key in ("cent", "edge", "edge_d2", "lambda_cb", "pq")}
+            ns = min(nq, 512)
+            T2 = po.term2(mh["cent"], mh["pq"])
+            Do, Io = po.search(xq[:ns].cpu().numpy(), mh["cent"], mh["edge"], mh["edge_d2"], mh["lambda_cb"], mh["pq"], off_u,
+                               codes_u, lamq_u, ids_u, P=P, W=W, k=k, T2=T2)
+            gD_, gI_ = D[:ns].cpu().numpy(), In[:ns]
+            qn = (xq[:ns].cpu().numpy().astype(np.float64) ** 2).sum(1, keepdims=True)
+            same = (Io >= 0) & (gI_ == Io)
+            rel = np.abs(gD_ - Do)[same] / (np.abs(Do) + qn)[same]
+            parity = {"queries": ns, "against": "oracle search of the union of the %d shards (%d entries)" % (world, nU),
+                      "id_match": float((gI_ == Io)[Io >= 0].mean()), "max_rel_dist_err": float(rel.max()),
+                      "set_overlap": float(np.mean([len(set(x) & set(y)) / max(1, len(set(y))) for x, y in zip(gI_, Io)]))}
+        del g_codes, g_lamq, g_ids, canon
+
+    # ---- the scan stage at BASELINE configs[3] list density (1 B entries, 477 per list) on SYNTHETIC lists (random codes /
+    #      lambda bytes / kappa: no 36 s encode), N = 1 only: the >= 0.70-of-HBM target of north_star applies to this density
+    c4_stage = None
+    if world == 1 and not a.no_c4_stage and not a.quick and M in (8, 16):
+        try:
+            lists = None
+            hidx.reset()
+            torch.cuda.empty_cache()
+            free_b, _ = torch.cuda.mem_get_info()
+            n_c4 = 1_000_000_000
+            if free_b > n_c4 * (M + 13) * 1.3:
+                c4_stage = scan_stage_at_density(ops, dev, n_c4, C * E, M, d, nq, W, k, hbm_peak, peak_src)
+                log("C4-density scan stage", c4_stage)
+        except Exception as exc:  # the headline line must survive this extra measurement
+            log("C4-density scan stage failed: %s: %s" % (type(exc).__name__, exc))
+    if c4_stage is not None:
+        roof["stages"].append(c4_stage)
 
     if rank == 0:
         qps = nq * a.steps / (total_ms * 1e-3)
         e2e_qps = nq * a.steps / (e2e_ms * 1e-3)
         line = {
-            "metric": "vlq_search_qps", "value": qps * world, "unit": "queries/s" if world == 1 else "shard-queries/s",
+            "metric": "vlq_search_qps", "value": qps, "unit": "queries/s",
             "n_gpus": world, "steps": a.steps, "warmup": a.warmup, "ms_per_step": total_ms / a.steps,
-            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32 (coarse GEMM: split-fp16 x3 tcgen05, fp32 accumulate)" if use_tc else "f32", "data": "synthetic",
-            "config": dict(workload_config(a, world), exchange=exchange), "merged_qps": qps,
-            "e2e": {"value": e2e_qps * world, "unit": "queries/s" if world == 1 else "shard-queries/s",
-                    "h2d_bytes_per_step": nq * d * 4, "d2h_bytes_per_step": nq * k * 12, "merged_qps": e2e_qps},
+            "higher_is_better": True, "scaling": "strong" if strong else "weak", "vs_baseline": None,
+            "dtype": "f32 (coarse GEMM: split-fp16 x3 tcgen05, fp32 accumulate)" if use_tc else "f32", "data": "synthetic",
+            "config": dict(workload_config(a, world), exchange=exchange,
+                           value_api="GpuIndexIVFPQ::search (C++ host layer), device pointers" if world == 1 else
+                           "sharding.QuerySplitSearch over the C-ABI stage entry points"),
+            "e2e": {"value": e2e_qps, "unit": "queries/s",
+                    "h2d_bytes_per_step": nq * d * 4 * world, "d2h_bytes_per_step": nq * k * 12},
             "gpu_launches": launches, "roofline": roof, "cpu_baseline": cpu_baseline, "clocks": clk, "recall": recall,
-            "encode": {"value": a.n * world / (enc_ms * 1e-3) / 1e6, "unit": "Mvec/s", "ms": enc_ms,
-                       "e2e": {"value": a.n * world / enc_e2e_s / 1e6, "unit": "Mvec/s",
+            "encode": {"value": n_loc_sum / (enc_ms * 1e-3) / 1e6, "unit": "Mvec/s", "ms": enc_ms,
+                       "e2e": {"value": n_loc_sum / enc_e2e_s / 1e6, "unit": "Mvec/s",
                                "h2d_bytes_per_vector": (d if use_u8 else d * 4) + 8,
                                "note": "GpuIndexIVFPQ::add_with_ids%s from pinned host memory in 2 Mi-vector chunks + "
                                        "list commit" % ("_u8" if use_u8 else "")},
                        "gpu_launches": enc_launches,
-                       "tensor_frac": (a.n * 2.0 * C * d / (enc_ms * 1e-3) / 1e12) / peaks.get("bf16_tflops_sustained", 1400.0)},
+                       "tensor_frac": (n_loc * 2.0 * C * d / (enc_ms * 1e-3) / 1e12) / peaks.get("bf16_tflops_sustained", 1400.0)},
             "scanned_entries_per_query": scanned_per_q, "parity_vs_oracle": parity,
             "host_api_matches_ops_bitwise": host_matches_ops,
         }
+        if world > 1:
+            line["shard_queries_per_s"] = qps * world  # (query, shard) searches per second, all ranks
         if sweep is not None:
             line["recall_sweep"] = sweep
     else:
@@ -730,6 +891,73 @@ def run_b200(a):
     if world > 1:
         dist.destroy_process_group()
     return line
+
+
+def scan_stage_at_density(ops, dev, n_target, nlists, M, d, nq, W, k, hbm_peak, peak_src):
+    """vlq_scan_topk alone on synthetic lists of the given density (see tools/bench_scan.py): list lengths are Poisson
+    around n_target / nlists with a Gamma(4) spread, queries pick lists size-biased (dense regions attract both vectors
+    and queries in the real index).  Returns a roofline stage object (SURVEY 8d algorithmic bytes / CUDA-event time)."""
+    import torch
+
+    g = torch.Generator(device=dev).manual_seed(1)
+    mean = n_target / nlists
+    spread = torch.distributions.Gamma(4.0, 4.0).sample((nlists,)).to(dev)
+    lens = torch.poisson(spread * mean, generator=g).to(torch.int64)
+    off = torch.zeros(nlists + 1, dtype=torch.int64, device=dev)
+    off[1:] = torch.cumsum(lens, 0)
+    n = int(off[-1])
+    codes = torch.empty((n, M), dtype=torch.uint8, device=dev)
+    lamq = torch.empty(n, dtype=torch.uint8, device=dev)
+    kappa = torch.empty(n, dtype=torch.float32, device=dev)
+    step = 1 << 26
+    for s in range(0, n, step):
+        e = min(n, s + step)
+        codes[s:e] = torch.randint(0, 256, (e - s, M), dtype=torch.uint8, device=dev, generator=g)
+        lamq[s:e] = torch.randint(0, 256, (e - s,), dtype=torch.uint8, device=dev, generator=g)
+        kappa[s:e] = torch.randn(e - s, device=dev, generator=g) * 100.0
+    lists = ops.Lists(off, codes, lamq, kappa, torch.arange(n, dtype=torch.int64, device=dev))
+    g2 = torch.Generator(device=dev).manual_seed(7)
+    line = torch.multinomial(lens.float() + 1e-3, nq * W, replacement=True, generator=g2).reshape(nq, W).to(torch.int32)
+    q = torch.randn(nq, d, device=dev, generator=g2)
+    pq = torch.randn(M, 256, d // M, device=dev, generator=g2)
+    lcb = torch.rand(256, device=dev, generator=g2)
+    t1 = torch.rand(nq, W, device=dev, generator=g2) * 10
+    t6 = torch.randn(nq, W, device=dev, generator=g2)
+    ed2 = torch.rand(nlists, device=dev, generator=g2) * 4 + 0.5
+    scanned = float(lens.clamp_max(1024)[line.to(torch.int64)].sum(dim=1).float().mean())
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+    outD = torch.empty((nq, k), dtype=torch.float32, device=dev)
+    outI = torch.empty((nq, k), dtype=torch.int64, device=dev)
+    tile = 4096
+
+    def run():
+        evs = []
+        for s in range(0, nq, tile):
+            e = min(nq, s + tile)
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            ops.scan_topk(q[s:e], pq, lcb, line[s:e], t1[s:e], t6[s:e], ed2, lists, k, 1024, list_len_hint=int(mean),
+                          out=(outD[s:e], outI[s:e]))
+            e1.record()
+            evs.append((e0, e1))
+        torch.cuda.synchronize()
+        return sum(x.elapsed_time(y) for x, y in evs), len(evs)
+
+    for _ in range(3):
+        run()
+    ms = []
+    for _ in range(5):
+        flush.fill_(1)
+        t, nl = run()
+        ms.append(t)
+    mean_ms = sum(ms) / len(ms)
+    alg = nq * (scanned * (M + 1) + 8 * k)
+    ach = alg / (mean_ms * 1e-3) / 1e9
+    return {"bound": "hbm", "achieved": ach, "peak": hbm_peak, "unit": "GB/s", "frac": ach / hbm_peak, "traffic": None,
+            "kernel": "scan_topk @ BASELINE configs[3] list density", "ms_per_launch": mean_ms / nl,
+            "ms_per_%d_queries" % nq: mean_ms, "peak_source": peak_src,
+            "workload": "synthetic lists: %d entries in %d lists (%.0f per list), %d queries x %d lines, %.0f entries scanned "
+                        "per query, k=%d; random codes / lambda bytes / kappa" % (n, nlists, n / nlists, nq, W, scanned, k)}
 
 
 def main():

@@ -78,7 +78,10 @@ def test_tc_rejects_unsupported_shapes(ops, cuda):
 
 
 @pytest.mark.parametrize("nq,C,d,P,W,E", [(100, 4096, 128, 64, 256, 32), (33, 1000, 96, 16, 100, 8), (10, 130, 64, 200, 1024, 16),
-                                          (7, 65536, 128, 64, 1024, 32)])
+                                          (7, 65536, 128, 64, 1024, 32),
+                                          # register-resident fast path with 16 keys per thread; W larger than the lines
+                                          (20, 65536, 128, 128, 512, 32), (9, 8192, 128, 64, 700, 64), (5, 2048, 96, 4, 1024, 32),
+                                          (6, 4096, 128, 1, 1, 32)])
 def test_fused_coarse_select_equals_two_step(ops, cuda, nq, C, d, P, W, E):
     """bucket-minimum route == select_rows(k=P) + select_lines on the same distance matrix, bit for bit"""
     import torch

@@ -1,0 +1,338 @@
+// Fast path of the fused top-P + line selection (SURVEY.md 8a rows a11 + a12; replaces l2SelectMinK + the line scoring and
+// BlockSelect of sumAlongRowsWithOrder2: gpu/impl/L2Select.cu:124-165, BroadcastSum.cu:477-560).
+//
+// The general kernel (search.cu coarse_select_lines_kernel) runs three block-wide selections over 2048 64-bit keys in
+// shared memory per query (bucket minima -> candidate columns -> lines) and was the dominant kernel of the C2 step
+// (ncu round 1: 158 M warp instructions per 4096 queries, 0.05 of the HBM roofline).  Here the keys of a selection
+// live in REGISTERS as 32-bit order-preserving images, R per thread, and only a threshold is computed:
+//
+//   kth32():   byte-wise radix select of the K-th smallest key -- shared memory only holds the 256-bin histogram; the
+//              bytes that do not vary are skipped, a bin that holds a single key ends the search early.  Returns the
+//              threshold, how many keys are strictly below it and how many equal it.
+//   taking:    key < threshold, plus the lowest-index keys equal to it (a block scan of the per-thread tie counts,
+//              only when there are more ties than needed).  Ties are COMMON in the line stage: every line of a
+//              centroid whose neighbour lies behind the query's Voronoi side scores exactly b2.
+//   ordering:  the few survivors (P columns, W lines) are ordered by counting ranks against (value, index) keys that
+//              sit in shared memory: rank = #keys smaller, O(n^2 / threads) broadcast reads, one barrier, no sorting
+//              network.
+//
+// The candidate columns of stage 2 are the entries of D not above the P-th smallest bucket minimum (at least P of them,
+// all inside the P selected buckets, typically 1.2 P), so stage 2 reads P 128-byte lines of D and orders ~80 keys.
+// Results are bit-identical to the general kernel and to select_rows + select_lines (lowest index on ties).
+#pragma once
+#include "topk.cuh"
+
+namespace vlq {
+namespace csl {
+
+constexpr int NT = 256;
+constexpr uint32_t kInf32 = 0xffffffffu;
+
+struct Kth {
+  uint32_t tau;  // K-th smallest key (kInf32: fewer than K valid keys -- take them all)
+  int n_lt;      // valid keys < tau
+  int n_eq;      // valid keys == tau
+};
+
+// Block-wide K-th smallest of the valid (!= kInf32) keys held R per thread.  hist: 256 ints, meta: 8 ints (shared).
+// K >= 1.  Every thread returns the same result.
+template <int R>
+__device__ __forceinline__ Kth kth32(const uint32_t (&key)[R], int K, int* hist, int* meta) {
+  const int lane = threadIdx.x & 31;
+  uint32_t o = 0, a = kInf32;
+  int nv = 0;
+#pragma unroll
+  for (int r = 0; r < R; r++) {
+    if (key[r] != kInf32) {
+      o |= key[r];
+      a &= key[r];
+      nv++;
+    }
+  }
+  o = __reduce_or_sync(kFull, o);
+  a = __reduce_and_sync(kFull, a);
+  nv = __reduce_add_sync(kFull, nv);
+  if (threadIdx.x == 0) {
+    meta[0] = 0;
+    meta[1] = (int)kInf32;
+    meta[2] = 0;
+  }
+  __syncthreads();
+  if (lane == 0) {
+    atomicOr(reinterpret_cast<unsigned*>(&meta[0]), o);
+    atomicAnd(reinterpret_cast<unsigned*>(&meta[1]), a);
+    atomicAdd(&meta[2], nv);
+  }
+  __syncthreads();
+  const uint32_t bor = (uint32_t)meta[0], band = (uint32_t)meta[1];
+  const int total = meta[2];
+  Kth out;
+  if (total < K || total == 0) {  // block-uniform
+    out.tau = kInf32;
+    out.n_lt = total;
+    out.n_eq = 0;
+    __syncthreads();
+    return out;
+  }
+  const uint32_t diff = bor ^ band;
+  const int top = diff ? (31 - __clz((int)diff)) >> 3 : 0;  // most significant byte that varies
+  uint32_t prefix = top == 3 ? 0u : (bor >> ((top + 1) * 8));
+  int need = K, in_bin = total;
+  bool found = false;
+#pragma unroll 1
+  for (int pass = top; pass >= 0; pass--) {
+    hist[threadIdx.x] = 0;  // NT == 256 bins
+    __syncthreads();
+    const int shift = pass * 8;
+#pragma unroll
+    for (int r = 0; r < R; r++) {
+      const uint32_t k_ = key[r];
+      const bool match = k_ != kInf32 && (pass == 3 || (k_ >> (shift + 8)) == prefix);
+      if (match) atomicAdd(&hist[(k_ >> shift) & 255], 1);
+    }
+    __syncthreads();
+    if (threadIdx.x < 32) {  // lane l owns bins [8l, 8l + 8)
+      int c[8], s = 0;
+#pragma unroll
+      for (int j = 0; j < 8; j++) {
+        c[j] = hist[lane * 8 + j];
+        s += c[j];
+      }
+      int inc = s;
+#pragma unroll
+      for (int d = 1; d < 32; d <<= 1) {
+        const int t = __shfl_up_sync(kFull, inc, d);
+        if (lane >= d) inc += t;
+      }
+      int before = inc - s;
+      if (before < need && need <= inc) {  // exactly one lane
+#pragma unroll
+        for (int j = 0; j < 8; j++) {
+          if (need <= before + c[j]) {
+            meta[4] = lane * 8 + j;
+            meta[5] = need - before;
+            meta[6] = c[j];
+            break;
+          }
+          before += c[j];
+        }
+      }
+    }
+    __syncthreads();
+    prefix = (prefix << 8) | (uint32_t)meta[4];
+    need = meta[5];
+    in_bin = meta[6];
+    if (in_bin == 1 && pass > 0) {  // the wanted key is alone under this prefix: look it up
+#pragma unroll
+      for (int r = 0; r < R; r++)
+        if (key[r] != kInf32 && (key[r] >> shift) == prefix) meta[7] = (int)key[r];
+      __syncthreads();
+      prefix = (uint32_t)meta[7];
+      found = true;
+      break;
+    }
+  }
+  (void)found;
+  out.tau = prefix;
+  out.n_eq = in_bin;
+  out.n_lt = K - need;
+  __syncthreads();  // hist / meta may be reused by the caller
+  return out;
+}
+
+// Which of the thread's keys belong to the K smallest: key < tau, plus the lowest-index ties (thread t holds the
+// indices [R t, R t + R), so index order = thread order).  wsum: 8 ints (shared).
+template <int R>
+__device__ __forceinline__ void take_k(const uint32_t (&key)[R], const Kth& kt, int K, int* wsum, bool (&take)[R]) {
+  const int need_eq = K - kt.n_lt;  // ties to take (<= n_eq)
+  if (kt.tau == kInf32) {
+#pragma unroll
+    for (int r = 0; r < R; r++) take[r] = key[r] != kInf32;
+    return;
+  }
+  if (need_eq >= kt.n_eq) {  // block-uniform: all ties are wanted
+#pragma unroll
+    for (int r = 0; r < R; r++) take[r] = key[r] <= kt.tau;
+    return;
+  }
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  int mine = 0;
+#pragma unroll
+  for (int r = 0; r < R; r++) mine += key[r] == kt.tau;
+  int inc = mine;
+#pragma unroll
+  for (int d = 1; d < 32; d <<= 1) {
+    const int t = __shfl_up_sync(kFull, inc, d);
+    if (lane >= d) inc += t;
+  }
+  if (lane == 31) wsum[warp] = inc;
+  __syncthreads();
+  int rank = inc - mine;
+  for (int w = 0; w < warp; w++) rank += wsum[w];
+#pragma unroll
+  for (int r = 0; r < R; r++) {
+    const bool eq = key[r] == kt.tau;
+    take[r] = key[r] < kt.tau || (eq && rank < need_eq);
+    rank += eq;
+  }
+  __syncthreads();
+}
+
+__device__ __forceinline__ uint32_t key32(float v) { return v == v ? f2ord(v) : kInf32; }  // NaN: never selected
+
+struct Smem {  // layout in dynamic shared memory (host and device agree through bytes())
+  __host__ __device__ static size_t bytes(int R, int P) {
+    return sizeof(uint64_t) * R * NT                 // keys: candidate columns / surviving lines
+           + sizeof(float) * 2 * 1024                // t1, t6 of the surviving lines
+           + sizeof(int) * 1024                      // list ids of the surviving lines
+           + sizeof(int) * (2 * P + 2 * 256 + 64);   // bucket list, top-P, hist, meta / wsum / counters (+ slack)
+  }
+};
+
+template <int R>
+__global__ void __launch_bounds__(NT, R == 8 ? 4 : 2)
+coarse_select_lines_fast_kernel(const float* __restrict__ D, int64_t ldD, const float* __restrict__ bmin, int nb, int C,
+                                int P, const int* __restrict__ edge, const float* __restrict__ edge_d2, int E, int W,
+                                int* __restrict__ out_coarse, int* __restrict__ out_list,
+                                float* __restrict__ out_term1, float* __restrict__ out_term6) {
+  extern __shared__ __align__(16) unsigned char smem[];
+  uint64_t* keys = reinterpret_cast<uint64_t*>(smem);             // [R * NT]
+  float* st1 = reinterpret_cast<float*>(keys + (size_t)R * NT);    // [1024]
+  float* st6 = st1 + 1024;                                         // [1024]
+  int* slist = reinterpret_cast<int*>(st6 + 1024);                 // [1024]
+  int* bk_s = slist + 1024;                                        // [P] selected buckets
+  int* top_s = bk_s + P;                                           // [P] top-P centroids, ascending
+  int* hist = top_s + P;                                           // [256]
+  int* meta = hist + 256;                                          // [8]
+  int* wsum = meta + 8;                                            // [8]
+  int* cnt = wsum + 8;                                             // [4] append cursors
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int64_t q = blockIdx.x;
+  const float* Dq = D + q * ldD;
+  const float* bq = bmin + q * nb;
+
+  // ---- 1: the P buckets (32 consecutive centroids each) with the smallest minima contain every top-P centroid
+  const int Pb = P < nb ? P : nb;
+  uint32_t kb[R];
+  {
+    const int j0 = R * (int)threadIdx.x;
+#pragma unroll
+    for (int r4 = 0; r4 < R; r4 += 4) {
+      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+      const bool in = j0 + r4 + 3 < nb;
+      if (in) v = *reinterpret_cast<const float4*>(bq + j0 + r4);
+      const float vv[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+      for (int r = 0; r < 4; r++) {
+        float x = vv[r];
+        if (!in) x = j0 + r4 + r < nb ? bq[j0 + r4 + r] : __int_as_float(0x7fc00000);
+        kb[r4 + r] = key32(x);
+      }
+    }
+  }
+  if (threadIdx.x < 4) cnt[threadIdx.x] = 0;
+  const Kth kt1 = kth32<R>(kb, Pb, hist, meta);
+  {
+    bool take[R];
+    take_k<R>(kb, kt1, Pb, wsum, take);
+#pragma unroll
+    for (int r = 0; r < R; r++)
+      if (take[r]) bk_s[atomicAdd(&cnt[0], 1)] = R * (int)threadIdx.x + r;  // <= Pb appends
+  }
+  __syncthreads();
+  const int nbk = cnt[0];
+  // ---- 2: candidate columns = entries of the selected buckets not above the P-th bucket minimum (>= P of them)
+  // (the bound needs P distinct buckets: with fewer buckets than P every entry of every bucket is a candidate)
+  const float tau1 = (kt1.tau == kInf32 || Pb < P) ? __int_as_float(0x7f800000) : ord2f(kt1.tau);
+  for (int b = warp; b < nbk; b += NT / 32) {
+    const int c = bk_s[b] * 32 + lane;
+    float v = __int_as_float(0x7fc00000);
+    if (c < C) v = Dq[c];
+    const bool pass = v <= tau1;  // NaN never passes
+    const unsigned m = __ballot_sync(kFull, pass);
+    int base = 0;
+    if (lane == 0 && m) base = atomicAdd(&cnt[1], __popc(m));
+    base = __shfl_sync(kFull, base, 0);
+    if (pass) keys[base + __popc(m & ((1u << lane) - 1))] = make_key(v, (uint32_t)c);
+  }
+  __syncthreads();
+  const int nc = cnt[1];  // <= nbk * 32 <= R * NT
+  const int Pk = P < C ? P : C;
+  // ---- exact top-P: rank of every candidate among the candidates
+  for (int i = threadIdx.x; i < P; i += NT) top_s[i] = -1;
+  __syncthreads();
+  for (int i = threadIdx.x; i < nc; i += NT) {
+    const uint64_t mykey = keys[i];
+    int rank = 0;
+    for (int j = 0; j < nc; j++) rank += keys[j] < mykey;
+    if (rank < Pk) top_s[rank] = (int)key_payload(mykey);
+  }
+  __syncthreads();
+  if (out_coarse)
+    for (int i = threadIdx.x; i < P; i += NT) out_coarse[q * P + i] = top_s[i];
+
+  // ---- 3: the W best of the P*E lines (BroadcastSum.cu:505-552); thread t scores the lines [R t, R t + R)
+  const int num = P * E;
+  uint32_t kl[R];
+  float a2r[R], b2r[R];
+  int lid[R];
+  int nvalid = 0;
+#pragma unroll
+  for (int r = 0; r < R; r++) {
+    const int i = R * (int)threadIdx.x + r;
+    kl[r] = kInf32;
+    a2r[r] = b2r[r] = 0.f;
+    lid[r] = -1;
+    if (i < num) {
+      const int c = top_s[i / E];
+      if (c >= 0) {
+        const int e = i % E;
+        const int s = edge[(int64_t)c * E + e];
+        const float a2 = Dq[s], b2 = Dq[c], c2 = edge_d2[(int64_t)c * E + e];
+        float v = __fsub_rn(a2, b2);
+        v = __fsub_rn(v, c2);
+        // BroadcastSum.cu:517: (v>0) ? b2 : b2 - 0.25 v^2 / c2
+        const float score = (v > 0.f) ? b2 : __fsub_rn(b2, __fdiv_rn(__fmul_rn(__fmul_rn(0.25f, v), v), c2));
+        kl[r] = key32(score);
+        a2r[r] = a2;
+        b2r[r] = b2;
+        lid[r] = c * E + e;
+        nvalid += kl[r] != kInf32;
+      }
+    }
+  }
+  const Kth kt3 = kth32<R>(kl, W, hist, meta);
+  {
+    bool take[R];
+    take_k<R>(kl, kt3, W, wsum, take);
+#pragma unroll
+    for (int r = 0; r < R; r++) {
+      if (take[r]) {
+        const int slot = atomicAdd(&cnt[2], 1);  // <= W appends
+        keys[slot] = ((uint64_t)kl[r] << 32) | (uint32_t)(R * (int)threadIdx.x + r);
+        st1[slot] = b2r[r];
+        st6[slot] = __fsub_rn(a2r[r], b2r[r]);
+        slist[slot] = lid[r];
+      }
+    }
+  }
+  (void)nvalid;
+  for (int w = threadIdx.x; w < W; w += NT) {  // slots the ranks below do not reach
+    out_list[q * W + w] = -1;
+    out_term1[q * W + w] = 0.f;
+    out_term6[q * W + w] = 0.f;
+  }
+  __syncthreads();
+  const int ns = cnt[2];
+  for (int i = threadIdx.x; i < ns; i += NT) {
+    const uint64_t mykey = keys[i];
+    int rank = 0;
+    for (int j = 0; j < ns; j++) rank += keys[j] < mykey;
+    out_list[q * W + rank] = slist[i];
+    out_term1[q * W + rank] = st1[i];
+    out_term6[q * W + rank] = st6[i];
+  }
+}
+
+}  // namespace csl
+}  // namespace vlq

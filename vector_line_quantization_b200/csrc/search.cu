@@ -20,6 +20,7 @@
 
 #include "scan.cuh"
 #include "topk.cuh"
+#include "coarse_select.cuh"
 
 #include <type_traits>
 
@@ -1057,6 +1058,23 @@ int vlq_coarse_select_lines(const float* D, int64_t nq, int64_t ldD, const float
   if (total < nb) total = nb;
   const int cap = select_capacity(kmax, Q_THREADS, Q_BATCH, total);
   const size_t smem = ((select_smem_bytes(cap) + 15) & ~size_t(15)) + 2 * VLQ_MAX_K * sizeof(int);
+  // fast path (coarse_select.cuh): the keys of each selection fit R per thread in registers
+  static const bool generic_only = getenv("VLQ_COARSE_GENERIC") != nullptr;  // tests: force the general kernel
+  const int need = nb > P * E ? (nb > P * 32 ? nb : P * 32) : (P * E > P * 32 ? P * E : P * 32);
+  if (!generic_only && need <= 16 * csl::NT && W <= 1024 && nb % 4 == 0 && (reinterpret_cast<uintptr_t>(bucket_min) & 15) == 0) {
+    const int R = need <= 8 * csl::NT ? 8 : 16;
+    const size_t fsmem = csl::Smem::bytes(R, P);
+    if (R == 8) {
+      VLQ_CUDA_TRY(cudaFuncSetAttribute(csl::coarse_select_lines_fast_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fsmem));
+      VLQ_LAUNCH(csl::coarse_select_lines_fast_kernel<8>, (unsigned)nq, csl::NT, fsmem, as_stream(stream), D, ldD, bucket_min,
+                 nb, C, P, edge, edge_d2, E, W, out_coarse, out_list, out_term1, out_term6);
+    } else {
+      VLQ_CUDA_TRY(cudaFuncSetAttribute(csl::coarse_select_lines_fast_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fsmem));
+      VLQ_LAUNCH(csl::coarse_select_lines_fast_kernel<16>, (unsigned)nq, csl::NT, fsmem, as_stream(stream), D, ldD, bucket_min,
+                 nb, C, P, edge, edge_d2, E, W, out_coarse, out_list, out_term1, out_term6);
+    }
+    return last_error();
+  }
   VLQ_CUDA_TRY(cudaFuncSetAttribute(coarse_select_lines_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   VLQ_LAUNCH(coarse_select_lines_kernel, (unsigned)nq, Q_THREADS, smem, as_stream(stream), D, ldD, bucket_min, nb, C, P,
              edge, edge_d2, E, W, cap, out_coarse, out_list, out_term1, out_term6);

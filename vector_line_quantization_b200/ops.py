@@ -168,16 +168,20 @@ def rotate_codes(offsets, codes, inverse=False):
     return torch.gather(codes, 1, idx).contiguous()
 
 
-def select_lines(D, coarse_ids, edge, edge_d2, W):
+def select_lines(D, coarse_ids, edge, edge_d2, W, out=None):
     """query-time line selection (a12): -> (list int32 [nq][W], term1, term6 f32 [nq][W])"""
     D = _chk(D, torch.float32, "D")
     coarse_ids = _chk(coarse_ids, torch.int32, "coarse_ids")
     nq, P = coarse_ids.shape
     E = edge.shape[1]
     dev = D.device
-    lst = torch.empty((nq, W), dtype=torch.int32, device=dev)
-    t1 = torch.empty((nq, W), dtype=torch.float32, device=dev)
-    t6 = torch.empty((nq, W), dtype=torch.float32, device=dev)
+    if out is not None:
+        lst, t1, t6 = out
+        assert lst.shape == (nq, W) and lst.is_contiguous() and t1.is_contiguous() and t6.is_contiguous()
+    else:
+        lst = torch.empty((nq, W), dtype=torch.int32, device=dev)
+        t1 = torch.empty((nq, W), dtype=torch.float32, device=dev)
+        t6 = torch.empty((nq, W), dtype=torch.float32, device=dev)
     _abi.call("vlq_select_lines", _ptr(D), nq, D.stride(0), _ptr(coarse_ids), P, _ptr(edge), _ptr(edge_d2), E, W,
               _ptr(lst), _ptr(t1), _ptr(t6), _stream())
     return lst, t1, t6
@@ -247,6 +251,46 @@ def km_update(x, assign, k):
     ws = torch.empty(wsb, dtype=torch.uint8, device=x.device)
     _abi.call("vlq_km_update", _ptr(x), n, d, _ptr(assign), k, _ptr(cent), _ptr(counts), _ptr(ws), wsb, _stream())
     return cent, counts
+
+
+def coarse_lines(q, cent, cnorm, edge, edge_d2, P, W, tile=4096, pack=None, out=None):
+    """First half of the query path (a11 + a12) for a batch of queries: -> (list int32, term1, term6 f32), each [nq][W].
+    This half does not touch the inverted lists, so shards can split the QUERIES for it (sharding.QuerySplitSearch)."""
+    nq = q.shape[0]
+    C = cent.shape[0]
+    P = min(P, C)
+    if out is None:
+        out = (torch.empty((nq, W), dtype=torch.int32, device=q.device), torch.empty((nq, W), dtype=torch.float32, device=q.device),
+               torch.empty((nq, W), dtype=torch.float32, device=q.device))
+    if nq == 0:
+        return out
+    Dbuf = torch.empty((min(tile, nq), C), dtype=torch.float32, device=q.device)
+    bbuf = torch.empty((min(tile, nq), num_buckets(C)), dtype=torch.float32, device=q.device) if pack is not None else None
+    for s in range(0, nq, tile):
+        e = min(nq, s + tile)
+        qt = q[s:e]
+        o = tuple(t[s:e] for t in out)
+        if pack is not None:
+            D = l2_distances_tc(qt, pack, out=Dbuf[: e - s], bucket_min=bbuf[: e - s])
+            coarse_select_lines(D, bbuf[: e - s], C, P, edge, edge_d2, W, out=o)
+        else:
+            D = l2_distances(qt, cent, cnorm, out=Dbuf[: e - s])
+            _, cid = select_rows(D, P)
+            select_lines(D, cid, edge, edge_d2, W, out=o)
+    return out
+
+
+def scan_lines(q, pq, lambda_cb, lines, edge_d2, lists, k, cap=1024, tile=4096, out=None):
+    """Second half of the query path (a13-a15): scan the selected lines of every query on THIS shard's lists"""
+    nq = q.shape[0]
+    lst, t1, t6 = lines
+    if out is None:
+        out = (torch.empty((nq, k), dtype=torch.float32, device=q.device), torch.empty((nq, k), dtype=torch.int64, device=q.device))
+    ed2_flat = edge_d2.reshape(-1)
+    for s in range(0, nq, tile):
+        e = min(nq, s + tile)
+        scan_topk(q[s:e], pq, lambda_cb, lst[s:e], t1[s:e], t6[s:e], ed2_flat, lists, k, cap, out=(out[0][s:e], out[1][s:e]))
+    return out
 
 
 def search(q, cent, cnorm, edge, edge_d2, lambda_cb, pq, lists, P, W, k, cap=1024, tile=4096, pack=None, out=None):
@@ -335,14 +379,18 @@ def num_buckets(C):
     return int(_abi.lib().vlq_tc_num_buckets(C))
 
 
-def coarse_select_lines(D, bucket_min, C, P, edge, edge_d2, W, want_coarse=False):
-    """fused top-P (through the bucket minima) + line selection (a11 + a12)"""
+def coarse_select_lines(D, bucket_min, C, P, edge, edge_d2, W, want_coarse=False, out=None):
+    """fused top-P (through the bucket minima) + line selection (a11 + a12); out = (list, term1, term6) destinations"""
     nq = D.shape[0]
     E = edge.shape[1]
     dev = D.device
-    lst = torch.empty((nq, W), dtype=torch.int32, device=dev)
-    t1 = torch.empty((nq, W), dtype=torch.float32, device=dev)
-    t6 = torch.empty((nq, W), dtype=torch.float32, device=dev)
+    if out is not None:
+        lst, t1, t6 = out
+        assert lst.shape == (nq, W) and lst.is_contiguous() and t1.is_contiguous() and t6.is_contiguous()
+    else:
+        lst = torch.empty((nq, W), dtype=torch.int32, device=dev)
+        t1 = torch.empty((nq, W), dtype=torch.float32, device=dev)
+        t6 = torch.empty((nq, W), dtype=torch.float32, device=dev)
     cid = torch.empty((nq, P), dtype=torch.int32, device=dev) if want_coarse else None
     _abi.call("vlq_coarse_select_lines", _ptr(D), nq, D.stride(0), _ptr(bucket_min), bucket_min.shape[1], C, P,
               _ptr(edge), _ptr(edge_d2), E, W, _ptr(cid), _ptr(lst), _ptr(t1), _ptr(t6), _stream())

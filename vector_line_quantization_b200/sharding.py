@@ -67,6 +67,86 @@ class PeerExchange:
                                     device=self.buf.device)
 
 
+class QuerySplitSearch:
+    """Strong-scaling form of the sharded search (database split R ways, fixed query batch):
+
+      1. the coarse stage (distances to the C centroids, top-P, line selection) does not touch the inverted lists, so
+         rank r runs it for ITS 1/R of the queries only and writes (list, term1, term6) -- 12 W bytes per query -- into
+         its peer-mapped symmetric buffer;
+      2. one device barrier; every rank pulls the other ranks' line slices over NVLink (R - 1 peer copies of
+         nq/R x 12 W bytes) and scans ALL queries on its shard of the lists;
+      3. one device barrier; rank r merges the R per-shard top-k lists of ITS query slice straight from the peers'
+         buffers (vlq_merge_topk_peers with row offsets) -- the final (nq, k) result is distributed by query slice.
+
+    Replicated work per rank is only the term-3 tables (16 KB per query).  Buffers are double-buffered per step like
+    PeerExchange.  Results equal the single-index search exactly up to ties (the merge is exact)."""
+
+    def __init__(self, nq, k, W, device, group=None):
+        import torch.distributed._symmetric_memory as symm
+
+        self.world, self.rank = dist.get_world_size(), dist.get_rank()
+        self.nq, self.k, self.W = nq, k, W
+        self.q0 = [r * nq // self.world for r in range(self.world + 1)]  # query slice of rank r: [q0[r], q0[r+1])
+        a256 = lambda v: (v + 255) // 256 * 256
+        self.off_l = 0
+        self.off_t1 = a256(self.off_l + nq * W * 4)
+        self.off_t6 = a256(self.off_t1 + nq * W * 4)
+        self.off_d = a256(self.off_t6 + nq * W * 4)
+        self.off_i = a256(self.off_d + nq * k * 4)
+        self.slot = a256(self.off_i + nq * k * 8)
+        self.buf = symm.empty(2 * self.slot, dtype=torch.uint8, device=device)
+        self.hdl = symm.rendezvous(self.buf, group if group is not None else dist.group.WORLD)
+        self.ptrs_dev = self.hdl.buffer_ptrs_dev
+        self.step = 0
+        self.device = device
+        self._peer = {}
+
+    def _views(self, base_tensor, b):
+        nq, k, W = self.nq, self.k, self.W
+        v = lambda off, n, dt, shape: base_tensor[b + off:b + off + n].view(dt).view(shape)
+        return (v(self.off_l, nq * W * 4, torch.int32, (nq, W)), v(self.off_t1, nq * W * 4, torch.float32, (nq, W)),
+                v(self.off_t6, nq * W * 4, torch.float32, (nq, W)), v(self.off_d, nq * k * 4, torch.float32, (nq, k)),
+                v(self.off_i, nq * k * 8, torch.int64, (nq, k)))
+
+    def _peer_buf(self, r):
+        if r not in self._peer:
+            self._peer[r] = self.hdl.get_buffer(r, (2 * self.slot,), torch.uint8)
+        return self._peer[r]
+
+    def my_slice(self):
+        return self.q0[self.rank], self.q0[self.rank + 1]
+
+    def search(self, q, coarse_fn, scan_fn, out=None):
+        """coarse_fn(q_slice, out=(lst, t1, t6)); scan_fn(q, (lst, t1, t6), out=(D, I)) on this rank's shard.
+        Returns (D, I) of THIS rank's query slice [q0[rank], q0[rank + 1])."""
+        from . import ops
+
+        b = (self.step & 1) * self.slot
+        self.step += 1
+        lst, t1, t6, D, I = self._views(self.buf, b)
+        s, e = self.my_slice()
+        coarse_fn(q[s:e], out=(lst[s:e], t1[s:e], t6[s:e]))
+        self.hdl.barrier(channel=0)  # every rank's line slice is written
+        for r in range(self.world):
+            if r == self.rank:
+                continue
+            pl, p1, p6, _, _ = self._views(self._peer_buf(r), b)
+            rs, re = self.q0[r], self.q0[r + 1]
+            lst[rs:re].copy_(pl[rs:re], non_blocking=True)
+            t1[rs:re].copy_(p1[rs:re], non_blocking=True)
+            t6[rs:re].copy_(p6[rs:re], non_blocking=True)
+        scan_fn(q, (lst, t1, t6), out=(D, I))
+        self.hdl.barrier(channel=0)  # every shard's results are written
+        n = e - s
+        if out is None:
+            out = (torch.empty((n, self.k), dtype=torch.float32, device=self.device),
+                   torch.empty((n, self.k), dtype=torch.int64, device=self.device))
+        if n > 0:
+            ops.merge_topk_peers(self.ptrs_dev, b + self.off_d + s * self.k * 4, b + self.off_i + s * self.k * 8, self.world,
+                                 n, self.k, out=out, device=self.device)
+        return out
+
+
 def sharded_search(local_search, merge, q, k, out_D=None, out_I=None):
     """local_search(q, k) -> (D, I) on this rank's shard (global ids); merge([R][nq][k] x2) -> (nq,k) x2"""
     D, I = local_search(q, k)
