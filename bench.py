@@ -316,9 +316,7 @@ def _run_reference(a):
               "density as the %d-vector database): %d vectors encoded on the CPU, tiled %d x with fresh ids; centroids = "
               "random training rows (no CPU k-means at C = %d); stock pieces by the reference CPU library = %s"
               % (ns, a.nq, nb, C * E, a.n, enc, reps, C, have_ref))
-    cfg = workload_config(a, 1)
-    cfg["db_vectors_searched"] = nb
-    cfg["db_vectors_encoded_on_cpu"] = enc
+    cfg = workload_config(a, a.gpus)  # the same object as our arm prints
     line = {
         "impl": "reference", "metric": "vlq_search_qps", "value": qps, "unit": "queries/s", "n_gpus": a.gpus,
         "steps": a.steps, "warmup": a.warmup, "ms_per_step": 1e3 * tot / a.steps, "higher_is_better": True,
@@ -328,7 +326,7 @@ def _run_reference(a):
         "e2e": {"value": qps, "unit": "queries/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "encode": {"value": enc / t_enc / 1e6, "unit": "Mvec/s", "kind": "reference" if have_ref else "port",
                    "sample": "%d vectors: IndexFlatL2 assign + oracle line stage + ProductQuantizer::compute_codes" % enc},
-        "setup_s": t_setup,
+        "setup_s": t_setup, "db_vectors_searched": nb, "db_vectors_encoded_on_cpu": enc,
     }
     return line
 
@@ -866,9 +864,10 @@ def run_b200(a):
             "n_gpus": world, "steps": a.steps, "warmup": a.warmup, "ms_per_step": total_ms / a.steps,
             "higher_is_better": True, "scaling": "strong" if strong else "weak", "vs_baseline": None,
             "dtype": "f32 (coarse GEMM: split-fp16 x3 tcgen05, fp32 accumulate)" if use_tc else "f32", "data": "synthetic",
-            "config": dict(workload_config(a, world), exchange=exchange,
-                           value_api="GpuIndexIVFPQ::search (C++ host layer), device pointers" if world == 1 else
-                           "sharding.QuerySplitSearch over the C-ABI stage entry points"),
+            "config": workload_config(a, world),
+            "plumbing": {"exchange": exchange,
+                         "value_api": "GpuIndexIVFPQ::search (C++ host layer), device pointers" if world == 1 else
+                         "sharding.QuerySplitSearch over the C-ABI stage entry points"},
             "e2e": {"value": e2e_qps, "unit": "queries/s",
                     "h2d_bytes_per_step": nq * d * 4 * world, "d2h_bytes_per_step": nq * k * 12},
             "gpu_launches": launches, "roofline": roof, "cpu_baseline": cpu_baseline, "clocks": clk, "recall": recall,

@@ -170,6 +170,12 @@ int vlq_coarse_select_lines(const float* D, int64_t nq, int64_t ldD, const float
                             const int* edge, const float* edge_d2, int E, int W, int* out_coarse, int* out_list,
                             float* out_term1, float* out_term6, vlq_stream_t stream);
 
+/* candidate lists (f4): ids of the entries of the W selected lines of every query in line order, first k of them, -1
+   padded -- the recall-of-the-candidate-list tool GpuIndexIVFPQ::search1 / IVFPQ::queryGraph1
+   (gpu/GpuIndexIVFPQ.cu:1646-1670, gpu/impl/IVFPQ.cu:778-870: a host loop over listOffsetToUserIndex_ there) */
+int vlq_gather_candidates(const int* line_list, int64_t nq, int W, const int64_t* offsets, const int64_t* ids, int64_t k,
+                          int64_t* out, vlq_stream_t stream);
+
 /* ------------------------------------------------------------------------------------------------------------------
  * a13-a15 ADC scan of the selected lists fused with exact top-k.
  *     replaces the term3 build (gpu/impl/IVFPQ.cu:1398-1432), pqScanPrecomputedMultiPassGraph
@@ -220,6 +226,9 @@ int vlq_gather_rows(const float* src, int d, const int64_t* rows, int64_t n, flo
 int vlq_u8_to_f32(const uint8_t* src, int64_t count, float* dst, vlq_stream_t stream);
 int vlq_iota_i64(int64_t* dst, int64_t n, int64_t start, vlq_stream_t stream);
 int vlq_i32_to_i64(const int* src, int64_t n, int64_t* dst, vlq_stream_t stream);
+/* ids[i] += shift for ids[i] >= 0: shard-local -> global labels after a shard search (replaces the host loop of
+   IndexShards::search, MetaIndexes.cpp:536-546) */
+int vlq_shift_ids(int64_t* ids, int64_t n, int64_t shift, vlq_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------------------------------
  * Memory / stream helpers (these DO allocate / synchronise; they exist so host layers need no CUDA toolkit).
@@ -237,6 +246,10 @@ int vlq_memcpy_d2h(void* dst, const void* src, size_t bytes, vlq_stream_t stream
 int vlq_memcpy_d2d(void* dst, const void* src, size_t bytes, vlq_stream_t stream);
 int vlq_memset(void* dst, int value, size_t bytes, vlq_stream_t stream);
 int vlq_pointer_is_device(const void* ptr); /* 1 device, 0 host, <0 error */
+/* let the CURRENT device read `peer_device`'s memory over NVLink (no-op for the same device or when already enabled);
+   the in-process shard merge reads the shards' result buffers straight from their GPUs (gpu/test/sift1b16_query.cpp:389-430
+   staged them through MPI and host memory) */
+int vlq_enable_peer_access(int peer_device);
 int vlq_stream_create(vlq_stream_t* stream);
 int vlq_stream_destroy(vlq_stream_t stream);
 int vlq_stream_synchronize(vlq_stream_t stream);

@@ -83,6 +83,22 @@ int vlq_host_proxy_add_index(void* proxy, void* index);
 int vlq_host_shards_new(int d, int threaded, int successive_ids, void** out);
 int vlq_host_shards_add_shard(void* shards, void* index);
 
+/* ---- f4: exchange with a CPU faiss::IndexIVFPQ (container: centroids, PQ codebook, per-list ids + codes), candidate
+   lists and the ground-truth builder (reference gpu/GpuIndexIVFPQ.cu:169-281, 1312-1398, 1646-1670) */
+int vlq_host_cpu_ivfpq_new(int d, long nlist, int M, int nbits, void** out);
+int vlq_host_cpu_ivfpq_free(void* cpu_index);
+int vlq_host_cpu_ivfpq_set_codebooks(void* cpu_index, const float* coarse, const float* pq);
+int vlq_host_cpu_ivfpq_get_codebooks(void* cpu_index, float* coarse, float* pq);
+int vlq_host_cpu_ivfpq_set_list(void* cpu_index, long list, long n, const long* ids, const unsigned char* codes);
+long vlq_host_cpu_ivfpq_list_size(void* cpu_index, long list);
+long vlq_host_cpu_ivfpq_ntotal(void* cpu_index);
+int vlq_host_cpu_ivfpq_get_list(void* cpu_index, long list, long* ids, unsigned char* codes);
+int vlq_host_ivfpq_copy_from(void* index, void* cpu_index);
+int vlq_host_ivfpq_copy_to(void* index, void* cpu_index);
+int vlq_host_ivfpq_search1(void* index, long n, const float* x, long k, long* labels);
+int vlq_host_ivfpq_add_with_ids2(void* index, long n, long nq, unsigned kgt, const float* x, const float* xq, const long* ids,
+                                 long* nns, float* dists);
+
 #ifdef __cplusplus
 }
 #endif

@@ -287,6 +287,34 @@ def test_shards_and_proxy(vi, res, small_model):
     assert np.array_equal(D2, D0) and np.array_equal(I2, I0)
 
 
+def test_shards_on_two_gpus_merge_over_peer_memory(vi, small_model):
+    """IndexShards with one GpuIndexIVFPQ per GPU: the merge kernel on GPU 0 reads the other shard's results straight from
+    its memory (vlq_enable_peer_access + vlq_merge_topk_peers); equals the single index, host and device buffers"""
+    import torch
+
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    m = small_model
+    r0, r1 = vi.StandardGpuResources(0), vi.StandardGpuResources(1)
+    whole = _build(vi, r0, m, m["xb"])
+    subs = [_build(vi, r0, m, m["xb"][:9000]), _build(vi, r1, m, m["xb"][9000:])]
+    shards = vi.IndexShards(128, threaded=True, successive_ids=True)
+    for s in [whole] + subs:
+        s.setNumProbes(16)
+        s.w1_ = 128
+        s.setListCap(1 << 20)
+    for s in subs:
+        shards.add_shard(s)
+    D0, I0 = whole.search(m["xq"], 10)
+    D1, I1 = shards.search(m["xq"], 10)
+    assert np.array_equal(D1, D0) and (I1 == I0).mean() > 0.999
+    xq_dev = torch.from_numpy(m["xq"]).to("cuda:0")
+    oD = torch.empty((len(m["xq"]), 10), dtype=torch.float32, device="cuda:0")
+    oI = torch.empty((len(m["xq"]), 10), dtype=torch.int64, device="cuda:0")
+    shards.search(xq_dev, 10, out=(oD, oI))
+    assert np.array_equal(oD.cpu().numpy(), D1) and np.array_equal(oI.cpu().numpy(), I1)
+
+
 def test_add_with_ids_and_reset(vi, res, small_model):
     m = small_model
     idx = vi.GpuIndexIVFPQ(res, 128, m["C"], m["M"], 8, m["E"], 256)
@@ -319,3 +347,33 @@ def test_add_u8_equals_add_f32(vi, res, small_model):
     Da, Ia = a.search(m["xq"], 10)
     Db, Ib = b.search(m["xq"], 10)
     assert np.array_equal(Ia, Ib) and np.array_equal(Da, Db)
+
+
+def test_search1_candidate_lists_and_ground_truth_builder(vi, res, small_model):
+    """f4: search1 returns the ids of the entries of the selected lines in line order (gpu/GpuIndexIVFPQ.cu:1646-1670);
+    add_with_ids2 is the brute-force ground-truth builder (:1354-1398)"""
+    m = small_model
+    idx = _build(vi, res, m, m["xb"])
+    idx.setNumProbes(8)
+    idx.w1_ = 32
+    idx.setListCap(1 << 20)
+    xq = m["xq"][:40]
+    kc = 4000  # room for every entry of 32 lines here
+    cand = idx.search1(xq, kc)
+    D, I = idx.search(xq, 10)
+    for q in range(len(xq)):
+        c = cand[q]
+        n = int((c >= 0).sum())
+        assert n > 0 and (c[:n] >= 0).all() and (c[n:] == -1).all() and len(set(c[:n].tolist())) == n
+        assert set(I[q][I[q] >= 0].tolist()) <= set(c[:n].tolist())  # the top-k comes out of the candidate list
+    short = idx.search1(xq, 7)
+    assert np.array_equal(short, cand[:, :7])
+    # ground truth of a chunk with its own labels
+    x = m["xb"][:3000]
+    ids = np.arange(3000, dtype=np.int64) * 3 + 11
+    dists, nns = idx.add_with_ids2(x, xq, 5, ids)
+    d2 = ((xq.astype(np.float64)[:, None, :] - x.astype(np.float64)[None, :, :]) ** 2).sum(2)
+    order = np.argsort(d2, axis=1, kind="stable")[:, :5]
+    ref_d = np.take_along_axis(d2, order, axis=1)
+    assert np.allclose(dists, ref_d, rtol=1e-4)
+    assert (nns == ids[order]).mean() > 0.99

@@ -41,6 +41,7 @@ SIGNATURES = {
     "vlq_recompute_kappa": (_i, [_l, _l, _p, _p, _p, _p, _i, _p, _i, _p, _p, _i, _p, _p]),
     "vlq_select_lines": (_i, [_p, _l, _l, _p, _i, _p, _p, _i, _i, _p, _p, _p, _p]),
     "vlq_coarse_select_lines": (_i, [_p, _l, _l, _p, _i, _i, _i, _p, _p, _i, _i, _p, _p, _p, _p, _p]),
+    "vlq_gather_candidates": (_i, [_p, _l, _i, _p, _p, _l, _p, _p]),
     "vlq_scan_topk_workspace_bytes": (_z, [_l, _i]),
     "vlq_scan_topk": (_i, [_p, _l, _i, _p, _i, _p, _i, _p, _p, _p, _p, _i, _p, _p, _p, _p, _p, _i, _i, _i, _p, _p, _p, _z, _p]),
     "vlq_merge_topk": (_i, [_p, _p, _i, _l, _i, _p, _p, _p]),
@@ -51,6 +52,7 @@ SIGNATURES = {
     "vlq_u8_to_f32": (_i, [_p, _l, _p, _p]),
     "vlq_iota_i64": (_i, [_p, _l, _l, _p]),
     "vlq_i32_to_i64": (_i, [_p, _l, _p, _p]),
+    "vlq_shift_ids": (_i, [_p, _l, _l, _p]),
     "vlq_device_count": (_i, [C.POINTER(_i)]),
     "vlq_set_device": (_i, [_i]),
     "vlq_get_device": (_i, [C.POINTER(_i)]),
@@ -64,6 +66,7 @@ SIGNATURES = {
     "vlq_memcpy_d2d": (_i, [_p, _p, _z, _p]),
     "vlq_memset": (_i, [_p, _i, _z, _p]),
     "vlq_pointer_is_device": (_i, [_p]),
+    "vlq_enable_peer_access": (_i, [_i]),
     "vlq_stream_create": (_i, [C.POINTER(_p)]),
     "vlq_stream_destroy": (_i, [_p]),
     "vlq_stream_synchronize": (_i, [_p]),

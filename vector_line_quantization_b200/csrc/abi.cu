@@ -63,6 +63,22 @@ int vlq_pointer_is_device(const void* ptr) {
   }
   return (attr.type == cudaMemoryTypeDevice || attr.type == cudaMemoryTypeManaged) ? 1 : 0;
 }
+int vlq_enable_peer_access(int peer_device) {
+  int cur = 0;
+  cudaError_t e = cudaGetDevice(&cur);
+  if (e != cudaSuccess) return (int)e;
+  if (cur == peer_device) return VLQ_OK;
+  int can = 0;
+  e = cudaDeviceCanAccessPeer(&can, cur, peer_device);
+  if (e != cudaSuccess) return (int)e;
+  if (!can) return VLQ_EUNSUPPORTED;
+  e = cudaDeviceEnablePeerAccess(peer_device, 0);
+  if (e == cudaErrorPeerAccessAlreadyEnabled) {
+    cudaGetLastError();
+    return VLQ_OK;
+  }
+  return (int)e;
+}
 int vlq_stream_create(vlq_stream_t* stream) {
   cudaStream_t s;
   cudaError_t e = cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking);

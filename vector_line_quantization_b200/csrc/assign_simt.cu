@@ -271,6 +271,10 @@ __global__ void u8_to_f32_kernel(const uint8_t* __restrict__ src, int64_t count,
   int64_t stride = (int64_t)gridDim.x * blockDim.x;
   for (; i < count; i += stride) dst[i] = (float)src[i];
 }
+__global__ void shift_ids_kernel(int64_t* __restrict__ ids, int64_t n, int64_t shift) {
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+    if (ids[i] >= 0) ids[i] += shift;
+}
 __global__ void iota_i64_kernel(int64_t* dst, int64_t n, int64_t start) {
   int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   int64_t stride = (int64_t)gridDim.x * blockDim.x;
@@ -339,6 +343,13 @@ int vlq_u8_to_f32(const uint8_t* src, int64_t count, float* dst, vlq_stream_t st
   if (count == 0) return VLQ_OK;
   if (!src || !dst) return VLQ_EINVAL;
   VLQ_LAUNCH(u8_to_f32_kernel, 148 * 8, 256, 0, as_stream(stream), src, count, dst);
+  return last_error();
+}
+int vlq_shift_ids(int64_t* ids, int64_t n, int64_t shift, vlq_stream_t stream) {
+  if (n < 0) return VLQ_EINVAL;
+  if (n == 0 || shift == 0) return VLQ_OK;
+  if (!ids) return VLQ_EINVAL;
+  VLQ_LAUNCH(shift_ids_kernel, 148 * 4, 256, 0, as_stream(stream), ids, n, shift);
   return last_error();
 }
 int vlq_iota_i64(int64_t* dst, int64_t n, int64_t start, vlq_stream_t stream) {

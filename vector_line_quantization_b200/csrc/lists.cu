@@ -355,6 +355,36 @@ __global__ void km_mean_kernel(const float* __restrict__ x, int d, const uint32_
   if (lane == 0) counts[c] = (int)(e - b);
 }
 
+// ------------------------------------------------------------------------------------------------ candidate lists
+// ids of the entries of the W selected lines of a query, in line order, first k of them (the reference's candidate-recall
+// tool IVFPQ::queryGraph1, gpu/impl/IVFPQ.cu:778-870, walks the lists on the host); unused slots get -1
+__global__ void __launch_bounds__(256)
+gather_candidates_kernel(const int* __restrict__ line_list, int W, const int64_t* __restrict__ offsets,
+                         const int64_t* __restrict__ ids, int64_t k, int64_t* __restrict__ out) {
+  extern __shared__ int64_t pre[];  // [W + 1] exclusive prefix of the list lengths
+  const int64_t q = blockIdx.x;
+  const int* lq = line_list + q * W;
+  if (threadIdx.x == 0) {
+    int64_t run = 0;
+    for (int w = 0; w < W; w++) {
+      pre[w] = run;
+      const int l = lq[w];
+      if (l >= 0) run += offsets[l + 1] - offsets[l];
+    }
+    pre[W] = run;
+  }
+  __syncthreads();
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  for (int w = warp; w < W; w += 8) {
+    const int l = lq[w];
+    if (l < 0 || pre[w] >= k) continue;
+    const int64_t st = offsets[l], n = min(pre[w + 1], k) - pre[w];
+    for (int64_t i = lane; i < n; i += 32) out[q * k + pre[w] + i] = ids[st + i];
+  }
+  const int64_t tot = min(pre[W], k);
+  for (int64_t i = tot + threadIdx.x; i < k; i += 256) out[q * k + i] = -1;
+}
+
 }  // namespace vlq
 
 using namespace vlq;
@@ -437,5 +467,16 @@ extern "C" int vlq_build_lists(int64_t nlists, int M, int64_t n_old, const int64
   if (n_new > 0) {
     VLQ_LAUNCH(gather_new_kernel, wide, 256, 0, st, w.perm, nlists, new_list, w.new_base, oo, out_offsets, nsrc, dst, M);
   }
+  return last_error();
+}
+
+extern "C" int vlq_gather_candidates(const int* line_list, int64_t nq, int W, const int64_t* offsets, const int64_t* ids,
+                                     int64_t k, int64_t* out, vlq_stream_t stream) {
+  using namespace vlq;
+  if (nq < 0 || W <= 0 || W > VLQ_MAX_K || k <= 0) return VLQ_EINVAL;
+  if (nq == 0) return VLQ_OK;
+  if (!line_list || !offsets || !ids || !out) return VLQ_EINVAL;
+  VLQ_LAUNCH(gather_candidates_kernel, (unsigned)nq, 256, sizeof(int64_t) * (W + 1), as_stream(stream), line_list, W, offsets,
+             ids, k, out);
   return last_error();
 }

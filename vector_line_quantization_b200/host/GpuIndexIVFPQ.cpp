@@ -584,3 +584,197 @@ void GpuIndexIVFPQ::readDbFromFile(const std::string& name, int pronum, int rank
 
 }  // namespace gpu
 }  // namespace faiss
+
+namespace faiss {
+namespace gpu {
+
+// ---------------------------------------------------------------------------------------------- f4: CPU index exchange
+void GpuIndexIVFPQ::copyFrom(const faiss::IndexIVFPQ* index) {
+  VLQ_THROW_IF_NOT_MSG(index != nullptr, "null index");
+  VLQ_THROW_IF_NOT_MSG(index->metric_type == faiss::METRIC_L2, "inner product unsupported");
+  VLQ_THROW_IF_NOT_MSG(index->d == d && (int)index->nlist == nlist_, "copyFrom: d / nlist differ from this index");
+  VLQ_THROW_IF_NOT_MSG((int)index->pq.M == subQuantizers_ && (int)index->pq.nbits == bitsPerCode_,
+                       "copyFrom: PQ geometry differs from this index");
+  VLQ_THROW_IF_NOT_MSG(index->by_residual && index->polysemous_ht == 0 && index->pq.byte_per_idx == 1,
+                       "copyFrom: only residual, non-polysemous, one-byte codes (gpu/GpuIndexIVFPQ.cu:185-188)");
+  DeviceScope scope(ivfConfig_.device);
+  nprobe_ = (int)std::max<size_t>(1, std::min<size_t>(index->nprobe, 1024));
+  reset();
+  if (!index->is_trained) {  // gpu/GpuIndexIVFPQ.cu:193-196
+    is_trained = false;
+    return;
+  }
+  const faiss::IndexFlatL2* coarse = dynamic_cast<const faiss::IndexFlatL2*>(index->quantizer);
+  VLQ_THROW_IF_NOT_MSG(coarse && coarse->ntotal == nlist_ && coarse->xb.size() == (size_t)nlist_ * d,
+                       "copyFrom: the quantizer must be an IndexFlatL2 holding the nlist centroids");
+  VLQ_THROW_IF_NOT_MSG(index->pq.centroids.size() == pqHost_.size(), "copyFrom: PQ codebook size");
+  quantizer_->reset();
+  quantizer_->add(nlist_, coarse->xb.data());
+  quantizer_->is_trained = true;
+  buildGraph_();
+  for (int j = 0; j < nLambda_; j++) lambdaInfo_[j] = 0.f;  // every entry sits ON its centroid
+  pqHost_ = index->pq.centroids;
+  uploadTables_();
+  is_trained = true;
+  const size_t L = (size_t)nlist_ * numedge_;
+  std::vector<int> counts(L, 0);
+  size_t tot = 0;
+  for (int c = 0; c < nlist_; c++) {
+    VLQ_THROW_IF_NOT_MSG(index->ids[c].size() * (size_t)subQuantizers_ == index->codes[c].size(), "copyFrom: list sizes");
+    counts[(size_t)c * numedge_] = (int)index->ids[c].size();
+    tot += index->ids[c].size();
+  }
+  std::vector<uint8_t> codes;
+  std::vector<long> ids;
+  codes.reserve(tot * subQuantizers_);
+  ids.reserve(tot);
+  for (int c = 0; c < nlist_; c++) {
+    codes.insert(codes.end(), index->codes[c].begin(), index->codes[c].end());
+    ids.insert(ids.end(), index->ids[c].begin(), index->ids[c].end());
+  }
+  std::vector<uint8_t> las(tot, 0);
+  installLists_(counts, codes, las, ids);
+}
+
+void GpuIndexIVFPQ::copyTo(faiss::IndexIVFPQ* index) const {
+  VLQ_THROW_IF_NOT_MSG(index != nullptr, "null index");
+  for (int j = 0; j < nLambda_; j++)
+    VLQ_THROW_IF_NOT_MSG(lambdaInfo_[j] == 0.f,
+                         "copyTo: entries of a VLQ index are residuals of line points, not of centroids; only an index "
+                         "whose lambda codebook is zero (copyFrom) is a stock IVFPQ");
+  DeviceScope scope(ivfConfig_.device);
+  index->d = d;
+  index->metric_type = faiss::METRIC_L2;
+  index->nlist = (size_t)nlist_;
+  index->nprobe = (size_t)nprobe_;
+  index->by_residual = true;
+  index->use_precomputed_table = 0;
+  index->code_size = (size_t)subQuantizers_;
+  index->polysemous_ht = 0;
+  index->pq = faiss::PQCodebook((size_t)d, (size_t)subQuantizers_, (size_t)bitsPerCode_);
+  index->pq.centroids = pqHost_;
+  faiss::IndexFlatL2* coarse = dynamic_cast<faiss::IndexFlatL2*>(index->quantizer);
+  VLQ_THROW_IF_NOT_MSG(coarse != nullptr, "copyTo: the target's quantizer must be an IndexFlatL2");
+  coarse->reset();
+  coarse->d = d;
+  std::vector<float> cent((size_t)nlist_ * d);
+  quantizer_->reconstruct_n(0, nlist_, cent.data());
+  coarse->add(nlist_, cent.data());
+  index->ids.assign((size_t)nlist_, std::vector<long>());
+  index->codes.assign((size_t)nlist_, std::vector<uint8_t>());
+  index->ntotal = 0;
+  index->is_trained = is_trained;
+  if (!is_trained) return;
+  for (int c = 0; c < nlist_; c++) {
+    for (int e = 0; e < numedge_; e++) {
+      const int l = c * numedge_ + e;
+      if (getListLength(l) == 0) continue;
+      const std::vector<long> li = getListIndices(l);
+      const std::vector<unsigned char> lc = getListCodes(l);
+      index->ids[c].insert(index->ids[c].end(), li.begin(), li.end());
+      index->codes[c].insert(index->codes[c].end(), lc.begin(), lc.end());
+      index->ntotal += (Index::idx_t)li.size();
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------- f4: candidate lists
+void GpuIndexIVFPQ::search1(Index::idx_t n, const float* x, Index::idx_t k, float* /*distances*/, Index::idx_t* labels) const {
+  VLQ_THROW_IF_NOT_MSG(is_trained, "Index not trained");
+  VLQ_THROW_IF_NOT_MSG(k >= 1, "k must be positive");
+  VLQ_THROW_IF_NOT_MSG(w1_ >= 1 && w1_ <= VLQ_MAX_K, "w1_ must be in [1, 1024]");
+  if (n == 0) return;
+  DeviceScope scope(ivfConfig_.device);
+  commit_();
+  vlq_stream_t st = resources_->getDefaultStream();
+  const int P = std::min(nprobe_, nlist_);
+  const int W = w1_;
+  const Index::idx_t tile = std::max<Index::idx_t>(64, std::min<Index::idx_t>(1000, ((Index::idx_t)1 << 28) / nlist_));
+  const bool tc = quantizer_->devicePack() != nullptr;
+  const int nb = vlq_tc_num_buckets(nlist_);
+  DeviceBuffer dmat((size_t)tile * nlist_ * sizeof(float));
+  DeviceBuffer work((size_t)tile * (P * (sizeof(float) + sizeof(int)) + W * (sizeof(int) + 2 * sizeof(float)) +
+                                    (tc ? nb * sizeof(float) : 0)));
+  float* cval = work.as<float>();
+  int* cidx = reinterpret_cast<int*>(cval + (size_t)tile * P);
+  int* lline = cidx + (size_t)tile * P;
+  float* t1 = reinterpret_cast<float*>(lline + (size_t)tile * W);
+  float* t6 = t1 + (size_t)tile * W;
+  float* bmin = t6 + (size_t)tile * W;
+  const bool xOnDevice = vlq_pointer_is_device(x) == 1, lOnDevice = vlq_pointer_is_device(labels) == 1;
+  DeviceBuffer xin, out;
+  if (!xOnDevice) xin.resize((size_t)tile * d * sizeof(float));
+  if (!lOnDevice) out.resize((size_t)tile * k * sizeof(int64_t));
+  for (Index::idx_t s = 0; s < n; s += tile) {  // tiles of 1000 queries as in the reference (gpu/GpuIndexIVFPQ.cu:1656)
+    const Index::idx_t m = std::min(tile, n - s);
+    const float* q = x + (size_t)s * d;
+    if (!xOnDevice) {
+      VLQ_CALL(vlq_memcpy_h2d(xin.get(), q, (size_t)m * d * sizeof(float), st));
+      q = xin.as<float>();
+    }
+    if (tc) {
+      quantizer_->distancesDevice(q, m, dmat.as<float>(), nlist_, bmin);
+      VLQ_CALL(vlq_coarse_select_lines(dmat.as<float>(), m, nlist_, bmin, nb, nlist_, P, dEdge_.as<int>(),
+                                       dEdgeDist_.as<float>(), numedge_, W, nullptr, lline, t1, t6, st));
+    } else {
+      quantizer_->distancesDevice(q, m, dmat.as<float>(), nlist_);
+      VLQ_CALL(vlq_select_rows(dmat.as<float>(), m, nlist_, nlist_, P, nullptr, cval, cidx, st));
+      VLQ_CALL(vlq_select_lines(dmat.as<float>(), m, nlist_, cidx, P, dEdge_.as<int>(), dEdgeDist_.as<float>(), numedge_,
+                                W, lline, t1, t6, st));
+    }
+    int64_t* o = lOnDevice ? reinterpret_cast<int64_t*>(labels + (size_t)s * k) : out.as<int64_t>();
+    VLQ_CALL(vlq_gather_candidates(lline, m, W, lOffsets_.as<int64_t>(), lIds_.as<int64_t>(), (int64_t)k, o, st));
+    if (!lOnDevice) VLQ_CALL(vlq_memcpy_d2h(labels + (size_t)s * k, o, (size_t)m * k * sizeof(int64_t), st));
+    resources_->syncDefaultStream();
+  }
+}
+
+// ---------------------------------------------------------------------------------------------- f4: ground truth
+void GpuIndexIVFPQ::add_with_ids2(Index::idx_t n, Index::idx_t nq, unsigned kgt, const float* x, const float* xq,
+                                  const Index::idx_t* ids, Index::idx_t* nns, float* dists) {
+  VLQ_THROW_IF_NOT_MSG(kgt >= 1 && kgt <= VLQ_MAX_K, "kgt must be in [1, 1024]");
+  VLQ_THROW_IF_NOT_MSG(n >= 1 && n <= 0x7fffffff, "the chunk must hold 1 .. INT_MAX rows (gpu/GpuIndexFlat.cu:226-232)");
+  if (nq == 0) return;
+  DeviceScope scope(ivfConfig_.device);
+  vlq_stream_t st = resources_->getDefaultStream();
+  DeviceBuffer dx, dq, xn, qn;
+  const float* px = x;
+  const float* pq_ = xq;
+  if (vlq_pointer_is_device(x) != 1) {
+    dx.resize((size_t)n * d * sizeof(float));
+    VLQ_CALL(vlq_memcpy_h2d(dx.get(), x, dx.bytes(), st));
+    px = dx.as<float>();
+  }
+  if (vlq_pointer_is_device(xq) != 1) {
+    dq.resize((size_t)nq * d * sizeof(float));
+    VLQ_CALL(vlq_memcpy_h2d(dq.get(), xq, dq.bytes(), st));
+    pq_ = dq.as<float>();
+  }
+  xn.resize((size_t)n * sizeof(float));
+  qn.resize((size_t)nq * sizeof(float));
+  VLQ_CALL(vlq_row_norms(px, n, d, xn.as<float>(), st));
+  VLQ_CALL(vlq_row_norms(pq_, nq, d, qn.as<float>(), st));
+  const Index::idx_t tile = std::max<Index::idx_t>(1, std::min<Index::idx_t>(nq, ((Index::idx_t)1 << 28) / n));
+  DeviceBuffer dmat((size_t)tile * n * sizeof(float)), oval((size_t)tile * kgt * sizeof(float)), oidx((size_t)tile * kgt * sizeof(int));
+  std::vector<int> hidx((size_t)tile * kgt);
+  std::vector<long> hids;
+  const long* pid = ids;
+  if (ids && vlq_pointer_is_device(ids) == 1) {
+    hids.resize((size_t)n);
+    VLQ_CALL(vlq_memcpy_d2h(hids.data(), ids, (size_t)n * sizeof(long), st));
+    pid = hids.data();
+  }
+  for (Index::idx_t s = 0; s < nq; s += tile) {
+    const Index::idx_t m = std::min(tile, nq - s);
+    VLQ_CALL(vlq_l2_distances(pq_ + (size_t)s * d, m, d, px, xn.as<float>(), (int)n, dmat.as<float>(), n, st));
+    VLQ_CALL(vlq_select_rows(dmat.as<float>(), m, (int)n, n, (int)kgt, qn.as<float>() + s, oval.as<float>(), oidx.as<int>(), st));
+    VLQ_CALL(vlq_memcpy_d2h(dists + (size_t)s * kgt, oval.get(), (size_t)m * kgt * sizeof(float), st));
+    VLQ_CALL(vlq_memcpy_d2h(hidx.data(), oidx.get(), (size_t)m * kgt * sizeof(int), st));
+    resources_->syncDefaultStream();
+    for (size_t i = 0; i < (size_t)m * kgt; i++)  // rank inside the chunk -> label (mergekernel1, gpu/GpuIndexIVFPQ.cu:1285-1308)
+      nns[(size_t)s * kgt + i] = hidx[i] < 0 ? -1 : (pid ? pid[hidx[i]] : (long)hidx[i]);
+  }
+}
+
+}  // namespace gpu
+}  // namespace faiss

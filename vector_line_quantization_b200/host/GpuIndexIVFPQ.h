@@ -10,6 +10,7 @@
 #include <vector>
 
 #include "GpuIndexFlat.h"
+#include "IndexIVFPQ.h"
 #include "ProductQuantizer.h"
 
 namespace faiss {
@@ -35,6 +36,7 @@ class GpuIndexIVF : public faiss::Index {
   GpuIndexIVF(GpuResources* resources, int dims, faiss::MetricType metric, int nlist, GpuIndexIVFConfig config);
   ~GpuIndexIVF() override;
   int getNumLists() const { return nlist_; }
+  int getDevice() const { return resources_->getDevice(); }
   GpuIndexFlat* getQuantizer() { return quantizer_; }
   /// nprobe in [1, 1024] (reference gpu/GpuIndexIVF.cu:201-207)
   void setNumProbes(int nprobe);
@@ -102,6 +104,23 @@ class GpuIndexIVFPQ : public GpuIndexIVF {
   void readDbFromFile(const std::string& name);
   void readDbFromFile(const std::string& name, int pronum, int rank);  ///< rank keeps lists [L/P*rank, L/P*(rank+1))
   void buildGraph_();
+
+  /// Populate from / export to a CPU IVFPQ index (reference gpu/GpuIndexIVFPQ.cu:169-281).  A stock IVFPQ entry is a VLQ
+  /// entry with lambda = 0: copyFrom takes the coarse centroids and the PQ codebook, rebuilds the centroid graph, zeroes
+  /// the lambda codebook and files every entry of coarse list c under line (c, edge 0).  With w1_ = nprobe * numedge_
+  /// (every line of the probed centroids) search() then returns exactly IndexIVFPQ::search(nprobe), distances without
+  /// the ||q||^2 term.  copyTo needs an index whose lambda codebook is all zero (it throws otherwise: entries on a line
+  /// are not residuals of a centroid) and merges the numedge_ lines of every centroid back into one list.
+  void copyFrom(const faiss::IndexIVFPQ* index);
+  void copyTo(faiss::IndexIVFPQ* index) const;
+  /// Candidate lists (reference search1 / searchImpl1_, gpu/GpuIndexIVFPQ.cu:1593-1670): labels[q][0..k) = ids of the
+  /// entries of the w1_ selected lines of query q in line order, -1 padded; k is not limited to 1024; `distances` is
+  /// not written (as in the reference).
+  void search1(Index::idx_t n, const float* x, Index::idx_t k, float* distances, Index::idx_t* labels) const;
+  /// Ground-truth builder (reference add_with_ids2 / generateNNs, gpu/GpuIndexIVFPQ.cu:1312-1398): exact kgt nearest
+  /// rows of the chunk x (n rows, labels ids) for every query of xq; nns (nq, kgt) labels, dists squared L2.
+  void add_with_ids2(Index::idx_t n, Index::idx_t nq, unsigned kgt, const float* x, const float* xq, const Index::idx_t* ids,
+                     Index::idx_t* nns, float* dists);
 
   /// install externally trained codebooks (tests / multi-GPU broadcast): pq is (M, 256, dsub)
   void setCodebooks(const float* coarse, const int* edge, const float* edgeDist, const float* lambdaCb, const float* pq);

@@ -5,6 +5,8 @@
 #include <thread>
 
 #include "DeviceBuffer.h"
+#include "GpuIndexFlat.h"
+#include "GpuIndexIVFPQ.h"
 
 namespace faiss {
 
@@ -108,10 +110,28 @@ void IndexShards::add(idx_t n, const float* x) {
   });
   ntotal += n;
 }
+// device a shard lives on, -1 for an index that is not one of the GPU classes
+static int deviceOfShard(const Index* ix) {
+  if (auto* p = dynamic_cast<const gpu::GpuIndexIVF*>(ix)) return p->getDevice();
+  if (auto* p = dynamic_cast<const gpu::GpuIndexFlat*>(ix)) return p->resources()->getDevice();
+  return -1;
+}
+
 void IndexShards::search(idx_t n, const float* x, idx_t k, float* distances, idx_t* labels) const {
   const size_t ns = shard_indexes.size();
   VLQ_THROW_IF_NOT(ns > 0);
   if (n == 0) return;
+  std::vector<int> dev(ns);
+  bool all_gpu = true;
+  for (size_t i = 0; i < ns; i++) {
+    dev[i] = deviceOfShard(shard_indexes[i]);
+    all_gpu = all_gpu && dev[i] >= 0;
+  }
+  if (all_gpu) {
+    searchPeers_(dev, n, x, k, distances, labels);
+    return;
+  }
+  // generic shards (any faiss::Index): results staged through host memory, merged on the current device
   std::vector<float> allD(ns * n * k);
   std::vector<idx_t> allI(ns * n * k);
   parallelFor(ns, threaded, [&](size_t i) {
@@ -127,7 +147,6 @@ void IndexShards::search(idx_t n, const float* x, idx_t k, float* distances, idx
       shift += shard_indexes[i]->ntotal;
     }
   }
-  // merge on the current device (vlq_merge_topk == mergekernel / merge_tables semantics)
   gpu::DeviceBuffer dD(allD.size() * sizeof(float)), dI(allI.size() * sizeof(int64_t));
   gpu::DeviceBuffer oD((size_t)n * k * sizeof(float)), oI((size_t)n * k * sizeof(int64_t));
   VLQ_CALL(vlq_memcpy_h2d(dD.get(), allD.data(), dD.bytes(), nullptr));
@@ -135,6 +154,65 @@ void IndexShards::search(idx_t n, const float* x, idx_t k, float* distances, idx
   VLQ_CALL(vlq_merge_topk(dD.as<float>(), dI.as<int64_t>(), (int)ns, n, (int)k, oD.as<float>(), oI.as<int64_t>(), nullptr));
   VLQ_CALL(vlq_memcpy_d2h(distances, oD.get(), oD.bytes(), nullptr));
   VLQ_CALL(vlq_memcpy_d2h(labels, oI.get(), oI.bytes(), nullptr));
+  VLQ_CALL(vlq_stream_synchronize(nullptr));
+}
+
+// GPU shards: nothing but the queries and the final (n, k) result crosses PCIe.  Every shard searches with DEVICE result
+// buffers on its own GPU (one thread per shard), shifts its labels there, and the merge kernel on the first shard's GPU
+// reads the shards' results straight from their memories over NVLink (vlq_merge_topk_peers: gather + merge in one
+// kernel).  Replaces the host staging of the reference drivers (gpu/test/sift1b16_query.cpp:389-430: MPI_Gather to
+// host, cudaMemcpy back, mergekernel, gpu/GpuIndexIVFPQ.cu:1467-1591).
+void IndexShards::searchPeers_(const std::vector<int>& dev, idx_t n, const float* x, idx_t k, float* distances,
+                               idx_t* labels) const {
+  const size_t ns = shard_indexes.size();
+  const size_t nk = (size_t)n * k;
+  const size_t i_off = (nk * sizeof(float) + 15) / 16 * 16;  // [D f32 (n, k) | I int64 (n, k)] per shard
+  const size_t buf_bytes = i_off + nk * sizeof(int64_t);
+  const bool x_dev = vlq_pointer_is_device(x) == 1;
+  const bool out_dev = vlq_pointer_is_device(distances) == 1;
+  std::vector<idx_t> shift(ns, 0);
+  if (successive_ids)
+    for (size_t i = 1; i < ns; i++) shift[i] = shift[i - 1] + shard_indexes[i - 1]->ntotal;
+  std::vector<gpu::DeviceBuffer> res(ns), xq(ns);
+  parallelFor(ns, threaded, [&](size_t i) {
+    gpu::DeviceScope scope(dev[i]);
+    res[i].resize(buf_bytes);
+    const float* xi = x;
+    if (!x_dev) {  // one upload per GPU (a device pointer is passed through: peer access covers it)
+      xq[i].resize((size_t)n * d * sizeof(float));
+      VLQ_CALL(vlq_memcpy_h2d(xq[i].get(), x, xq[i].bytes(), nullptr));
+      VLQ_CALL(vlq_stream_synchronize(nullptr));
+      xi = xq[i].as<float>();
+    }
+    float* Di = res[i].as<float>();
+    idx_t* Ii = reinterpret_cast<idx_t*>(res[i].as<unsigned char>() + i_off);
+    shard_indexes[i]->search(n, xi, k, Di, Ii);  // device pointers in and out; returns with the results complete
+    if (shift[i]) {
+      VLQ_CALL(vlq_shift_ids(reinterpret_cast<int64_t*>(Ii), (int64_t)nk, shift[i], nullptr));
+      VLQ_CALL(vlq_stream_synchronize(nullptr));
+    }
+  });
+  gpu::DeviceScope scope(dev[0]);
+  for (size_t i = 1; i < ns; i++) VLQ_CALL(vlq_enable_peer_access(dev[i]));
+  std::vector<const void*> ptrs(ns);
+  for (size_t i = 0; i < ns; i++) ptrs[i] = res[i].get();
+  gpu::DeviceBuffer table(ns * sizeof(void*));
+  VLQ_CALL(vlq_memcpy_h2d(table.get(), ptrs.data(), table.bytes(), nullptr));
+  gpu::DeviceBuffer oD, oI;
+  float* outD = distances;
+  idx_t* outI = labels;
+  if (!out_dev) {
+    oD.resize(nk * sizeof(float));
+    oI.resize(nk * sizeof(int64_t));
+    outD = oD.as<float>();
+    outI = oI.as<idx_t>();
+  }
+  VLQ_CALL(vlq_merge_topk_peers(table.as<const void*>(), 0, i_off, (int)ns, n, (int)k, outD,
+                                reinterpret_cast<int64_t*>(outI), nullptr));
+  if (!out_dev) {
+    VLQ_CALL(vlq_memcpy_d2h(distances, oD.get(), oD.bytes(), nullptr));
+    VLQ_CALL(vlq_memcpy_d2h(labels, oI.get(), oI.bytes(), nullptr));
+  }
   VLQ_CALL(vlq_stream_synchronize(nullptr));
 }
 

@@ -42,6 +42,10 @@ class IndexShards : public faiss::Index {
   std::vector<Index*> shard_indexes;
   bool threaded;
   bool successive_ids;
+
+ private:
+  /// all shards are GPU indexes: device result buffers + merge kernel reading them over NVLink
+  void searchPeers_(const std::vector<int>& dev, idx_t n, const float* x, idx_t k, float* distances, idx_t* labels) const;
 };
 
 }  // namespace faiss

@@ -230,4 +230,60 @@ int vlq_host_shards_add_shard(void* shards, void* index) {
   })
 }
 
+// ---- f4: CPU IVFPQ container + copyFrom / copyTo, candidate lists, ground-truth builder
+static IndexIVFPQ* CPU(void* h) { return static_cast<IndexIVFPQ*>(h); }
+int vlq_host_cpu_ivfpq_new(int d, long nlist, int M, int nbits, void** out) {
+  GUARD({
+    IndexFlatL2* q = new IndexFlatL2(d);
+    IndexIVFPQ* ix = new IndexIVFPQ(q, (size_t)d, (size_t)nlist, (size_t)M, (size_t)nbits);
+    ix->own_fields = true;
+    *out = ix;
+  })
+}
+int vlq_host_cpu_ivfpq_free(void* h) { GUARD(delete CPU(h)) }
+int vlq_host_cpu_ivfpq_set_codebooks(void* h, const float* coarse, const float* pq) {
+  GUARD({
+    IndexIVFPQ* ix = CPU(h);
+    ix->quantizer->reset();
+    ix->quantizer->add((long)ix->nlist, coarse);
+    std::memcpy(ix->pq.centroids.data(), pq, ix->pq.centroids.size() * sizeof(float));
+    ix->is_trained = true;
+  })
+}
+int vlq_host_cpu_ivfpq_get_codebooks(void* h, float* coarse, float* pq) {
+  GUARD({
+    IndexIVFPQ* ix = CPU(h);
+    const IndexFlatL2* q = dynamic_cast<const IndexFlatL2*>(ix->quantizer);
+    std::memcpy(coarse, q->xb.data(), q->xb.size() * sizeof(float));
+    std::memcpy(pq, ix->pq.centroids.data(), ix->pq.centroids.size() * sizeof(float));
+  })
+}
+int vlq_host_cpu_ivfpq_set_list(void* h, long list, long n, const long* ids, const unsigned char* codes) {
+  GUARD({
+    IndexIVFPQ* ix = CPU(h);
+    if (list < 0 || list >= (long)ix->nlist) throw FaissException("list out of range");
+    ix->ntotal += n - (long)ix->ids[list].size();
+    ix->ids[list].assign(ids, ids + n);
+    ix->codes[list].assign(codes, codes + (size_t)n * ix->code_size);
+  })
+}
+long vlq_host_cpu_ivfpq_list_size(void* h, long list) { return (long)CPU(h)->ids[list].size(); }
+long vlq_host_cpu_ivfpq_ntotal(void* h) { return CPU(h)->ntotal; }
+int vlq_host_cpu_ivfpq_get_list(void* h, long list, long* ids, unsigned char* codes) {
+  GUARD({
+    IndexIVFPQ* ix = CPU(h);
+    std::memcpy(ids, ix->ids[list].data(), ix->ids[list].size() * sizeof(long));
+    std::memcpy(codes, ix->codes[list].data(), ix->codes[list].size());
+  })
+}
+int vlq_host_ivfpq_copy_from(void* index, void* cpu_index) { GUARD(V(index)->copyFrom(CPU(cpu_index))) }
+int vlq_host_ivfpq_copy_to(void* index, void* cpu_index) { GUARD(V(index)->copyTo(CPU(cpu_index))) }
+int vlq_host_ivfpq_search1(void* index, long n, const float* x, long k, long* labels) {
+  GUARD(V(index)->search1(n, x, k, nullptr, labels))
+}
+int vlq_host_ivfpq_add_with_ids2(void* index, long n, long nq, unsigned kgt, const float* x, const float* xq, const long* ids,
+                                 long* nns, float* dists) {
+  GUARD(V(index)->add_with_ids2(n, nq, kgt, x, xq, ids, nns, dists))
+}
+
 }  // extern "C"

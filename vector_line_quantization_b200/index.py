@@ -296,6 +296,83 @@ class GpuIndexIVFPQ(Index):
         _call("vlq_host_vlq_read_db", self.h, name.encode(), int(pronum), int(rank))
 
 
+    # ---- f4 (gpu/GpuIndexIVFPQ.cu:169-281, 1312-1398, 1646-1670)
+    def copyFrom(self, cpu_index):
+        _call("vlq_host_ivfpq_copy_from", self.h, cpu_index.h)
+
+    def copyTo(self, cpu_index):
+        _call("vlq_host_ivfpq_copy_to", self.h, cpu_index.h)
+
+    def search1(self, x, k):
+        """candidate lists: ids of the entries of the w1_ selected lines of every query, first k, -1 padded"""
+        px, _keep, _ = _in(x, np.float32)
+        n = x.shape[0]
+        labels = np.empty((n, k), np.int64)
+        _call("vlq_host_ivfpq_search1", self.h, C.c_long(n), px, C.c_long(k), C.c_void_p(labels.ctypes.data))
+        return labels
+
+    def add_with_ids2(self, x, xq, kgt, ids=None):
+        """exact kgt nearest rows of the chunk x for every query of xq: -> (dists, nns)"""
+        x = np.ascontiguousarray(x, np.float32)
+        xq = np.ascontiguousarray(xq, np.float32)
+        ids = np.ascontiguousarray(ids, np.int64) if ids is not None else None
+        nns = np.empty((xq.shape[0], kgt), np.int64)
+        dists = np.empty((xq.shape[0], kgt), np.float32)
+        _call("vlq_host_ivfpq_add_with_ids2", self.h, C.c_long(x.shape[0]), C.c_long(xq.shape[0]), C.c_uint(kgt),
+              C.c_void_p(x.ctypes.data), C.c_void_p(xq.ctypes.data), C.c_void_p(ids.ctypes.data) if ids is not None else None,
+              C.c_void_p(nns.ctypes.data), C.c_void_p(dists.ctypes.data))
+        return dists, nns
+
+
+class CpuIndexIVFPQ:
+    """faiss::IndexIVFPQ as a CONTAINER (host/IndexIVFPQ.h): coarse centroids, PQ codebook, per-list ids + codes -- what
+    GpuIndexIVFPQ.copyFrom / copyTo exchange with a CPU index"""
+
+    def __init__(self, d, nlist, M, nbits=8):
+        self.d, self.nlist, self.M, self.nbits = d, nlist, M, nbits
+        self.h = C.c_void_p()
+        _call("vlq_host_cpu_ivfpq_new", d, C.c_long(nlist), M, nbits, C.byref(self.h))
+
+    def set_codebooks(self, coarse, pq):
+        coarse = np.ascontiguousarray(coarse, np.float32)
+        pq = np.ascontiguousarray(pq, np.float32)
+        assert coarse.shape == (self.nlist, self.d) and pq.size == self.d << self.nbits
+        _call("vlq_host_cpu_ivfpq_set_codebooks", self.h, C.c_void_p(coarse.ctypes.data), C.c_void_p(pq.ctypes.data))
+
+    def codebooks(self):
+        coarse = np.empty((self.nlist, self.d), np.float32)
+        pq = np.empty((self.M, 1 << self.nbits, self.d // self.M), np.float32)
+        _call("vlq_host_cpu_ivfpq_get_codebooks", self.h, C.c_void_p(coarse.ctypes.data), C.c_void_p(pq.ctypes.data))
+        return coarse, pq
+
+    def set_list(self, l, ids, codes):
+        ids = np.ascontiguousarray(ids, np.int64)
+        codes = np.ascontiguousarray(codes, np.uint8)
+        _call("vlq_host_cpu_ivfpq_set_list", self.h, C.c_long(l), C.c_long(len(ids)), C.c_void_p(ids.ctypes.data),
+              C.c_void_p(codes.ctypes.data))
+
+    def get_list(self, l):
+        host().vlq_host_cpu_ivfpq_list_size.restype = C.c_long
+        n = host().vlq_host_cpu_ivfpq_list_size(self.h, C.c_long(l))
+        ids = np.empty(n, np.int64)
+        codes = np.empty((n, self.M), np.uint8)
+        if n:
+            _call("vlq_host_cpu_ivfpq_get_list", self.h, C.c_long(l), C.c_void_p(ids.ctypes.data), C.c_void_p(codes.ctypes.data))
+        return ids, codes
+
+    @property
+    def ntotal(self):
+        host().vlq_host_cpu_ivfpq_ntotal.restype = C.c_long
+        return host().vlq_host_cpu_ivfpq_ntotal(self.h)
+
+    def __del__(self):
+        try:
+            if self.h:
+                host().vlq_host_cpu_ivfpq_free(self.h)
+        except Exception:
+            pass
+
+
 class IndexProxy(Index):
     """replicas: queries are split over the sub-indexes (gpu/IndexProxy.cpp:124-168)"""
 
