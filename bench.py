@@ -199,9 +199,12 @@ def run_reference(a):
 
 
 def run_imipq(a):
-    """--impl imipq: BASELINE configs[4]'s baseline -- MultiIndexQuantizer(d, 2, bits) + IndexIVFPQ, the UNMODIFIED reference
-    CPU classes (tests/sift1b_imi_pq.cpp:216-236 through oracle/_ref) -- on a bounded sample of the synthetic SIFT-shaped
-    workload, with the same recall definition as the VLQ runs.  Host cores only; reported beside, not against, the GPU."""
+    """--impl imipq: BASELINE configs[4] on a bounded sample -- the reference's IMI-PQ baseline index
+    (MultiIndexQuantizer(d, 2, bits) + IndexIVFPQ, the UNMODIFIED reference CPU classes through oracle/_ref,
+    tests/sift1b_imi_pq.cpp:216-236) on the host cores, beside the SAME index on the GPU (GpuIndexIMIPQ with the
+    reference-trained codebooks: identical cells and codes, so equal recall and a like-for-like speed ratio) and the VLQ
+    index at (almost) equal bytes per vector (M code bytes + 1 lambda byte) on the same vectors."""
+    _all_host_cores()
     with _StdoutToStderr():
         from oracle import pyoracle as po
         from vector_line_quantization_b200 import data
@@ -221,25 +224,73 @@ def run_imipq(a):
         idx.add(xb)
         t_add = time.time() - t0
         gt = po.ref_flat_search(xb, xq, 1)[1][:, 0]
-        sweep = []
-        for nprobe in (8, 64, 512):
-            idx.search(xq[:64], k, nprobe)
-            t0 = time.time()
-            D, I = idx.search(xq, k, nprobe)
-            dt = time.time() - t0
-            sweep.append({"nprobe": nprobe, "qps": nq / dt, "R@1": data.recall_at(I, gt, 1),
-                          "R@10": data.recall_at(I, gt, 10), "R@100": data.recall_at(I, gt, min(100, k))})
-            print("[bench] imipq", sweep[-1], file=sys.stderr, flush=True)
-        mid = sweep[1]
+        probes = (8, 64, 512)
+
+        def sweep_of(search, reps=1):
+            out = []
+            for nprobe in probes:
+                search(xq[:64], nprobe)
+                t0 = time.time()
+                for _ in range(reps):
+                    D, I = search(xq, nprobe)
+                dt = (time.time() - t0) / reps
+                out.append({"nprobe": nprobe, "qps": nq / dt, "R@1": data.recall_at(I, gt, 1),
+                            "R@10": data.recall_at(I, gt, 10), "R@100": data.recall_at(I, gt, min(100, k))})
+                print("[bench] imipq", out[-1], file=sys.stderr, flush=True)
+            return out
+
+        cpu_sweep = sweep_of(lambda q, p_: idx.search(q, k, p_))
+        gpu_sweep, vlq_sweep, gpu_note = None, None, None
+        try:
+            import torch
+
+            if torch.cuda.is_available():
+                from vector_line_quantization_b200 import _abi, index as vi
+
+                _abi.lib()
+                res = vi.StandardGpuResources(0)
+                g = vi.GpuIndexIMIPQ(res, d, a.imi_bits, M)
+                g.setCodebooks(*idx.codebooks())  # the reference-trained codebooks: the same index on both sides
+                t0 = time.time()
+                g.add(xb)
+                g.search(xq[:8], k)
+                t_gadd = time.time() - t0
+
+                def gsearch(q, p_):
+                    g.setNumProbes(p_)
+                    return g.search(q, k)
+
+                gpu_sweep = sweep_of(gsearch, reps=5)
+                gpu_note = {"add_vec_per_s": nb / t_gadd, "api": "GpuIndexIMIPQ::search, host buffers"}
+                # VLQ at equal code bytes on the same vectors (device-trained codebooks)
+                C_, E_ = min(a.nlist, 16384), a.nedge
+                v = vi.GpuIndexIVFPQ(res, d, C_, M, 8, E_, a.nlambda)
+                v.setTrainIters(10)
+                v.train(xt)
+                v.add(xb)
+
+                def vsearch(q, p_):
+                    v.setNumProbes(p_)
+                    v.w1_ = min(1024, 4 * p_)
+                    return v.search(q, k)
+
+                vlq_sweep = sweep_of(vsearch, reps=5)
+                for s_, p_ in zip(vlq_sweep, probes):
+                    s_["w1"] = min(1024, 4 * p_)
+                gpu_note["vlq"] = {"nlist": C_, "nedge": E_, "bytes_per_vector": M + 1}
+        except Exception as exc:
+            gpu_note = {"error": "%s: %s" % (type(exc).__name__, exc)}
+        mid = cpu_sweep[1]
         line = {"impl": "imipq", "metric": "imipq_search_qps", "value": mid["qps"], "unit": "queries/s",
                 "higher_is_better": True, "data": "synthetic", "dtype": "f32",
-                "config": {"workload": "BASELINE.json configs[4] baseline, bounded sample: reference IMI-PQ "
+                "config": {"workload": "BASELINE.json configs[4], bounded sample: IMI-PQ "
                                        "(MultiIndexQuantizer(d,2,%d) + IndexIVFPQ m=%d) on %d synthetic SIFT-shaped "
                                        "vectors, %d queries, k=%d" % (a.imi_bits, M, nb, nq, k),
                            "cells": 1 << (2 * a.imi_bits), "bytes_per_vector": M, "db_vectors": nb, "nq": nq},
                 "cpu_baseline": {"value": mid["qps"], "unit": "queries/s", "cores": po.ref_num_threads(), "kind": "reference",
                                  "sample": "nprobe 64 of the sweep below"},
-                "sweep": sweep, "train_s": t_train, "add_vec_per_s": nb / t_add}
+                "sweep": cpu_sweep, "gpu_imipq_sweep": gpu_sweep, "gpu_vlq_sweep": vlq_sweep, "gpu": gpu_note,
+                "train_s": t_train, "add_vec_per_s": nb / t_add}
     print(json.dumps(line))
 
 

@@ -184,7 +184,8 @@ int vlq_gather_candidates(const int* line_list, int64_t nq, int W, const int64_t
  *     dist = term1 + l*term6 + (l*l-l)*term5 + kappa_i - 2 q.p(code_i),  l = lambda_cb[lamq_i]
  *          = ||q - ((1-l)c + l s) - p(code_i)||^2 - ||q||^2              (same value as the reference's formula)
  *     over the first min(len, cap) entries of each selected list; k smallest ascending, padded (FLT_MAX, -1).
- *     edge_d2 is indexed by list id (term5).  k <= VLQ_MAX_K, W <= VLQ_MAX_K.
+ *     edge_d2 is indexed by list id (term5); NULL = 0 (an index whose lambda codebook is {0}: stock IVFPQ / IMI-PQ).
+ *     k <= VLQ_MAX_K, W <= VLQ_MAX_K.
  *     list_len_hint: average list length of the index (entries / lists; 0 = unknown).  >= 24 selects the
  *     warp-per-list walk (1B-scale lists), otherwise the flattened entry stream (lists of a few entries).  Results are
  *     identical either way.
@@ -220,6 +221,26 @@ int vlq_merge_topk_peers(const void* const* peer_bufs, size_t d_offset_bytes, si
 size_t vlq_km_update_workspace_bytes(int64_t n, int k);
 int vlq_km_update(const float* x, int64_t n, int d, const int* assign, int k, float* centroids, int* counts,
                   void* workspace, size_t workspace_bytes, vlq_stream_t stream);
+
+
+/* ------------------------------------------------------------------------------------------------------------------
+ * f3  inverted multi-index (IMI-PQ baseline of BASELINE configs[4]; csrc/imi.cu).
+ *     vlq_imi_top_cells: the nprobe cells (label i1 | i2 << nbits) with the smallest d1[i1] + d2[i2] per query, ascending,
+ *       ties to the lowest label, padded (-1, FLT_MAX); v1/i1, v2/i2 are the [nq][L] ascending prefixes of the two
+ *       half-distance tables (vlq_select_rows), L >= min(nprobe, K).  nprobe <= VLQ_MAX_K.
+ *       replaces MultiIndexQuantizer::search / MinSumK, IndexPQ.cpp:637-857 (which may report a cell twice; this does not).
+ *     vlq_imi_encode: cell label, residual PQ codes (first minimum wins, ProductQuantizer.cpp:311-336) and
+ *       kappa = ||p||^2 + 2 c.p per vector from its two half assignments a1, a2 (-1 -> cell -1).
+ *       replaces IndexIVFPQ::add_core_o with a MultiIndexQuantizer (IndexIVFPQ.cpp:160-260) and the per-half
+ *       precomputed tables of use_precomputed_table = 2 (IndexIVFPQ.cpp:645-687).
+ *     vlq_copy_columns: dst[n][ncols] = src[n][col0 : col0 + ncols] (row stride ld).
+ * ---------------------------------------------------------------------------------------------------------------- */
+int vlq_copy_columns(const float* src, int64_t n, int64_t ld, int col0, int ncols, float* dst, vlq_stream_t stream);
+int vlq_imi_top_cells(const float* v1, const int* i1, const float* v2, const int* i2, int64_t nq, int L, int nbits,
+                      int nprobe, int* out_cell, float* out_dist, vlq_stream_t stream);
+int vlq_imi_encode(const float* x, int64_t n, int d, const int* a1, const int* a2, const float* cb1, const float* cb2,
+                   int nbits, const float* pq, int M, int* out_cell, uint8_t* out_codes, float* out_kappa,
+                   vlq_stream_t stream);
 
 /* small device utilities used by the host layer */
 int vlq_gather_rows(const float* src, int d, const int64_t* rows, int64_t n, float* dst, vlq_stream_t stream);

@@ -99,6 +99,18 @@ int vlq_host_ivfpq_search1(void* index, long n, const float* x, long k, long* la
 int vlq_host_ivfpq_add_with_ids2(void* index, long n, long nq, unsigned kgt, const float* x, const float* xq, const long* ids,
                                  long* nns, float* dists);
 
+/* ---- f3: GpuIndexIMIPQ = MultiIndexQuantizer(d, 2, nbits_coarse) + IndexIVFPQ over the 2^(2 nbits_coarse) cells on the
+   device (reference CPU composition: tests/sift1b_imi_pq.cpp:216-236); train / add / search / reset through the
+   vlq_host_index_* calls above; search returns full squared distances like IndexIVFPQ::search */
+int vlq_host_imipq_new(void* res, int d, int nbits_coarse, int M, int nbits, void** out);
+int vlq_host_imipq_set_nprobe(void* index, int nprobe);
+int vlq_host_imipq_set_train_iters(void* index, int niter);
+int vlq_host_imipq_set_codebooks(void* index, const float* coarse, const float* pq); /* (2, K, d/2), (M, 256, d/M) */
+int vlq_host_imipq_get_codebooks(void* index, float* coarse, float* pq);
+/* MultiIndexQuantizer::search: the nprobe cells (label i1 | i2 << nbits_coarse) with the smallest d1 + d2, ascending */
+int vlq_host_imipq_search_cells(void* index, long n, const float* x, int nprobe, float* distances, long* labels);
+int vlq_host_imipq_list_length(void* index, long cell, int* out);
+
 #ifdef __cplusplus
 }
 #endif

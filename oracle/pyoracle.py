@@ -364,8 +364,15 @@ class RefIMIPQ:
     def __init__(self, d, nbits_coarse, M, nbits=8):
         r = ref()
         r.ref_imipq_new.restype = C.c_void_p
-        self.d = d
+        self.d, self.nbits_coarse, self.M, self.nbits = d, nbits_coarse, M, nbits
         self.h = C.c_void_p(r.ref_imipq_new(d, nbits_coarse, M, nbits))
+
+    def codebooks(self):
+        """-> coarse (2, K, d/2), pq (M, 2^nbits, d/M) of the trained index"""
+        coarse = np.empty((2, 1 << self.nbits_coarse, self.d // 2), _f32)
+        pq = np.empty((self.M, 1 << self.nbits, self.d // self.M), _f32)
+        ref().ref_imipq_get_codebooks(self.h, _p(coarse, c_float_p), _p(pq, c_float_p))
+        return coarse, pq
 
     def train(self, x):
         x = _c(x, _f32)

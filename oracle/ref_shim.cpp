@@ -186,6 +186,12 @@ void ref_imipq_search(void* hv, long nq, const float* xq, long k, long nprobe, f
   h->index->nprobe = nprobe;
   h->index->search(nq, xq, k, D, I);
 }
+// trained codebooks: coarse = (2, 2^nbits_coarse, d/2), pq = (M, 2^nbits, d/M)
+void ref_imipq_get_codebooks(void* hv, float* coarse, float* pq) {
+  RefIMIPQ* h = (RefIMIPQ*)hv;
+  memcpy(coarse, h->miq->pq.centroids.data(), sizeof(float) * h->miq->pq.centroids.size());
+  memcpy(pq, h->index->pq.centroids.data(), sizeof(float) * h->index->pq.centroids.size());
+}
 void ref_imipq_free(void* hv) {
   RefIMIPQ* h = (RefIMIPQ*)hv;
   delete h->index;

@@ -112,3 +112,74 @@ def test_copy_from_reference_cpu_index_and_back(cuda, oracle, nedge):
         i0, k0 = ref.get_list(l)
         i1, k1 = back.get_list(l)
         assert np.array_equal(i0, i1) and np.array_equal(k0, k1)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("d,nbc,M", [(64, 5, 8), (128, 6, 16)])
+def test_gpu_imipq_matches_reference_imipq(cuda, oracle, d, nbc, M):
+    """f3: GpuIndexIMIPQ with the codebooks of the UNMODIFIED reference IMI-PQ index (MultiIndexQuantizer(d, 2, nbc) +
+    IndexIVFPQ, tests/sift1b_imi_pq.cpp:216-236, trained and filled on the CPU) returns the reference's cells
+    (MultiIndexQuantizer::search, IndexPQ.cpp:804-857; oracle restatement vlqo_imi_search) and the reference's
+    search results (IndexIVFPQ::search, full squared distances)"""
+    if not oracle.ref_available():
+        pytest.skip("reference library not built")
+    from vector_line_quantization_b200 import data, index as vi
+
+    k = 10
+    xt = data.sift_like(20000, d=d, kc=256, seed=71)
+    xb = data.sift_like(30000, d=d, kc=256, seed=72)
+    xq = data.sift_like(150, d=d, kc=256, seed=73)
+    ref = oracle.RefIMIPQ(d, nbc, M)
+    ref.train(xt)
+    ref.add(xb)
+    coarse, pq = ref.codebooks()
+    res = vi.StandardGpuResources(0)
+    gpu = vi.GpuIndexIMIPQ(res, d, nbc, M)
+    gpu.setCodebooks(coarse, pq)
+    gpu.add(xb)
+    assert gpu.ntotal == len(xb)
+    K = 1 << nbc
+    # ---- coarse cells against the reference MultiIndexQuantizer and the oracle restatement
+    for nprobe in (1, 16, 100):
+        Dc, Ic = gpu.searchCells(xq, nprobe)
+        Dm, Im = oracle.ref_imi_search(xq, coarse, nprobe)
+        Do, Io = oracle.imi_search(xq, coarse, nprobe)
+        assert np.allclose(Dc, Do, rtol=1e-4) and np.all(np.diff(Dc, axis=1) >= 0)
+        for r in range(len(xq)):  # same cell SETS up to near-ties at the boundary (the reference may repeat a cell)
+            got, want = set(Ic[r].tolist()), set(Io[r].tolist())
+            assert len(got) == nprobe and all(0 <= c < K * K for c in got)
+            for c in got ^ want:  # a cell only one side has must tie with the boundary distance
+                i1, i2 = c % K, c // K
+                dc = ((xq[r, : d // 2].astype(np.float64) - coarse[0, i1]) ** 2).sum() + \
+                     ((xq[r, d // 2:].astype(np.float64) - coarse[1, i2]) ** 2).sum()
+                assert abs(dc - Do[r, -1]) <= 1e-5 * abs(Do[r, -1]) + 1e-3
+        assert np.mean([len(set(a) & set(b)) / len(set(b)) for a, b in zip(Ic, Im)]) > 0.99
+    # ---- the lists hold what the reference's lists hold (sizes per cell; coarse near-ties may move a vector)
+    _, c1 = gpu.searchCells(xb[:2000], 1)
+    assert sum(gpu.getListLength(int(c)) > 0 for c in np.unique(c1)) == len(np.unique(c1))
+    # ---- end to end: IndexIVFPQ::search of the reference with nprobe cells
+    for nprobe in (8, 64):
+        Dr, Ir = ref.search(xq, k, nprobe)
+        gpu.setNumProbes(nprobe)
+        D, I = gpu.search(xq, k)
+        same = I == Ir
+        assert same.mean() > 0.97
+        np.testing.assert_allclose(D[same], Dr[same], rtol=2e-4)
+        assert np.mean([len(set(a) & set(b)) / k for a, b in zip(I, Ir)]) > 0.99
+
+
+@pytest.mark.gpu
+def test_gpu_imipq_trains_on_the_device(cuda):
+    """GpuIndexIMIPQ::train (two half k-means + PQ on the residuals, all on the device): a usable index"""
+    from vector_line_quantization_b200 import data, index as vi
+
+    d, nbc, M, k = 64, 5, 8, 10
+    xt = data.sift_like(20000, d=d, kc=256, seed=81)
+    xb = data.sift_like(20000, d=d, kc=256, seed=82)
+    res = vi.StandardGpuResources(0)
+    gpu = vi.GpuIndexIMIPQ(res, d, nbc, M)
+    gpu.train(xt)
+    gpu.add(xb)
+    gpu.setNumProbes(64)
+    D, I = gpu.search(xb[:200], k)  # database vectors as queries: they find themselves
+    assert np.mean(I[:, 0] == np.arange(200)) > 0.9 and np.all(np.diff(D, axis=1) >= 0)

@@ -48,6 +48,9 @@ SIGNATURES = {
     "vlq_merge_topk_peers": (_i, [_p, _z, _z, _i, _l, _i, _p, _p, _p]),
     "vlq_km_update_workspace_bytes": (_z, [_l, _i]),
     "vlq_km_update": (_i, [_p, _l, _i, _p, _i, _p, _p, _p, _z, _p]),
+    "vlq_copy_columns": (_i, [_p, _l, _l, _i, _i, _p, _p]),
+    "vlq_imi_top_cells": (_i, [_p, _p, _p, _p, _l, _i, _i, _i, _p, _p, _p]),
+    "vlq_imi_encode": (_i, [_p, _l, _i, _p, _p, _p, _p, _i, _p, _i, _p, _p, _p, _p]),
     "vlq_gather_rows": (_i, [_p, _i, _p, _l, _p, _p]),
     "vlq_u8_to_f32": (_i, [_p, _l, _p, _p]),
     "vlq_iota_i64": (_i, [_p, _l, _l, _p]),

@@ -274,7 +274,7 @@ __global__ void __launch_bounds__(NT, 2) scan_long_kernel(ScanArgs a, int look, 
       d.st = a.offsets[list];
       const int64_t l = a.offsets[list + 1] - d.st;
       d.len = (int)(l < a.cap ? l : a.cap);
-      d.t5 = a.edge_d2[list];
+      d.t5 = a.edge_d2 ? a.edge_d2[list] : 0.f;
     }
     d.t1 = a.term1[qi * W + w];
     d.t6 = a.term6[qi * W + w];

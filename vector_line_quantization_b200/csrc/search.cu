@@ -366,7 +366,7 @@ __global__ void __launch_bounds__(Q_THREADS, M_T == 16 ? 3 : 2) scan_topk_kernel
       st = a.offsets[list];
       int64_t l = a.offsets[list + 1] - st;
       len = (int)(l < a.cap ? l : a.cap);
-      t5 = a.edge_d2[list];
+      t5 = a.edge_d2 ? a.edge_d2[list] : 0.f;
     }
     lstart[w] = st;
     prefix[w + 1] = len;  // turned into an inclusive scan below
@@ -764,7 +764,7 @@ __global__ void __launch_bounds__(SKEW ? AQ_THREADS_SKEW : Q_THREADS, SKEW ? 2 :
       dsc.st = a.offsets[list];
       const int64_t l = a.offsets[list + 1] - dsc.st;
       dsc.len = (int)(l < a.cap ? l : a.cap);
-      dsc.t5 = a.edge_d2[list];
+      dsc.t5 = a.edge_d2 ? a.edge_d2[list] : 0.f;
     }
     dsc.t1 = a.term1[qi * W + w];
     dsc.t6 = a.term6[qi * W + w];
@@ -1089,7 +1089,7 @@ int vlq_scan_topk(const float* q, int64_t nq, int d, const float* pq, int M, con
                   const int64_t* offsets, const uint8_t* codes, const uint8_t* lamq, const float* kappa,
                   const int64_t* ids, int k, int cap, int list_len_hint, float* outD, int64_t* outI, void* workspace,
                   size_t workspace_bytes, vlq_stream_t stream) {
-  if (nq > 0 && (!q || !pq || !lambda_cb || !line_list || !term1 || !term6 || !edge_d2 || !offsets || !outD || !outI))
+  if (nq > 0 && (!q || !pq || !lambda_cb || !line_list || !term1 || !term6 || !offsets || !outD || !outI))
     return VLQ_EINVAL;
   if (nq < 0 || d <= 0 || M <= 0 || M > 64 || d % M != 0 || nL <= 0 || nL > 256 || W <= 0 || W > VLQ_MAX_K ||
       k <= 0 || k > VLQ_MAX_K || cap <= 0 || cap > (1 << 20) / 1 || (int64_t)W * cap > (int64_t)0x7fffffff)

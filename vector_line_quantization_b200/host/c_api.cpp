@@ -4,6 +4,7 @@
 #include <string>
 
 #include "Clustering.h"
+#include "GpuIndexIMIPQ.h"
 #include "GpuIndexIVFPQ.h"
 #include "IndexProxy.h"
 #include "filehelper.h"
@@ -285,5 +286,25 @@ int vlq_host_ivfpq_add_with_ids2(void* index, long n, long nq, unsigned kgt, con
                                  long* nns, float* dists) {
   GUARD(V(index)->add_with_ids2(n, nq, kgt, x, xq, ids, nns, dists))
 }
+
+// ---- f3: IMI-PQ on the GPU (the baseline index of BASELINE configs[4])
+static GpuIndexIMIPQ* IMI(void* h) {
+  GpuIndexIMIPQ* p = dynamic_cast<GpuIndexIMIPQ*>(static_cast<Index*>(h));
+  if (!p) throw FaissException("handle is not an IMI-PQ index");
+  return p;
+}
+int vlq_host_imipq_new(void* res, int d, int nbits_coarse, int M, int nbits, void** out) {
+  GUARD(*out = static_cast<Index*>(new GpuIndexIMIPQ(static_cast<GpuResources*>(res), d, nbits_coarse, M, nbits)))
+}
+int vlq_host_imipq_set_nprobe(void* index, int nprobe) { GUARD(IMI(index)->setNumProbes(nprobe)) }
+int vlq_host_imipq_set_train_iters(void* index, int niter) { GUARD(IMI(index)->cp_.niter = niter) }
+int vlq_host_imipq_set_codebooks(void* index, const float* coarse, const float* pq) {
+  GUARD(IMI(index)->setCodebooks(coarse, pq))
+}
+int vlq_host_imipq_get_codebooks(void* index, float* coarse, float* pq) { GUARD(IMI(index)->getCodebooks(coarse, pq)) }
+int vlq_host_imipq_search_cells(void* index, long n, const float* x, int nprobe, float* distances, long* labels) {
+  GUARD(IMI(index)->searchCells(n, x, nprobe, distances, labels))
+}
+int vlq_host_imipq_list_length(void* index, long cell, int* out) { GUARD(*out = IMI(index)->getListLength(cell)) }
 
 }  // extern "C"

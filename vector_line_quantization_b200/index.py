@@ -373,6 +373,46 @@ class CpuIndexIVFPQ:
             pass
 
 
+class GpuIndexIMIPQ(Index):
+    """IMI-PQ on the device (host/GpuIndexIMIPQ.h): MultiIndexQuantizer(d, 2, nbits_coarse) + IVFPQ over the K^2 cells"""
+
+    def __init__(self, res, d, nbits_coarse, M, nbits=8):
+        super().__init__(d)
+        self.res, self.nbits_coarse, self.M, self.nbits = res, nbits_coarse, M, nbits
+        _call("vlq_host_imipq_new", res.h, d, nbits_coarse, M, nbits, C.byref(self.h))
+
+    def setNumProbes(self, nprobe):
+        _call("vlq_host_imipq_set_nprobe", self.h, int(nprobe))
+
+    def setTrainIters(self, niter):
+        _call("vlq_host_imipq_set_train_iters", self.h, int(niter))
+
+    def setCodebooks(self, coarse, pq):
+        coarse = np.ascontiguousarray(coarse, np.float32)
+        pq = np.ascontiguousarray(pq, np.float32)
+        assert coarse.shape == (2, 1 << self.nbits_coarse, self.d // 2) and pq.size == self.d << self.nbits
+        _call("vlq_host_imipq_set_codebooks", self.h, C.c_void_p(coarse.ctypes.data), C.c_void_p(pq.ctypes.data))
+
+    def codebooks(self):
+        coarse = np.empty((2, 1 << self.nbits_coarse, self.d // 2), np.float32)
+        pq = np.empty((self.M, 1 << self.nbits, self.d // self.M), np.float32)
+        _call("vlq_host_imipq_get_codebooks", self.h, C.c_void_p(coarse.ctypes.data), C.c_void_p(pq.ctypes.data))
+        return coarse, pq
+
+    def searchCells(self, x, nprobe):
+        x = np.ascontiguousarray(x, np.float32)
+        D = np.empty((x.shape[0], nprobe), np.float32)
+        I = np.empty((x.shape[0], nprobe), np.int64)
+        _call("vlq_host_imipq_search_cells", self.h, C.c_long(x.shape[0]), C.c_void_p(x.ctypes.data), int(nprobe),
+              C.c_void_p(D.ctypes.data), C.c_void_p(I.ctypes.data))
+        return D, I
+
+    def getListLength(self, cell):
+        out = C.c_int()
+        _call("vlq_host_imipq_list_length", self.h, C.c_long(int(cell)), C.byref(out))
+        return out.value
+
+
 class IndexProxy(Index):
     """replicas: queries are split over the sub-indexes (gpu/IndexProxy.cpp:124-168)"""
 
