@@ -52,6 +52,10 @@ def parse():
                     "(the reference's default, gpu/GpuIndexIVF.cu:50)")
     ap.add_argument("--scaling", default=None, choices=["strong", "weak"],
                     help="N > 1: strong (default) = the --n database sharded N ways; weak = --n vectors per GPU")
+    ap.add_argument("--shard-by", default="auto", choices=["auto", "ids", "lists"],
+                    help="N > 1: ids = every rank holds all lists with its 1/N of the entries; lists = rank r owns the lists "
+                         "[r L/N, (r+1) L/N) at full length (the reference's readDbFromFile(name, pronum, rank) split; "
+                         "entries routed to the owner after the encode); auto = lists once the lists are long")
     ap.add_argument("--no-c4-stage", action="store_true",
                     help="skip the extra scan measurement at BASELINE configs[3] list density (1 B synthetic entries)")
     ap.add_argument("--kc", type=int, default=1 << 18, help="mixture components of the synthetic generator")
@@ -400,7 +404,7 @@ def workload_config(a, n_gpus):
                     % (cfg, a.nlist, a.nedge, a.m, a.nlambda, a.d, a.shape.upper(), total, per_gpu, a.nq, a.nprobe, a.w1, a.k),
         "db_vectors_per_gpu": per_gpu, "db_vectors_total": total, "nlist": a.nlist, "nedge": a.nedge, "m": a.m,
         "nq": a.nq, "nprobe": a.nprobe, "w1": a.w1, "k": a.k, "train_iters": a.train_iters,
-        "parallelism": ("id-range database shards (%s scaling); coarse stage split by queries, line lists exchanged "
+        "parallelism": ("database shards (%s scaling); coarse stage split by queries, line lists exchanged "
                         "through peer-mapped memory, every shard scans all queries, per-shard top-k merged by query slice "
                         "over NVLink" % ("strong" if strong else "weak")) if n_gpus > 1 else "single GPU",
         "l2": "an L2-sized (256 MiB) buffer is overwritten between timed steps",
@@ -494,8 +498,26 @@ def run_b200(a):
     e0.record()
     new_list = torch.cat([p.list for p in parts])
     ids = torch.arange(id0, id1, dtype=torch.int64, device=dev)
-    lists = ops.build_lists(C * E, M, new_list, torch.cat([p.codes for p in parts]), torch.cat([p.lamq for p in parts]),
-                            torch.cat([p.kappa for p in parts]), ids)
+    all_codes, all_lamq, all_kappa = (torch.cat([getattr(p, f) for p in parts]) for f in ("codes", "lamq", "kappa"))
+    shard_by = a.shard_by if a.shard_by != "auto" else ("lists" if world > 1 and n_total / (C * E) >= 64 else "ids")
+    if world == 1:
+        shard_by = "ids"
+    route_s = 0.0
+    if shard_by == "lists":  # route every encoded entry to the rank that owns its list (one all-to-all per array);
+        # timed on its own (host clock, includes the NCCL calls): it is index distribution, not encode arithmetic
+        del parts
+        e1.record()
+        evs.append((e0, e1))
+        torch.cuda.synchronize()
+        t_r = time.perf_counter()
+        new_list, (all_codes, all_lamq, all_kappa, ids) = sharding.route_by_list(new_list, [all_codes, all_lamq, all_kappa, ids], C * E)
+        torch.cuda.synchronize()
+        route_s = time.perf_counter() - t_r
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+    lists = ops.build_lists(C * E, M, new_list, all_codes, all_lamq, all_kappa, ids)
+    # average length of the lists this rank scans (kernel choice): a list-range shard holds 1/N of the lists at full length
+    len_hint = int(lists.ids.shape[0] // max(1, (C * E) // (world if shard_by == "lists" else 1)))
     e1.record()
     evs.append((e0, e1))
     barrier()
@@ -506,9 +528,11 @@ def run_b200(a):
         dist.all_reduce(enc_ms, op=dist.ReduceOp.MAX)
     enc_ms = float(enc_ms)
     enc_launches = ops.launch_count() - n_before
-    del parts, new_list, ids
+    parts = None
+    del new_list, ids, all_codes, all_lamq, all_kappa
     torch.cuda.empty_cache()
-    log("encoded %d vectors/GPU in %.1f ms" % (n_loc, enc_ms))
+    n_listed0 = int(lists.ids.shape[0])
+    log("encoded %d vectors/GPU in %.1f ms (shards by %s, %d entries on this rank)" % (n_loc, enc_ms, shard_by, n_listed0))
     n_loc_sum = n_total  # vectors encoded by all ranks together
 
     # ---- queries + exact ground truth (brute force over every shard, for recall)
@@ -547,7 +571,7 @@ def run_b200(a):
     gI = torch.empty((world, nq, k), dtype=torch.int64, device=dev) if world > 1 else None
 
     def ops_search(q):  # the whole query path on this rank's lists through the C-ABI (ops = ctypes bindings)
-        return ops.search(q, cent, cn, edge, ed2, lcb, pq, lists, P, W, k, pack=pack)
+        return ops.search(q, cent, cn, edge, ed2, lcb, pq, lists, P, W, k, pack=pack, list_len_hint=len_hint)
 
     def step_nccl(q):
         D, I = ops_search(q)
@@ -573,7 +597,7 @@ def run_b200(a):
         return ops.coarse_lines(qs, cent, cn, edge, ed2, P, W, pack=pack, out=out)
 
     def scan_fn(q, lines, out):
-        return ops.scan_lines(q, pq, lcb, lines, ed2, lists, k, out=out)
+        return ops.scan_lines(q, pq, lcb, lines, ed2, lists, k, out=out, list_len_hint=len_hint)
 
     def step_peer(q):  # -> (D, I) of this rank's query slice
         return qss.search(q, coarse_fn, scan_fn)
@@ -843,7 +867,7 @@ def run_b200(a):
         canon = ops.rotate_codes(lists.offsets, lists.codes, inverse=True)
         lens_r = (lists.offsets[1:] - lists.offsets[:-1]).to(torch.int32)
         szs = [torch.zeros(1, dtype=torch.int64, device=dev) for _ in range(world)]
-        dist.all_gather(szs, torch.tensor([n_loc], dtype=torch.int64, device=dev))
+        dist.all_gather(szs, torch.tensor([int(lists.ids.shape[0])], dtype=torch.int64, device=dev))
         szs = [int(x) for x in szs]
         mx = max(szs)
 
@@ -916,7 +940,7 @@ def run_b200(a):
             "higher_is_better": True, "scaling": "strong" if strong else "weak", "vs_baseline": None,
             "dtype": "f32 (coarse GEMM: split-fp16 x3 tcgen05, fp32 accumulate)" if use_tc else "f32", "data": "synthetic",
             "config": workload_config(a, world),
-            "plumbing": {"exchange": exchange,
+            "plumbing": {"exchange": exchange, "shard_by": shard_by, "entries_on_rank0": int(n_listed0),
                          "value_api": "GpuIndexIVFPQ::search (C++ host layer), device pointers" if world == 1 else
                          "sharding.QuerySplitSearch over the C-ABI stage entry points"},
             "e2e": {"value": e2e_qps, "unit": "queries/s",
@@ -927,7 +951,7 @@ def run_b200(a):
                                "h2d_bytes_per_vector": (d if use_u8 else d * 4) + 8,
                                "note": "GpuIndexIVFPQ::add_with_ids%s from pinned host memory in 2 Mi-vector chunks + "
                                        "list commit" % ("_u8" if use_u8 else "")},
-                       "gpu_launches": enc_launches,
+                       "gpu_launches": enc_launches, "route_to_list_owner_s": route_s,
                        "tensor_frac": (n_loc * 2.0 * C * d / (enc_ms * 1e-3) / 1e12) / peaks.get("bf16_tflops_sustained", 1400.0)},
             "scanned_entries_per_query": scanned_per_q, "parity_vs_oracle": parity,
             "host_api_matches_ops_bitwise": host_matches_ops,

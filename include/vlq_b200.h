@@ -267,6 +267,7 @@ int vlq_memcpy_d2h(void* dst, const void* src, size_t bytes, vlq_stream_t stream
 int vlq_memcpy_d2d(void* dst, const void* src, size_t bytes, vlq_stream_t stream);
 int vlq_memset(void* dst, int value, size_t bytes, vlq_stream_t stream);
 int vlq_pointer_is_device(const void* ptr); /* 1 device, 0 host, <0 error */
+int vlq_pointer_device(const void* ptr, int* device); /* ordinal of the GPU a device pointer lives on (-1: host memory) */
 /* let the CURRENT device read `peer_device`'s memory over NVLink (no-op for the same device or when already enabled);
    the in-process shard merge reads the shards' result buffers straight from their GPUs (gpu/test/sift1b16_query.cpp:389-430
    staged them through MPI and host memory) */

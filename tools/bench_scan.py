@@ -6,7 +6,7 @@ peak ((M + 1) bytes per scanned entry + 8 k bytes per query).
   python tools/bench_scan.py [--entries 1e9] [--nlists 2097152] [--m 16] [--nq 10000] [--w1 256] [--k 100]
   VLQ_SCAN_KERNEL=skew|long python tools/bench_scan.py ...   # force the register-pipelined warp-autonomous kernel /
                                                              # the long-list kernel (default: chosen by list length)
-  VLQ_SCAN_LOOK=n VLQ_SCAN_EPL=2|3|4 VLQ_SCAN_LPT=0|1        # tuning knobs of the long-list kernel (scan_long.cu)
+  VLQ_SCAN_LOOK=n VLQ_SCAN_LPT=0|1                           # tuning knobs of the long-list kernel (scan_long.cu)
 
 List lengths are Poisson around entries/nlists with a Gamma(4) spread and queries pick lists size-biased (dense regions
 attract both vectors and queries, as in the real index: 193 k scanned entries per query at 1 B vs 256 x 477 = 122 k).

@@ -69,6 +69,7 @@ SIGNATURES = {
     "vlq_memcpy_d2d": (_i, [_p, _p, _z, _p]),
     "vlq_memset": (_i, [_p, _i, _z, _p]),
     "vlq_pointer_is_device": (_i, [_p]),
+    "vlq_pointer_device": (_i, [_p, C.POINTER(_i)]),
     "vlq_enable_peer_access": (_i, [_i]),
     "vlq_stream_create": (_i, [C.POINTER(_p)]),
     "vlq_stream_destroy": (_i, [_p]),

@@ -63,6 +63,18 @@ int vlq_pointer_is_device(const void* ptr) {
   }
   return (attr.type == cudaMemoryTypeDevice || attr.type == cudaMemoryTypeManaged) ? 1 : 0;
 }
+int vlq_pointer_device(const void* ptr, int* device) {
+  if (!device) return VLQ_EINVAL;
+  *device = -1;
+  cudaPointerAttributes attr;
+  cudaError_t e = cudaPointerGetAttributes(&attr, ptr);
+  if (e != cudaSuccess) {
+    cudaGetLastError();
+    return VLQ_OK;
+  }
+  if (attr.type == cudaMemoryTypeDevice || attr.type == cudaMemoryTypeManaged) *device = attr.device;
+  return VLQ_OK;
+}
 int vlq_enable_peer_access(int peer_device) {
   int cur = 0;
   cudaError_t e = cudaGetDevice(&cur);

@@ -467,12 +467,10 @@ static int launch_t(const ScanArgs& a, int64_t nq, int look, int lpt, cudaStream
   return last_error();
 }
 
-// entries per lane and segment (tuning knob; measured at 1 B entries, ms per 10 k queries: 4 -> 7.54, 3 -> 7.81,
-// 2 -> 8.81; sixteen warps per CTA at 64 registers: 8.5-9.4)
+// four entries per lane and segment (measured at 1 B entries, ms per 10 k queries: 4 -> 7.54, 3 -> 7.81, 2 -> 8.81;
+// sixteen warps per CTA at 64 registers: 8.5-9.4)
 template <int MS, bool FOLD>
-static int launch_epl(const ScanArgs& a, int64_t nq, int look, int lpt, int epl, cudaStream_t st) {
-  if (epl == 2) return launch_t<MS, FOLD, 2, 384>(a, nq, look, lpt, st);
-  if (epl == 3) return launch_t<MS, FOLD, 3, 384>(a, nq, look, lpt, st);
+static int launch_epl(const ScanArgs& a, int64_t nq, int look, int lpt, cudaStream_t st) {
   return launch_t<MS, FOLD, 4, 384>(a, nq, look, lpt, st);
 }
 
@@ -501,15 +499,11 @@ int launch_scan_long(const ScanArgs& a, int64_t nq, cudaStream_t st) {
     return e ? atoi(e) : 0;
   }();
   const bool fold = lscan::smem_base_ok();
-  static const int epl = [] {  // entries per lane and segment (tuning knob)
-    const char* e = getenv("VLQ_SCAN_EPL");
-    return e ? atoi(e) : 4;
-  }();
   if (a.M == 16)
-    return fold ? lscan::launch_epl<16, true>(a, nq, look, lpt, epl, st)
-                : lscan::launch_epl<16, false>(a, nq, look, lpt, epl, st);
-  return fold ? lscan::launch_epl<8, true>(a, nq, look, lpt, epl, st)
-              : lscan::launch_epl<8, false>(a, nq, look, lpt, epl, st);
+    return fold ? lscan::launch_epl<16, true>(a, nq, look, lpt, st)
+                : lscan::launch_epl<16, false>(a, nq, look, lpt, st);
+  return fold ? lscan::launch_epl<8, true>(a, nq, look, lpt, st)
+              : lscan::launch_epl<8, false>(a, nq, look, lpt, st);
 }
 
 }  // namespace vlq

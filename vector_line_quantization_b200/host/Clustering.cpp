@@ -1,5 +1,7 @@
 #include "Clustering.h"
 
+#include <cmath>
+
 #include <stdlib.h>
 
 #include <algorithm>
@@ -115,22 +117,26 @@ void Clustering::train(idx_t nx, const float* x_in, gpu::GpuIndexFlat& index) {
   std::vector<int> counts(k);
   std::vector<long> hassign(k);
   obj.clear();
+  std::vector<float> dis(nx);
   for (int it = 0; it < niter; it++) {  // Clustering.cpp:161-193
-    index.assignDevice(dx, nx, dassign.as<int>(), verbose ? ddis.as<float>() : nullptr, true);
-    if (verbose) {
-      std::vector<float> dis(nx);
-      VLQ_CALL(vlq_memcpy_d2h(dis.data(), ddis.get(), ddis.bytes(), st));
-      res->syncDefaultStream();
-      double err = 0;
-      for (float v : dis) err += v;
-      obj.push_back((float)err);
-      printf("  Iteration %d  objective=%g\n", it, err);
-    }
-    VLQ_CALL(vlq_km_update(dx, nx, (int)d, dassign.as<int>(), (int)k, dcent.as<float>(), dcount.as<int>(), ws.get(),
+    index.assignDevice(dx, nx, dassign.as<int>(), ddis.as<float>(), true);
+    VLQ_CALL(vlq_memcpy_d2h(dis.data(), ddis.get(), ddis.bytes(), st));  // the objective of every iteration, like the
+    VLQ_CALL(vlq_km_update(dx, nx, (int)d, dassign.as<int>(), (int)k, dcent.as<float>(), dcount.as<int>(), ws.get(),  // reference
                            ws.bytes(), st));
     VLQ_CALL(vlq_memcpy_d2h(counts.data(), dcount.get(), dcount.bytes(), st));
     VLQ_CALL(vlq_memcpy_d2h(centroids.data(), dcent.get(), dcent.bytes(), st));
     res->syncDefaultStream();
+    {
+      double err = 0;
+      for (float v : dis) err += v;
+      obj.push_back((float)err);
+      if (verbose) printf("  Iteration %d  objective=%g\n", it, err);
+      // rows with NaN / Inf components get no centroid (label -1) and would silently drop out of the means: the
+      // reference refuses such input up front (Clustering.cpp:70-73 "input contains NaN's or Inf's")
+      long assigned = 0;
+      for (size_t c = 0; c < k; c++) assigned += counts[c];
+      VLQ_THROW_IF_NOT_MSG(assigned == (long)nx && std::isfinite(err), "input contains NaN's or Inf's");
+    }
     for (size_t c = 0; c < k; c++) hassign[c] = counts[c];
     split_empty(centroids, hassign, d, k, (size_t)nx);
     index.reset();

@@ -25,7 +25,7 @@ struct Clustering : ClusteringParameters {
   size_t d;
   size_t k;
   std::vector<float> centroids;  // (k * d) on the host after train()
-  std::vector<float> obj;        // objective per iteration (only filled when verbose)
+  std::vector<float> obj;        // objective (sum of squared distances) of every iteration
 
   Clustering(int d, int k);
   Clustering(int d, int k, const ClusteringParameters& cp);

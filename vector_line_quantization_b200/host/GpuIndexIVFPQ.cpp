@@ -48,9 +48,9 @@ void GpuIndexIVF::trainQuantizer_(Index::idx_t n, const float* x) {
 // ================================================================================================ GpuIndexIVFPQ (VLQ)
 GpuIndexIVFPQ::GpuIndexIVFPQ(GpuResources* resources, int dims, int nlist, int subQuantizers, int bitsPerCode,
                              int nedge, int nLambda, faiss::MetricType metric, GpuIndexIVFPQConfig config)
-    : GpuIndexIVF(resources, dims, metric, nlist, config), nLambda_(nLambda), numedge_(nedge), begin_(0), end_(0),
+    : GpuIndexIVF(resources, dims, metric, nlist, config), nLambda_(nLambda), numedge_(nedge), begin_(0), end_(nlist),
       w1_(256), edgeInfo_(nullptr), edgeDistInfo_(nullptr), lambdaInfo_(nullptr), constInfo_(nullptr), listCap_(VLQ_LIST_CAP),
-      ivfpqConfig_(config), subQuantizers_(subQuantizers), bitsPerCode_(bitsPerCode), reserveVecs_(0), nListed_(0),
+      ivfpqConfig_(config), subQuantizers_(subQuantizers), bitsPerCode_(bitsPerCode), reserveVecs_(0), nListed_(0), populatedLists_((size_t)nlist * nedge),
       nPending_(0), capPending_(0) {
   VLQ_THROW_IF_NOT_MSG(bitsPerCode == 8, "the scan kernels are written for 8-bit PQ codes");
   VLQ_THROW_IF_NOT_MSG(subQuantizers > 0 && subQuantizers <= 64 && dims % subQuantizers == 0,
@@ -86,6 +86,9 @@ void GpuIndexIVFPQ::reset() {
   nListed_ = 0;
   nPending_ = 0;
   ntotal = 0;
+  populatedLists_ = (size_t)nlist_ * numedge_;
+  begin_ = 0;
+  end_ = nlist_;
 }
 
 void GpuIndexIVFPQ::uploadTables_() {
@@ -284,6 +287,18 @@ void GpuIndexIVFPQ::commit_() const {
   lIds_.swap(ni);
   nListed_ = (size_t)live;
   nPending_ = 0;
+  // the pending arena has done its job: keep at most one add-chunk worth of it (a bulk load followed by searches would
+  // otherwise hold 33 B per vector next to the 29 B per vector of the lists)
+  const size_t keep = (size_t)1 << 21;
+  if (capPending_ > keep) {
+    pList_.release();
+    pCodes_.release();
+    pLamq_.release();
+    pKappa_.release();
+    pIds_.release();
+    capPending_ = 0;
+    reserveVecs_ = 0;
+  }
 }
 
 // searchImpl_ -> IVFPQ::queryGraph (gpu/GpuIndexIVFPQ.cu:1400-1464, gpu/impl/IVFPQ.cu:685-775)
@@ -359,7 +374,7 @@ void GpuIndexIVFPQ::search(Index::idx_t n, const float* x, Index::idx_t k, float
       VLQ_CALL(vlq_scan_topk(q, m, d, dPq_.as<float>(), M, dLambda_.as<float>(), nLambda_, lline, t1, t6,
                              dEdgeDist_.as<float>(), W, lOffsets_.as<int64_t>(), lCodes_.as<uint8_t>(),
                              lLamq_.as<uint8_t>(), lKappa_.as<float>(), lIds_.as<int64_t>(), (int)k, listCap_,
-                             (int)std::min<size_t>(nListed_ / ((size_t)nlist_ * numedge_), 1 << 20), oD, oI, t3ws_.get(),
+                             (int)std::min<size_t>(nListed_ / populatedLists_, 1 << 20), oD, oI, t3ws_.get(),
                              t3ws_.bytes(), st));
       float* hD = distances + (size_t)(p0 + s) * k;
       Index::idx_t* hI = labels + (size_t)(p0 + s) * k;
@@ -580,6 +595,14 @@ void GpuIndexIVFPQ::readDbFromFile(const std::string& name, int pronum, int rank
   fl.read((char*)las.data(), keep);
   VLQ_THROW_IF_NOT_MSG((keep == 0) || (fi.good() && fc.good() && fl.good()), "database files are truncated");
   installLists_(counts, codes, las, ids);
+  // The reference also restricts the COARSE search of rank r to its centroid range [begin_, end_]
+  // (gpu/GpuIndexIVFPQ.cu:2132-2137 -> queryGraph(..., begin_, end_)), so its R ranks together visit R x w1_ lines and
+  // the merged result differs from the single-index result.  Here every rank selects the global top-w1_ lines and
+  // scans those it owns: the merge over the ranks IS the single-index result (deviations).  begin_ / end_
+  // record the slice; populatedLists_ keeps the kernel choice honest (average length of the lists that hold entries).
+  begin_ = (nlist_ / pronum) * rank;
+  end_ = rank == pronum - 1 ? nlist_ - 1 : begin_ + nlist_ / pronum - 1;
+  populatedLists_ = std::max<size_t>(1, l1 - l0);
 }
 
 }  // namespace gpu

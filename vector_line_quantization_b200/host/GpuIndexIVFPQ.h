@@ -140,13 +140,14 @@ class GpuIndexIVFPQ : public GpuIndexIVF {
   int subQuantizers_;
   int bitsPerCode_;
   std::vector<float> pqHost_;  // (M, 256, dsub)
-  size_t reserveVecs_;
+  mutable size_t reserveVecs_;  // bulk-load hint of reserveMemory(): consumed by the first commit
 
   // device tables
   DeviceBuffer dEdge_, dEdgeDist_, dLambda_, dPq_;
   // CSR lists
   mutable DeviceBuffer lOffsets_, lCodes_, lLamq_, lKappa_, lIds_;
   mutable size_t nListed_;
+  size_t populatedLists_;  ///< lists that can hold entries (all of them; the slice of readDbFromFile(name, pronum, rank))
   // pending (encoded, arrival order)
   mutable DeviceBuffer pList_, pCodes_, pLamq_, pKappa_, pIds_;
   mutable size_t nPending_, capPending_;

@@ -168,7 +168,8 @@ void IndexShards::searchPeers_(const std::vector<int>& dev, idx_t n, const float
   const size_t nk = (size_t)n * k;
   const size_t i_off = (nk * sizeof(float) + 15) / 16 * 16;  // [D f32 (n, k) | I int64 (n, k)] per shard
   const size_t buf_bytes = i_off + nk * sizeof(int64_t);
-  const bool x_dev = vlq_pointer_is_device(x) == 1;
+  int x_on = -1;  // GPU the queries live on (-1: host memory)
+  VLQ_CALL(vlq_pointer_device(x, &x_on));
   const bool out_dev = vlq_pointer_is_device(distances) == 1;
   std::vector<idx_t> shift(ns, 0);
   if (successive_ids)
@@ -178,9 +179,10 @@ void IndexShards::searchPeers_(const std::vector<int>& dev, idx_t n, const float
     gpu::DeviceScope scope(dev[i]);
     res[i].resize(buf_bytes);
     const float* xi = x;
-    if (!x_dev) {  // one upload per GPU (a device pointer is passed through: peer access covers it)
+    if (x_on != dev[i]) {  // one copy of the queries per GPU: from the host, or from the GPU they live on (NVLink)
       xq[i].resize((size_t)n * d * sizeof(float));
-      VLQ_CALL(vlq_memcpy_h2d(xq[i].get(), x, xq[i].bytes(), nullptr));
+      if (x_on < 0) VLQ_CALL(vlq_memcpy_h2d(xq[i].get(), x, xq[i].bytes(), nullptr));
+      else VLQ_CALL(vlq_memcpy_d2d(xq[i].get(), x, xq[i].bytes(), nullptr));
       VLQ_CALL(vlq_stream_synchronize(nullptr));
       xi = xq[i].as<float>();
     }

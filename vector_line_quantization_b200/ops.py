@@ -280,7 +280,7 @@ def coarse_lines(q, cent, cnorm, edge, edge_d2, P, W, tile=4096, pack=None, out=
     return out
 
 
-def scan_lines(q, pq, lambda_cb, lines, edge_d2, lists, k, cap=1024, tile=4096, out=None):
+def scan_lines(q, pq, lambda_cb, lines, edge_d2, lists, k, cap=1024, tile=4096, out=None, list_len_hint=None):
     """Second half of the query path (a13-a15): scan the selected lines of every query on THIS shard's lists"""
     nq = q.shape[0]
     lst, t1, t6 = lines
@@ -289,11 +289,13 @@ def scan_lines(q, pq, lambda_cb, lines, edge_d2, lists, k, cap=1024, tile=4096, 
     ed2_flat = edge_d2.reshape(-1)
     for s in range(0, nq, tile):
         e = min(nq, s + tile)
-        scan_topk(q[s:e], pq, lambda_cb, lst[s:e], t1[s:e], t6[s:e], ed2_flat, lists, k, cap, out=(out[0][s:e], out[1][s:e]))
+        scan_topk(q[s:e], pq, lambda_cb, lst[s:e], t1[s:e], t6[s:e], ed2_flat, lists, k, cap, out=(out[0][s:e], out[1][s:e]),
+                  list_len_hint=list_len_hint)
     return out
 
 
-def search(q, cent, cnorm, edge, edge_d2, lambda_cb, pq, lists, P, W, k, cap=1024, tile=4096, pack=None, out=None):
+def search(q, cent, cnorm, edge, edge_d2, lambda_cb, pq, lists, P, W, k, cap=1024, tile=4096, pack=None, out=None,
+           list_len_hint=None):
     """Full query path on resident tensors (a11-a15), tiled over queries so the coarse matrix stays L2-sized.
     pack (a CentPack) routes the coarse distances through the tcgen05 kernel."""
     nq = q.shape[0]
@@ -317,7 +319,8 @@ def search(q, cent, cnorm, edge, edge_d2, lambda_cb, pq, lists, P, W, k, cap=102
             D = l2_distances(qt, cent, cnorm, out=Dbuf[: e - s])
             _, cid = select_rows(D, P)
             lst, t1, t6 = select_lines(D, cid, edge, edge_d2, W)
-        scan_topk(qt, pq, lambda_cb, lst, t1, t6, ed2_flat, lists, k, cap, out=(outD[s:e], outI[s:e]))
+        scan_topk(qt, pq, lambda_cb, lst, t1, t6, ed2_flat, lists, k, cap, out=(outD[s:e], outI[s:e]),
+                  list_len_hint=list_len_hint)
     return outD, outI
 
 

@@ -15,6 +15,33 @@ def shard_range(n_total, world, rank):
     return rank * n_total // world, (rank + 1) * n_total // world
 
 
+def route_by_list(new_list, arrays, nlists, group=None):
+    """List-range shards (the reference's own split, readDbFromFile(name, pronum, rank), gpu/GpuIndexIVFPQ.cu:2132-2163):
+    rank r owns lists [r * nlists / R, (r + 1) * nlists / R).  Every rank has encoded its rows; this sends each encoded
+    entry (list id + the per-entry arrays) to the owner of its list with one variable-size all-to-all per array.
+    Entries without a list (-1) are dropped.  Returns (list ids, arrays) of the entries this rank now owns, ordered by
+    source rank and, inside a source, by arrival -- i.e. by global row when the ranks hold consecutive id ranges."""
+    world = dist.get_world_size(group)
+    owner = torch.div(new_list.to(torch.int64) * world, nlists, rounding_mode="floor")
+    owner = torch.where(new_list >= 0, owner, torch.full_like(owner, world))  # world = dropped
+    order = torch.argsort(owner, stable=True)
+    counts = torch.bincount(owner, minlength=world + 1)[:world]
+    recv = torch.empty_like(counts)
+    dist.all_to_all_single(recv, counts, group=group)
+    send_sizes = counts.tolist()
+    recv_sizes = recv.tolist()
+    n_send, n_recv = sum(send_sizes), sum(recv_sizes)
+    order = order[:n_send]
+
+    def xchg(t):
+        src = t[order].contiguous()
+        out = torch.empty((n_recv,) + tuple(t.shape[1:]), dtype=t.dtype, device=t.device)
+        dist.all_to_all_single(out, src, output_split_sizes=recv_sizes, input_split_sizes=send_sizes, group=group)
+        return out
+
+    return xchg(new_list), [xchg(t) for t in arrays]
+
+
 def gather_topk(D, I, out_D=None, out_I=None):
     """all-gather per-shard results (nq,k) -> ([world][nq][k], [world][nq][k]) on every rank"""
     world = dist.get_world_size()
