@@ -65,17 +65,34 @@ __device__ __forceinline__ float lds_imm(uint32_t addr) {
   asm("ld.shared.f32 %0, [%1+%2];" : "=f"(v) : "r"(addr), "n"(IMM));
   return v;
 }
+template <int IMM>
+__device__ __forceinline__ int lds_imm_i(uint32_t addr) {
+  int v;
+  asm("ld.shared.s32 %0, [%1+%2];" : "=r"(v) : "r"(addr), "n"(IMM));
+  return v;
+}
+// The term-3 tables are held as FIXED-POINT int32 (value * 2^e, e per query such that 16 terms cannot overflow): the M
+// lookups of an entry are then summed with M / 2 three-input integer adds (IADD3) instead of M FADDs, and the sum is
+// exact -- the only rounding is the conversion of each table entry, <= 2^-27 of the largest |T3| of the query, which is
+// below the fp32 rounding of a float accumulation.  acc + sum over steps S.. of the lane's table word: PRMT (code << 8 |
+// 4 * lane) + LDS per step, one IADD3 per two steps.
 template <int MS, int S, bool FOLD>
-struct Adc {  // acc + sum over steps S.. of the lane's table word: PRMT (code << 8 | 4 * lane) + LDS + FADD per step
-  static __device__ __forceinline__ float run(const uint32_t* cw, uint32_t lofs, const unsigned char* tbl, float acc) {
+struct Adc {
+  static __device__ __forceinline__ int run(const uint32_t* cw, uint32_t lofs, const unsigned char* tbl, int acc) {
     if constexpr (S == MS) {
       return acc;
     } else {
-      const uint32_t o = __byte_perm(cw[S >> 2], lofs, 0x5504 | ((S & 3) << 4));
-      float t;
-      if constexpr (FOLD) t = lds_imm<(int)kDynBase + 4 * S>(o);
-      else t = *reinterpret_cast<const float*>(tbl + o + 4 * S);
-      return Adc<MS, S + 1, FOLD>::run(cw, lofs, tbl, acc + t);
+      const uint32_t o0 = __byte_perm(cw[S >> 2], lofs, 0x5504 | ((S & 3) << 4));
+      const uint32_t o1 = __byte_perm(cw[(S + 1) >> 2], lofs, 0x5504 | (((S + 1) & 3) << 4));
+      int t0, t1;
+      if constexpr (FOLD) {
+        t0 = lds_imm_i<(int)kDynBase + 4 * S>(o0);
+        t1 = lds_imm_i<(int)kDynBase + 4 * (S + 1)>(o1);
+      } else {
+        t0 = *reinterpret_cast<const int*>(tbl + o0 + 4 * S);
+        t1 = *reinterpret_cast<const int*>(tbl + o1 + 4 * (S + 1));
+      }
+      return Adc<MS, S + 2, FOLD>::run(cw, lofs, tbl, acc + t0 + t1);
     }
   }
 };
@@ -107,7 +124,7 @@ __host__ __device__ inline size_t smem_bytes(int W) {
   off += (select_smem_bytes(kSharedSelCap) + 15) & ~size_t(15);
   off += sizeof(LDesc) * W;
   off += ((size_t)W * 2 + 15) & ~size_t(15);
-  off += sizeof(int) * 32;
+  off += sizeof(int) * 32;  // misc: [0] next line, [1] lines, [2 + b] bucket cursors, [31] max |T3| of the query
   return off;
 }
 
@@ -244,19 +261,50 @@ __global__ void __launch_bounds__(NT, 2) scan_long_kernel(ScanArgs a, int look, 
   int* misc = reinterpret_cast<int*>(smem + off);  // [0] next line, [1] lines, [2 + b] bucket cursors
 
   const int64_t qi = blockIdx.x;
-  {  // word c of row `code` = T3[c mod M][code] (a.t3 is code-major): whole float4s; words 48..63 = lambda_cb[code]
+  float inv_scale;  // 2^-e of the fixed-point tables
+  {  // word c of row `code` = T3[c mod M][code] * 2^e as int32 (a.t3 is code-major); words 48..63 = lambda_cb[code] (float)
     const float4* src4 = reinterpret_cast<const float4*>(a.t3 + (size_t)qi * MS * 256);
-    float4* dst4 = reinterpret_cast<float4*>(tbl);
     constexpr int Q4 = (31 + MS + 3) / 4, S4 = MS / 4;
+    constexpr int NSRC = 256 * S4, PER = (NSRC + NT - 1) / NT;
     static_assert(Q4 * 4 <= LCB_W0, "table words overlap the lambda words");
-    for (int i = threadIdx.x; i < 256 * Q4; i += NT) {
-      const int code = i / Q4, q4 = i % Q4;
-      dst4[code * (ROW_WORDS / 4) + q4] = src4[code * S4 + (q4 & (S4 - 1))];
+    float4 v[PER];
+    float mx = 0.f;
+#pragma unroll
+    for (int t = 0; t < PER; t++) {
+      const int j = threadIdx.x + t * NT;
+      v[t] = j < NSRC ? src4[j] : make_float4(0.f, 0.f, 0.f, 0.f);
+      mx = fmaxf(mx, fmaxf(fmaxf(fabsf(v[t].x), fabsf(v[t].y)), fmaxf(fabsf(v[t].z), fabsf(v[t].w))));
     }
+    const unsigned mxb = __reduce_max_sync(kFull, __float_as_uint(mx));  // non-negative floats order like their bit patterns
+    if (threadIdx.x == 0) misc[31] = 0;
+    __syncthreads();
+    if (lane == 0) atomicMax(reinterpret_cast<unsigned*>(&misc[31]), mxb);
+    __syncthreads();
+    const float qmax = __uint_as_float((unsigned)misc[31]);
+    // largest power of two with qmax * scale < 2^26 (the M <= 16 terms of an entry then sum below 2^30); NaN / Inf
+    // tables (NaN queries) keep scale 1: their entries are never selected anyway
+    int e = 0;
+    if (qmax > 0.f && qmax < 3.0e38f) e = 25 - ilogbf(qmax);
+    e = max(-100, min(100, e));
+    const float scale = ldexpf(1.f, e);
+    inv_scale = ldexpf(1.f, -e);
+    int4* dst4 = reinterpret_cast<int4*>(tbl);
+#pragma unroll
+    for (int t = 0; t < PER; t++) {
+      const int j = threadIdx.x + t * NT;
+      if (j < NSRC) {
+        const int code = j / S4, part = j % S4;
+        const int4 w = make_int4(__float2int_rn(v[t].x * scale), __float2int_rn(v[t].y * scale),
+                                 __float2int_rn(v[t].z * scale), __float2int_rn(v[t].w * scale));
+#pragma unroll
+        for (int q4 = part; q4 < Q4; q4 += S4) dst4[code * (ROW_WORDS / 4) + q4] = w;
+      }
+    }
+    float4* dstf = reinterpret_cast<float4*>(tbl);
     for (int i = threadIdx.x; i < 256 * 4; i += NT) {
       const int code = i >> 2;
-      const float v = code < a.nL ? a.lambda_cb[code] : 0.f;
-      dst4[code * (ROW_WORDS / 4) + LCB_W0 / 4 + (i & 3)] = make_float4(v, v, v, v);
+      const float lv = code < a.nL ? a.lambda_cb[code] : 0.f;
+      dstf[code * (ROW_WORDS / 4) + LCB_W0 / 4 + (i & 3)] = make_float4(lv, lv, lv, lv);
     }
   }
   for (int i = threadIdx.x; i < CAP; i += NT) skeys[i] = kKeyInf;
@@ -360,18 +408,36 @@ __global__ void __launch_bounds__(NT, 2) scan_long_kernel(ScanArgs a, int look, 
         uint32_t cw[EPL][MS / 4];
         float kap[EPL];
         uint32_t lq[EPL];
+        if (e0 + SEG - 1 <= last) {  // full segment: one address per array, the four entries at immediate offsets
+          const unsigned char* cp = cb + (size_t)(e0 + lane) * MS;
+          const float* kp = kb + (e0 + lane);
+          const unsigned char* lp = lb + (e0 + lane);
 #pragma unroll
-        for (int u = 0; u < EPL; u++) {  // clamped, never predicated: duplicates of the last entry are masked below
-          const uint32_t i = (uint32_t)min(e0 + u * 32 + lane, last);
-          if constexpr (MS == 16) {
-            const uint4 c = ld_nc_v4(cb + (size_t)i * 16);
-            cw[u][0] = c.x; cw[u][1] = c.y; cw[u][MS / 4 - 2] = c.z; cw[u][MS / 4 - 1] = c.w;
-          } else {
-            const uint2 c = ld_nc_v2(cb + (size_t)i * 8);
-            cw[u][0] = c.x; cw[u][MS / 4 - 1] = c.y;
+          for (int u = 0; u < EPL; u++) {
+            if constexpr (MS == 16) {
+              const uint4 c = ld_nc_v4(cp + u * 32 * 16);
+              cw[u][0] = c.x; cw[u][1] = c.y; cw[u][MS / 4 - 2] = c.z; cw[u][MS / 4 - 1] = c.w;
+            } else {
+              const uint2 c = ld_nc_v2(cp + u * 32 * 8);
+              cw[u][0] = c.x; cw[u][MS / 4 - 1] = c.y;
+            }
+            kap[u] = __ldg(kp + u * 32);
+            lq[u] = __ldg(lp + u * 32);
           }
-          kap[u] = __ldg(kb + i);
-          lq[u] = __ldg(lb + i);
+        } else {
+#pragma unroll
+          for (int u = 0; u < EPL; u++) {  // clamped, never predicated: duplicates of the last entry are masked below
+            const uint32_t i = (uint32_t)min(e0 + u * 32 + lane, last);
+            if constexpr (MS == 16) {
+              const uint4 c = ld_nc_v4(cb + (size_t)i * 16);
+              cw[u][0] = c.x; cw[u][1] = c.y; cw[u][MS / 4 - 2] = c.z; cw[u][MS / 4 - 1] = c.w;
+            } else {
+              const uint2 c = ld_nc_v2(cb + (size_t)i * 8);
+              cw[u][0] = c.x; cw[u][MS / 4 - 1] = c.y;
+            }
+            kap[u] = __ldg(kb + i);
+            lq[u] = __ldg(lb + i);
+          }
         }
         const float thr = ord2f((uint32_t)ld_volatile(&smeta[M_THR]));
         float dist[EPL];
@@ -384,7 +450,7 @@ __global__ void __launch_bounds__(NT, 2) scan_long_kernel(ScanArgs a, int look, 
           if constexpr (FOLD) la = lds_imm<(int)kDynBase>(ol);
           else la = *reinterpret_cast<const float*>(tbl + ol);
           const float base_d = t1 + la * t6 + (la * la - la) * t5;
-          const float acc = Adc<MS, 0, FOLD>::run(cw[u], lofs, tbl, 0.f);
+          const float acc = (float)Adc<MS, 0, FOLD>::run(cw[u], lofs, tbl, 0) * inv_scale;
           dist[u] = (kap[u] + acc) + base_d;
           valid[u] = e0 + u * 32 + lane <= last;
           pass |= valid[u] && dist[u] <= thr;
