@@ -660,10 +660,13 @@ def run_b200(a):
         else:
             hidx.add_with_ids(hx[:m_], hids[:m_])
         enc_e2e_s += time.perf_counter() - t0
+        log("e2e add of %d vectors: %.1f ms" % (m_, (time.perf_counter() - t0) * 1e3))
+    xq8 = xq[:8].cpu().numpy()
     t0 = time.perf_counter()
-    hidx.search(xq[:8].cpu().numpy(), k)  # first search commits the pending entries into the CSR lists
+    hidx.search(xq8, k)  # first search commits the pending entries into the CSR lists
     torch.cuda.synchronize()
     enc_e2e_s += time.perf_counter() - t0
+    log("e2e list commit + first search: %.1f ms" % ((time.perf_counter() - t0) * 1e3))
     enc_e2e = torch.tensor([enc_e2e_s], device=dev)
     if world > 1:
         dist.all_reduce(enc_e2e, op=dist.ReduceOp.MAX)

@@ -369,9 +369,10 @@ __global__ void __launch_bounds__(NT, 2) scan_long_kernel(ScanArgs a, int look, 
   const uint32_t lofs = 4u * (uint32_t)lane;                      // column of the lane in the skewed table rows
   const uint32_t lcbofs = 4u * (uint32_t)(LCB_W0 + (lane & 15));  // its replica of the lambda codebook
 
-  // ---- every warp walks whole lines in segments of SEG = 32 * EPL entries.  (A register double-buffered form of this
-  // loop -- loads of segment i + 1 in flight while segment i is scored -- was measured: the extra registers cost a third
-  // of the resident warps and the scan got slower, 8.05 vs 7.5 ms per 10 k queries at 1 B entries.)
+  // ---- every warp walks whole lines in segments of SEG = 32 * EPL entries.  (Measured and dropped: a register
+  // double buffer -- loads of segment i + 1 in flight while segment i is scored -- costs a third of the resident warps,
+  // 8.05 vs 7.5 ms per 10 k queries at 1 B entries; a rolling half-segment pipeline in the same registers spills the
+  // in-flight kappa / lambda values at 80 registers, 9.2 ms, and with 10 warps at 96 registers reaches 8.4 ms.)
   bool first = true;  // the first segment of every warp ends in a block-wide rendezvous (see below)
   for (;;) {
     int li = 0;
