@@ -191,6 +191,9 @@ int vlq_gather_candidates(const int* line_list, int64_t nq, int W, const int64_t
  *     identical either way.
  *     workspace (optional, vlq_scan_topk_workspace_bytes): holds the term-3 tables of the batch, built by one
  *     persistent kernel with the PQ codebook in shared memory; with workspace == NULL every query CTA builds its own.
+ *     The one exception to "never synchronises": the FIRST call of a process that selects the long-list kernel
+ *     (list_len_hint >= 160) runs a one-thread probe kernel and copies 4 bytes back (base address of the dynamic shared
+ *     memory, which that kernel folds into its load instructions); later calls only enqueue work.
  * ---------------------------------------------------------------------------------------------------------------- */
 size_t vlq_scan_topk_workspace_bytes(int64_t nq, int M);
 int vlq_scan_topk(const float* q, int64_t nq, int d, const float* pq, int M, const float* lambda_cb, int nL,
