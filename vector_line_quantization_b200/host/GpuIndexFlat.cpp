@@ -15,10 +15,12 @@ void Index::assign(idx_t n, const float* x, idx_t* labels, idx_t k) {
 namespace gpu {
 
 // ------------------------------------------------------------------------------------------------ resources
-StandardGpuResources::StandardGpuResources(int device) : device_(device), stream_(nullptr), copyStream_(nullptr) {
+StandardGpuResources::StandardGpuResources(int device)
+    : device_(device), stream_(nullptr), copyStream_(nullptr), downStream_(nullptr) {
   DeviceScope scope(device_);
   VLQ_CALL(vlq_stream_create(&stream_));
   VLQ_CALL(vlq_stream_create(&copyStream_));
+  VLQ_CALL(vlq_stream_create(&downStream_));
 }
 StandardGpuResources::~StandardGpuResources() {
   if (stream_) {
@@ -28,6 +30,10 @@ StandardGpuResources::~StandardGpuResources() {
   if (copyStream_) {
     vlq_stream_synchronize(copyStream_);
     vlq_stream_destroy(copyStream_);
+  }
+  if (downStream_) {
+    vlq_stream_synchronize(downStream_);
+    vlq_stream_destroy(downStream_);
   }
 }
 void StandardGpuResources::syncDefaultStream() { VLQ_CALL(vlq_stream_synchronize(stream_)); }

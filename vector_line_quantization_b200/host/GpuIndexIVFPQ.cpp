@@ -331,9 +331,11 @@ void GpuIndexIVFPQ::search(Index::idx_t n, const float* x, Index::idx_t k, float
   float* t6 = t1 + (size_t)tile * W;
   float* bmin = t6 + (size_t)tile * W;
   t3ws_.reserve(vlq_scan_topk_workspace_bytes(tile, M));
-  // Host buffers: the queries of tile i+1 go up and the results of tile i-1 come down on the copy stream while tile i is
-  // computed (cross-stream order by vlq_stream_wait); device buffers are used in place.
+  // Host buffers: the queries of tile i+1 go up on the copy stream and the results of tile i-1 come down on the download
+  // stream while tile i is computed (cross-stream order by vlq_stream_wait: the compute stream only ever waits for
+  // uploads); device buffers are used in place (the scan writes straight into the caller's arrays).
   vlq_stream_t cs = resources_->getAsyncCopyStream();
+  vlq_stream_t ds = resources_->getAsyncDownloadStream();
   const bool xOnDevice = vlq_pointer_is_device(x) == 1;
   const bool dOnDevice = vlq_pointer_is_device(distances) == 1, lOnDevice = vlq_pointer_is_device(labels) == 1;
   for (Index::idx_t p0 = 0; p0 < n; p0 += page) {
@@ -369,25 +371,24 @@ void GpuIndexIVFPQ::search(Index::idx_t n, const float* x, Index::idx_t k, float
         VLQ_CALL(vlq_select_lines(dmat.as<float>(), m, nlist_, cidx, P, dEdge_.as<int>(), dEdgeDist_.as<float>(),
                                   numedge_, W, lline, t1, t6, st));
       }
-      float* oD = outD.as<float>() + (size_t)s * k;
-      int64_t* oI = outI.as<int64_t>() + (size_t)s * k;
+      float* hD = distances + (size_t)(p0 + s) * k;
+      Index::idx_t* hI = labels + (size_t)(p0 + s) * k;
+      const bool inPlace = dOnDevice && lOnDevice;
+      float* oD = inPlace ? hD : outD.as<float>() + (size_t)s * k;
+      int64_t* oI = inPlace ? reinterpret_cast<int64_t*>(hI) : outI.as<int64_t>() + (size_t)s * k;
       VLQ_CALL(vlq_scan_topk(q, m, d, dPq_.as<float>(), M, dLambda_.as<float>(), nLambda_, lline, t1, t6,
                              dEdgeDist_.as<float>(), W, lOffsets_.as<int64_t>(), lCodes_.as<uint8_t>(),
                              lLamq_.as<uint8_t>(), lKappa_.as<float>(), lIds_.as<int64_t>(), (int)k, listCap_,
                              (int)std::min<size_t>(nListed_ / populatedLists_, 1 << 20), oD, oI, t3ws_.get(),
                              t3ws_.bytes(), st));
-      float* hD = distances + (size_t)(p0 + s) * k;
-      Index::idx_t* hI = labels + (size_t)(p0 + s) * k;
-      if (dOnDevice && lOnDevice) {
-        VLQ_CALL(vlq_memcpy_d2d(hD, oD, (size_t)m * k * sizeof(float), st));
-        VLQ_CALL(vlq_memcpy_d2d(hI, oI, (size_t)m * k * sizeof(int64_t), st));
-      } else {
-        VLQ_CALL(vlq_stream_wait(cs, st));  // results of this tile are complete
-        fromDevice(hD, oD, (size_t)m * k * sizeof(float), cs);
-        fromDevice(hI, oI, (size_t)m * k * sizeof(int64_t), cs);
+      if (!inPlace) {
+        VLQ_CALL(vlq_stream_wait(ds, st));  // results of this tile are complete
+        fromDevice(hD, oD, (size_t)m * k * sizeof(float), ds);
+        fromDevice(hI, oI, (size_t)m * k * sizeof(int64_t), ds);
       }
     }
     VLQ_CALL(vlq_stream_synchronize(cs));
+    VLQ_CALL(vlq_stream_synchronize(ds));
     resources_->syncDefaultStream();
   }
 }

@@ -15,6 +15,9 @@ class GpuResources {
   virtual void syncDefaultStream() = 0;
   /// second stream for host->device staging that overlaps compute (reference: getAsyncCopyStream)
   virtual vlq_stream_t getAsyncCopyStream() = 0;
+  /// stream of the device->host result copies: kept apart from the uploads so that the compute stream, which waits for
+  /// the upload of the next query tile, never waits behind the download of the previous one
+  virtual vlq_stream_t getAsyncDownloadStream() { return getAsyncCopyStream(); }
 };
 
 class StandardGpuResources : public GpuResources {
@@ -25,6 +28,7 @@ class StandardGpuResources : public GpuResources {
   vlq_stream_t getDefaultStream() override { return stream_; }
   void syncDefaultStream() override;
   vlq_stream_t getAsyncCopyStream() override { return copyStream_; }
+  vlq_stream_t getAsyncDownloadStream() override { return downStream_; }
   /// kept for source compatibility with the reference (gpu/StandardGpuResources.h): sizes are managed on demand
   void noTempMemory() {}
   void setTempMemory(size_t) {}
@@ -34,6 +38,7 @@ class StandardGpuResources : public GpuResources {
   int device_;
   vlq_stream_t stream_;
   vlq_stream_t copyStream_;
+  vlq_stream_t downStream_;
 };
 
 /// binds the calling thread to the resource's device for the lifetime of the scope (reference DeviceScope)
