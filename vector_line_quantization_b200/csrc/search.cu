@@ -315,7 +315,7 @@ struct CodeRegs {
 //               lanes busy);  LONG = true: every warp owns whole lists (slot w -> warp w % 8) and strides their entries,
 //               so the per-list scalars are warp-uniform and nothing has to be searched per entry.
 template <int M_T, bool LONG>
-__global__ void __launch_bounds__(Q_THREADS, M_T == 16 ? 3 : 2) scan_topk_kernel(ScanArgs a) {  // 3 CTAs per SM: <= 80 registers
+__global__ void __launch_bounds__(Q_THREADS, M_T == 16 ? 3 : 2) scan_topk_kernel(ScanArgs a) {  // 3 CTAs per SM (80 registers): measured 0.86 ms per 10 k queries at C2; 2 CTAs 1.03, 4 CTAs (spills) 1.63
   extern __shared__ __align__(16) unsigned char smem[];
   // smem: [topk keys S*8 + 16][T3 M*ksub f32][lambda nL f32][per line: start i64, prefix i32 (W+1), t1, t6, t5 f32]
   const int M = a.M, ksub = a.ksub, dsub = a.dsub, W = a.W;
@@ -457,6 +457,59 @@ __global__ void __launch_bounds__(Q_THREADS, M_T == 16 ? 3 : 2) scan_topk_kernel
     for (int w = threadIdx.x; w < W; w += Q_THREADS)
       for (int p = prefix[w]; p < prefix[w + 1]; p++) owner[p] = (uint16_t)w;
     __syncthreads();
+  }
+
+  // ---- small queries (a few thousand entries in all, the C2 regime): every distance of the query fits in registers,
+  // kSmallR per thread, so the selection is ONE register-resident radix threshold (csl::kth32, coarse_select.cuh) +
+  // a rank ordering of the k survivors instead of the append / compact / sort machinery of BlockSelect, which was 80 %
+  // of this kernel's instructions at 2.7 k entries per query.  Thread t owns the stream positions [R t, R t + R), so
+  // ties resolve to the lowest position exactly as in the general path; same arithmetic, same bits.
+  constexpr int kSmallR = 16;
+  if (!LONG && use_owner && total <= kSmallR * Q_THREADS && a.k <= a.sel_cap) {  // block-uniform
+    uint32_t key[kSmallR];
+#pragma unroll
+    for (int r = 0; r < kSmallR; r++) {
+      const int pos = kSmallR * (int)threadIdx.x + r;
+      key[r] = csl::kInf32;
+      if (pos < total) {
+        const int lo = owner[pos];
+        const int pl = pos - prefix[lo];
+        const int64_t ent = lstart[lo] + pl;
+        CodeRegs<M_T> cr;
+        cr.load(a.codes + ent * M, pl);
+        const float la = lcb[a.lamq[ent]];
+        const float base_d = lt1[lo] + la * lt6[lo] + (la * la - la) * lt5[lo];
+        const float dist = (a.kappa[ent] + cr.adc(T3, M, ksub)) + base_d;
+        key[r] = csl::key32(dist);
+      }
+    }
+    uint64_t* skeys = reinterpret_cast<uint64_t*>(smem);  // the BlockSelect key area: <= k survivors
+    int* shist = reinterpret_cast<int*>(skeys + a.sel_cap);
+    int* smeta = shist + 256;
+    int* swsum = reinterpret_cast<int*>(owner + ((a.owner_cap + 1) & ~1));  // 16 ints behind the owner table
+    if (threadIdx.x == 0) swsum[8] = 0;
+    const csl::Kth kt = csl::kth32<kSmallR>(key, a.k, shist, smeta);
+    bool take[kSmallR];
+    csl::take_k<kSmallR>(key, kt, a.k, swsum, take);
+#pragma unroll
+    for (int r = 0; r < kSmallR; r++)
+      if (take[r]) skeys[atomicAdd(&swsum[8], 1)] = ((uint64_t)key[r] << 32) | (uint32_t)(kSmallR * (int)threadIdx.x + r);
+    for (int i = threadIdx.x; i < a.k; i += Q_THREADS) {
+      a.outD[qi * a.k + i] = FLT_MAX;
+      a.outI[qi * a.k + i] = -1;
+    }
+    __syncthreads();
+    const int ns = swsum[8];  // <= k
+    for (int i = threadIdx.x; i < ns; i += Q_THREADS) {
+      const uint64_t mykey = skeys[i];
+      int rank = 0;
+      for (int j = 0; j < ns; j++) rank += skeys[j] < mykey;
+      const int pos = (int)key_payload(mykey);
+      const int lo = owner[pos];
+      a.outD[qi * a.k + rank] = ord2f((uint32_t)(mykey >> 32));
+      a.outI[qi * a.k + rank] = a.ids[lstart[lo] + (pos - prefix[lo])];
+    }
+    return;
   }
 
   for (int base = 0; !LONG && base < total; base += Q_BATCH * Q_THREADS) {
@@ -942,7 +995,7 @@ static size_t scan_smem_bytes(int sel_cap, int M, int ksub, int nL, int W, int o
   off += sizeof(int64_t) * W;
   off += sizeof(int) * ((W + 1 + 3) & ~3);
   off += sizeof(float) * W * 3;
-  off += sizeof(uint16_t) * owner_cap;
+  off += sizeof(uint16_t) * ((owner_cap + 1) & ~1) + sizeof(int) * 16;  // owner table + scratch of the small-query path
   return off;
 }
 
