@@ -436,13 +436,20 @@ __global__ void __launch_bounds__(THREADS, 1) l2_tc_kernel(const Params p) {
           for (int c = 0; c < 2; c++) {
             const int col0 = t * TILE_ROWS + col_half * 64 + c * 32;
             if (MODE == 0) {
+              // running minimum with ONE min per element; the column is located only when the minimum of the chunk
+              // beats the row's best, which happens O(log C) times per row over the whole sweep (compare + two
+              // selects per element cost as much as an MMA pass at K = 128).  Same semantics as a strict `<` scan:
+              // first column on exact ties, NaN never selected.
+              float cmin = best[r];
 #pragma unroll
-              for (int i = 0; i < 32; i++) {
-                const float dv = fmaf(__uint_as_float(v[c][i]), m2s[r], cn[c * 32 + i]);
-                if (dv < best[r]) {
-                  best[r] = dv;
-                  bidx[r] = col0 + i;
-                }
+              for (int i = 0; i < 32; i++) cmin = fminf(cmin, fmaf(__uint_as_float(v[c][i]), m2s[r], cn[c * 32 + i]));
+              if (cmin < best[r]) {
+                int first = 32;
+#pragma unroll
+                for (int i = 31; i >= 0; i--)
+                  if (fmaf(__uint_as_float(v[c][i]), m2s[r], cn[c * 32 + i]) == cmin) first = i;
+                best[r] = cmin;
+                bidx[r] = col0 + first;
               }
             } else {
               // D tile: registers -> per-warp shared-memory transpose -> coalesced 128-byte row segments
