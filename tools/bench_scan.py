@@ -22,11 +22,14 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 
 
-def synthetic_lists(ops, n_target, nlists, M, dev, seed=1):
+def synthetic_lists(ops, n_target, nlists, M, dev, seed=1, keep_frac=1.0):
     g = torch.Generator(device=dev).manual_seed(seed)
     mean = n_target / nlists
     spread = torch.distributions.Gamma(4.0, 4.0).sample((nlists,)).to(dev)
-    lens = torch.poisson(spread * mean, generator=g).to(torch.int64)
+    lens_full = torch.poisson(spread * mean, generator=g).to(torch.int64)
+    lens = lens_full.clone()
+    if keep_frac < 1.0:  # a list-range shard: this rank holds the first keep_frac of the lists, the others are empty here
+        lens[int(nlists * keep_frac):] = 0
     off = torch.zeros(nlists + 1, dtype=torch.int64, device=dev)
     off[1:] = torch.cumsum(lens, 0)
     n = int(off[-1])
@@ -41,7 +44,7 @@ def synthetic_lists(ops, n_target, nlists, M, dev, seed=1):
         lamq[s:e] = torch.randint(0, 256, (e - s,), dtype=torch.uint8, device=dev, generator=g)
         kappa[s:e] = torch.randn(e - s, device=dev, generator=g) * 100.0
     ids = torch.arange(n, dtype=torch.int64, device=dev)
-    return ops.Lists(off, codes[:n], lamq[:n], kappa[:n], ids), lens
+    return ops.Lists(off, codes[:n], lamq[:n], kappa[:n], ids), lens, lens_full
 
 
 def main():
@@ -56,15 +59,18 @@ def main():
     ap.add_argument("--tile", type=int, default=4096)
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--hint", type=int, default=-1)
+    ap.add_argument("--keep-frac", type=float, default=1.0,
+                    help="emulate one rank of R list-range shards: only this fraction of the lists is populated, the "
+                         "queries still select lines over the whole index (1/R of each query's lines are non-empty)")
     a = ap.parse_args()
     from vector_line_quantization_b200 import _abi, ops
 
     _abi.lib()
     dev = torch.device("cuda:0")
     M, W, k, nq = a.m, a.w1, a.k, a.nq
-    lists, lens = synthetic_lists(ops, int(a.entries), a.nlists, M, dev)
+    lists, lens, lens_full = synthetic_lists(ops, int(a.entries), a.nlists, M, dev, keep_frac=a.keep_frac)
     g = torch.Generator(device=dev).manual_seed(7)
-    line = torch.multinomial(lens.float() + 1e-3, nq * W, replacement=True, generator=g).reshape(nq, W).to(torch.int32)
+    line = torch.multinomial(lens_full.float() + 1e-3, nq * W, replacement=True, generator=g).reshape(nq, W).to(torch.int32)
     q = torch.randn(nq, a.d, device=dev, generator=g)
     pq = torch.randn(M, 256, a.d // M, device=dev, generator=g)
     lcb = torch.rand(256, device=dev, generator=g)
@@ -107,7 +113,7 @@ def main():
     chk = int(outI.clamp_min(0).sum()) & 0xffffffff
     print(json.dumps({
         "kernel": os.environ.get("VLQ_SCAN_KERNEL", "auto"),
-        "entries": int(lists.ids.shape[0]), "avg_len": lists.ids.shape[0] / a.nlists, "M": M, "nq": nq, "w1": W, "k": k,
+        "entries": int(lists.ids.shape[0]), "avg_len": int(a.entries) / a.nlists, "keep_frac": a.keep_frac, "M": M, "nq": nq, "w1": W, "k": k,
         "scanned_per_query": scanned, "ms_mean": mean, "ms_best": best,
         "algorithmic_GBs": alg / (mean * 1e-3) / 1e9, "streamed_GBs": streamed / (mean * 1e-3) / 1e9,
         "frac_of_hbm_peak": alg / (mean * 1e-3) / 1e9 / peak, "peak": peak, "checksum": chk}))
