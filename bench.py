@@ -753,11 +753,11 @@ def run_b200(a):
 
     # ---- per-stage device times of one step (CUDA events on the launching stream) -> roofline of the dominant kernel
     def stage_times():
-        names = ["l2_distances", "select_rows", "select_lines", "coarse_select_lines", "scan_topk"]
+        names = ["l2_distances", "l2_bucket_min", "select_rows", "select_lines", "coarse_select_lines", "scan_topk"]
         acc = dict.fromkeys(names, 0.0)
         cnt = dict.fromkeys(names, 0)
         tile = 4096
-        Dbuf = torch.empty((tile, C), dtype=torch.float32, device=dev)
+        Dbuf = None if coarse_exact else torch.empty((tile, C), dtype=torch.float32, device=dev)
         bbuf = torch.empty((tile, ops.num_buckets(C)), dtype=torch.float32, device=dev)
         ed2f = ed2.reshape(-1)
 
@@ -772,7 +772,12 @@ def run_b200(a):
         pending = []
         for s in range(0, nq, tile):
             qt = xq[s:s + tile]
-            if use_tc:
+            if coarse_exact:  # no distance matrix: bucket minima from the tcgen05 sweep + exact re-evaluation
+                bm = bbuf[: qt.shape[0]]
+                t("l2_bucket_min", lambda: ops.l2_bucket_min_tc(qt, pack, bm))
+                lst, t1, t6 = t("coarse_select_lines",
+                                lambda: ops.coarse_select_lines_exact(qt, cent, cn, bm, P, edge, ed2, W))
+            elif use_tc:
                 bm = bbuf[: qt.shape[0]]
                 Dm = t("l2_distances", lambda: ops.l2_distances_tc(qt, pack, out=Dbuf[: qt.shape[0]], bucket_min=bm))
                 lst, t1, t6 = t("coarse_select_lines", lambda: ops.coarse_select_lines(Dm, bm, C, P, edge, ed2, W))
@@ -787,6 +792,7 @@ def run_b200(a):
             cnt[name] += 1
         return acc, cnt
 
+    coarse_exact = bool(use_tc and ops.CoarseStage(cent, cn, edge, ed2, P, W, 1, pack).exact)
     stage_times()
     st_ms, st_cnt = stage_times()
 
@@ -818,10 +824,19 @@ def run_b200(a):
         if name == "scan_topk":  # codes + lambda of every scanned entry, ids of the k winners
             r = {"bound": "hbm", "achieved": rows * (scanned_per_q * (M + 1) + k * 8) / (ms * 1e-3) / 1e9,
                  "peak": hbm_peak, "unit": "GB/s"}
+        elif name == "coarse_select_lines" and coarse_exact:
+            # HBM side: bucket minima + the query + W outputs; the (32 P + P E) centroid rows it re-evaluates come from
+            # the L2-resident centroid table (C d 4 bytes), reported as l2_GBs
+            nbk = ops.num_buckets(C)
+            r = {"bound": "hbm", "achieved": rows * (nbk * 4 + d * 4 + W * 12) / (ms * 1e-3) / 1e9,
+                 "peak": hbm_peak, "unit": "GB/s", "l2_GBs": rows * (32 * P + P * E) * d * 4.0 / (ms * 1e-3) / 1e9}
         elif name == "coarse_select_lines":  # bucket minima + P 128-byte lines of D + P*E gathers + W outputs
             nbk = ops.num_buckets(C)
             r = {"bound": "hbm", "achieved": rows * (nbk * 4 + P * 128 + P * E * 4 + W * 12) / (ms * 1e-3) / 1e9,
                  "peak": hbm_peak, "unit": "GB/s"}
+        elif name == "l2_bucket_min":  # tensor bound: 2 C d flop per query (x 2-3 fp16 passes executed)
+            r = {"bound": "tensor", "achieved": rows * 2.0 * C * d / (ms * 1e-3) / 1e12, "peak": tc_peak, "unit": "TFLOP/s",
+                 "executed_passes": "2 (integer-valued queries: x_lo = 0) or 3"}
         elif name in ("select_rows", "select_lines"):  # the whole row of D is read
             r = {"bound": "hbm", "achieved": rows * C * 4.0 / (ms * 1e-3) / 1e9, "peak": hbm_peak, "unit": "GB/s"}
         else:  # coarse distance tile: the GEMM is cheap next to writing 4*C bytes of distances (+ bucket minima) per query

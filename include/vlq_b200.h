@@ -77,6 +77,11 @@ int vlq_l2_assign_tc(const float* x, int64_t n, int d, const void* cent_pack, fl
 int vlq_tc_num_buckets(int C);
 int vlq_l2_distances_tc(const float* x, int64_t n, int d, const void* cent_pack, float scale, int C, float* D,
                         int64_t ldD, float* bucket_min, void* workspace, size_t workspace_bytes, vlq_stream_t stream);
+/* the same sweep WITHOUT the distance matrix: only bucket_min [n][vlq_tc_num_buckets(C)] is written (the query path
+ * re-evaluates the few columns it needs, vlq_coarse_select_lines_exact).  Replaces the nq x C matrix the reference
+ * materialises in runL2Distance, gpu/impl/Distance.cu:233-383. */
+int vlq_l2_bucket_min_tc(const float* x, int64_t n, int d, const void* cent_pack, float scale, int C, float* bucket_min,
+                         void* workspace, size_t workspace_bytes, vlq_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------------------------------
  * a11 coarse distance matrix for a query tile, D[i][j] = ||c_j||^2 - 2 x_i.c_j  (NO ||x||^2, Distance.cu:287-290).
@@ -169,6 +174,21 @@ int vlq_select_lines(const float* D, int64_t nq, int64_t ldD, const int* coarse_
 int vlq_coarse_select_lines(const float* D, int64_t nq, int64_t ldD, const float* bucket_min, int nb, int C, int P,
                             const int* edge, const float* edge_d2, int E, int W, int* out_coarse, int* out_list,
                             float* out_term1, float* out_term6, vlq_stream_t stream);
+
+/* a11 + a12 without a distance matrix: the top-P buckets come from bucket_min (vlq_l2_bucket_min_tc), the 32 columns of
+ *     each of them and the P*E neighbour centroids of the top-P are re-evaluated in fp32 from cent [C][d] / cnorm [C]
+ *     (D[c] = ||c||^2 - 2 q.c, the same definition).  Same outputs as vlq_coarse_select_lines up to the rounding of D
+ *     (near-ties only).  vlq_coarse_exact_supported: d % 4 == 0, d <= 128, max(num_buckets, 32 P, P E) <= 4096, W <= 1024;
+ *     otherwise VLQ_EUNSUPPORTED (callers fall back to the matrix path).  q, cent, bucket_min 16-byte aligned.
+ *     replaces l2SelectMinK + sumAlongRowsWithOrder2, gpu/impl/L2Select.cu:124-165, gpu/impl/BroadcastSum.cu:477-560.
+ *     vlq_coarse_exact_preferred: supported AND faster than the matrix route (at most 256 KiB of centroid rows per
+ *     query, i.e. small nprobe: P (32 + E) d 4 bytes from L2 against 4 C bytes of D written to HBM). */
+int vlq_coarse_exact_supported(int d, int C, int P, int E, int W);
+int vlq_coarse_exact_preferred(int d, int C, int P, int E, int W);
+int vlq_coarse_select_lines_exact(const float* q, int64_t nq, int d, const float* cent, const float* cnorm,
+                                  const float* bucket_min, int nb, int C, int P, const int* edge, const float* edge_d2,
+                                  int E, int W, int* out_coarse, int* out_list, float* out_term1, float* out_term6,
+                                  vlq_stream_t stream);
 
 /* candidate lists (f4): ids of the entries of the W selected lines of every query in line order, first k of them, -1
    padded -- the recall-of-the-candidate-list tool GpuIndexIVFPQ::search1 / IVFPQ::queryGraph1

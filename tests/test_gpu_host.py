@@ -178,9 +178,8 @@ def _search_vs_oracle_same_index(idx, oracle, m, xq, P, W, k, tmp_path, model=No
     cent = t(mm["cent"])
     pack = ops.CentPack(cent)
     qd = t(xq)
-    bm = torch.empty((len(xq), ops.num_buckets(m["C"])), dtype=torch.float32, device=dev)
-    Dm = ops.l2_distances_tc(qd, pack, bucket_min=bm)
-    lst, _, _ = ops.coarse_select_lines(Dm, bm, m["C"], min(P, m["C"]), t(mm["edge"]), t(mm["edge_d2"]), W)
+    stage = ops.CoarseStage(cent, pack.cnorm, t(mm["edge"]), t(mm["edge_d2"]), P, W, len(xq), pack)  # the host's dispatch
+    lst, _, _ = stage.run(qd)
     same_lines = check_lines(lst.cpu().numpy(), lines, xq, mm)
     # strict for every query: against the oracle's scan of the device's own line choice
     Dl, Il = oracle.scan_lines(xq, mm["cent"], mm["edge"], mm["edge_d2"], mm["lambda_cb"], mm["pq"], off, codes, las, ids,

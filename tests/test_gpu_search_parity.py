@@ -110,6 +110,14 @@ def _coarse_and_lines(ops, cuda, m, gi, P, W, route):
         bm = torch.empty((q.shape[0], ops.num_buckets(m["C"])), dtype=torch.float32, device=cuda)
         D = ops.l2_distances_tc(q, pack, bucket_min=bm)
         lst, t1, t6, cid = ops.coarse_select_lines(D, bm, m["C"], min(P, m["C"]), gi["edge"], gi["ed2"], W, want_coarse=True)
+    elif route == "tc_exact":  # no distance matrix: bucket minima + exact re-evaluation of the needed columns
+        pack = ops.CentPack(gi["cent"], gi["cn"])
+        if not ops._abi.lib().vlq_coarse_exact_supported(q.shape[1], m["C"], min(P, m["C"]), gi["edge"].shape[1], W):
+            pytest.skip("shape outside the matrix-free kernel")
+        bm = torch.empty((q.shape[0], ops.num_buckets(m["C"])), dtype=torch.float32, device=cuda)
+        ops.l2_bucket_min_tc(q, pack, bm)
+        lst, t1, t6, cid = ops.coarse_select_lines_exact(q, gi["cent"], gi["cn"], bm, min(P, m["C"]), gi["edge"], gi["ed2"],
+                                                         W, want_coarse=True)
     else:
         D = ops.l2_distances(q, gi["cent"], gi["cn"])
         _, cid = ops.select_rows(D, min(P, m["C"]))
@@ -128,7 +136,7 @@ CASES = [
 ]
 
 
-@pytest.mark.parametrize("route", ["simt", "tc"])
+@pytest.mark.parametrize("route", ["simt", "tc", "tc_exact"])
 @pytest.mark.parametrize("name,P,W,k,cap", CASES)
 def test_query_path_vs_oracle_near_tie_verified(ops, cuda, oracle, models, name, P, W, k, cap, route):
     m = models[name]

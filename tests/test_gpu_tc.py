@@ -141,3 +141,65 @@ def test_assign_tc_rows_of_any_magnitude(ops, cuda, n, C, d, kind):
     mag = np.linalg.norm(x64, axis=1)[:, None] * np.linalg.norm(c64, axis=1)[None, :] + (c64 ** 2).sum(1)[None, :]
     assert (np.abs(Dm.cpu().numpy() - ref) / mag).max() < 3e-6
     assert (np.abs(D0.cpu().numpy() - ref) / mag).max() < 3e-6
+
+
+@pytest.mark.parametrize("nq,C,d,P,W,E", [(100, 4096, 128, 8, 256, 32), (64, 65536, 128, 8, 256, 32), (33, 1000, 96, 16, 100, 8),
+                                          (10, 130, 64, 120, 1024, 16), (20, 65536, 128, 128, 512, 32),
+                                          (9, 8192, 128, 64, 700, 64), (5, 2048, 96, 4, 1024, 32), (6, 4096, 128, 1, 1, 32)])
+def test_matrix_free_coarse_select_against_float64(ops, cuda, nq, C, d, P, W, E):
+    """vlq_l2_bucket_min_tc + vlq_coarse_select_lines_exact (no distance matrix): the top-P centroids and the W lines are
+    the float64 ones up to near-ties (1e-5 of the magnitude of the terms), term1 / term6 are D[c] and D[s] - D[c]"""
+    import torch
+
+    x, c = _data(nq, C, d, 11, "sift")
+    xt, ct = torch.from_numpy(x).to(cuda), torch.from_numpy(c).to(cuda)
+    pack = ops.CentPack(ct)
+    assert ops._abi.lib().vlq_coarse_exact_supported(d, C, min(P, C), E, W)
+    bm = torch.empty((nq, ops.num_buckets(C)), dtype=torch.float32, device=cuda)
+    ops.l2_bucket_min_tc(xt, pack, bm)
+    bm1 = torch.empty_like(bm)
+    ops.l2_distances_tc(xt, pack, bucket_min=bm1)
+    assert torch.equal(bm, bm1)  # the matrix-free sweep writes the bucket minima of the matrix sweep
+    g = torch.Generator(device="cpu").manual_seed(5)
+    edge = torch.randint(0, C, (C, E), generator=g, dtype=torch.int32).to(cuda)
+    ed2 = (torch.rand((C, E), generator=g) * 1000 + 1).to(cuda)
+    Pk = min(P, C)
+    lst, t1, t6, cid = ops.coarse_select_lines_exact(xt, ct, pack.cnorm, bm, Pk, edge, ed2, W, want_coarse=True)
+    x64, c64 = xt.double(), ct.double()
+    D = (c64 * c64).sum(1)[None, :] - 2.0 * x64 @ c64.T  # [nq][C] float64
+    mag = (c64 * c64).sum(1)[None, :] + 2.0 * (x64.abs() @ c64.abs().T)
+    tol = 1e-5 * mag.max(dim=1).values  # per query
+    cid64 = cid.long()
+    assert int((cid64 < 0).sum()) == 0 and all(len(set(r.tolist())) == Pk for r in cid64.cpu())
+    dsel = torch.gather(D, 1, cid64)
+    assert bool((dsel[:, 1:] - dsel[:, :-1] >= -tol[:, None]).all())  # ascending
+    kth = torch.topk(D, Pk, dim=1, largest=False).values[:, -1]
+    assert bool((dsel.max(dim=1).values <= kth + tol).all())  # the selected set is a top-P set up to near-ties
+    # lines of the kernel's own top-P
+    s = edge.long()[cid64]  # [nq][Pk][E]
+    a2 = torch.gather(D, 1, s.reshape(nq, -1)).reshape(nq, Pk, E)
+    b2 = dsel[:, :, None].expand(-1, -1, E)
+    c2 = ed2.double()[cid64]
+    v = a2 - b2 - c2
+    score = torch.where(v > 0, b2, b2 - 0.25 * v * v / c2).reshape(nq, -1)
+    lid = (cid64[:, :, None] * E + torch.arange(E, device=cuda)[None, None, :]).reshape(nq, -1)
+    Wk = min(W, Pk * E)
+    assert int((lst[:, :Wk] < 0).sum()) == 0 and int((lst[:, Wk:] >= 0).sum()) == 0
+    pos = {}
+    for r in range(nq):
+        where = {int(l): i for i, l in enumerate(lid[r].tolist())}
+        got = [where[int(l)] for l in lst[r, :Wk].tolist()]
+        assert len(set(got)) == Wk
+        sg = score[r, got]
+        stol = 4 * tol[r]
+        assert bool((sg[1:] - sg[:-1] >= -stol).all())
+        assert float(sg.max()) <= float(torch.topk(score[r], Wk, largest=False).values[-1]) + float(stol)
+        torch.testing.assert_close(t1[r, :Wk].double(), b2.reshape(nq, -1)[r, got], rtol=0, atol=float(tol[r]))
+        torch.testing.assert_close(t6[r, :Wk].double(), (a2 - b2).reshape(nq, -1)[r, got], rtol=0, atol=float(2 * tol[r]))
+    # NaN / inf queries select nothing
+    xt2 = xt.clone()
+    xt2[0, 3] = float("nan")
+    ops.l2_bucket_min_tc(xt2, pack, bm)
+    lst2, _, _, cid2 = ops.coarse_select_lines_exact(xt2, ct, pack.cnorm, bm, Pk, edge, ed2, W, want_coarse=True)
+    assert int((lst2[0] >= 0).sum()) == 0 and int((cid2[0] >= 0).sum()) == 0
+    assert torch.equal(lst2[1:], lst[1:])

@@ -29,6 +29,7 @@ SIGNATURES = {
     "vlq_l2_assign_tc": (_i, [_p, _l, _i, _p, _f, _i, _i, _p, _p, _p, _z, _p]),
     "vlq_tc_num_buckets": (_i, [_i]),
     "vlq_l2_distances_tc": (_i, [_p, _l, _i, _p, _f, _i, _p, _l, _p, _p, _z, _p]),
+    "vlq_l2_bucket_min_tc": (_i, [_p, _l, _i, _p, _f, _i, _p, _p, _z, _p]),
     "vlq_l2_distances": (_i, [_p, _l, _i, _p, _p, _i, _p, _l, _p]),
     "vlq_select_rows": (_i, [_p, _l, _i, _l, _i, _p, _p, _p, _p]),
     "vlq_knn_graph_workspace_bytes": (_z, [_i, _i]),
@@ -41,6 +42,9 @@ SIGNATURES = {
     "vlq_recompute_kappa": (_i, [_l, _l, _p, _p, _p, _p, _i, _p, _i, _p, _p, _i, _p, _p]),
     "vlq_select_lines": (_i, [_p, _l, _l, _p, _i, _p, _p, _i, _i, _p, _p, _p, _p]),
     "vlq_coarse_select_lines": (_i, [_p, _l, _l, _p, _i, _i, _i, _p, _p, _i, _i, _p, _p, _p, _p, _p]),
+    "vlq_coarse_exact_supported": (_i, [_i, _i, _i, _i, _i]),
+    "vlq_coarse_exact_preferred": (_i, [_i, _i, _i, _i, _i]),
+    "vlq_coarse_select_lines_exact": (_i, [_p, _l, _i, _p, _p, _p, _i, _i, _i, _p, _p, _i, _i, _p, _p, _p, _p, _p]),
     "vlq_gather_candidates": (_i, [_p, _l, _i, _p, _p, _l, _p, _p]),
     "vlq_scan_topk_workspace_bytes": (_z, [_l, _i]),
     "vlq_scan_topk": (_i, [_p, _l, _i, _p, _i, _p, _i, _p, _p, _p, _p, _i, _p, _p, _p, _p, _p, _i, _i, _i, _p, _p, _p, _z, _p]),

@@ -254,7 +254,7 @@ struct Params {
   float* bmin;             // mode 1 (nullable): [n][n_ctiles*4] minimum of every 32-column bucket of D
 };
 
-template <int MODE>  // 0 = fused arg-min, 1 = store the distance tile
+template <int MODE>  // 0 = fused arg-min, 1 = store the distance tile (+ bucket minima), 2 = bucket minima only
 __global__ void __launch_bounds__(THREADS, 1) l2_tc_kernel(const Params p) {
   extern __shared__ __align__(1024) uint8_t smem[];
   const int nkb = p.d / KB;
@@ -432,6 +432,8 @@ __global__ void __launch_bounds__(THREADS, 1) l2_tc_kernel(const Params p) {
           tmem_ld32(taddr, v[0]);  // both 32-column chunks in flight before the first use
           tmem_ld32(taddr + 32, v[1]);
           tmem_ld_wait();
+          float mn_prev = 0.f;
+          (void)mn_prev;
 #pragma unroll
           for (int c = 0; c < 2; c++) {
             const int col0 = t * TILE_ROWS + col_half * 64 + c * 32;
@@ -451,6 +453,15 @@ __global__ void __launch_bounds__(THREADS, 1) l2_tc_kernel(const Params p) {
                 best[r] = cmin;
                 bidx[r] = col0 + first;
               }
+            } else if (MODE == 2) {
+              // bucket minima only: the distance matrix never leaves the SM (the query path re-evaluates the few
+              // columns it needs exactly, coarse_select.cuh)
+              float mn = __int_as_float(0x7f800000);
+#pragma unroll
+              for (int i = 0; i < 32; i++) mn = fminf(mn, fmaf(__uint_as_float(v[c][i]), m2s[r], cn[c * 32 + i]));
+              if (c == 0) mn_prev = mn;
+              if (c == 1 && row < n_rows)  // buckets (col0 >> 5) - 1 and col0 >> 5: one 8-byte store (nb is a multiple of 4)
+                *reinterpret_cast<float2*>(p.bmin + row * nb + (col0 >> 5) - 1) = make_float2(mn_prev, mn);
             } else {
               // D tile: registers -> per-warp shared-memory transpose -> coalesced 128-byte row segments
               // (a thread owns one ROW of the accumulator; storing straight from registers would make every warp
@@ -626,6 +637,7 @@ static int tc_run(int mode, const float* x, int64_t n, int d, const void* cent_p
   if (!x || !cent_pack || !workspace) return VLQ_EINVAL;
   if (mode == 0 && !out_ids) return VLQ_EINVAL;
   if (mode == 1 && (!D || ldD < C)) return VLQ_EINVAL;
+  if (mode == 2 && !bmin) return VLQ_EINVAL;
   if (reinterpret_cast<uintptr_t>(x) & 15) return VLQ_EINVAL;
   if (workspace_bytes < vlq_l2_tc_workspace_bytes(n, d, C)) return VLQ_EWORKSPACE;
   cudaStream_t st = as_stream(stream);
@@ -674,7 +686,7 @@ static int tc_run(int mode, const float* x, int64_t n, int d, const void* cent_p
     p.keys = keys;
     p.D = mode == 1 ? D + r0 * ldD : nullptr;
     p.ldD = ldD;
-    p.bmin = (mode == 1 && bmin) ? bmin + r0 * (int64_t)(Cpad / 32) : nullptr;
+    p.bmin = (mode != 0 && bmin) ? bmin + r0 * (int64_t)(Cpad / 32) : nullptr;
     int rc;
     if (mode == 0) {
       VLQ_CUDA_TRY(cudaMemsetAsync(keys, 0xff, sizeof(unsigned long long) * rows, st));
@@ -688,7 +700,7 @@ static int tc_run(int mode, const float* x, int64_t n, int d, const void* cent_p
       VLQ_LAUNCH(tc::finalize_keys_kernel, (unsigned)div_up(rows, 256), 256, 0, st, keys, rows, xn, out_ids + r0,
                  out_dist ? out_dist + r0 : nullptr);
     } else {
-      rc = tc::launch<1>(p, st);
+      rc = mode == 1 ? tc::launch<1>(p, st) : tc::launch<2>(p, st);
       if (rc) return rc;
     }
   }
@@ -705,6 +717,12 @@ int vlq_l2_distances_tc(const float* x, int64_t n, int d, const void* cent_pack,
                         int64_t ldD, float* bucket_min, void* workspace, size_t workspace_bytes, vlq_stream_t stream) {
   return tc_run(1, x, n, d, cent_pack, scale, C, 0, nullptr, nullptr, D, ldD, bucket_min, workspace, workspace_bytes,
                 stream);
+}
+
+int vlq_l2_bucket_min_tc(const float* x, int64_t n, int d, const void* cent_pack, float scale, int C, float* bucket_min,
+                         void* workspace, size_t workspace_bytes, vlq_stream_t stream) {
+  return tc_run(2, x, n, d, cent_pack, scale, C, 0, nullptr, nullptr, nullptr, 0, bucket_min, workspace,
+                workspace_bytes, stream);
 }
 
 int vlq_tc_num_buckets(int C) { return (int)(div_up(C, tc::TILE_ROWS) * tc::TILE_ROWS / 32); }

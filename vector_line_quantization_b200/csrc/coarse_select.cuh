@@ -334,5 +334,254 @@ coarse_select_lines_fast_kernel(const float* __restrict__ D, int64_t ldD, const 
   }
 }
 
+// ------------------------------------------------------------------------------------------------------------------
+// The same selection WITHOUT a distance matrix (north_star: "stop materialising D").  The tensor-core sweep emits only
+// the bucket minima (l2_tc_kernel<2>); the few hundred columns a query really needs -- the 32 columns of each of its P
+// best buckets and the P*E neighbour centroids of its top-P -- are re-evaluated here in fp32 from the centroid table,
+// which (C * d * 4 = 32 MiB at C2) stays L2-resident because nothing streams a gigabyte of D through the L2 any more.
+//   per query: (32 P + P E) rows of d floats from L2 instead of 4 C bytes written + ~(P + P E) random DRAM sectors read.
+// Every distance is produced by the same routine (dot8: fixed summation tree, independent of the row's slot), so
+// D[c] of a centroid that is both a top-P centroid and somebody's neighbour is one number, as with a stored matrix.
+
+// 8 rows at once: p[r] = this lane's share of x . row_r; afterwards every lane of a quad holds the complete sum of row
+// ((lane >> 4) & 1) * 4 + ((lane >> 3) & 1) * 2 + ((lane >> 2) & 1)      (9 shuffles for 8 rows)
+__device__ __forceinline__ float reduce8(float (&p)[8], int lane) {
+  const bool b4 = lane & 16, b3 = lane & 8, b2 = lane & 4;
+  float a[4];
+#pragma unroll
+  for (int j = 0; j < 4; j++) {
+    const float send = b4 ? p[j] : p[j + 4];
+    const float keep = b4 ? p[j + 4] : p[j];
+    a[j] = keep + __shfl_xor_sync(kFull, send, 16);
+  }
+  float b[2];
+#pragma unroll
+  for (int j = 0; j < 2; j++) {
+    const float send = b3 ? a[j] : a[j + 2];
+    const float keep = b3 ? a[j + 2] : a[j];
+    b[j] = keep + __shfl_xor_sync(kFull, send, 8);
+  }
+  const float send = b2 ? b[0] : b[1];
+  const float keep = b2 ? b[1] : b[0];
+  float c = keep + __shfl_xor_sync(kFull, send, 4);
+  c += __shfl_xor_sync(kFull, c, 2);
+  c += __shfl_xor_sync(kFull, c, 1);
+  return c;
+}
+__device__ __forceinline__ int reduce8_row(int lane) { return ((lane >> 4) & 1) * 4 + ((lane >> 3) & 1) * 2 + ((lane >> 2) & 1); }
+
+// x . row for 8 rows; qv = the lane's 4 query components (zero beyond d), act = lane * 4 < d
+__device__ __forceinline__ float dot8(const float* __restrict__ cent, int d, const int (&rows)[8], const float4& qv,
+                                      bool act, int lane) {
+  float p[8];
+  float4 c[8];
+#pragma unroll
+  for (int r = 0; r < 8; r++) {
+    c[r] = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (act) c[r] = __ldg(reinterpret_cast<const float4*>(cent + (size_t)rows[r] * d) + lane);
+  }
+#pragma unroll
+  for (int r = 0; r < 8; r++) p[r] = fmaf(c[r].w, qv.w, fmaf(c[r].z, qv.z, fmaf(c[r].y, qv.y, c[r].x * qv.x)));
+  return reduce8(p, lane);
+}
+
+struct SmemExact {
+  __host__ __device__ static size_t bytes(int R, int P) {
+    return Smem::bytes(R, P) + sizeof(float) * ((size_t)R * NT + P);  // + distances of the candidates / lines, top-P values
+  }
+};
+
+__host__ __device__ inline bool exact_supported(int d, int nb, int P, int E, int W) {
+  const int need = nb > P * E ? (nb > P * 32 ? nb : P * 32) : (P * E > P * 32 ? P * E : P * 32);
+  return d >= 4 && d <= 128 && d % 4 == 0 && need <= 16 * NT && W <= 1024 && nb % 4 == 0;
+}
+
+template <int R>
+__global__ void __launch_bounds__(NT, R == 8 ? 4 : 2)
+coarse_select_lines_exact_kernel(const float* __restrict__ xq, int d, const float* __restrict__ cent,
+                                 const float* __restrict__ cnorm, const float* __restrict__ bmin, int nb, int C, int P,
+                                 const int* __restrict__ edge, const float* __restrict__ edge_d2, int E, int W,
+                                 int* __restrict__ out_coarse, int* __restrict__ out_list,
+                                 float* __restrict__ out_term1, float* __restrict__ out_term6) {
+  extern __shared__ __align__(16) unsigned char smem[];
+  uint64_t* keys = reinterpret_cast<uint64_t*>(smem);             // [R * NT]
+  float* st1 = reinterpret_cast<float*>(keys + (size_t)R * NT);    // [1024]
+  float* st6 = st1 + 1024;                                         // [1024]
+  int* slist = reinterpret_cast<int*>(st6 + 1024);                 // [1024]
+  int* bk_s = slist + 1024;                                        // [P] selected buckets
+  int* top_s = bk_s + P;                                           // [P] top-P centroids, ascending
+  int* hist = top_s + P;                                           // [256]
+  int* meta = hist + 256;                                          // [8]
+  int* wsum = meta + 8;                                            // [8]
+  int* cnt = wsum + 8;                                             // [4] append cursors, [3] = bound of the candidates
+  float* fbuf = reinterpret_cast<float*>(smem + Smem::bytes(R, P));  // [R * NT] candidate / line distances
+  float* top_v = fbuf + (size_t)R * NT;                            // [P] distances of the top-P centroids
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int64_t q = blockIdx.x;
+  const float* bq = bmin + q * nb;
+  const bool act = lane * 4 < d;
+  float4 qv = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (act) qv = __ldg(reinterpret_cast<const float4*>(xq + q * d) + lane);
+
+  // ---- 1: the P buckets (32 consecutive centroids each) with the smallest minima (tensor-core values)
+  const int Pb = P < nb ? P : nb;
+  {
+    uint32_t kb[R];
+    const int j0 = R * (int)threadIdx.x;
+#pragma unroll
+    for (int r4 = 0; r4 < R; r4 += 4) {
+      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+      const bool in = j0 + r4 + 3 < nb;
+      if (in) v = *reinterpret_cast<const float4*>(bq + j0 + r4);
+      const float vv[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+      for (int r = 0; r < 4; r++) {
+        float x = vv[r];
+        if (!in) x = j0 + r4 + r < nb ? bq[j0 + r4 + r] : __int_as_float(0x7fc00000);
+        kb[r4 + r] = key32(x);
+      }
+    }
+    if (threadIdx.x < 4) cnt[threadIdx.x] = 0;
+    const Kth kt1 = kth32<R>(kb, Pb, hist, meta);
+    bool take[R];
+    take_k<R>(kb, kt1, Pb, wsum, take);
+#pragma unroll
+    for (int r = 0; r < R; r++)
+      if (take[r]) bk_s[atomicAdd(&cnt[0], 1)] = R * (int)threadIdx.x + r;  // <= Pb appends
+  }
+  __syncthreads();
+  const int nbk = cnt[0];
+  // ---- 2: exact distances of the 32 columns of every selected bucket; warp <- groups of 8 consecutive rows
+  for (int g = warp; g < nbk * 4; g += NT / 32) {
+    const int c0 = bk_s[g >> 2] * 32 + (g & 3) * 8;
+    int rows[8];
+#pragma unroll
+    for (int r = 0; r < 8; r++) rows[r] = min(c0 + r, C - 1);
+    const float dot = dot8(cent, d, rows, qv, act, lane);
+    if ((lane & 3) == 0) {
+      const int r = reduce8_row(lane), c = c0 + r;
+      fbuf[(g >> 2) * 32 + (g & 3) * 8 + r] = c < C ? fmaf(-2.f, dot, __ldg(cnorm + c)) : __int_as_float(0x7fc00000);
+    }
+  }
+  __syncthreads();
+  // bound: the largest exact bucket minimum.  The P minima are P different columns, so the P-th smallest candidate
+  // cannot be above it (with fewer buckets than P every column of every bucket is a candidate).
+  for (int i = threadIdx.x; i < nbk * 32; i += NT) {  // NT is a multiple of 32: a warp covers one bucket
+    const uint32_t mk = __reduce_min_sync(kFull, key32(fbuf[i]));
+    if (lane == 0) atomicMax(reinterpret_cast<unsigned*>(&cnt[3]), mk);
+  }
+  __syncthreads();
+  const uint32_t tau1 = Pb < P ? kInf32 : (uint32_t)cnt[3];
+  for (int i = threadIdx.x; i < nbk * 32; i += NT) {
+    const float v = fbuf[i];
+    const uint32_t kv = key32(v);
+    const bool pass = kv != kInf32 && kv <= tau1;
+    const unsigned m = __ballot_sync(kFull, pass);
+    int base = 0;
+    if (lane == 0 && m) base = atomicAdd(&cnt[1], __popc(m));
+    base = __shfl_sync(kFull, base, 0);
+    if (pass) keys[base + __popc(m & ((1u << lane) - 1))] = make_key(v, (uint32_t)(bk_s[i >> 5] * 32 + (i & 31)));
+  }
+  __syncthreads();
+  const int nc = cnt[1];  // <= nbk * 32 <= R * NT
+  const int Pk = P < C ? P : C;
+  // ---- exact top-P: rank of every candidate among the candidates
+  for (int i = threadIdx.x; i < P; i += NT) top_s[i] = -1;
+  __syncthreads();
+  for (int i = threadIdx.x; i < nc; i += NT) {
+    const uint64_t mykey = keys[i];
+    int rank = 0;
+    for (int j = 0; j < nc; j++) rank += keys[j] < mykey;
+    if (rank < Pk) {
+      top_s[rank] = (int)key_payload(mykey);
+      top_v[rank] = key_val(mykey);
+    }
+  }
+  __syncthreads();
+  if (out_coarse)
+    for (int i = threadIdx.x; i < P; i += NT) out_coarse[q * P + i] = top_s[i];
+
+  // ---- 3a: exact distances of the P*E neighbour centroids (line i = centroid i / E, edge i % E)
+  const int num = P * E;
+  for (int g = warp; g * 8 < num; g += NT / 32) {
+    int rows[8];
+    int sid = -1;  // lane 4 r' of the quad that ends up with row r' keeps its neighbour id
+#pragma unroll
+    for (int r = 0; r < 8; r++) {
+      const int i = g * 8 + r;
+      int s = -1;
+      if (i < num) {
+        const int c = top_s[i / E];
+        if (c >= 0) s = __ldg(edge + (int64_t)c * E + (i % E));
+      }
+      if (s >= C) s = -1;
+      rows[r] = s < 0 ? 0 : s;
+      if (r == reduce8_row(lane)) sid = s;
+    }
+    const float dot = dot8(cent, d, rows, qv, act, lane);
+    if ((lane & 3) == 0) {
+      const int i = g * 8 + reduce8_row(lane);
+      if (i < num) fbuf[i] = sid >= 0 ? fmaf(-2.f, dot, __ldg(cnorm + sid)) : __int_as_float(0x7fc00000);
+    }
+  }
+  __syncthreads();
+  // ---- 3b: the W best of the P*E lines (BroadcastSum.cu:505-552); thread t scores the lines [R t, R t + R)
+  uint32_t kl[R];
+  float a2r[R], b2r[R];
+  int lid[R];
+#pragma unroll
+  for (int r = 0; r < R; r++) {
+    const int i = R * (int)threadIdx.x + r;
+    kl[r] = kInf32;
+    a2r[r] = b2r[r] = 0.f;
+    lid[r] = -1;
+    if (i < num) {
+      const int c = top_s[i / E];
+      if (c >= 0) {
+        const int e = i % E;
+        const float a2 = fbuf[i], b2 = top_v[i / E], c2 = edge_d2[(int64_t)c * E + e];
+        float v = __fsub_rn(a2, b2);
+        v = __fsub_rn(v, c2);
+        // BroadcastSum.cu:517: (v>0) ? b2 : b2 - 0.25 v^2 / c2
+        const float score = (v > 0.f) ? b2 : __fsub_rn(b2, __fdiv_rn(__fmul_rn(__fmul_rn(0.25f, v), v), c2));
+        kl[r] = key32(score);
+        a2r[r] = a2;
+        b2r[r] = b2;
+        lid[r] = c * E + e;
+      }
+    }
+  }
+  const Kth kt3 = kth32<R>(kl, W, hist, meta);
+  {
+    bool take[R];
+    take_k<R>(kl, kt3, W, wsum, take);
+#pragma unroll
+    for (int r = 0; r < R; r++) {
+      if (take[r]) {
+        const int slot = atomicAdd(&cnt[2], 1);  // <= W appends
+        keys[slot] = ((uint64_t)kl[r] << 32) | (uint32_t)(R * (int)threadIdx.x + r);
+        st1[slot] = b2r[r];
+        st6[slot] = __fsub_rn(a2r[r], b2r[r]);
+        slist[slot] = lid[r];
+      }
+    }
+  }
+  for (int w = threadIdx.x; w < W; w += NT) {  // slots the ranks below do not reach
+    out_list[q * W + w] = -1;
+    out_term1[q * W + w] = 0.f;
+    out_term6[q * W + w] = 0.f;
+  }
+  __syncthreads();
+  const int ns = cnt[2];
+  for (int i = threadIdx.x; i < ns; i += NT) {
+    const uint64_t mykey = keys[i];
+    int rank = 0;
+    for (int j = 0; j < ns; j++) rank += keys[j] < mykey;
+    out_list[q * W + rank] = slist[i];
+    out_term1[q * W + rank] = st1[i];
+    out_term6[q * W + rank] = st6[i];
+  }
+}
+
 }  // namespace csl
 }  // namespace vlq

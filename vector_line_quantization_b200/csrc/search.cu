@@ -1134,6 +1134,48 @@ int vlq_coarse_select_lines(const float* D, int64_t nq, int64_t ldD, const float
   return last_error();
 }
 
+int vlq_coarse_exact_supported(int d, int C, int P, int E, int W) {
+  if (d <= 0 || C <= 0 || P <= 0 || E <= 0 || W <= 0) return 0;
+  return csl::exact_supported(d, vlq_tc_num_buckets(C), P, E, W) ? 1 : 0;
+}
+
+// The matrix-free route reads (32 P + P E) centroid rows per query from L2 where the matrix route reads ~(P + P E) 32-byte
+// sectors of D from DRAM but must first write 4 C bytes per query: measured on B200 (tools/bench_coarse.py, C = 65536,
+// d = 128, E = 32, per 8192 queries) 0.45 / 0.67 / 0.93 / 2.5 ms against 0.78 / 0.81 / 0.82 / 0.97 ms at P = 1 / 8 / 16 / 64
+// -- it wins up to 256 KiB of rows per query.
+int vlq_coarse_exact_preferred(int d, int C, int P, int E, int W) {
+  if (!vlq_coarse_exact_supported(d, C, P, E, W)) return 0;
+  return (int64_t)P * (32 + E) * d * 4 <= (256 << 10) ? 1 : 0;
+}
+
+int vlq_coarse_select_lines_exact(const float* q, int64_t nq, int d, const float* cent, const float* cnorm,
+                                  const float* bucket_min, int nb, int C, int P, const int* edge, const float* edge_d2,
+                                  int E, int W, int* out_coarse, int* out_list, float* out_term1, float* out_term6,
+                                  vlq_stream_t stream) {
+  if (nq < 0 || d <= 0 || P <= 0 || P > VLQ_MAX_K || E <= 0 || W <= 0 || W > VLQ_MAX_K || C <= 0 || nb <= 0 ||
+      (int64_t)nb * 32 < C)
+    return VLQ_EINVAL;
+  if (!csl::exact_supported(d, nb, P, E, W)) return VLQ_EUNSUPPORTED;
+  if (nq == 0) return VLQ_OK;
+  if (!q || !cent || !cnorm || !bucket_min || !edge || !edge_d2 || !out_list || !out_term1 || !out_term6)
+    return VLQ_EINVAL;
+  if ((reinterpret_cast<uintptr_t>(q) | reinterpret_cast<uintptr_t>(cent) | reinterpret_cast<uintptr_t>(bucket_min)) & 15)
+    return VLQ_EINVAL;
+  const int need = nb > P * E ? (nb > P * 32 ? nb : P * 32) : (P * E > P * 32 ? P * E : P * 32);
+  const int R = need <= 8 * csl::NT ? 8 : 16;
+  const size_t smem = csl::SmemExact::bytes(R, P);
+  if (R == 8) {
+    VLQ_CUDA_TRY(cudaFuncSetAttribute(csl::coarse_select_lines_exact_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    VLQ_LAUNCH(csl::coarse_select_lines_exact_kernel<8>, (unsigned)nq, csl::NT, smem, as_stream(stream), q, d, cent, cnorm,
+               bucket_min, nb, C, P, edge, edge_d2, E, W, out_coarse, out_list, out_term1, out_term6);
+  } else {
+    VLQ_CUDA_TRY(cudaFuncSetAttribute(csl::coarse_select_lines_exact_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    VLQ_LAUNCH(csl::coarse_select_lines_exact_kernel<16>, (unsigned)nq, csl::NT, smem, as_stream(stream), q, d, cent, cnorm,
+               bucket_min, nb, C, P, edge, edge_d2, E, W, out_coarse, out_list, out_term1, out_term6);
+  }
+  return last_error();
+}
+
 // term-3 tables of the batch (+ 256 spare bytes)
 size_t vlq_scan_topk_workspace_bytes(int64_t nq, int M) { return (size_t)(nq > 0 ? nq : 0) * M * 256 * sizeof(float) + 256; }
 

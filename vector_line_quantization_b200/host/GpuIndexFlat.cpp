@@ -160,6 +160,13 @@ void GpuIndexFlat::distancesDevice(const float* dx, Index::idx_t n, float* dD, I
   }
 }
 
+void GpuIndexFlat::bucketMinDevice(const float* dx, Index::idx_t n, float* bucketMin) const {
+  VLQ_THROW_IF_NOT_MSG(pack_.get() != nullptr, "bucket minima are produced by the tensor-core path only");
+  vlq_stream_t st = resources_->getDefaultStream();
+  scratch_.reserve(vlq_l2_tc_workspace_bytes(n, d, (int)ntotal));
+  VLQ_CALL(vlq_l2_bucket_min_tc(dx, n, d, pack_.get(), packScale_, (int)ntotal, bucketMin, scratch_.get(), scratch_.bytes(), st));
+}
+
 void GpuIndexFlat::search(Index::idx_t n, const float* x, Index::idx_t k, float* distances, Index::idx_t* labels) const {
   searchCore_(n, x, k, distances, labels, nullptr);
 }

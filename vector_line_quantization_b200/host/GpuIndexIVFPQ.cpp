@@ -302,6 +302,38 @@ void GpuIndexIVFPQ::commit_() const {
 }
 
 // searchImpl_ -> IVFPQ::queryGraph (gpu/GpuIndexIVFPQ.cu:1400-1464, gpu/impl/IVFPQ.cu:685-775)
+// a11 + a12 for one query tile: (line, term1, term6) of the W best lines of every query.  On the tensor-core path the
+// distance matrix is not materialised when nprobe is small (vlq_coarse_exact_preferred): the sweep writes the bucket
+// minima only and the select kernel re-evaluates the columns it needs from the L2-resident centroid table.
+bool GpuIndexIVFPQ::coarseMatrixFree_(int P, int W) const {
+  static const bool forceMatrix = getenv("VLQ_COARSE_MATRIX") != nullptr;
+  static const bool forceExact = getenv("VLQ_COARSE_EXACT") != nullptr;
+  if (forceMatrix || quantizer_->devicePack() == nullptr) return false;
+  return (forceExact ? vlq_coarse_exact_supported(d, nlist_, P, numedge_, W)
+                     : vlq_coarse_exact_preferred(d, nlist_, P, numedge_, W)) == 1;
+}
+
+void GpuIndexIVFPQ::coarseLines_(const float* q, Index::idx_t m, int P, int W, DeviceBuffer& dmat, float* cval, int* cidx,
+                                 float* bmin, int* lline, float* t1, float* t6) const {
+  vlq_stream_t st = resources_->getDefaultStream();
+  const int nb = vlq_tc_num_buckets(nlist_);
+  if (coarseMatrixFree_(P, W)) {
+    quantizer_->bucketMinDevice(q, m, bmin);
+    VLQ_CALL(vlq_coarse_select_lines_exact(q, m, d, quantizer_->deviceVectors(), quantizer_->deviceNorms(), bmin, nb,
+                                           nlist_, P, dEdge_.as<int>(), dEdgeDist_.as<float>(), numedge_, W, nullptr,
+                                           lline, t1, t6, st));
+  } else if (quantizer_->devicePack() != nullptr) {  // tensor-core GEMM + bucket minima -> fused top-P / line selection
+    quantizer_->distancesDevice(q, m, dmat.as<float>(), nlist_, bmin);
+    VLQ_CALL(vlq_coarse_select_lines(dmat.as<float>(), m, nlist_, bmin, nb, nlist_, P, dEdge_.as<int>(),
+                                     dEdgeDist_.as<float>(), numedge_, W, nullptr, lline, t1, t6, st));
+  } else {
+    quantizer_->distancesDevice(q, m, dmat.as<float>(), nlist_);
+    VLQ_CALL(vlq_select_rows(dmat.as<float>(), m, nlist_, nlist_, P, nullptr, cval, cidx, st));
+    VLQ_CALL(vlq_select_lines(dmat.as<float>(), m, nlist_, cidx, P, dEdge_.as<int>(), dEdgeDist_.as<float>(), numedge_, W,
+                              lline, t1, t6, st));
+  }
+}
+
 void GpuIndexIVFPQ::search(Index::idx_t n, const float* x, Index::idx_t k, float* distances, Index::idx_t* labels) const {
   VLQ_THROW_IF_NOT_MSG(is_trained, "Index not trained");
   VLQ_THROW_IF_NOT_MSG(k >= 1 && k <= VLQ_MAX_K, "k must be in [1, 1024]");
@@ -319,8 +351,8 @@ void GpuIndexIVFPQ::search(Index::idx_t n, const float* x, Index::idx_t k, float
   DeviceBuffer& outD = outD_;
   DeviceBuffer& outI = outI_;
   DeviceBuffer& dmat = scratch_;
-  dmat.reserve((size_t)tile * nlist_ * sizeof(float));
   const bool tc = quantizer_->devicePack() != nullptr;
+  if (!coarseMatrixFree_(P, W)) dmat.reserve((size_t)tile * nlist_ * sizeof(float));
   const int nb = vlq_tc_num_buckets(nlist_);
   scratchB_.reserve((size_t)tile * (P * (sizeof(float) + sizeof(int)) + W * (sizeof(int) + 2 * sizeof(float)) +
                                     (tc ? nb * sizeof(float) : 0)));
@@ -361,16 +393,7 @@ void GpuIndexIVFPQ::search(Index::idx_t n, const float* x, Index::idx_t k, float
                                   (size_t)m2 * d * sizeof(float), cs));
         }
       }
-      if (tc) {  // tensor-core GEMM emits bucket minima; top-P and the line selection are one fused kernel
-        quantizer_->distancesDevice(q, m, dmat.as<float>(), nlist_, bmin);
-        VLQ_CALL(vlq_coarse_select_lines(dmat.as<float>(), m, nlist_, bmin, nb, nlist_, P, dEdge_.as<int>(),
-                                         dEdgeDist_.as<float>(), numedge_, W, nullptr, lline, t1, t6, st));
-      } else {
-        quantizer_->distancesDevice(q, m, dmat.as<float>(), nlist_);
-        VLQ_CALL(vlq_select_rows(dmat.as<float>(), m, nlist_, nlist_, P, nullptr, cval, cidx, st));
-        VLQ_CALL(vlq_select_lines(dmat.as<float>(), m, nlist_, cidx, P, dEdge_.as<int>(), dEdgeDist_.as<float>(),
-                                  numedge_, W, lline, t1, t6, st));
-      }
+      coarseLines_(q, m, P, W, dmat, cval, cidx, bmin, lline, t1, t6);
       float* hD = distances + (size_t)(p0 + s) * k;
       Index::idx_t* hI = labels + (size_t)(p0 + s) * k;
       const bool inPlace = dOnDevice && lOnDevice;
@@ -716,7 +739,8 @@ void GpuIndexIVFPQ::search1(Index::idx_t n, const float* x, Index::idx_t k, floa
   const Index::idx_t tile = std::max<Index::idx_t>(64, std::min<Index::idx_t>(1000, ((Index::idx_t)1 << 28) / nlist_));
   const bool tc = quantizer_->devicePack() != nullptr;
   const int nb = vlq_tc_num_buckets(nlist_);
-  DeviceBuffer dmat((size_t)tile * nlist_ * sizeof(float));
+  DeviceBuffer dmat;
+  if (!coarseMatrixFree_(P, W)) dmat.resize((size_t)tile * nlist_ * sizeof(float));
   DeviceBuffer work((size_t)tile * (P * (sizeof(float) + sizeof(int)) + W * (sizeof(int) + 2 * sizeof(float)) +
                                     (tc ? nb * sizeof(float) : 0)));
   float* cval = work.as<float>();
@@ -736,16 +760,7 @@ void GpuIndexIVFPQ::search1(Index::idx_t n, const float* x, Index::idx_t k, floa
       VLQ_CALL(vlq_memcpy_h2d(xin.get(), q, (size_t)m * d * sizeof(float), st));
       q = xin.as<float>();
     }
-    if (tc) {
-      quantizer_->distancesDevice(q, m, dmat.as<float>(), nlist_, bmin);
-      VLQ_CALL(vlq_coarse_select_lines(dmat.as<float>(), m, nlist_, bmin, nb, nlist_, P, dEdge_.as<int>(),
-                                       dEdgeDist_.as<float>(), numedge_, W, nullptr, lline, t1, t6, st));
-    } else {
-      quantizer_->distancesDevice(q, m, dmat.as<float>(), nlist_);
-      VLQ_CALL(vlq_select_rows(dmat.as<float>(), m, nlist_, nlist_, P, nullptr, cval, cidx, st));
-      VLQ_CALL(vlq_select_lines(dmat.as<float>(), m, nlist_, cidx, P, dEdge_.as<int>(), dEdgeDist_.as<float>(), numedge_,
-                                W, lline, t1, t6, st));
-    }
+    coarseLines_(q, m, P, W, dmat, cval, cidx, bmin, lline, t1, t6);
     int64_t* o = lOnDevice ? reinterpret_cast<int64_t*>(labels + (size_t)s * k) : out.as<int64_t>();
     VLQ_CALL(vlq_gather_candidates(lline, m, W, lOffsets_.as<int64_t>(), lIds_.as<int64_t>(), (int64_t)k, o, st));
     if (!lOnDevice) VLQ_CALL(vlq_memcpy_d2h(labels + (size_t)s * k, o, (size_t)m * k * sizeof(int64_t), st));

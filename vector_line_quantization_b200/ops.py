@@ -6,6 +6,8 @@ include/vlq_b200.h.
 """
 from collections import namedtuple
 
+import os
+
 import torch
 
 from . import _abi
@@ -264,20 +266,45 @@ def coarse_lines(q, cent, cnorm, edge, edge_d2, P, W, tile=4096, pack=None, out=
                torch.empty((nq, W), dtype=torch.float32, device=q.device))
     if nq == 0:
         return out
-    Dbuf = torch.empty((min(tile, nq), C), dtype=torch.float32, device=q.device)
-    bbuf = torch.empty((min(tile, nq), num_buckets(C)), dtype=torch.float32, device=q.device) if pack is not None else None
+    stage = CoarseStage(cent, cnorm, edge, edge_d2, P, W, min(tile, nq), pack)
     for s in range(0, nq, tile):
         e = min(nq, s + tile)
-        qt = q[s:e]
-        o = tuple(t[s:e] for t in out)
-        if pack is not None:
-            D = l2_distances_tc(qt, pack, out=Dbuf[: e - s], bucket_min=bbuf[: e - s])
-            coarse_select_lines(D, bbuf[: e - s], C, P, edge, edge_d2, W, out=o)
-        else:
-            D = l2_distances(qt, cent, cnorm, out=Dbuf[: e - s])
-            _, cid = select_rows(D, P)
-            select_lines(D, cid, edge, edge_d2, W, out=o)
+        stage.run(q[s:e], out=tuple(t[s:e] for t in out))
     return out
+
+
+class CoarseStage:
+    """a11 + a12 for one query tile -- the dispatch GpuIndexIVFPQ::coarseLines_ makes.  With a CentPack and a small
+    nprobe (vlq_coarse_exact_preferred) the distance matrix is never written: the tcgen05 sweep emits the bucket minima
+    only and vlq_coarse_select_lines_exact re-evaluates the columns it needs; otherwise vlq_l2_distances_tc +
+    vlq_coarse_select_lines (VLQ_COARSE_MATRIX=1 forces this route, VLQ_COARSE_EXACT=1 the other wherever it is
+    supported).  Without a pack: fp32 matrix + select_rows + select_lines."""
+
+    def __init__(self, cent, cnorm, edge, edge_d2, P, W, tile, pack=None):
+        self.cent, self.cnorm, self.edge, self.edge_d2, self.pack = cent, cnorm, edge, edge_d2, pack
+        self.C, self.d = cent.shape
+        self.P, self.W = min(P, self.C), W
+        dev = cent.device
+        fn = "vlq_coarse_exact_supported" if os.environ.get("VLQ_COARSE_EXACT") else "vlq_coarse_exact_preferred"
+        self.exact = (pack is not None and os.environ.get("VLQ_COARSE_MATRIX") is None and
+                      bool(getattr(_abi.lib(), fn)(self.d, self.C, self.P, edge.shape[1], W)))
+        self.Dbuf = None if self.exact else torch.empty((tile, self.C), dtype=torch.float32, device=dev)
+        self.bbuf = torch.empty((tile, num_buckets(self.C)), dtype=torch.float32, device=dev) if pack is not None else None
+
+    def run(self, qt, out=None, want_coarse=False):
+        m = qt.shape[0]
+        if self.exact:
+            l2_bucket_min_tc(qt, self.pack, self.bbuf[:m])
+            return coarse_select_lines_exact(qt, self.cent, self.cnorm, self.bbuf[:m], self.P, self.edge, self.edge_d2,
+                                             self.W, want_coarse=want_coarse, out=out)
+        if self.pack is not None:
+            D = l2_distances_tc(qt, self.pack, out=self.Dbuf[:m], bucket_min=self.bbuf[:m])
+            return coarse_select_lines(D, self.bbuf[:m], self.C, self.P, self.edge, self.edge_d2, self.W,
+                                       want_coarse=want_coarse, out=out)
+        D = l2_distances(qt, self.cent, self.cnorm, out=self.Dbuf[:m])
+        _, cid = select_rows(D, self.P)
+        r = select_lines(D, cid, self.edge, self.edge_d2, self.W, out=out)
+        return (*r, cid) if want_coarse else r
 
 
 def scan_lines(q, pq, lambda_cb, lines, edge_d2, lists, k, cap=1024, tile=4096, out=None, list_len_hint=None):
@@ -306,19 +333,12 @@ def search(q, cent, cnorm, edge, edge_d2, lambda_cb, pq, lists, P, W, k, cap=102
     else:
         outD = torch.empty((nq, k), dtype=torch.float32, device=q.device)
         outI = torch.empty((nq, k), dtype=torch.int64, device=q.device)
-    Dbuf = torch.empty((min(tile, nq), C), dtype=torch.float32, device=q.device)
-    bbuf = torch.empty((min(tile, nq), num_buckets(C)), dtype=torch.float32, device=q.device) if pack is not None else None
+    stage = CoarseStage(cent, cnorm, edge, edge_d2, P, W, min(tile, max(nq, 1)), pack)
     ed2_flat = edge_d2.reshape(-1)
     for s in range(0, nq, tile):
         e = min(nq, s + tile)
         qt = q[s:e]
-        if pack is not None:  # tensor-core GEMM (+ bucket minima) -> fused top-P / line selection
-            D = l2_distances_tc(qt, pack, out=Dbuf[: e - s], bucket_min=bbuf[: e - s])
-            lst, t1, t6 = coarse_select_lines(D, bbuf[: e - s], C, P, edge, edge_d2, W)
-        else:
-            D = l2_distances(qt, cent, cnorm, out=Dbuf[: e - s])
-            _, cid = select_rows(D, P)
-            lst, t1, t6 = select_lines(D, cid, edge, edge_d2, W)
+        lst, t1, t6 = stage.run(qt)
         scan_topk(qt, pq, lambda_cb, lst, t1, t6, ed2_flat, lists, k, cap, out=(outD[s:e], outI[s:e]),
                   list_len_hint=list_len_hint)
     return outD, outI
@@ -376,6 +396,37 @@ def l2_distances_tc(x, pack, out=None, bucket_min=None):
     _abi.call("vlq_l2_distances_tc", _ptr(x), n, d, _ptr(pack.buf), pack.scale, pack.C, _ptr(D), D.stride(0),
               _ptr(bucket_min), _ptr(ws), ws.numel(), _stream())
     return D
+
+
+def l2_bucket_min_tc(x, pack, bucket_min):
+    """the tcgen05 sweep without the distance matrix: only the minima of the 32-column buckets are written"""
+    x = _chk(x, torch.float32, "x")
+    n, d = x.shape
+    assert bucket_min.shape == (n, num_buckets(pack.C)) and bucket_min.is_contiguous()
+    ws = pack.workspace(n)
+    _abi.call("vlq_l2_bucket_min_tc", _ptr(x), n, d, _ptr(pack.buf), pack.scale, pack.C, _ptr(bucket_min), _ptr(ws),
+              ws.numel(), _stream())
+    return bucket_min
+
+
+def coarse_select_lines_exact(q, cent, cnorm, bucket_min, P, edge, edge_d2, W, want_coarse=False, out=None):
+    """a11 + a12 without a distance matrix (vlq_coarse_select_lines_exact); out = (list, term1, term6) destinations"""
+    q = _chk(q, torch.float32, "q")
+    nq, d = q.shape
+    C, E = cent.shape[0], edge.shape[1]
+    dev = q.device
+    if out is not None:
+        lst, t1, t6 = out
+        assert lst.shape == (nq, W) and lst.is_contiguous() and t1.is_contiguous() and t6.is_contiguous()
+    else:
+        lst = torch.empty((nq, W), dtype=torch.int32, device=dev)
+        t1 = torch.empty((nq, W), dtype=torch.float32, device=dev)
+        t6 = torch.empty((nq, W), dtype=torch.float32, device=dev)
+    cid = torch.empty((nq, P), dtype=torch.int32, device=dev) if want_coarse else None
+    _abi.call("vlq_coarse_select_lines_exact", _ptr(q), nq, d, _ptr(cent), _ptr(cnorm), _ptr(bucket_min),
+              bucket_min.shape[1], C, P, _ptr(edge), _ptr(edge_d2), E, W, _ptr(cid), _ptr(lst), _ptr(t1), _ptr(t6),
+              _stream())
+    return (lst, t1, t6, cid) if want_coarse else (lst, t1, t6)
 
 
 def num_buckets(C):
