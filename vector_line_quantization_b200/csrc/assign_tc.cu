@@ -37,8 +37,6 @@ constexpr int TILE_ROWS = 128;               // UMMA M and N
 constexpr int KB = 32;                       // K elements per pipeline stage
 constexpr int TILE_KB_BYTES = TILE_ROWS * KB * 2;  // 8 KiB: one (tile, part, kb) block
 constexpr int STAGES = 3;
-constexpr int STG_ROW_BYTES = 144;            // 32 floats + 16 B pad: conflict-free 128-bit row writes and reads
-constexpr int STG_WARP_BYTES = 32 * STG_ROW_BYTES;  // per-epilogue-warp transpose buffer (MODE 1)
 constexpr int ROW_TILES = 2;                 // 256 rows per CTA
 constexpr int ACC_BUFS = 2;
 constexpr int TMEM_COLS = ROW_TILES * ACC_BUFS * TILE_ROWS;  // 512
@@ -114,6 +112,21 @@ __device__ __forceinline__ void umma_commit(uint64_t* bar) {
 __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
   asm volatile(
       "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+        "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+        "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr)
+      : "memory");
+}
+// 16 TMEM lanes x 64 columns: thread t, register 4 j + i <- lane t / 4 + 8 (i / 2), column 8 j + 2 (t % 4) + (i % 2)
+// (the m16n8 accumulator fragment repeated over 8 column blocks; layout verified on the device with a tcgen05.st.32x32b
+// fill).  A quad of threads holds 8 consecutive floats of a row.
+__device__ __forceinline__ void tmem_ld16x64(uint32_t taddr, uint32_t (&r)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.16x256b.x8.b32 "
       "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
       "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
       : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
@@ -262,8 +275,7 @@ __global__ void __launch_bounds__(THREADS, 1) l2_tc_kernel(const Params p) {
   uint8_t* a_s = smem;                                // [ROW_TILES][hi,lo][nkb][8 KiB]
   uint8_t* b_s = a_s + ROW_TILES * a_tile_bytes;      // [STAGES][hi,lo][8 KiB]
   float* cn_s = reinterpret_cast<float*>(b_s + STAGES * 2 * TILE_KB_BYTES);  // [ACC_BUFS][128]
-  uint8_t* stg_s = reinterpret_cast<uint8_t*>(cn_s + ACC_BUFS * TILE_ROWS);  // [EPI_WARPS][32 rows][144 B] (MODE 1)
-  uint64_t* bars = reinterpret_cast<uint64_t*>(stg_s + (MODE == 1 ? EPI_WARPS * STG_WARP_BYTES : 0));
+  uint64_t* bars = reinterpret_cast<uint64_t*>(cn_s + ACC_BUFS * TILE_ROWS);
   uint64_t* full = bars;                 // [STAGES]
   uint64_t* empty = bars + STAGES;       // [STAGES]
   uint64_t* a_full = bars + 2 * STAGES;  // [1]
@@ -410,6 +422,17 @@ __global__ void __launch_bounds__(THREADS, 1) l2_tc_kernel(const Params p) {
         const int64_t row = ((int64_t)rb * ROW_TILES + r) * TILE_ROWS + row_in_tile;
         m2s[r] = p.m2s * (row < n_rows ? p.row_inv[row] : 1.f);  // -2 / (centroid scale * this row's scale): exact
       }
+      float m2q[ROW_TILES][4];  // MODE 1: the same factor for the four rows of the thread's 16x64 fragments
+      if (MODE == 1) {
+#pragma unroll
+        for (int r = 0; r < ROW_TILES; r++)
+#pragma unroll
+          for (int hi = 0; hi < 4; hi++) {
+            const int64_t row = ((int64_t)rb * ROW_TILES + r) * TILE_ROWS + lane_grp * 32 + (hi >> 1) * 16 + (lane >> 2) + 8 * (hi & 1);
+            m2q[r][hi] = p.m2s * (row < n_rows ? p.row_inv[row] : 1.f);
+          }
+      }
+      (void)m2q;
       float cn_next = (et < TILE_ROWS && t0 < t1) ? p.cnorm_pad[t0 * TILE_ROWS + et] : 0.f;
       for (int t = t0; t < t1; t++) {
         // stage ||c||^2 of this centroid tile (safe: every epilogue thread passed the previous use of this slot
@@ -423,6 +446,74 @@ __global__ void __launch_bounds__(THREADS, 1) l2_tc_kernel(const Params p) {
         mbar_wait(&t_full[acc_buf], acc_phase);
         tc_fence_after();
         const float* cn = cn_s + acc_buf * TILE_ROWS + col_half * 64;
+        if (MODE == 1) {
+          // D tile straight from registers.  With the 16x256b fragment a quad of threads owns 8 consecutive columns of a
+          // row; one exchange between lanes t and t ^ 1 over a pair of column blocks gives every thread 4 consecutive
+          // columns, so a store instruction writes 8 rows x 64 contiguous bytes: the same 64-byte store wavefronts as
+          // fully coalesced rows, and 32 shuffles instead of the 128 shared-memory wavefronts of a transpose through
+          // shared memory (which kept the L1 data pipe 76 % busy next to the MMA's operand reads: 284 us per 4096
+          // queries, now 265).  Measured bounds of this sweep (tools/bench_coarse.py): no D at all 116 us;
+          // stores that all hit L2 230 us; 32-byte-per-row stores or a 128 KiB-contiguous blocked D layout: no gain --
+          // the SM's 32 B/clk write path to L2 (128 KiB per 256 x 128 tile = 4096 clk, twice the MMA time of the
+          // tile) is what the D tile costs.
+          const int qd = lane & 3;
+          float2 cnv[8];
+#pragma unroll
+          for (int j = 0; j < 8; j++) cnv[j] = *reinterpret_cast<const float2*>(cn + 8 * j + 2 * qd);
+          const int colq = t * TILE_ROWS + col_half * 64;
+          const bool vec_ok = (p.ldD & 3) == 0 && (reinterpret_cast<uintptr_t>(p.D) & 15) == 0;
+#pragma unroll
+          for (int r = 0; r < ROW_TILES; r++) {
+            const uint32_t taddr = tmem_base + ((uint32_t)(lane_grp * 32) << 16) +
+                                   (acc_buf * ROW_TILES + r) * TILE_ROWS + col_half * 64;
+            uint32_t v[2][32];
+            tmem_ld16x64(taddr, v[0]);
+            tmem_ld16x64(taddr + (16u << 16), v[1]);
+            tmem_ld_wait();
+#pragma unroll
+            for (int h = 0; h < 2; h++) {
+#pragma unroll
+              for (int i2 = 0; i2 < 2; i2++) {
+                const int64_t row = ((int64_t)rb * ROW_TILES + r) * TILE_ROWS + lane_grp * 32 + h * 16 + (lane >> 2) + 8 * i2;
+                const bool row_ok = row < n_rows;
+                const float ms = m2q[r][h * 2 + i2];
+                float* out = p.D + row * p.ldD + colq;
+                float mn[2] = {__int_as_float(0x7f800000), __int_as_float(0x7f800000)};
+#pragma unroll
+                for (int m = 0; m < 4; m++) {  // column blocks 2 m and 2 m + 1
+                  float2 a, b;
+                  a.x = fmaf(__uint_as_float(v[h][8 * m + 2 * i2]), ms, cnv[2 * m].x);
+                  a.y = fmaf(__uint_as_float(v[h][8 * m + 2 * i2 + 1]), ms, cnv[2 * m].y);
+                  b.x = fmaf(__uint_as_float(v[h][8 * m + 4 + 2 * i2]), ms, cnv[2 * m + 1].x);
+                  b.y = fmaf(__uint_as_float(v[h][8 * m + 4 + 2 * i2 + 1]), ms, cnv[2 * m + 1].y);
+                  mn[m >> 1] = fminf(mn[m >> 1], fminf(fminf(a.x, a.y), fminf(b.x, b.y)));
+                  const bool odd = qd & 1;
+                  const float s0 = odd ? a.x : b.x, s1 = odd ? a.y : b.y;
+                  const float r0 = __shfl_xor_sync(0xffffffffu, s0, 1), r1 = __shfl_xor_sync(0xffffffffu, s1, 1);
+                  // even lane of the pair: columns 2 qd .. 2 qd + 3 of block 2 m; odd lane: 2 (qd - 1) .. of block 2 m + 1
+                  const float4 o = odd ? make_float4(r0, r1, b.x, b.y) : make_float4(a.x, a.y, r0, r1);
+                  const int cc = 16 * m + (odd ? 8 + 2 * (qd - 1) : 2 * qd);
+                  if (row_ok) {
+                    if (vec_ok && colq + cc + 3 < p.C) {
+                      *reinterpret_cast<float4*>(out + cc) = o;
+                    } else {
+                      if (colq + cc + 0 < p.C) out[cc + 0] = o.x;
+                      if (colq + cc + 1 < p.C) out[cc + 1] = o.y;
+                      if (colq + cc + 2 < p.C) out[cc + 2] = o.z;
+                      if (colq + cc + 3 < p.C) out[cc + 3] = o.w;
+                    }
+                  }
+                }
+#pragma unroll
+                for (int b = 0; b < 2; b++) {
+                  mn[b] = fminf(mn[b], __shfl_xor_sync(0xffffffffu, mn[b], 1));
+                  mn[b] = fminf(mn[b], __shfl_xor_sync(0xffffffffu, mn[b], 2));
+                }
+                if (row_ok && p.bmin && qd < 2) p.bmin[row * nb + t * 4 + col_half * 2 + qd] = mn[qd];
+              }
+            }
+          }
+        } else {
 #pragma unroll
         for (int r = 0; r < ROW_TILES; r++) {
           const uint32_t taddr = tmem_base + ((uint32_t)(lane_grp * 32) << 16) +
@@ -462,49 +553,9 @@ __global__ void __launch_bounds__(THREADS, 1) l2_tc_kernel(const Params p) {
               if (c == 0) mn_prev = mn;
               if (c == 1 && row < n_rows)  // buckets (col0 >> 5) - 1 and col0 >> 5: one 8-byte store (nb is a multiple of 4)
                 *reinterpret_cast<float2*>(p.bmin + row * nb + (col0 >> 5) - 1) = make_float2(mn_prev, mn);
-            } else {
-              // D tile: registers -> per-warp shared-memory transpose -> coalesced 128-byte row segments
-              // (a thread owns one ROW of the accumulator; storing straight from registers would make every warp
-              //  store instruction touch 32 different lines with 16 bytes each: measured 1.9 TB/s instead of ~6)
-              float mn = __int_as_float(0x7f800000);
-              uint8_t* stg = stg_s + (warp - 2) * STG_WARP_BYTES;
-              float4* srow = reinterpret_cast<float4*>(stg + lane * STG_ROW_BYTES);
-#pragma unroll
-              for (int i = 0; i < 32; i += 4) {
-                float4 o;
-                o.x = fmaf(__uint_as_float(v[c][i + 0]), m2s[r], cn[c * 32 + i + 0]);
-                o.y = fmaf(__uint_as_float(v[c][i + 1]), m2s[r], cn[c * 32 + i + 1]);
-                o.z = fmaf(__uint_as_float(v[c][i + 2]), m2s[r], cn[c * 32 + i + 2]);
-                o.w = fmaf(__uint_as_float(v[c][i + 3]), m2s[r], cn[c * 32 + i + 3]);
-                mn = fminf(fminf(mn, fminf(o.x, o.y)), fminf(o.z, o.w));
-                srow[i >> 2] = o;
-              }
-              if (row < n_rows && p.bmin) p.bmin[row * nb + (col0 >> 5)] = mn;
-              __syncwarp();
-              const int cg = lane & 7;  // 8 lanes cover the 32 columns of one row, 4 rows per instruction
-              const int64_t row_base = ((int64_t)rb * ROW_TILES + r) * TILE_ROWS + lane_grp * 32;
-              const bool vec_ok = (p.ldD & 3) == 0 && col0 + cg * 4 + 3 < p.C;
-#pragma unroll
-              for (int it = 0; it < 8; it++) {
-                const int rr = it * 4 + (lane >> 3);
-                const float4 o = *reinterpret_cast<const float4*>(stg + rr * STG_ROW_BYTES + cg * 16);
-                const int64_t grow = row_base + rr;
-                if (grow < n_rows) {
-                  float* out = p.D + grow * p.ldD + col0 + cg * 4;
-                  if (vec_ok) {
-                    *reinterpret_cast<float4*>(out) = o;
-                  } else {
-                    const int cc = col0 + cg * 4;
-                    if (cc + 0 < p.C) out[0] = o.x;
-                    if (cc + 1 < p.C) out[1] = o.y;
-                    if (cc + 2 < p.C) out[2] = o.z;
-                    if (cc + 3 < p.C) out[3] = o.w;
-                  }
-                }
-              }
-              __syncwarp();
             }
           }
+        }
         }
         tc_fence_before();
         mbar_arrive(&t_empty[acc_buf]);
@@ -557,7 +608,7 @@ __global__ void row_norms_f32_kernel(const float* __restrict__ x, int64_t n, int
 static size_t smem_bytes(int d) {
   const int nkb = d / KB;
   return (size_t)ROW_TILES * 2 * nkb * TILE_KB_BYTES + (size_t)STAGES * 2 * TILE_KB_BYTES +
-         ACC_BUFS * TILE_ROWS * sizeof(float) + (size_t)EPI_WARPS * STG_WARP_BYTES + 16 * sizeof(uint64_t) + 16;
+         ACC_BUFS * TILE_ROWS * sizeof(float) + 16 * sizeof(uint64_t) + 16;
 }
 
 static inline size_t align256(size_t v) { return (v + 255) & ~size_t(255); }
