@@ -562,6 +562,33 @@ def test_scan_modes_identical(ops, cuda, oracle, small_model, P, W, k, cap):
             assert I1n[r, c] in I0n[r][near] or c == k - 1 or near[-1]
 
 
+@pytest.mark.parametrize("P,W,k,cap", [(8, 32, 10, 1024), (8, 64, 100, 1024), (16, 128, 50, 8), (4, 16, 1024, 1024), (1, 1, 1, 1024)])
+def test_small_query_scan_path_equals_general_path(ops, cuda, oracle, small_model, P, W, k, cap, monkeypatch):
+    """scan_topk_kernel's register-resident path for queries of <= 4096 entries (strided stream positions, one radix
+    threshold, tie ranks in position order) returns the bits of the general BlockSelect path -- on an index that stores
+    every vector three times, so exact distance ties straddle the k-th place for most queries"""
+    import torch
+
+    m = small_model
+    gi = _gpu_index(ops, cuda, oracle, m, np.concatenate([m["xb"][:6000]] * 3))
+    q = T(m["xq"], cuda)
+    D = ops.l2_distances(q, gi["cent"], gi["cn"])
+    _, cid = ops.select_rows(D, P)
+    lst, t1, t6 = ops.select_lines(D, cid, gi["edge"], gi["ed2"], W)
+    args = (q, gi["pq"], gi["lcb"], lst, t1, t6, gi["ed2"].reshape(-1), gi["lists"], k, cap)
+    lens = (gi["lists"].offsets[1:] - gi["lists"].offsets[:-1]).clamp_max(cap)
+    total = lens[lst.clamp_min(0).long()].mul(lst >= 0).sum(dim=1)
+    assert int((total <= 4096).sum()) > len(q) // 2  # the small path really is the one exercised
+    D0, I0 = ops.scan_topk(*args, list_len_hint=0)
+    monkeypatch.setenv("VLQ_SCAN_NO_SMALL", "1")
+    D1, I1 = ops.scan_topk(*args, list_len_hint=0)
+    monkeypatch.delenv("VLQ_SCAN_NO_SMALL")
+    assert torch.equal(D0, D1) and torch.equal(I0, I1)
+    ties = (D0[:, 1:] == D0[:, :-1]) & (I0[:, 1:] >= 0)
+    if k > 1 and k <= 100:
+        assert int(ties.sum()) > 0
+
+
 @pytest.mark.parametrize("M,d,k", [(16, 128, 100), (8, 96, 100), (8, 64, 10), (4, 32, 50), (16, 64, 128)])
 def test_scan_modes_random_index(ops, cuda, M, d, k):
     """flattened-stream scan vs the warp-autonomous scans (plain tables: hint 30; bank-skewed tables: hint 100 and the long-list kernel: hint 400, M = 8/16)

@@ -178,6 +178,44 @@ __device__ __forceinline__ void take_k(const uint32_t (&key)[R], const Kth& kt, 
   __syncthreads();
 }
 
+// take_k for keys held STRIDED: key[r] of thread t is index r * NT + t (adjacent threads own adjacent indices, so the
+// loads behind the keys coalesce and every thread has work when fewer than R * NT indices exist).  Same rule: key < tau,
+// plus the lowest-index ties.  wsum: 8 ints (shared).
+template <int R>
+__device__ __forceinline__ void take_k_strided(const uint32_t (&key)[R], const Kth& kt, int K, int* wsum, bool (&take)[R]) {
+  const int need_eq = K - kt.n_lt;  // ties to take (<= n_eq)
+  if (kt.tau == kInf32) {
+#pragma unroll
+    for (int r = 0; r < R; r++) take[r] = key[r] != kInf32;
+    return;
+  }
+  if (need_eq >= kt.n_eq) {  // block-uniform: all ties are wanted
+#pragma unroll
+    for (int r = 0; r < R; r++) take[r] = key[r] <= kt.tau;
+    return;
+  }
+  // rare: more ties at the threshold than places left; index order = row r first, then thread
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  int before = 0;
+#pragma unroll
+  for (int r = 0; r < R; r++) {  // (unrolled: key[] and take[] must stay in registers)
+    const bool eq = key[r] == kt.tau;
+    const unsigned m = __ballot_sync(kFull, eq);
+    if (lane == 0) wsum[warp] = __popc(m);
+    __syncthreads();
+    int rank = before + __popc(m & ((1u << lane) - 1));
+    int all = 0;
+    for (int w = 0; w < NT / 32; w++) {
+      const int c = wsum[w];
+      if (w < warp) rank += c;
+      all += c;
+    }
+    take[r] = key[r] < kt.tau || (eq && rank < need_eq);
+    before += all;
+    __syncthreads();
+  }
+}
+
 __device__ __forceinline__ uint32_t key32(float v) { return v == v ? f2ord(v) : kInf32; }  // NaN: never selected
 
 struct Smem {  // layout in dynamic shared memory (host and device agree through bytes())

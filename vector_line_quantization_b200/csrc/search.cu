@@ -462,25 +462,48 @@ __global__ void __launch_bounds__(Q_THREADS, M_T == 16 ? 3 : 2) scan_topk_kernel
   // ---- small queries (a few thousand entries in all, the C2 regime): every distance of the query fits in registers,
   // kSmallR per thread, so the selection is ONE register-resident radix threshold (csl::kth32, coarse_select.cuh) +
   // a rank ordering of the k survivors instead of the append / compact / sort machinery of BlockSelect, which was 80 %
-  // of this kernel's instructions at 2.7 k entries per query.  Thread t owns the stream positions [R t, R t + R), so
-  // ties resolve to the lowest position exactly as in the general path; same arithmetic, same bits.
-  constexpr int kSmallR = 16;
-  if (!LONG && use_owner && total <= kSmallR * Q_THREADS && a.k <= a.sel_cap) {  // block-uniform
+  // of this kernel's instructions at 2.7 k entries per query.  Ties resolve to the lowest stream position exactly as in
+  // the general path (take_k_strided); same arithmetic, same bits.
+  constexpr int kSmallR = 16, kSmallB = 4;
+  if (!LONG && use_owner && !a.no_small && total <= kSmallR * Q_THREADS && a.k <= a.sel_cap) {  // block-uniform
+    // stream position of key[r] = r * Q_THREADS + t: adjacent threads read adjacent entries of a list, every thread has
+    // work (a C2 query has ~1800 entries: 7 rows of 256), and the loads of kSmallB rows are in flight together
     uint32_t key[kSmallR];
 #pragma unroll
-    for (int r = 0; r < kSmallR; r++) {
-      const int pos = kSmallR * (int)threadIdx.x + r;
-      key[r] = csl::kInf32;
-      if (pos < total) {
-        const int lo = owner[pos];
-        const int pl = pos - prefix[lo];
-        const int64_t ent = lstart[lo] + pl;
-        CodeRegs<M_T> cr;
-        cr.load(a.codes + ent * M, pl);
-        const float la = lcb[a.lamq[ent]];
-        const float base_d = lt1[lo] + la * lt6[lo] + (la * la - la) * lt5[lo];
-        const float dist = (a.kappa[ent] + cr.adc(T3, M, ksub)) + base_d;
-        key[r] = csl::key32(dist);
+    for (int r = 0; r < kSmallR; r++) key[r] = csl::kInf32;
+#pragma unroll
+    for (int r0 = 0; r0 < kSmallR; r0 += kSmallB) {
+      if (r0 * Q_THREADS >= total) break;  // block-uniform
+      CodeRegs<M_T> cr[kSmallB];
+      uint8_t lq[kSmallB];
+      float kp[kSmallB];
+      int lo_[kSmallB];
+#pragma unroll
+      for (int u = 0; u < kSmallB; u++) {
+        const int pos = (r0 + u) * Q_THREADS + (int)threadIdx.x;
+        lq[u] = 0;
+        kp[u] = 0.f;
+        lo_[u] = 0;
+        if (pos < total) {
+          const int lo = owner[pos];
+          const int pl = pos - prefix[lo];
+          const int64_t ent = lstart[lo] + pl;
+          cr[u].load(a.codes + ent * M, pl);
+          lq[u] = a.lamq[ent];
+          kp[u] = a.kappa[ent];
+          lo_[u] = lo;
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < kSmallB; u++) {
+        const int pos = (r0 + u) * Q_THREADS + (int)threadIdx.x;
+        if (pos < total) {
+          const int lo = lo_[u];
+          const float la = lcb[lq[u]];
+          const float base_d = lt1[lo] + la * lt6[lo] + (la * la - la) * lt5[lo];
+          const float dist = (kp[u] + cr[u].adc(T3, M, ksub)) + base_d;
+          key[r0 + u] = csl::key32(dist);
+        }
       }
     }
     uint64_t* skeys = reinterpret_cast<uint64_t*>(smem);  // the BlockSelect key area: <= k survivors
@@ -490,10 +513,10 @@ __global__ void __launch_bounds__(Q_THREADS, M_T == 16 ? 3 : 2) scan_topk_kernel
     if (threadIdx.x == 0) swsum[8] = 0;
     const csl::Kth kt = csl::kth32<kSmallR>(key, a.k, shist, smeta);
     bool take[kSmallR];
-    csl::take_k<kSmallR>(key, kt, a.k, swsum, take);
+    csl::take_k_strided<kSmallR>(key, kt, a.k, swsum, take);
 #pragma unroll
     for (int r = 0; r < kSmallR; r++)
-      if (take[r]) skeys[atomicAdd(&swsum[8], 1)] = ((uint64_t)key[r] << 32) | (uint32_t)(kSmallR * (int)threadIdx.x + r);
+      if (take[r]) skeys[atomicAdd(&swsum[8], 1)] = ((uint64_t)key[r] << 32) | (uint32_t)(r * Q_THREADS + (int)threadIdx.x);
     for (int i = threadIdx.x; i < a.k; i += Q_THREADS) {
       a.outD[qi * a.k + i] = FLT_MAX;
       a.outI[qi * a.k + i] = -1;
@@ -1246,6 +1269,7 @@ int vlq_scan_topk(const float* q, int64_t nq, int d, const float* pq, int M, con
     a.t3 = t3;
   }
   a.owner_cap = (int)((long long)W * cap < 4096 ? (long long)W * cap : 4096);
+  a.no_small = getenv("VLQ_SCAN_NO_SMALL") != nullptr;  // read per call: tests flip it between calls
   if (use_long) return launch_scan_long(a, nq, as_stream(stream));
   if (use_async) {
     cudaStream_t st_ = as_stream(stream);
