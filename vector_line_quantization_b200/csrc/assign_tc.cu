@@ -455,13 +455,14 @@ __global__ void __launch_bounds__(THREADS, 1) l2_tc_kernel(const Params p) {
           // queries, now 265).  Measured bounds of this sweep (tools/bench_coarse.py): no D at all 116 us;
           // stores that all hit L2 230 us; 32-byte-per-row stores or a 128 KiB-contiguous blocked D layout: no gain --
           // the SM's 32 B/clk write path to L2 (128 KiB per 256 x 128 tile = 4096 clk, twice the MMA time of the
-          // tile) is what the D tile costs.
+          // tile) is what the D tile costs: ncu l1tex__m_l1tex2xbar_write_bytes 64 % of peak where a pure fill kernel
+          // reaches 80 %.  16 epilogue warps of 32 columns each instead of 8 x 64: slower (290 us).
           const int qd = lane & 3;
           float2 cnv[8];
 #pragma unroll
           for (int j = 0; j < 8; j++) cnv[j] = *reinterpret_cast<const float2*>(cn + 8 * j + 2 * qd);
           const int colq = t * TILE_ROWS + col_half * 64;
-          const bool vec_ok = (p.ldD & 3) == 0 && (reinterpret_cast<uintptr_t>(p.D) & 15) == 0;
+          const bool vec_ok = (p.ldD & 3) == 0 && (reinterpret_cast<uintptr_t>(p.D) & 15) == 0 && colq + 64 <= p.C;  // warp-uniform
 #pragma unroll
           for (int r = 0; r < ROW_TILES; r++) {
             const uint32_t taddr = tmem_base + ((uint32_t)(lane_grp * 32) << 16) +
@@ -494,7 +495,7 @@ __global__ void __launch_bounds__(THREADS, 1) l2_tc_kernel(const Params p) {
                   const float4 o = odd ? make_float4(r0, r1, b.x, b.y) : make_float4(a.x, a.y, r0, r1);
                   const int cc = 16 * m + (odd ? 8 + 2 * (qd - 1) : 2 * qd);
                   if (row_ok) {
-                    if (vec_ok && colq + cc + 3 < p.C) {
+                    if (vec_ok) {
                       *reinterpret_cast<float4*>(out + cc) = o;
                     } else {
                       if (colq + cc + 0 < p.C) out[cc + 0] = o.x;
