@@ -236,6 +236,14 @@ int vlq_merge_topk(const float* D, const int64_t* I, int R, int64_t nq, int k, f
  * loads.  The caller orders it after the producers (a cross-GPU barrier); results are identical to vlq_merge_topk. */
 int vlq_merge_topk_peers(const void* const* peer_bufs, size_t d_offset_bytes, size_t i_offset_bytes, int R, int64_t nq,
                          int k, float* outD, int64_t* outI, vlq_stream_t stream);
+/* Query-split sharding: every rank holds narr (<= 4) row-major arrays of nq rows x row_bytes at arr_offset_bytes[a] of
+ * its peer-mapped buffer and has filled the rows [self nq / R, (self + 1) nq / R); this call copies the rows of every
+ * other rank r, [r nq / R, (r + 1) nq / R), from peer_bufs[r] into peer_bufs[self] (one kernel of P2P loads).  Offsets
+ * and row_bytes are multiples of 16.  The caller orders it after the producers (a cross-GPU barrier).  It is the
+ * exchange step of the line lists (12 W bytes per query) where gpu/test/sift1b16_query.cpp broadcasts the queries to
+ * every rank and repeats the coarse stage on each of them. */
+int vlq_gather_peer_slices(const void* const* peer_bufs, int R, int self, const int64_t* arr_offset_bytes, int narr,
+                           int64_t nq, int64_t row_bytes, vlq_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------------------------------
  * f1 (next row) k-means centroid update on the device: deterministic per-centroid mean in row order + the

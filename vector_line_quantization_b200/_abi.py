@@ -50,6 +50,7 @@ SIGNATURES = {
     "vlq_scan_topk": (_i, [_p, _l, _i, _p, _i, _p, _i, _p, _p, _p, _p, _i, _p, _p, _p, _p, _p, _i, _i, _i, _p, _p, _p, _z, _p]),
     "vlq_merge_topk": (_i, [_p, _p, _i, _l, _i, _p, _p, _p]),
     "vlq_merge_topk_peers": (_i, [_p, _z, _z, _i, _l, _i, _p, _p, _p]),
+    "vlq_gather_peer_slices": (_i, [_p, _i, _i, _p, _i, _l, _l, _p]),
     "vlq_km_update_workspace_bytes": (_z, [_l, _i]),
     "vlq_km_update": (_i, [_p, _l, _i, _p, _i, _p, _p, _p, _z, _p]),
     "vlq_copy_columns": (_i, [_p, _l, _l, _i, _i, _p, _p]),

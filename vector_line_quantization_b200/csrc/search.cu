@@ -1105,6 +1105,29 @@ static int graph_tile_rows(int C) {
 
 using namespace vlq;
 
+// ------------------------------------------------------------------------------------------------ peer slice gather
+// Query-split sharding (the strong-scaling protocol): rank r computed the coarse stage of the queries [q0(r), q0(r + 1))
+// and left (list, term1, term6) in its peer-mapped buffer.  This kernel pulls every OTHER rank's slice of up to four
+// row-major arrays into the same place of the local buffer in ONE launch of P2P loads (was: one peer copy per rank and
+// array, 3 (R - 1) launches per step).  blockIdx.y = source rank, blockIdx.z = array.
+struct PeerSlices {
+  int64_t arr_off[4];  // byte offset of each array inside the buffers
+};
+__global__ void __launch_bounds__(256)
+gather_peer_slices_kernel(const unsigned char* const* __restrict__ peers, int R, int self, PeerSlices ps, int64_t nq,
+                          int64_t row_bytes) {
+  const int r = blockIdx.y;
+  if (r == self) return;
+  const int64_t b0 = (int64_t)r * nq / R * row_bytes, b1 = (int64_t)(r + 1) * nq / R * row_bytes;
+  const unsigned char* src = peers[r] + ps.arr_off[blockIdx.z];
+  unsigned char* dst = const_cast<unsigned char*>(peers[self]) + ps.arr_off[blockIdx.z];
+  const int64_t n16 = (b1 - b0) >> 4;  // offsets and row_bytes are multiples of 16 (checked by the caller)
+  const uint4* s4 = reinterpret_cast<const uint4*>(src + b0);
+  uint4* d4 = reinterpret_cast<uint4*>(dst + b0);
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n16; i += (int64_t)gridDim.x * blockDim.x)
+    d4[i] = s4[i];
+}
+
 extern "C" {
 
 int vlq_select_lines(const float* D, int64_t nq, int64_t ldD, const int* coarse_ids, int P, const int* edge,
@@ -1331,6 +1354,25 @@ int vlq_merge_topk_peers(const void* const* peer_bufs, size_t d_offset_bytes, si
   VLQ_LAUNCH(merge_topk_kernel, (unsigned)nq, Q_THREADS, smem, as_stream(stream), (const float*)nullptr,
              (const int64_t*)nullptr, reinterpret_cast<const unsigned char* const*>(peer_bufs), d_offset_bytes,
              i_offset_bytes, R, nq, k, cap, outD, outI);
+  return last_error();
+}
+
+int vlq_gather_peer_slices(const void* const* peer_bufs, int R, int self, const int64_t* arr_offset_bytes, int narr,
+                           int64_t nq, int64_t row_bytes, vlq_stream_t stream) {
+  if (R <= 0 || self < 0 || self >= R || narr <= 0 || narr > 4 || nq < 0 || row_bytes <= 0 || (row_bytes & 15)) return VLQ_EINVAL;
+  if (nq == 0 || R == 1) return VLQ_OK;
+  if (!peer_bufs || !arr_offset_bytes) return VLQ_EINVAL;
+  PeerSlices ps{};
+  for (int a = 0; a < narr; a++) {
+    if (arr_offset_bytes[a] < 0 || (arr_offset_bytes[a] & 15)) return VLQ_EINVAL;
+    ps.arr_off[a] = arr_offset_bytes[a];
+  }
+  const int64_t per = (nq / R + 1) * row_bytes / 16;  // 16-byte words of the largest slice
+  unsigned gx = (unsigned)((per + 255) / 256);
+  if (gx > 64) gx = 64;
+  if (gx < 1) gx = 1;
+  VLQ_LAUNCH(gather_peer_slices_kernel, dim3(gx, (unsigned)R, (unsigned)narr), 256, 0, as_stream(stream),
+             reinterpret_cast<const unsigned char* const*>(peer_bufs), R, self, ps, nq, row_bytes);
   return last_error();
 }
 

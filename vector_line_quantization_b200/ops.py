@@ -242,6 +242,16 @@ def merge_topk_peers(peer_ptrs_dev, d_off, i_off, R, nq, k, out=None, device=Non
     return out
 
 
+def gather_peer_slices(peer_ptrs_dev, R, rank, arr_offsets, nq, row_bytes):
+    """query-split sharding: pull the other ranks' row slices of the arrays at arr_offsets (bytes inside the symmetric
+    buffers) into this rank's buffer, one launch of P2P loads"""
+    import ctypes
+
+    offs = (ctypes.c_int64 * len(arr_offsets))(*[int(o) for o in arr_offsets])
+    _abi.call("vlq_gather_peer_slices", int(peer_ptrs_dev), R, rank, ctypes.addressof(offs), len(arr_offsets), nq,
+              row_bytes, _stream())
+
+
 def km_update(x, assign, k):
     """k-means mean step, deterministic row order (f1): -> (centroids f32 [k][d], counts int32 [k])"""
     x = _chk(x, torch.float32, "x")

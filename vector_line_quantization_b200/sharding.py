@@ -100,8 +100,8 @@ class QuerySplitSearch:
       1. the coarse stage (distances to the C centroids, top-P, line selection) does not touch the inverted lists, so
          rank r runs it for ITS 1/R of the queries only and writes (list, term1, term6) -- 12 W bytes per query -- into
          its peer-mapped symmetric buffer;
-      2. one device barrier; every rank pulls the other ranks' line slices over NVLink (R - 1 peer copies of
-         nq/R x 12 W bytes) and scans ALL queries on its shard of the lists;
+      2. one device barrier; every rank pulls the other ranks' line slices over NVLink (vlq_gather_peer_slices: one
+         kernel of P2P loads, (R - 1) x nq/R x 12 W bytes) and scans ALL queries on its shard of the lists;
       3. one device barrier; rank r merges the R per-shard top-k lists of ITS query slice straight from the peers'
          buffers (vlq_merge_topk_peers with row offsets) -- the final (nq, k) result is distributed by query slice.
 
@@ -154,14 +154,18 @@ class QuerySplitSearch:
         s, e = self.my_slice()
         coarse_fn(q[s:e], out=(lst[s:e], t1[s:e], t6[s:e]))
         self.hdl.barrier(channel=0)  # every rank's line slice is written
-        for r in range(self.world):
-            if r == self.rank:
-                continue
-            pl, p1, p6, _, _ = self._views(self._peer_buf(r), b)
-            rs, re = self.q0[r], self.q0[r + 1]
-            lst[rs:re].copy_(pl[rs:re], non_blocking=True)
-            t1[rs:re].copy_(p1[rs:re], non_blocking=True)
-            t6[rs:re].copy_(p6[rs:re], non_blocking=True)
+        if (self.W * 4) % 16 == 0:  # one kernel of P2P loads pulls the other ranks' slices of the three arrays
+            ops.gather_peer_slices(self.ptrs_dev, self.world, self.rank,
+                                   [b + self.off_l, b + self.off_t1, b + self.off_t6], self.nq, self.W * 4)
+        else:
+            for r in range(self.world):
+                if r == self.rank:
+                    continue
+                pl, p1, p6, _, _ = self._views(self._peer_buf(r), b)
+                rs, re = self.q0[r], self.q0[r + 1]
+                lst[rs:re].copy_(pl[rs:re], non_blocking=True)
+                t1[rs:re].copy_(p1[rs:re], non_blocking=True)
+                t6[rs:re].copy_(p6[rs:re], non_blocking=True)
         scan_fn(q, (lst, t1, t6), out=(D, I))
         self.hdl.barrier(channel=0)  # every shard's results are written
         n = e - s
