@@ -400,6 +400,42 @@ def test_merge_topk_exact(ops, cuda, oracle, R, nq, k):
     assert np.array_equal(N(oI), wI)
 
 
+@pytest.mark.parametrize("R,nq,W", [(2, 100, 256), (8, 1001, 64), (3, 2, 4), (4, 10000, 256)])
+def test_gather_peer_slices(ops, cuda, R, nq, W):
+    """exchange step of the query-split search (vlq_gather_peer_slices): rank r holds rows [r nq / R, (r + 1) nq / R) of
+    three (nq, W) arrays; after the call every rank's buffer holds all rows of all arrays.  The R buffers are separate
+    allocations of one device here; on an NVLink domain they are peer-mapped memory of R GPUs."""
+    import torch
+
+    a256 = lambda v: (v + 255) // 256 * 256
+    base = 512
+    offs = [base, base + a256(nq * W * 4), base + 2 * a256(nq * W * 4)]
+    size = offs[2] + a256(nq * W * 4) + 256
+    g = torch.Generator(device="cpu").manual_seed(R * 7 + nq)
+    want = [torch.randint(-2 ** 31, 2 ** 31 - 1, (nq, W), generator=g, dtype=torch.int32).to(cuda) for _ in range(3)]
+    q0 = [r * nq // R for r in range(R + 1)]
+    bufs = []
+    for r in range(R):  # own slice filled, everything else poisoned
+        b = torch.full((size,), 0x5A, dtype=torch.uint8, device=cuda)
+        for a in range(3):
+            v = b[offs[a]:offs[a] + nq * W * 4].view(torch.int32).view(nq, W)
+            v[q0[r]:q0[r + 1]] = want[a][q0[r]:q0[r + 1]]
+        bufs.append(b)
+    ptrs = torch.tensor([b.data_ptr() for b in bufs], dtype=torch.int64, device=cuda)
+    before = [b.clone() for b in bufs]
+    for r in range(R):
+        ops.gather_peer_slices(ptrs.data_ptr(), R, r, offs, nq, W * 4)
+    torch.cuda.synchronize()
+    mask = torch.ones(size, dtype=torch.bool, device=cuda)
+    for a in range(3):
+        mask[offs[a]:offs[a] + nq * W * 4] = False
+    for r in range(R):
+        for a in range(3):
+            v = bufs[r][offs[a]:offs[a] + nq * W * 4].view(torch.int32).view(nq, W)
+            assert torch.equal(v, want[a])
+        assert torch.equal(bufs[r][mask], before[r][mask])  # nothing outside the three arrays is touched
+
+
 @pytest.mark.parametrize("R,nq,k", [(2, 10, 1), (8, 33, 100), (4, 7, 1024)])
 def test_merge_topk_peers_equals_gathered(ops, cuda, R, nq, k):
     """gather fused into the merge (vlq_merge_topk_peers): shard r's results are read from its own buffer through a
