@@ -308,6 +308,13 @@ int vlq_stream_destroy(vlq_stream_t stream);
 int vlq_stream_synchronize(vlq_stream_t stream);
 /* work enqueued on `waiter` after this call starts only when everything enqueued on `producer` so far has finished */
 int vlq_stream_wait(vlq_stream_t waiter, vlq_stream_t producer);
+/* the same in two halves (record now, wait wherever the dependent work is enqueued later): a plain cudaEvent_t without
+   timing.  Used by GpuIndexIVFPQ::search to run the scan of query tile i beside the coarse stage of tile i + 1. */
+typedef void* vlq_event_t;
+int vlq_event_create(vlq_event_t* ev);
+int vlq_event_destroy(vlq_event_t ev);
+int vlq_event_record(vlq_event_t ev, vlq_stream_t stream);
+int vlq_stream_wait_event(vlq_stream_t waiter, vlq_event_t ev);
 
 #ifdef __cplusplus
 }

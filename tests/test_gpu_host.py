@@ -189,6 +189,30 @@ def _search_vs_oracle_same_index(idx, oracle, m, xq, P, W, k, tmp_path, model=No
     return I, Il
 
 
+def test_search_tile_pipeline_many_tiles(vi, res, cuda, small_model):
+    """GpuIndexIVFPQ::search runs the scan of query tile i on a second stream beside the coarse stage of tile i + 1, on two
+    alternating sets of line buffers: a batch of many tiles (slot reuse, several 32768-query pages, host and device
+    buffers) must return what the same queries return one small batch at a time"""
+    import torch
+
+    m = small_model
+    idx = _build(vi, res, m, m["xb"])
+    idx.setNumProbes(16)
+    idx.w1_ = 64
+    k = 10
+    rng = np.random.RandomState(3)
+    xq = m["xq"][rng.randint(0, len(m["xq"]), 40000)] + rng.randint(-2, 3, (40000, m["d"])).astype(np.float32)
+    D, I = idx.search(xq, k)  # 40000 queries: pages of 32768, tiles of <= 5120
+    for s in range(0, len(xq), 7000):
+        Ds, Is = idx.search(xq[s:s + 1500], k)
+        assert np.array_equal(Ds, D[s:s + 1500]) and np.array_equal(Is, I[s:s + 1500])
+    qd = torch.from_numpy(xq).to(cuda)
+    oD = torch.empty((len(xq), k), dtype=torch.float32, device=cuda)
+    oI = torch.empty((len(xq), k), dtype=torch.int64, device=cuda)
+    idx.search(qd, k, out=(oD, oI))
+    assert np.array_equal(oD.cpu().numpy(), D) and np.array_equal(oI.cpu().numpy(), I)
+
+
 def test_vlq_train_on_device(vi, res, oracle, small_model, tmp_path):
     """train() end to end on the device; quality must match the oracle-trained model (same algorithm, same seeds)"""
     from vector_line_quantization_b200 import data

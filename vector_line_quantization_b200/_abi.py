@@ -80,6 +80,10 @@ SIGNATURES = {
     "vlq_stream_destroy": (_i, [_p]),
     "vlq_stream_synchronize": (_i, [_p]),
     "vlq_stream_wait": (_i, [_p, _p]),
+    "vlq_event_create": (_i, [_p]),
+    "vlq_event_destroy": (_i, [_p]),
+    "vlq_event_record": (_i, [_p, _p]),
+    "vlq_stream_wait_event": (_i, [_p, _p]),
 }
 
 

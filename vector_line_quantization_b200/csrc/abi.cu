@@ -110,4 +110,20 @@ int vlq_stream_wait(vlq_stream_t waiter, vlq_stream_t producer) {
   return (int)e;
 }
 
+// events for pipelines whose wait must be placed later than the record (two compute streams working on alternating buffers)
+int vlq_event_create(vlq_event_t* ev) {
+  if (!ev) return VLQ_EINVAL;
+  cudaEvent_t e;
+  cudaError_t rc = cudaEventCreateWithFlags(&e, cudaEventDisableTiming);
+  *ev = rc == cudaSuccess ? static_cast<vlq_event_t>(e) : nullptr;
+  return (int)rc;
+}
+int vlq_event_destroy(vlq_event_t ev) { return ev ? (int)cudaEventDestroy(static_cast<cudaEvent_t>(ev)) : VLQ_OK; }
+int vlq_event_record(vlq_event_t ev, vlq_stream_t stream) {
+  return ev ? (int)cudaEventRecord(static_cast<cudaEvent_t>(ev), vlq::as_stream(stream)) : VLQ_EINVAL;
+}
+int vlq_stream_wait_event(vlq_stream_t waiter, vlq_event_t ev) {
+  return ev ? (int)cudaStreamWaitEvent(vlq::as_stream(waiter), static_cast<cudaEvent_t>(ev), 0) : VLQ_EINVAL;
+}
+
 }  // extern "C"

@@ -16,11 +16,12 @@ namespace gpu {
 
 // ------------------------------------------------------------------------------------------------ resources
 StandardGpuResources::StandardGpuResources(int device)
-    : device_(device), stream_(nullptr), copyStream_(nullptr), downStream_(nullptr) {
+    : device_(device), stream_(nullptr), copyStream_(nullptr), downStream_(nullptr), scanStream_(nullptr) {
   DeviceScope scope(device_);
   VLQ_CALL(vlq_stream_create(&stream_));
   VLQ_CALL(vlq_stream_create(&copyStream_));
   VLQ_CALL(vlq_stream_create(&downStream_));
+  VLQ_CALL(vlq_stream_create(&scanStream_));
 }
 StandardGpuResources::~StandardGpuResources() {
   if (stream_) {
@@ -34,6 +35,10 @@ StandardGpuResources::~StandardGpuResources() {
   if (downStream_) {
     vlq_stream_synchronize(downStream_);
     vlq_stream_destroy(downStream_);
+  }
+  if (scanStream_) {
+    vlq_stream_synchronize(scanStream_);
+    vlq_stream_destroy(scanStream_);
   }
 }
 void StandardGpuResources::syncDefaultStream() { VLQ_CALL(vlq_stream_synchronize(stream_)); }

@@ -71,6 +71,10 @@ GpuIndexIVFPQ::~GpuIndexIVFPQ() {
   delete[] edgeDistInfo_;
   delete[] lambdaInfo_;
   delete[] constInfo_;
+  for (int i = 0; i < 2; i++) {
+    vlq_event_destroy(evCoarse_[i]);
+    vlq_event_destroy(evScan_[i]);
+  }
 }
 
 void GpuIndexIVFPQ::reserveMemory(size_t numVecs) { reserveVecs_ = numVecs; }
@@ -346,32 +350,42 @@ void GpuIndexIVFPQ::search(Index::idx_t n, const float* x, Index::idx_t k, float
   const int W = w1_;
   const int M = subQuantizers_;
   const Index::idx_t page = 32768;  // gpu/GpuIndex.cu:109-147
-  const Index::idx_t tile = std::max<Index::idx_t>(64, std::min<Index::idx_t>(4096, ((Index::idx_t)1 << 28) / nlist_));
+  // query tiles: at most 5120 queries / 1.25 GiB of coarse distances, equal sizes within a page (10 000 queries = 2 x 5000)
+  const Index::idx_t tileCap = std::max<Index::idx_t>(64, std::min<Index::idx_t>(5120, ((Index::idx_t)5 << 26) / nlist_));
   DeviceBuffer& xin = qIn_;
   DeviceBuffer& outD = outD_;
   DeviceBuffer& outI = outI_;
   DeviceBuffer& dmat = scratch_;
   const bool tc = quantizer_->devicePack() != nullptr;
-  if (!coarseMatrixFree_(P, W)) dmat.reserve((size_t)tile * nlist_ * sizeof(float));
+  if (!coarseMatrixFree_(P, W)) dmat.reserve((size_t)tileCap * nlist_ * sizeof(float));
   const int nb = vlq_tc_num_buckets(nlist_);
-  scratchB_.reserve((size_t)tile * (P * (sizeof(float) + sizeof(int)) + W * (sizeof(int) + 2 * sizeof(float)) +
-                                    (tc ? nb * sizeof(float) : 0)));
-  float* cval = scratchB_.as<float>();
-  int* cidx = reinterpret_cast<int*>(cval + (size_t)tile * P);
-  int* lline = cidx + (size_t)tile * P;
-  float* t1 = reinterpret_cast<float*>(lline + (size_t)tile * W);
-  float* t6 = t1 + (size_t)tile * W;
-  float* bmin = t6 + (size_t)tile * W;
-  t3ws_.reserve(vlq_scan_topk_workspace_bytes(tile, M));
+  // two slots of per-tile line buffers: the scan of tile i (scan stream) reads slot i & 1 while the coarse stage of tile
+  // i + 1 (default stream) fills the other one
+  const size_t slotBytes = (((size_t)tileCap * (P * (sizeof(float) + sizeof(int)) + W * (sizeof(int) + 2 * sizeof(float)) +
+                                               (tc ? nb * sizeof(float) : 0))) + 255) & ~size_t(255);
+  scratchB_.reserve(2 * slotBytes);
+  t3ws_.reserve(vlq_scan_topk_workspace_bytes(tileCap, M));
   // Host buffers: the queries of tile i+1 go up on the copy stream and the results of tile i-1 come down on the download
   // stream while tile i is computed (cross-stream order by vlq_stream_wait: the compute stream only ever waits for
   // uploads); device buffers are used in place (the scan writes straight into the caller's arrays).
   vlq_stream_t cs = resources_->getAsyncCopyStream();
   vlq_stream_t ds = resources_->getAsyncDownloadStream();
+  vlq_stream_t sb = resources_->getScanStream();
+  static const bool noOverlap = getenv("VLQ_SEARCH_NO_OVERLAP") != nullptr;
+  const bool overlap = sb != st && !noOverlap;
+  if (!overlap) sb = st;
+  if (overlap && !evCoarse_[0]) {
+    for (int i = 0; i < 2; i++) {
+      VLQ_CALL(vlq_event_create(&evCoarse_[i]));
+      VLQ_CALL(vlq_event_create(&evScan_[i]));
+    }
+  }
   const bool xOnDevice = vlq_pointer_is_device(x) == 1;
   const bool dOnDevice = vlq_pointer_is_device(distances) == 1, lOnDevice = vlq_pointer_is_device(labels) == 1;
   for (Index::idx_t p0 = 0; p0 < n; p0 += page) {
     const Index::idx_t pn = std::min(page, n - p0);
+    const Index::idx_t ntiles = (pn + tileCap - 1) / tileCap;
+    const Index::idx_t tile = std::min<Index::idx_t>(tileCap, (((pn + ntiles - 1) / ntiles) + 255) / 256 * 256);
     const float* xp = x + (size_t)p0 * d;
     const float* dx = xp;
     if (!xOnDevice) {
@@ -382,9 +396,19 @@ void GpuIndexIVFPQ::search(Index::idx_t n, const float* x, Index::idx_t k, float
     }
     outD.reserve((size_t)pn * k * sizeof(float));
     outI.reserve((size_t)pn * k * sizeof(int64_t));
-    for (Index::idx_t s = 0; s < pn; s += tile) {
+    if (overlap) VLQ_CALL(vlq_stream_wait(sb, st));  // everything before this page (commit, earlier calls)
+    Index::idx_t ti = 0;
+    for (Index::idx_t s = 0; s < pn; s += tile, ti++) {
       const Index::idx_t m = std::min(tile, pn - s);
       const float* q = dx + (size_t)s * d;
+      const int slot = (int)(ti & 1);
+      unsigned char* sbase = scratchB_.as<unsigned char>() + slot * slotBytes;
+      float* cval = reinterpret_cast<float*>(sbase);
+      int* cidx = reinterpret_cast<int*>(cval + (size_t)tileCap * P);
+      int* lline = cidx + (size_t)tileCap * P;
+      float* t1 = reinterpret_cast<float*>(lline + (size_t)tileCap * W);
+      float* t6 = t1 + (size_t)tileCap * W;
+      float* bmin = t6 + (size_t)tileCap * W;
       if (!xOnDevice) {
         VLQ_CALL(vlq_stream_wait(st, cs));  // this tile's queries have arrived
         if (s + tile < pn) {
@@ -393,7 +417,12 @@ void GpuIndexIVFPQ::search(Index::idx_t n, const float* x, Index::idx_t k, float
                                   (size_t)m2 * d * sizeof(float), cs));
         }
       }
+      if (overlap && ti >= 2) VLQ_CALL(vlq_stream_wait_event(st, evScan_[slot]));  // the slot's last scan has finished
       coarseLines_(q, m, P, W, dmat, cval, cidx, bmin, lline, t1, t6);
+      if (overlap) {
+        VLQ_CALL(vlq_event_record(evCoarse_[slot], st));
+        VLQ_CALL(vlq_stream_wait_event(sb, evCoarse_[slot]));
+      }
       float* hD = distances + (size_t)(p0 + s) * k;
       Index::idx_t* hI = labels + (size_t)(p0 + s) * k;
       const bool inPlace = dOnDevice && lOnDevice;
@@ -403,15 +432,17 @@ void GpuIndexIVFPQ::search(Index::idx_t n, const float* x, Index::idx_t k, float
                              dEdgeDist_.as<float>(), W, lOffsets_.as<int64_t>(), lCodes_.as<uint8_t>(),
                              lLamq_.as<uint8_t>(), lKappa_.as<float>(), lIds_.as<int64_t>(), (int)k, listCap_,
                              (int)std::min<size_t>(nListed_ / populatedLists_, 1 << 20), oD, oI, t3ws_.get(),
-                             t3ws_.bytes(), st));
+                             t3ws_.bytes(), sb));
+      if (overlap) VLQ_CALL(vlq_event_record(evScan_[slot], sb));
       if (!inPlace) {
-        VLQ_CALL(vlq_stream_wait(ds, st));  // results of this tile are complete
+        VLQ_CALL(vlq_stream_wait(ds, sb));  // results of this tile are complete
         fromDevice(hD, oD, (size_t)m * k * sizeof(float), ds);
         fromDevice(hI, oI, (size_t)m * k * sizeof(int64_t), ds);
       }
     }
     VLQ_CALL(vlq_stream_synchronize(cs));
     VLQ_CALL(vlq_stream_synchronize(ds));
+    if (overlap) VLQ_CALL(vlq_stream_synchronize(sb));
     resources_->syncDefaultStream();
   }
 }

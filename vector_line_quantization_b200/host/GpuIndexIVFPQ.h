@@ -154,6 +154,7 @@ class GpuIndexIVFPQ : public GpuIndexIVF {
   // pending (encoded, arrival order)
   mutable DeviceBuffer pList_, pCodes_, pLamq_, pKappa_, pIds_;
   mutable size_t nPending_, capPending_;
+  mutable vlq_event_t evCoarse_[2] = {nullptr, nullptr}, evScan_[2] = {nullptr, nullptr};  // search(): two-stream tile pipeline
   mutable DeviceBuffer scratch_, scratchB_, qIn_, outD_, outI_, addIn_[2], addA_, addF32_, t3ws_;  // grow-only staging / workspace
 };
 

@@ -18,6 +18,9 @@ class GpuResources {
   /// stream of the device->host result copies: kept apart from the uploads so that the compute stream, which waits for
   /// the upload of the next query tile, never waits behind the download of the previous one
   virtual vlq_stream_t getAsyncDownloadStream() { return getAsyncCopyStream(); }
+  /// second COMPUTE stream: the scan of query tile i runs here beside the coarse stage of tile i + 1 on the default
+  /// stream (default: the default stream itself = no overlap)
+  virtual vlq_stream_t getScanStream() { return getDefaultStream(); }
 };
 
 class StandardGpuResources : public GpuResources {
@@ -29,6 +32,7 @@ class StandardGpuResources : public GpuResources {
   void syncDefaultStream() override;
   vlq_stream_t getAsyncCopyStream() override { return copyStream_; }
   vlq_stream_t getAsyncDownloadStream() override { return downStream_; }
+  vlq_stream_t getScanStream() override { return scanStream_; }
   /// kept for source compatibility with the reference (gpu/StandardGpuResources.h): sizes are managed on demand
   void noTempMemory() {}
   void setTempMemory(size_t) {}
@@ -39,6 +43,7 @@ class StandardGpuResources : public GpuResources {
   vlq_stream_t stream_;
   vlq_stream_t copyStream_;
   vlq_stream_t downStream_;
+  vlq_stream_t scanStream_;
 };
 
 /// binds the calling thread to the resource's device for the lifetime of the scope (reference DeviceScope)
