@@ -216,6 +216,34 @@ __device__ __forceinline__ void take_k_strided(const uint32_t (&key)[R], const K
   }
 }
 
+// Ascending bitonic sort of NT = 256 keys, one per thread (unused slots: ~0).  Exchanges at distance < 32 are shuffles, the
+// six at distance >= 32 go through xch[NT] (shared).  ~390 instructions per thread where ranking every key against every
+// other key costs 5 per pair (1300 at 256 keys: it was 31 % of the line-selection kernel's instructions).  Keys are
+// unique, so the result is THE order the rank loop produced.  All threads of the block must call it.
+__device__ __forceinline__ uint64_t block_sort256(uint64_t k, uint64_t* xch) {
+  const int t = threadIdx.x;
+#pragma unroll
+  for (int size = 2; size <= NT; size <<= 1) {
+    const bool up = (t & size) == 0;
+#pragma unroll
+    for (int j = size >> 1; j > 0; j >>= 1) {
+      uint64_t o;
+      if (j >= 32) {
+        xch[t] = k;
+        __syncthreads();
+        o = xch[t ^ j];
+        __syncthreads();
+      } else {
+        o = __shfl_xor_sync(kFull, k, j);
+      }
+      const bool keep_min = ((t & j) == 0) == up;
+      const uint64_t lo = k < o ? k : o, hi = k < o ? o : k;
+      k = keep_min ? lo : hi;
+    }
+  }
+  return k;
+}
+
 __device__ __forceinline__ uint32_t key32(float v) { return v == v ? f2ord(v) : kInf32; }  // NaN: never selected
 
 struct Smem {  // layout in dynamic shared memory (host and device agree through bytes())
@@ -347,7 +375,8 @@ coarse_select_lines_fast_kernel(const float* __restrict__ D, int64_t ldD, const 
     for (int r = 0; r < R; r++) {
       if (take[r]) {
         const int slot = atomicAdd(&cnt[2], 1);  // <= W appends
-        keys[slot] = ((uint64_t)kl[r] << 32) | (uint32_t)(R * (int)threadIdx.x + r);
+        // order = (score, line index); the slot rides in the low 10 bits (line index < 4096, slot < 1024)
+        keys[slot] = ((uint64_t)kl[r] << 32) | ((uint32_t)(R * (int)threadIdx.x + r) << 10) | (uint32_t)slot;
         st1[slot] = b2r[r];
         st6[slot] = __fsub_rn(a2r[r], b2r[r]);
         slist[slot] = lid[r];
@@ -362,6 +391,18 @@ coarse_select_lines_fast_kernel(const float* __restrict__ D, int64_t ldD, const 
   }
   __syncthreads();
   const int ns = cnt[2];
+  if (ns > 128 && ns <= NT) {  // block-uniform: one key per thread, bitonic sort (cheaper than ranking from 128 keys on)
+    uint64_t mykey = (int)threadIdx.x < ns ? keys[threadIdx.x] : ~0ull;
+    __syncthreads();  // keys[] becomes the exchange buffer
+    mykey = block_sort256(mykey, keys);
+    if ((int)threadIdx.x < ns) {
+      const int slot = (int)(mykey & 1023u);
+      out_list[q * W + threadIdx.x] = slist[slot];
+      out_term1[q * W + threadIdx.x] = st1[slot];
+      out_term6[q * W + threadIdx.x] = st6[slot];
+    }
+    return;
+  }
   for (int i = threadIdx.x; i < ns; i += NT) {
     const uint64_t mykey = keys[i];
     int rank = 0;

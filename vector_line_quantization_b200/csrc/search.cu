@@ -523,6 +523,19 @@ __global__ void __launch_bounds__(Q_THREADS, M_T == 16 ? 3 : 2) scan_topk_kernel
     }
     __syncthreads();
     const int ns = swsum[8];  // <= k
+    if (ns > 128 && ns <= Q_THREADS) {  // block-uniform: one survivor per thread, bitonic sort (coarse_select.cuh);
+                                        // up to 128 survivors the rank loop below is cheaper (4 warps x ns compares)
+      uint64_t mykey = (int)threadIdx.x < ns ? skeys[threadIdx.x] : ~0ull;
+      __syncthreads();  // skeys[] becomes the exchange buffer (sel_cap >= 256 keys)
+      mykey = csl::block_sort256(mykey, skeys);
+      if ((int)threadIdx.x < ns) {
+        const int pos = (int)key_payload(mykey);
+        const int lo = owner[pos];
+        a.outD[qi * a.k + threadIdx.x] = ord2f((uint32_t)(mykey >> 32));
+        a.outI[qi * a.k + threadIdx.x] = a.ids[lstart[lo] + (pos - prefix[lo])];
+      }
+      return;
+    }
     for (int i = threadIdx.x; i < ns; i += Q_THREADS) {
       const uint64_t mykey = skeys[i];
       int rank = 0;
