@@ -478,6 +478,9 @@ def run_b200(a):
         return parts_[0] if len(parts_) == 1 else torch.cat(parts_)
 
     lists = None
+    x0_ = db_chunk(0)[:65536]
+    enc_passes = 2 if use_tc and bool(torch.equal(x0_.half().float(), x0_)) else (3 if use_tc else 1)
+    del x0_
     barrier()
     prof = os.environ.get("VLQ_PROFILE", "")  # ncu --profile-from-start off: wrap one region in cudaProfilerStart/Stop
     if prof == "encode":
@@ -971,7 +974,11 @@ def run_b200(a):
                                "note": "GpuIndexIVFPQ::add_with_ids%s from pinned host memory in 2 Mi-vector chunks + "
                                        "list commit" % ("_u8" if use_u8 else "")},
                        "gpu_launches": enc_launches, "route_to_list_owner_s": route_s,
-                       "tensor_frac": (n_loc * 2.0 * C * d / (enc_ms * 1e-3) / 1e12) / peaks.get("bf16_tflops_sustained", 1400.0)},
+                       "tensor_frac": (n_loc * 2.0 * C * d / (enc_ms * 1e-3) / 1e12) / peaks.get("bf16_tflops_sustained", 1400.0),
+                       # the split-fp16 scheme EXECUTES 2 passes (fp16-exact vectors: x_lo = 0) or 3: that is the work the
+                       # tensor pipe does for one fp32-grade product (the arg-min GEMM is ~2/3 of the encode time)
+                       "tensor_passes_executed": enc_passes,
+                       "tensor_executed_tflops": enc_passes * n_loc * 2.0 * C * d / (enc_ms * 1e-3) / 1e12},
             "scanned_entries_per_query": scanned_per_q, "parity_vs_oracle": parity,
             "host_api_matches_ops_bitwise": host_matches_ops,
         }
