@@ -265,7 +265,15 @@ def km_update(x, assign, k):
     return cent, counts
 
 
-def coarse_lines(q, cent, cnorm, edge, edge_d2, P, W, tile=4096, pack=None, out=None):
+def _tile_rows(nq, tile):
+    """equal query tiles of at most `tile` rows, multiples of 256 (GpuIndexIVFPQ::search makes the same split)"""
+    if nq <= tile:
+        return max(nq, 1)
+    nt = -(-nq // tile)
+    return min(tile, (-(-nq // nt) + 255) // 256 * 256)
+
+
+def coarse_lines(q, cent, cnorm, edge, edge_d2, P, W, tile=5120, pack=None, out=None):
     """First half of the query path (a11 + a12) for a batch of queries: -> (list int32, term1, term6 f32), each [nq][W].
     This half does not touch the inverted lists, so shards can split the QUERIES for it (sharding.QuerySplitSearch)."""
     nq = q.shape[0]
@@ -276,7 +284,8 @@ def coarse_lines(q, cent, cnorm, edge, edge_d2, P, W, tile=4096, pack=None, out=
                torch.empty((nq, W), dtype=torch.float32, device=q.device))
     if nq == 0:
         return out
-    stage = CoarseStage(cent, cnorm, edge, edge_d2, P, W, min(tile, nq), pack)
+    tile = _tile_rows(nq, tile)
+    stage = CoarseStage(cent, cnorm, edge, edge_d2, P, W, tile, pack)
     for s in range(0, nq, tile):
         e = min(nq, s + tile)
         stage.run(q[s:e], out=tuple(t[s:e] for t in out))
@@ -317,13 +326,14 @@ class CoarseStage:
         return (*r, cid) if want_coarse else r
 
 
-def scan_lines(q, pq, lambda_cb, lines, edge_d2, lists, k, cap=1024, tile=4096, out=None, list_len_hint=None):
+def scan_lines(q, pq, lambda_cb, lines, edge_d2, lists, k, cap=1024, tile=5120, out=None, list_len_hint=None):
     """Second half of the query path (a13-a15): scan the selected lines of every query on THIS shard's lists"""
     nq = q.shape[0]
     lst, t1, t6 = lines
     if out is None:
         out = (torch.empty((nq, k), dtype=torch.float32, device=q.device), torch.empty((nq, k), dtype=torch.int64, device=q.device))
     ed2_flat = edge_d2.reshape(-1)
+    tile = _tile_rows(nq, tile)
     for s in range(0, nq, tile):
         e = min(nq, s + tile)
         scan_topk(q[s:e], pq, lambda_cb, lst[s:e], t1[s:e], t6[s:e], ed2_flat, lists, k, cap, out=(out[0][s:e], out[1][s:e]),
@@ -331,9 +341,9 @@ def scan_lines(q, pq, lambda_cb, lines, edge_d2, lists, k, cap=1024, tile=4096, 
     return out
 
 
-def search(q, cent, cnorm, edge, edge_d2, lambda_cb, pq, lists, P, W, k, cap=1024, tile=4096, pack=None, out=None,
+def search(q, cent, cnorm, edge, edge_d2, lambda_cb, pq, lists, P, W, k, cap=1024, tile=5120, pack=None, out=None,
            list_len_hint=None):
-    """Full query path on resident tensors (a11-a15), tiled over queries so the coarse matrix stays L2-sized.
+    """Full query path on resident tensors (a11-a15), tiled over queries (at most 5120 per tile: 1.25 GiB of coarse distances).
     pack (a CentPack) routes the coarse distances through the tcgen05 kernel."""
     nq = q.shape[0]
     C = cent.shape[0]
@@ -343,7 +353,8 @@ def search(q, cent, cnorm, edge, edge_d2, lambda_cb, pq, lists, P, W, k, cap=102
     else:
         outD = torch.empty((nq, k), dtype=torch.float32, device=q.device)
         outI = torch.empty((nq, k), dtype=torch.int64, device=q.device)
-    stage = CoarseStage(cent, cnorm, edge, edge_d2, P, W, min(tile, max(nq, 1)), pack)
+    tile = _tile_rows(nq, tile)
+    stage = CoarseStage(cent, cnorm, edge, edge_d2, P, W, tile, pack)
     ed2_flat = edge_d2.reshape(-1)
     for s in range(0, nq, tile):
         e = min(nq, s + tile)
