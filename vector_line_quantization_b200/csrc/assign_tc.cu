@@ -16,7 +16,7 @@
 //             (or D-tile store for the query path); TMEM accumulators are double buffered so the epilogue of
 //             centroid tile t overlaps the MMAs of tile t+1
 //   A (the 256 x d block of vectors, hi+lo) stays resident in SMEM for the whole centroid sweep; B (128 centroids x 32 K,
-//   hi+lo = 16 KiB) streams through a 4-stage ring.  256 rows per CTA halve the L2->SM operand traffic per vector
+//   hi+lo = 16 KiB) streams through a 3-stage ring (4 stages: no change).  256 rows per CTA halve the L2->SM operand traffic per vector
 //   compared with one 128-row tile (the sweep is otherwise L2-bandwidth bound at ~42 B/clk/SM).
 //
 // Packed operand layout (written by pack_rows_kernel; shared by A and B):
