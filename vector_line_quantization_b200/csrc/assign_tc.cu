@@ -12,9 +12,10 @@
 //   warp 0    producer : cp.async.bulk (TMA engine, SASS UBLKCP) of pre-packed operand tiles, mbarrier complete_tx
 //   warp 1    MMA issuer (one elected lane): tcgen05.mma.cta_group::1.kind::f16, M=128 x N=128 x K=16, SMEM descriptors
 //             on the no-swizzle K-major canonical layout the pack kernel writes; tcgen05.commit releases stages
-//   warps 2-5 epilogue : tcgen05.ld 32x32b.x32 (one accumulator row per thread) -> fused per-row arg-min
-//             (or D-tile store for the query path); TMEM accumulators are double buffered so the epilogue of
-//             centroid tile t overlaps the MMAs of tile t+1
+//   warps 2-9 epilogue : fused per-row arg-min (tcgen05.ld 32x32b.x32, one accumulator row per thread), or bucket minima
+//             only, or the D tile of the query path (tcgen05.ld 16x256b fragments, lane-pair exchange, 64-byte row
+//             stores straight from registers); TMEM accumulators are double buffered so the epilogue of centroid tile
+//             t overlaps the MMAs of tile t+1
 //   A (the 256 x d block of vectors, hi+lo) stays resident in SMEM for the whole centroid sweep; B (128 centroids x 32 K,
 //   hi+lo = 16 KiB) streams through a 3-stage ring (4 stages: no change).  256 rows per CTA halve the L2->SM operand traffic per vector
 //   compared with one 128-row tile (the sweep is otherwise L2-bandwidth bound at ~42 B/clk/SM).
