@@ -315,7 +315,7 @@ struct CodeRegs {
 //               lanes busy);  LONG = true: every warp owns whole lists (slot w -> warp w % 8) and strides their entries,
 //               so the per-list scalars are warp-uniform and nothing has to be searched per entry.
 template <int M_T, bool LONG>
-__global__ void __launch_bounds__(Q_THREADS, M_T == 16 ? 3 : 2) scan_topk_kernel(ScanArgs a) {  // 3 CTAs per SM (80 registers): measured 0.86 ms per 10 k queries at C2; 2 CTAs 1.03, 4 CTAs (spills) 1.63
+__global__ void __launch_bounds__(Q_THREADS, M_T == 16 ? 3 : 2) scan_topk_kernel(ScanArgs a) {  // 3 CTAs per SM (80 registers); measured at C2 before the strided small-query path: 0.86 ms per 10 k queries, 2 CTAs 1.03, 4 CTAs (spills) 1.63 -- now 0.57
   extern __shared__ __align__(16) unsigned char smem[];
   // smem: [topk keys S*8 + 16][T3 M*ksub f32][lambda nL f32][per line: start i64, prefix i32 (W+1), t1, t6, t5 f32]
   const int M = a.M, ksub = a.ksub, dsub = a.dsub, W = a.W;
