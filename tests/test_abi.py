@@ -71,3 +71,33 @@ def test_invalid_arguments_return_codes():
     assert h.vlq_l2_assign(None, 1, 8, None, None, 4, 1, None, None, None) == -1
     assert h.vlq_merge_topk(None, None, 2, 4, 8, None, None, None) == -1
     assert h.vlq_select_rows(None, 1, 10, 10, 2000, None, None, None, None) == -1
+
+
+def test_coarse_route_dispatch_rule(built):
+    """host-side dispatch of the coarse stage (no GPU): the matrix-free route is supported for d % 4 == 0, d <= 128,
+    max(num_buckets, 32 P, P E) <= 4096, W <= 1024 and preferred up to 256 KiB of centroid rows per query"""
+    lib = ctypes.CDLL(built[0])
+    f = lambda name, *a: getattr(lib, name)(*[ctypes.c_int(x) for x in a])  # noqa: E731
+    assert lib.vlq_tc_num_buckets(ctypes.c_int(65536)) == 2048 and lib.vlq_tc_num_buckets(ctypes.c_int(130)) == 8
+    # (d, C, P, E, W)
+    assert f("vlq_coarse_exact_supported", 128, 65536, 64, 32, 256) == 1
+    assert f("vlq_coarse_exact_preferred", 128, 65536, 64, 32, 256) == 0   # 2 MiB of rows per query: matrix route
+    assert f("vlq_coarse_exact_preferred", 128, 65536, 8, 32, 32) == 1     # 256 KiB: matrix-free
+    assert f("vlq_coarse_exact_preferred", 128, 65536, 16, 32, 64) == 0
+    assert f("vlq_coarse_exact_preferred", 96, 65536, 8, 64, 32) == 0      # P (32 + E) d 4 = 288 KiB
+    assert f("vlq_coarse_exact_preferred", 96, 65536, 4, 64, 16) == 1      # 144 KiB
+    assert f("vlq_coarse_exact_supported", 130, 65536, 8, 32, 32) == 0     # d % 4
+    assert f("vlq_coarse_exact_supported", 256, 65536, 8, 32, 32) == 0     # d > 128
+    assert f("vlq_coarse_exact_supported", 128, 65536, 200, 32, 256) == 0  # 32 P > 4096
+    assert f("vlq_coarse_exact_supported", 128, 1 << 20, 8, 32, 32) == 0   # 32768 buckets
+    assert f("vlq_coarse_exact_supported", 128, 65536, 0, 32, 32) == 0
+
+
+def test_query_tile_split():
+    """equal query tiles of at most 5120 rows, multiples of 256 (the split GpuIndexIVFPQ::search makes per page)"""
+    from vector_line_quantization_b200.ops import _tile_rows
+
+    assert [_tile_rows(n, 5120) for n in (1, 100, 5120, 5121, 10000, 32768)] == [1, 100, 5120, 2816, 5120, 4864]
+    for n in (5121, 10000, 12345, 32768, 40000):
+        t = _tile_rows(n, 5120)
+        assert t <= 5120 and t % 256 == 0 and -(-n // t) == -(-n // 5120)  # no more tiles than the cap requires
