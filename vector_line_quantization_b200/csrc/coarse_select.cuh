@@ -13,8 +13,12 @@
 //              only when there are more ties than needed).  Ties are COMMON in the line stage: every line of a
 //              centroid whose neighbour lies behind the query's Voronoi side scores exactly b2.
 //   ordering:  the few survivors (P columns, W lines) are ordered by counting ranks against (value, index) keys that
-//              sit in shared memory: rank = #keys smaller, O(n^2 / threads) broadcast reads, one barrier, no sorting
-//              network.
+//              sit in shared memory (rank = #keys smaller, O(n^2 / threads) broadcast reads, one barrier) up to 128
+//              keys; 129 .. 256 keys (the W = 256 lines of the headline configuration) go through block_sort256(), a
+//              bitonic network with one key per thread (shuffles below distance 32).
+//
+// The same file holds the MATRIX-FREE variant (coarse_select_lines_exact_kernel, further down): same selections, but the
+// distances it needs are re-evaluated in fp32 from the centroid table instead of being read from a stored matrix.
 //
 // The candidate columns of stage 2 are the entries of D not above the P-th smallest bucket minimum (at least P of them,
 // all inside the P selected buckets, typically 1.2 P), so stage 2 reads P 128-byte lines of D and orders ~80 keys.
